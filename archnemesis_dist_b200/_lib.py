@@ -1,0 +1,68 @@
+"""ctypes binding of libansb200.so (include/ansb200.h).  No torch types cross this boundary:
+device pointers and sizes only.  There is no CPU fallback -- if the library is missing the import
+fails, and every compute entry point raises on a machine without a CUDA device."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libansb200.so")
+
+OK, EINVAL, ECUDA, ENOMEM = 0, -1, -2, -3
+RAD_GRAD, RAD_NAN_TO_NUM = 1, 2
+MAX_NG, MAX_NGAS = 22, 15
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_d = ctypes.c_double
+_u = ctypes.c_uint
+
+EXPORTS = {
+    "ansb200_last_error": (ctypes.c_char_p, []),
+    "ansb200_version": (_i, []),
+    "ansb200_table_create": (_i, [_vp, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_vp), _vp]),
+    "ansb200_table_destroy": (_i, [_vp]),
+    "ansb200_table_shape": (_i, [_vp] + [ctypes.POINTER(_i)] * 5),
+    "ansb200_table_k": (_vp, [_vp]),
+    "ansb200_table_lnk": (_vp, [_vp]),
+    "ansb200_kinterp": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "ansb200_koverlap": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "ansb200_gas_opacity": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "ansb200_radiance": (_i, [_i, _u] + [_vp] * 20 + [_i, _d] + [_i] * 8 + [_vp] * 4),
+    "ansb200_jacobian_project": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ansb200_lbl_absorption": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _d, _d, _d, _d, _d, _d,
+                                    _d, _i, _vp, _vp]),
+    "ansb200_voigt": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+}
+
+_lib = None
+
+
+class Ansb200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load libansb200.so (building nothing: see archnemesis_dist_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libansb200.so not found at %s -- run `python -m archnemesis_dist_b200.build` "
+                          "(there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)     # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != OK:
+        msg = load().ansb200_last_error().decode("utf-8", "replace")
+        if rc == EINVAL:
+            raise ValueError("ansb200: " + msg)
+        if rc == ENOMEM:
+            raise MemoryError("ansb200: " + msg)
+        raise Ansb200Error("ansb200 (code %d): %s" % (rc, msg))

@@ -1,0 +1,81 @@
+// koverlap.cu -- C entry points of the random-overlap kernels (implementation: koverlap_impl.cuh).
+#include "koverlap_impl.cuh"
+
+// NGAS == 1: ForwardModel_0.py:5871-5876 / :6056-6058
+template <bool GRAD>
+__global__ void ans_koverlap_single_kernel(OvParams P)
+{
+    const size_t n = (size_t)P.NWAVE * P.NG * P.NLAY;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (size_t)gridDim.x * blockDim.x) {
+        const int l = (int)(o % P.NLAY);
+        double kv, dv = 0.0;
+        if (P.fused) {
+            const size_t pair = o / P.NLAY;
+            const size_t slab = (size_t)P.NP * P.NT;
+            const double *w = P.plan.w4 + 4 * l;
+            ans_kinterp_elem<GRAD>(P.lnK, P.K, pair * slab + (size_t)P.plan.ip_lo[l] * P.NT + P.plan.it_lo[l], P.NT, 1,
+                                   w[0], w[1], w[2], w[3], GRAD ? P.plan.omv[l] : 0.0, GRAD ? P.plan.vv[l] : 0.0,
+                                   GRAD ? P.plan.dudt[l] : 0.0, kv, dv);
+        } else {
+            kv = P.k[o];
+            if (GRAD) dv = P.dkdT[o];
+        }
+        const double am = P.amount[l];
+        P.tau[o] = __dmul_rn(kv, am);
+        if (GRAD) { P.dk[o * 2] = kv; P.dk[o * 2 + 1] = __dmul_rn(dv, am); }
+    }
+}
+
+static int ov_run(OvParams &P, bool grad, cudaStream_t stream)
+{
+    ANS_REQUIRE(P.NWAVE > 0 && P.NG > 0 && P.NLAY > 0 && P.NGAS > 0, "koverlap: bad shape");
+    ANS_REQUIRE(P.NG <= ANSB200_MAX_NG, "koverlap: NG=%d exceeds %d", P.NG, ANSB200_MAX_NG);
+    ANS_REQUIRE(P.NGAS <= ANSB200_MAX_NGAS, "koverlap: NGAS=%d exceeds %d", P.NGAS, ANSB200_MAX_NGAS);
+    ANS_REQUIRE(P.amount && P.tau && (!grad || P.dk), "koverlap: null pointer");
+    if (P.NGAS == 1) {
+        const size_t n = (size_t)P.NWAVE * P.NG * P.NLAY;
+        int grid = (int)((n + 255) / 256);
+        if (grid > 148 * 16) grid = 148 * 16;
+        if (grad) ans_koverlap_single_kernel<true><<<grid, 256, 0, stream>>>(P);
+        else ans_koverlap_single_kernel<false><<<grid, 256, 0, stream>>>(P);
+        ANS_LAUNCH_CHECK();
+        return ANSB200_OK;
+    }
+    ANS_REQUIRE(P.weight && P.g_ord, "koverlap: weight/g_ord tables are required for NGAS > 1");
+    const int NN = P.NG * P.NG;
+    if (NN <= 128) return ov_dispatch_4(P, grad, stream);
+    if (NN <= 256) return ov_dispatch_8(P, grad, stream);
+    return ov_dispatch_16(P, grad, stream);
+}
+
+// The host checks (plan.overlap_tables) that no sorted element can straddle two bin edges; if it
+// can, bit 1 of want_grad requests the literal sequential bin-edge scan.
+extern "C" int ansb200_koverlap(const double *k, const double *dkdT, const double *amount, const double *weight,
+                                const double *g_ord, int NWAVE, int NG, int NLAY, int NGAS, int want_grad,
+                                double *tau, double *dk, void *stream_)
+{
+    const bool grad = (want_grad & 1) != 0;
+    ANS_REQUIRE(k && (!grad || dkdT), "koverlap: null k/dkdT");
+    OvParams P{};
+    P.k = k; P.dkdT = dkdT; P.amount = amount; P.weight = weight; P.g_ord = g_ord;
+    P.NWAVE = NWAVE; P.NG = NG; P.NLAY = NLAY; P.NGAS = NGAS; P.tau = tau; P.dk = dk;
+    P.fused = 0; P.seq_rebin = (want_grad & 2) ? 1 : 0;
+    return ov_run(P, grad, (cudaStream_t)stream_);
+}
+
+extern "C" int ansb200_gas_opacity(const ansb200_table *t, int NLAY, const int32_t *ip_lo, const int32_t *it_lo,
+                                   const double *w4, const double *omv, const double *vv, const double *dudt,
+                                   const double *amount, const double *weight, const double *g_ord, int want_grad,
+                                   double *tau, double *dk, void *stream_)
+{
+    const bool grad = (want_grad & 1) != 0;
+    ANS_REQUIRE(t && ip_lo && it_lo && w4, "gas_opacity: null pointer");
+    ANS_REQUIRE(!grad || (omv && vv && dudt), "gas_opacity: gradient requested without omv/vv/dudt");
+    OvParams P{};
+    P.lnK = t->lnK; P.K = t->K; P.plan = AnsLayerPlan{ip_lo, it_lo, w4, omv, vv, dudt};
+    P.NP = t->NP; P.NT = t->NT;
+    P.amount = amount; P.weight = weight; P.g_ord = g_ord;
+    P.NWAVE = t->NWAVE; P.NG = t->NG; P.NLAY = NLAY; P.NGAS = t->NGAS; P.tau = tau; P.dk = dk;
+    P.fused = 1; P.seq_rebin = (want_grad & 2) ? 1 : 0;
+    return ov_run(P, grad, (cudaStream_t)stream_);
+}

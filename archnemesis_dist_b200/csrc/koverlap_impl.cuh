@@ -1,0 +1,460 @@
+// koverlap.cu -- random-overlap gas mixing (k_overlap/rank, k_overlapg/rankg) on sm_100a.
+//
+// Reference: archnemesis/ForwardModel_0.py:6029-6173 (no gradients), :5842-6026 (gradients).
+//
+// Work decomposition: one warp owns one (wavenumber, layer) cell and folds the NGAS gases in
+// sequence exactly like the reference.  For every fold that needs the sort/rebin:
+//   1. the NG*NG keys  tau_i + k_j*amount  are formed in registers (EPL per lane, padded with +inf
+//      to 32*EPL), un-fused mul/add so the keys carry the reference's rounding;
+//   2. a register bitonic network (shuffles for the cross-lane stages) sorts (key, packed index)
+//      pairs -- total order, ties broken by index;
+//   3. the cumulative weight is a warp scan; every element finds its g-bin from the cumulative
+//      weight of its predecessor and the bin edges g_ord (host-made in del_g's dtype), and the
+//      element that straddles an edge publishes (position, frac) to shared memory;
+//   4. lane m (< NG) walks the sorted indices of bin m in order and accumulates
+//      cont*weight, weight and the gradient columns in the reference's order and rounding.
+// With identical k inputs the result is bit-identical to the reference whenever no element
+// straddles two bin edges (checked on the host: max weight < min bin width; otherwise the host
+// requests the literal sequential rebin, seq_rebin=1).
+//
+// k and dk/dT of the cell come either from the arrays produced by ansb200_kinterp or, in the
+// fused entry point, straight from the resident ln K table (k_gas never touches HBM).
+#pragma once
+#include "kinterp.cuh"
+
+constexpr int OV_WARPS = 4;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int OV_NONE = 0x7fffffff;
+
+struct OvParams {
+    const double *k, *dkdT;                 // unfused source [NWAVE,NG,NLAY,NGAS]
+    const double *lnK, *K;                  // fused source (table)
+    AnsLayerPlan plan;
+    int NP, NT;
+    const double *amount, *weight, *g_ord;
+    int NWAVE, NG, NLAY, NGAS;
+    double *tau, *dk;
+    int fused, seq_rebin;
+};
+
+__device__ __forceinline__ double shfl_xor_d(double v, int m)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_xor_sync(FULL, lo, m);
+    hi = __shfl_xor_sync(FULL, hi, m);
+    return __hiloint2double(hi, lo);
+}
+
+__device__ __forceinline__ double shfl_up_d(double v, int d)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_up_sync(FULL, lo, d);
+    hi = __shfl_up_sync(FULL, hi, d);
+    return __hiloint2double(hi, lo);
+}
+
+// Bitonic sort of 32*EPL (key, idx) pairs held blocked across the warp: element e = lane*EPL + r.
+template <int EPL>
+__device__ __forceinline__ void ov_bitonic_sort(double (&key)[EPL], int (&idx)[EPL], int lane)
+{
+    constexpr int N = 32 * EPL;
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= EPL) {
+                const int lm = j / EPL;
+                const bool lower = (lane & lm) == 0;
+#pragma unroll
+                for (int r = 0; r < EPL; ++r) {
+                    const bool up = (((lane * EPL + r) & k) == 0);
+                    const double pk = shfl_xor_d(key[r], lm);
+                    const int pi = __shfl_xor_sync(FULL, idx[r], lm);
+                    const bool partner_less = (pk < key[r]) || (pk == key[r] && pi < idx[r]);
+                    const bool take = (lower == up) ? partner_less : !partner_less;
+                    if (take) { key[r] = pk; idx[r] = pi; }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < EPL; ++r) {
+                    if ((r & j) == 0) {
+                        const int q = r | j;
+                        const bool up = (((lane * EPL + r) & k) == 0);
+                        const bool gt = (key[r] > key[q]) || (key[r] == key[q] && idx[r] > idx[q]);
+                        if (gt == up) {
+                            const double tk = key[r]; key[r] = key[q]; key[q] = tk;
+                            const int ti = idx[r]; idx[r] = idx[q]; idx[q] = ti;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Per-warp shared-memory view.
+struct OvWarpSmem {
+    double *kbuf, *dbuf;     // [NG*NGAS] k and dk/dT of the cell
+    double *a, *b, *bT;      // [NG] running tau_g, next gas tau, next gas dk/dT*amount
+    double *dkp;             // [NG*NP1] running dk_g_param
+    double *frac;            // [NG+1]
+    int *strad;              // [NG+1]
+    unsigned short *sidx;    // [NG*NG] sorted packed indices
+};
+
+// One sort/rebin fold.  a[] holds the running tau_g, b[] the next gas; with GRAD the gradient row of
+// element (i,j) is { dkp[i][0..igas], kbuf[j][g1], dkp[i][igas+1] + bT[j] } (ForwardModel_0.py:5946-5949).
+template <int EPL, int NPMAX, bool GRAD>
+__device__ __forceinline__ void ov_fold(const OvWarpSmem &s, const double *__restrict__ wtab,
+                                        const double *__restrict__ gord, int NG, int NGAS, int igas, int lane,
+                                        int seq_rebin)
+{
+    const int NN = NG * NG;
+    const int NP1 = NGAS + 1;
+    const int g1 = igas + 1;
+    double key[EPL];
+    int idx[EPL];
+    {
+        int e = lane * EPL;
+        int i = e / NG, j = e - i * NG;
+#pragma unroll
+        for (int r = 0; r < EPL; ++r) {
+            if (e < NN) {
+                key[r] = __dadd_rn(s.a[i], s.b[j]);
+                idx[r] = (i << 5) | j;
+            } else {
+                key[r] = INFINITY;
+                idx[r] = (32 << 5) + (e - NN);   // distinct, above every live index
+            }
+            ++e;
+            if (++j == NG) { j = 0; ++i; }
+        }
+    }
+    ov_bitonic_sort<EPL>(key, idx, lane);
+
+    // cumulative weight in sorted order
+    double gd[EPL];
+    {
+        double run = 0.0;
+#pragma unroll
+        for (int r = 0; r < EPL; ++r) {
+            const int pi = idx[r];
+            const double w = (pi >> 5) < NG ? wtab[(pi >> 5) * NG + (pi & 31)] : 0.0;
+            run = __dadd_rn(run, w);
+            gd[r] = run;
+        }
+        double incl = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double up = shfl_up_d(incl, d);
+            if (lane >= d) incl = __dadd_rn(incl, up);
+        }
+        const double base = __dsub_rn(incl, run);   // exclusive prefix of this lane
+#pragma unroll
+        for (int r = 0; r < EPL; ++r) gd[r] = __dadd_rn(base, gd[r]);
+        // publish sorted order, find the straddling elements
+        for (int m = lane; m <= NG; m += 32) { s.strad[m] = OV_NONE; s.frac[m] = 0.0; }
+        __syncwarp();
+        double prev = base;
+        int ig = 0;
+        {   // number of edges g_ord[1..NG] that are <= prev
+            int lo = 0, hi = NG;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (gord[mid] <= prev) lo = mid; else hi = mid - 1;
+            }
+            ig = lo;
+        }
+#pragma unroll
+        for (int r = 0; r < EPL; ++r) {
+            const int pi = idx[r];
+            const int pos = lane * EPL + r;
+            if (pos < NN) s.sidx[pos] = (unsigned short)pi;
+            if ((pi >> 5) < NG) {
+                while (ig < NG && gord[ig + 1] <= prev) ++ig;
+                if (ig < NG && !(gd[r] < gord[ig + 1])) {
+                    s.strad[ig + 1] = pos;
+                    s.frac[ig + 1] = __ddiv_rn(__dsub_rn(gord[ig + 1], prev), __dsub_rn(gd[r], prev));
+                }
+            }
+            prev = gd[r];
+        }
+    }
+    __syncwarp();
+
+    double res_tau = 0.0;
+    double res_g[GRAD ? NPMAX : 1];
+    const int n = igas + 3;   // live gradient columns
+    if (GRAD) {
+#pragma unroll
+        for (int p = 0; p < NPMAX; ++p) res_g[p] = 0.0;
+    }
+
+    auto elem = [&](int pos, double &w, double &cw, double (&gw)[GRAD ? NPMAX : 1]) {
+        const int pi = s.sidx[pos];
+        const int i = pi >> 5, j = pi & 31;
+        w = wtab[i * NG + j];
+        cw = __dmul_rn(__dadd_rn(s.a[i], s.b[j]), w);
+        if (GRAD) {
+#pragma unroll
+            for (int p = 0; p < NPMAX; ++p) {
+                if (p < n) {
+                    double g;
+                    if (p <= igas) g = s.dkp[i * NP1 + p];
+                    else if (p == g1) g = s.kbuf[j * NGAS + g1];
+                    else g = __dadd_rn(s.dkp[i * NP1 + g1], s.bT[j]);
+                    gw[p] = __dmul_rn(g, w);
+                }
+            }
+        }
+    };
+
+    if (seq_rebin) {
+        // Literal sequential bin-edge scan of rank/rankg (ForwardModel_0.py:6155-6172) by lane 0,
+        // requested by the host when an element could straddle two edges: an element closes at
+        // most one bin, exactly like the reference loop.
+        if (lane == 0) {
+            for (int m = 0; m <= NG; ++m) { s.strad[m] = OV_NONE; s.frac[m] = 0.0; }
+            double run = 0.0, gprev = 0.0;
+            int ig = 0;
+            for (int pos = 0; pos < NN && ig < NG; ++pos) {
+                const int pi = s.sidx[pos];
+                run = __dadd_rn(run, wtab[(pi >> 5) * NG + (pi & 31)]);
+                if (!(run < gord[ig + 1])) {
+                    s.strad[ig + 1] = pos;
+                    s.frac[ig + 1] = __ddiv_rn(__dsub_rn(gord[ig + 1], gprev), __dsub_rn(run, gprev));
+                    ++ig;
+                }
+                gprev = run;
+            }
+        }
+        __syncwarp();
+    }
+
+    // lane m accumulates bin m in sorted order with the reference's rounding sequence
+    const int m = lane;
+    if (m < NG) {
+        const int e0 = (m == 0) ? -1 : s.strad[m];
+        const int e1 = s.strad[m + 1];
+        if (e0 != OV_NONE) {
+            double acc = 0.0, sum1 = 0.0, w, cw;
+            double gw[GRAD ? NPMAX : 1];
+            if (m > 0) {
+                const double omf = __dsub_rn(1.0, s.frac[m]);
+                elem(e0, w, cw, gw);
+                acc = __dmul_rn(omf, cw);
+                sum1 = __dmul_rn(omf, w);
+                if (GRAD) {
+#pragma unroll
+                    for (int p = 0; p < NPMAX; ++p) if (p < n) res_g[p] = __dmul_rn(omf, gw[p]);
+                }
+            }
+            const int stop = (e1 == OV_NONE) ? NN : e1;
+            for (int pos = e0 + 1; pos < stop; ++pos) {
+                elem(pos, w, cw, gw);
+                acc = __dadd_rn(acc, cw);
+                sum1 = __dadd_rn(sum1, w);
+                if (GRAD) {
+#pragma unroll
+                    for (int p = 0; p < NPMAX; ++p) if (p < n) res_g[p] = __dadd_rn(res_g[p], gw[p]);
+                }
+            }
+            bool norm = (m == NG - 1);
+            if (e1 != OV_NONE) {
+                const double f = s.frac[m + 1];
+                elem(e1, w, cw, gw);
+                acc = __dadd_rn(acc, __dmul_rn(f, cw));
+                sum1 = __dadd_rn(sum1, __dmul_rn(f, w));
+                if (GRAD) {
+#pragma unroll
+                    for (int p = 0; p < NPMAX; ++p) if (p < n) res_g[p] = __dadd_rn(res_g[p], __dmul_rn(f, gw[p]));
+                }
+                norm = true;
+            }
+            if (norm) {
+                acc = __ddiv_rn(acc, sum1);
+                if (GRAD) {
+#pragma unroll
+                    for (int p = 0; p < NPMAX; ++p) if (p < n) res_g[p] = __ddiv_rn(res_g[p], sum1);
+                }
+            }
+            res_tau = acc;
+        }
+    }
+    __syncwarp();
+    if (m < NG) {
+        s.a[m] = res_tau;
+        if (GRAD) {
+#pragma unroll
+            for (int p = 0; p < NPMAX; ++p) if (p < NP1) s.dkp[m * NP1 + p] = (p < n) ? res_g[p] : 0.0;
+        }
+    }
+    __syncwarp();
+}
+
+template <int EPL, int NPMAX, bool GRAD>
+__global__ void __launch_bounds__(OV_WARPS * 32)
+ans_koverlap_kernel(OvParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int NG = P.NG, NGAS = P.NGAS, NLAY = P.NLAY, NN = NG * NG, NP1 = NGAS + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    double *wtab = reinterpret_cast<double *>(smem_raw);
+    double *gord = wtab + NN;
+    double *wbase = gord + (NG + 1);
+    // per-warp carve-up (doubles first, then ints, then shorts)
+    const int per_warp_d = NG * NGAS * (GRAD ? 2 : 1) + 3 * NG + (GRAD ? NG * NP1 : 0) + (NG + 1);
+    const size_t per_warp_bytes = ((size_t)per_warp_d * 8 + (size_t)(NG + 1) * 4 + (size_t)NN * 2 + 15) & ~(size_t)15;
+    unsigned char *mine = reinterpret_cast<unsigned char *>(wbase) + per_warp_bytes * warp;
+    OvWarpSmem s;
+    {
+        double *d = reinterpret_cast<double *>(mine);
+        s.kbuf = d; d += NG * NGAS;
+        s.dbuf = d; if (GRAD) d += NG * NGAS;
+        s.a = d; d += NG;
+        s.b = d; d += NG;
+        s.bT = d; d += NG;
+        s.dkp = d; if (GRAD) d += NG * NP1;
+        s.frac = d; d += NG + 1;
+        s.strad = reinterpret_cast<int *>(d);
+        s.sidx = reinterpret_cast<unsigned short *>(s.strad + NG + 1);
+    }
+    for (int i = threadIdx.x; i < NN; i += blockDim.x) wtab[i] = P.weight[i];
+    for (int i = threadIdx.x; i <= NG; i += blockDim.x) gord[i] = P.g_ord[i];
+    __syncthreads();
+
+    const long long ncell = (long long)P.NWAVE * NLAY;
+    const long long cell = (long long)blockIdx.x * OV_WARPS + warp;
+    if (cell >= ncell) return;
+    const int iw = (int)(cell / NLAY);
+    const int l = (int)(cell - (long long)iw * NLAY);
+
+    // stage k (and dk/dT) of the cell
+    if (P.fused) {
+        const size_t slab = (size_t)P.NP * P.NT * NGAS;
+        const size_t toff = ((size_t)__ldg(P.plan.ip_lo + l) * P.NT + __ldg(P.plan.it_lo + l)) * NGAS;
+        const double *w = P.plan.w4 + 4 * l;
+        const double w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+        const double omv = GRAD ? __ldg(P.plan.omv + l) : 0.0, v = GRAD ? __ldg(P.plan.vv + l) : 0.0,
+                     dudt = GRAD ? __ldg(P.plan.dudt + l) : 0.0;
+        for (int e = lane; e < NG * NGAS; e += 32) {
+            const int g = e / NGAS, gas = e - g * NGAS;
+            double kv, dv = 0.0;
+            ans_kinterp_elem<GRAD>(P.lnK, P.K, ((size_t)iw * NG + g) * slab + toff + gas, P.NT, NGAS, w0, w1, w2, w3,
+                                   omv, v, dudt, kv, dv);
+            s.kbuf[e] = kv;
+            if (GRAD) s.dbuf[e] = dv;
+        }
+    } else {
+        for (int e = lane; e < NG * NGAS; e += 32) {
+            const int g = e / NGAS, gas = e - g * NGAS;
+            const size_t o = (((size_t)iw * NG + g) * NLAY + l) * NGAS + gas;
+            s.kbuf[e] = __ldg(P.k + o);
+            if (GRAD) s.dbuf[e] = __ldg(P.dkdT + o);
+        }
+    }
+    for (int i = lane; i < NG; i += 32) s.a[i] = 0.0;
+    if (GRAD) for (int i = lane; i < NG * NP1; i += 32) s.dkp[i] = 0.0;
+    __syncwarp();
+
+#define KB(g, gas) s.kbuf[(g) * NGAS + (gas)]
+#define DB(g, gas) s.dbuf[(g) * NGAS + (gas)]
+    for (int igas = 0; igas < NGAS - 1; ++igas) {
+        const int g1 = igas + 1;
+        const double am1 = __ldg(P.amount + (size_t)g1 * NLAY + l);
+        const bool next_neg = __dmul_rn(KB(NG - 1, g1), am1) <= 0.0;
+        bool do_fold = false;
+        if (igas == 0) {
+            const double am0 = __ldg(P.amount + l);
+            const bool first_neg = __dmul_rn(KB(NG - 1, 0), am0) <= 0.0;
+            if (first_neg) {
+                for (int i = lane; i < NG; i += 32) {
+                    s.a[i] = __dmul_rn(KB(i, 1), am1);
+                    if (GRAD) { s.dkp[i * NP1 + 1] = KB(i, 1); s.dkp[i * NP1 + 2] = __dmul_rn(DB(i, 1), am1); }
+                }
+                __syncwarp();
+            } else if (next_neg) {
+                for (int i = lane; i < NG; i += 32) {
+                    s.a[i] = __dmul_rn(KB(i, 0), am0);
+                    if (GRAD) { s.dkp[i * NP1 + 0] = KB(i, 0); s.dkp[i * NP1 + 2] = __dmul_rn(DB(i, 0), am0); }
+                }
+                __syncwarp();
+            } else {
+                for (int i = lane; i < NG; i += 32) {
+                    s.a[i] = __dmul_rn(KB(i, 0), am0);
+                    s.b[i] = __dmul_rn(KB(i, 1), am1);
+                    if (GRAD) {
+                        s.dkp[i * NP1 + 0] = KB(i, 0);
+                        s.dkp[i * NP1 + 1] = __dmul_rn(DB(i, 0), am0);
+                        s.bT[i] = __dmul_rn(DB(i, 1), am1);
+                    }
+                }
+                do_fold = true;
+            }
+        } else {
+            if (next_neg) {
+                if (GRAD) {
+                    for (int i = lane; i < NG; i += 32) {
+                        s.dkp[i * NP1 + igas + 2] = s.dkp[i * NP1 + igas + 1];
+                        s.dkp[i * NP1 + igas + 1] = __dmul_rn(s.dkp[i * NP1 + igas + 1], 0.0);
+                    }
+                    __syncwarp();
+                }
+            } else if (s.a[NG - 1] <= 0.0) {
+                __syncwarp();
+                for (int i = lane; i < NG; i += 32) {
+                    s.a[i] = __dmul_rn(KB(i, g1), am1);
+                    if (GRAD) { s.dkp[i * NP1 + g1] = KB(i, g1); s.dkp[i * NP1 + igas + 2] = __dmul_rn(DB(i, g1), am1); }
+                }
+                __syncwarp();
+            } else {
+                for (int i = lane; i < NG; i += 32) {
+                    s.b[i] = __dmul_rn(KB(i, g1), am1);
+                    if (GRAD) s.bT[i] = __dmul_rn(DB(i, g1), am1);
+                }
+                do_fold = true;
+            }
+        }
+        if (do_fold) {
+            __syncwarp();
+            ov_fold<EPL, NPMAX, GRAD>(s, wtab, gord, NG, NGAS, igas, lane, P.seq_rebin);
+        }
+    }
+#undef KB
+#undef DB
+    for (int g = lane; g < NG; g += 32) {
+        const size_t o = ((size_t)iw * NG + g) * NLAY + l;
+        P.tau[o] = s.a[g];
+        if (GRAD) for (int p = 0; p < NP1; ++p) P.dk[o * NP1 + p] = s.dkp[g * NP1 + p];
+    }
+}
+
+template <int EPL, int NPMAX, bool GRAD>
+inline int ov_launch(const OvParams &P, cudaStream_t stream)
+{
+    const int NG = P.NG, NGAS = P.NGAS, NN = NG * NG, NP1 = NGAS + 1;
+    const int per_warp_d = NG * NGAS * (GRAD ? 2 : 1) + 3 * NG + (GRAD ? NG * NP1 : 0) + (NG + 1);
+    const size_t per_warp_bytes = ((size_t)per_warp_d * 8 + (size_t)(NG + 1) * 4 + (size_t)NN * 2 + 15) & ~(size_t)15;
+    const size_t smem = (size_t)(NN + NG + 1) * 8 + per_warp_bytes * OV_WARPS + 16;
+    auto kern = ans_koverlap_kernel<EPL, NPMAX, GRAD>;
+    if (smem > 48 * 1024) ANS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long ncell = (long long)P.NWAVE * P.NLAY;
+    kern<<<ans_div_up(ncell, OV_WARPS), OV_WARPS * 32, smem, stream>>>(P);
+    ANS_LAUNCH_CHECK();
+    return ANSB200_OK;
+}
+
+template <int EPL>
+int ov_dispatch_np(const OvParams &P, bool grad, cudaStream_t stream)
+{
+    if (!grad) return ov_launch<EPL, 1, false>(P, stream);
+    const int NP1 = P.NGAS + 1;
+    if (NP1 <= 4) return ov_launch<EPL, 4, true>(P, stream);
+    if (NP1 <= 8) return ov_launch<EPL, 8, true>(P, stream);
+    return ov_launch<EPL, 16, true>(P, stream);
+}
+
+int ov_dispatch_4(const OvParams &P, bool grad, cudaStream_t stream);
+int ov_dispatch_8(const OvParams &P, bool grad, cudaStream_t stream);
+int ov_dispatch_16(const OvParams &P, bool grad, cudaStream_t stream);

@@ -1,0 +1,181 @@
+"""Device-side operators: thin Python wrappers that marshal torch CUDA tensors (buffer carriers
+only) into the C ABI of libansb200.so.  Every function enqueues on torch's current stream and
+returns device tensors; nothing here computes on the CPU and nothing falls back to it."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import plan as _plan
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("archnemesis_dist_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "device-contiguous tensor required"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def to_dev(a, dtype=torch.float64):
+    """Host array (or tensor) -> contiguous device tensor of `dtype`."""
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        return a.to(device="cuda", dtype=dtype).contiguous()
+    npdt = {torch.float64: np.float64, torch.int32: np.int32}[dtype]
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=npdt)).cuda()
+
+
+class Table:
+    """Device-resident k-table (K and ln K), replacing the per-call read_tables of
+    archnemesis/Spectroscopy_0.py:1448-1528.  `K` is [NWAVE,NG,NP,NT,NGAS] float64 (host array
+    or device tensor)."""
+
+    def __init__(self, K):
+        _require_cuda()
+        lib = _lib.load()
+        self.shape = tuple(int(x) for x in K.shape)
+        assert len(self.shape) == 5, "K must be [NWAVE,NG,NP,NT,NGAS]"
+        h = ctypes.c_void_p()
+        if isinstance(K, torch.Tensor):
+            Kd = K.to(device="cuda", dtype=torch.float64).contiguous()
+            src, is_dev = ctypes.c_void_p(Kd.data_ptr()), 1
+        else:
+            Kh = np.ascontiguousarray(K, dtype=np.float64)
+            src, is_dev = ctypes.c_void_p(Kh.ctypes.data), 0
+        _lib.check(lib.ansb200_table_create(src, is_dev, *self.shape, ctypes.byref(h), _stream()))
+        torch.cuda.current_stream().synchronize()   # the source buffer may be released now
+        self._h = h
+        self.nbytes = 2 * 8 * int(np.prod(self.shape))
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise RuntimeError("table already destroyed")
+        return self._h
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            _lib.load().ansb200_table_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DevicePlan:
+    """kinterp plan (plan.kinterp_plan) uploaded to the device."""
+
+    def __init__(self, host_plan, grad):
+        self.host = host_plan
+        self.grad = grad
+        self.NLAY = len(host_plan["ip_lo"])
+        self.ip_lo = to_dev(host_plan["ip_lo"], torch.int32)
+        self.it_lo = to_dev(host_plan["it_lo"], torch.int32)
+        self.w4 = to_dev(host_plan["w4"])
+        self.omv = to_dev(host_plan["omv"])
+        self.vv = to_dev(host_plan["vv"])
+        self.dudt = to_dev(host_plan["dudt"])
+
+
+def kinterp(table, dplan, want_grad=False):
+    """calc_k / calc_kg on the device: k[NWAVE,NG,NLAY,NGAS] (and dkdT)."""
+    _require_cuda()
+    NWAVE, NG, NP, NT, NGAS = table.shape
+    k = torch.empty((NWAVE, NG, dplan.NLAY, NGAS), dtype=torch.float64, device="cuda")
+    dkdT = torch.empty_like(k) if want_grad else None
+    _lib.check(_lib.load().ansb200_kinterp(table.handle, dplan.NLAY, _ptr(dplan.ip_lo), _ptr(dplan.it_lo), _ptr(dplan.w4),
+                                           _ptr(dplan.omv), _ptr(dplan.vv), _ptr(dplan.dudt), int(want_grad),
+                                           _ptr(k), _ptr(dkdT), _stream()))
+    return (k, dkdT) if want_grad else k
+
+
+class OverlapTables:
+    def __init__(self, del_g):
+        w, g, seq = _plan.overlap_tables(del_g)
+        self.weight = to_dev(w)
+        self.g_ord = to_dev(g)
+        self.seq = seq
+        self.NG = len(g) - 1
+
+
+def koverlap(k, amount, otab, dkdT=None, force_seq=False):
+    """k_overlap / k_overlapg on the device.  k[NWAVE,NG,NLAY,NGAS], amount[NGAS,NLAY] (cm-2)."""
+    _require_cuda()
+    NWAVE, NG, NLAY, NGAS = k.shape
+    grad = dkdT is not None
+    tau = torch.empty((NWAVE, NG, NLAY), dtype=torch.float64, device="cuda")
+    dk = torch.empty((NWAVE, NG, NLAY, NGAS + 1), dtype=torch.float64, device="cuda") if grad else None
+    flag = int(grad) | (2 if (otab.seq or force_seq) else 0)
+    _lib.check(_lib.load().ansb200_koverlap(_ptr(k), _ptr(dkdT), _ptr(amount), _ptr(otab.weight), _ptr(otab.g_ord),
+                                            NWAVE, NG, NLAY, NGAS, flag, _ptr(tau), _ptr(dk), _stream()))
+    return (tau, dk) if grad else tau
+
+
+def gas_opacity(table, dplan, amount, otab, want_grad=False, force_seq=False):
+    """Fused calc_k[g] + k_overlap[g] (K_TABLES branch of calculate_gaseous_line_opacity)."""
+    _require_cuda()
+    NWAVE, NG, NP, NT, NGAS = table.shape
+    NLAY = dplan.NLAY
+    tau = torch.empty((NWAVE, NG, NLAY), dtype=torch.float64, device="cuda")
+    dk = torch.empty((NWAVE, NG, NLAY, NGAS + 1), dtype=torch.float64, device="cuda") if want_grad else None
+    flag = int(want_grad) | (2 if (otab.seq or force_seq) else 0)
+    _lib.check(_lib.load().ansb200_gas_opacity(table.handle, NLAY, _ptr(dplan.ip_lo), _ptr(dplan.it_lo), _ptr(dplan.w4),
+                                               _ptr(dplan.omv), _ptr(dplan.vv), _ptr(dplan.dudt), _ptr(amount),
+                                               _ptr(otab.weight), _ptr(otab.g_ord), flag, _ptr(tau), _ptr(dk),
+                                               _stream()))
+    return (tau, dk) if want_grad else tau
+
+
+THERMAL, TRANSMISSION = 0, 1
+
+
+def radiance(mode, tau, dk, gas_slot, taucia, taudust, tauray, dtaucon, layinc, scale, nlayin, emtemp, laypress,
+             wave, delg, emissivity, xfac, solflux, reflectance, sol_ang, emiss_ang, ispace, tsurf, NVMR, NPAR,
+             want_grad, nan_to_num=True):
+    """Path radiance (+ layer-space Jacobian) for all paths; see include/ansb200.h.
+    Returns spec[NWAVE,NPATH] and, with gradients, dspec[NWAVE,NPATH,NPAR,NLAYMAX], dtsurf[NWAVE,NPATH]."""
+    _require_cuda()
+    NWAVE, NG, NLAY = tau.shape
+    NLAYMAX, NPATH = layinc.shape
+    NGAS = 0 if gas_slot is None else int(gas_slot.numel())
+    spec = torch.empty((NWAVE, NPATH), dtype=torch.float64, device="cuda")
+    dspec = dtsurf = None
+    flags = 0
+    if want_grad:
+        flags |= _lib.RAD_GRAD
+        if nan_to_num:
+            flags |= _lib.RAD_NAN_TO_NUM
+        dspec = torch.empty((NWAVE, NPATH, NPAR, NLAYMAX), dtype=torch.float64, device="cuda")
+        dtsurf = torch.zeros((NWAVE, NPATH), dtype=torch.float64, device="cuda")
+    _lib.check(_lib.load().ansb200_radiance(
+        int(mode), flags, _ptr(tau), _ptr(dk), _ptr(gas_slot), _ptr(taucia), _ptr(taudust), _ptr(tauray),
+        _ptr(dtaucon), _ptr(layinc), _ptr(scale), _ptr(nlayin), _ptr(emtemp), _ptr(laypress), _ptr(wave), _ptr(delg),
+        _ptr(emissivity), _ptr(xfac), _ptr(solflux), _ptr(reflectance), _ptr(sol_ang), _ptr(emiss_ang), int(ispace),
+        float(tsurf), NWAVE, NG, NLAY, NGAS, int(NVMR), int(NPAR), NLAYMAX, NPATH, _ptr(spec), _ptr(dspec),
+        _ptr(dtsurf), _stream()))
+    return (spec, dspec, dtsurf) if want_grad else spec
+
+
+def jacobian_project(dspec, M):
+    """dspec[NWAVE,NPATH,NPAR,NLAYMAX] x M[NPATH,NPAR*NLAYMAX,NX] -> [NWAVE,NPATH,NX] (map2pro+map2xvec)."""
+    _require_cuda()
+    NWAVE, NPATH, NPAR, NLM = dspec.shape
+    NX = M.shape[2]
+    out = torch.empty((NWAVE, NPATH, NX), dtype=torch.float64, device="cuda")
+    _lib.check(_lib.load().ansb200_jacobian_project(_ptr(dspec), _ptr(M), NWAVE, NPAR, NLM, NPATH, NX, _ptr(out),
+                                                    _stream()))
+    return out

@@ -1,0 +1,144 @@
+/*
+ * ansb200.h -- C ABI of libansb200.so: the B200 (sm_100a) correlated-k forward model + Jacobian
+ * hot path of archNEMESIS (reference: juanaldayparejo/archnemesis-dist v1.1.0).
+ *
+ * The reference has no FFI layer: its "operator API" is the Python method surface of
+ * ForwardModel_0 and the module-level numba functions it calls.  Each entry point below replaces
+ * one of those functions; the reference file:line it stands in for is cited beside it.
+ *
+ * Conventions
+ *   - every function returns 0 (ANSB200_OK) or a negative error code; ansb200_last_error() gives
+ *     a thread-local message for the last failure;
+ *   - every array argument is a DEVICE pointer owned by the caller unless the name ends in
+ *     `_host`; the library never frees or retains caller memory except through the opaque table
+ *     handle; arrays are C-order float64 unless stated;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no internal
+ *     synchronisation, so calls are asynchronous with respect to the host;
+ *   - no global mutable state besides the handles; distinct handles/streams may be used from
+ *     distinct threads.
+ */
+#ifndef ANSB200_H
+#define ANSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ANSB200_OK 0
+#define ANSB200_EINVAL (-1)  /* bad argument / unsupported shape */
+#define ANSB200_ECUDA (-2)   /* CUDA runtime error (message holds cudaGetErrorString) */
+#define ANSB200_ENOMEM (-3)  /* device allocation failed */
+
+#define ANSB200_MAX_NG 22    /* NG*NG <= 512 keys per register sort */
+#define ANSB200_MAX_NGAS 15  /* NGAS+1 gradient columns <= 16 */
+
+/* ansb200_radiance flags */
+#define ANSB200_RAD_GRAD 1u          /* produce layer-space gradients */
+#define ANSB200_RAD_NAN_TO_NUM 2u    /* np.nan_to_num on g-integrated gradients (ForwardModel_0.py:4507) */
+
+typedef struct ansb200_table ansb200_table;
+
+const char *ansb200_last_error(void);
+int ansb200_version(void);
+
+/* ---- table residency ---------------------------------------------------------------------
+ * Replaces the per-call Spectroscopy_0.read_tables (archnemesis/Spectroscopy_0.py:1448-1528):
+ * the cropped table K[NWAVE,NG,NP,NT,NGAS] (gas fastest, :213) is copied to the device once and
+ * ln K is tabulated beside it (-inf for K==0, NaN for K<0) so k-interp costs one exp per output.
+ * `K` may be a host or a device pointer (is_device selects). */
+int ansb200_table_create(const double *K, int is_device, int NWAVE, int NG, int NP, int NT, int NGAS,
+                         ansb200_table **out, void *stream);
+int ansb200_table_destroy(ansb200_table *t);
+int ansb200_table_shape(const ansb200_table *t, int *NWAVE, int *NG, int *NP, int *NT, int *NGAS);
+/* device pointers to the resident copies (for tests / diagnostics) */
+const double *ansb200_table_k(const ansb200_table *t);
+const double *ansb200_table_lnk(const ansb200_table *t);
+
+/* ---- k-table interpolation ----------------------------------------------------------------
+ * Replaces Spectroscopy_0.calc_k (Spectroscopy_0.py:2298-2437, WAVECALC=None) and calc_kg
+ * (:2147-2295).  The bracket search and the (v,u) weights are evaluated on the host with the
+ * reference's dtypes (float32 PRESS/TEMP on the .kta path) and passed per layer:
+ *   ip_lo[NLAY], it_lo[NLAY] int32   lower bracket (upper = lower+1 in every branch)
+ *   w4[NLAY,4]   (1-v)(1-u), v(1-u), v*u, (1-v)u       omv/vv/dudt[NLAY]: 1-v, v, 1/(thi-tlo)
+ * Output k[NWAVE,NG,NLAY,NGAS] and, if want_grad, dkdT of the same shape. */
+int ansb200_kinterp(const ansb200_table *t, int NLAY, const int32_t *ip_lo, const int32_t *it_lo,
+                    const double *w4, const double *omv, const double *vv, const double *dudt,
+                    int want_grad, double *k, double *dkdT, void *stream);
+
+/* ---- random-overlap gas mixing ------------------------------------------------------------
+ * Replaces k_overlap + rank (archnemesis/ForwardModel_0.py:6029-6173) and k_overlapg + rankg
+ * (:5842-6026).  weight[NG*NG] = del_g[i]*del_g[j] and g_ord[NG+1] = {0, cumsum(del_g)[..], 1}
+ * are made on the host in del_g's own dtype (float32 on the .kta path) and widened.
+ * amount[NGAS,NLAY] in cm-2.  Output tau[NWAVE,NG,NLAY]; if want_grad also
+ * dk[NWAVE,NG,NLAY,NGAS+1] (d tau/d amount_gas ..., d tau/dT).
+ * Ties between sort keys are broken by original index (the reference's numba quicksort leaves
+ * their order unspecified). */
+int ansb200_koverlap(const double *k, const double *dkdT, const double *amount, const double *weight,
+                     const double *g_ord, int NWAVE, int NG, int NLAY, int NGAS, int want_grad,
+                     double *tau, double *dk, void *stream);
+
+/* Fused k-interp + overlap: k_gas / dkgasdT never reach HBM.  Replaces the K_TABLES branch of
+ * ForwardModel_0.calculate_gaseous_line_opacity (ForwardModel_0.py:3850-3877). */
+int ansb200_gas_opacity(const ansb200_table *t, int NLAY, const int32_t *ip_lo, const int32_t *it_lo,
+                        const double *w4, const double *omv, const double *vv, const double *dudt,
+                        const double *amount, const double *weight, const double *g_ord, int want_grad,
+                        double *tau, double *dk, void *stream);
+
+/* ---- path radiance + layer-space Jacobian -------------------------------------------------
+ * Replaces, for every path at once, the opacity assembly of calculate_layer_opacity
+ * (ForwardModel_0.py:3989-4012: continuum add, gas-gradient scatter :3868-3872, LAYINC gather and
+ * SCALE), calc_thermal_emission_spectrum[g] (:6287-6504) with the unit scaling of :4244-4247, or
+ * calculate_transmission_spectrum (:4104-4129), and the g-integration of CIRSrad (:4504-4508).
+ *   mode            0 = thermal emission (IMOD THERMAL_EMISSION), 1 = transmission
+ *   tau[NWAVE,NG,NLAY], dk[NWAVE,NG,NLAY,NGAS+1] (NULL unless GRAD)   gas opacity (koverlap output)
+ *   gas_slot[NGAS] int32   parameter index of each active gas (Atmosphere.locate_gas)
+ *   taucia/taudust/tauray[NWAVE,NLAY]   continuum opacities, added in the reference's order
+ *                          TAUGAS + TAUCIA + TAUDUST + TAURAY (:3989); any may be NULL
+ *   dtaucon[NWAVE,NPAR,NLAY] (NULL -> zeros)
+ *   layinc[NLAYMAX,NPATH] int32, scale[NLAYMAX,NPATH], nlayin[NPATH] int32, emtemp[NLAYMAX,NPATH]
+ *   laypress[NLAY]         layer pressures (for the limb/nadir test of :6354-6357)
+ *   wave[NWAVE], delg[NG] (float64 copy of DELG), emissivity[NWAVE], xfac[NWAVE]
+ *   solflux/reflectance[NWAVE], sol_ang/emiss_ang[NPATH]: non-gradient solar term (:6368-6373); may be NULL
+ * Outputs spec[NWAVE,NPATH]; with GRAD dspec[NWAVE,NPATH,NPAR,NLAYMAX] (path-major, unlike the
+ * reference's (NWAVE,NPAR,NLAYIN,NPATH); the Python face transposes) and, thermal only,
+ * dtsurf[NWAVE,NPATH].  The (NWAVE,NG,NPAR,NLAYIN,NPATH) tensor of the reference is never formed. */
+int ansb200_radiance(int mode, unsigned flags, const double *tau, const double *dk, const int32_t *gas_slot,
+                     const double *taucia, const double *taudust, const double *tauray, const double *dtaucon,
+                     const int32_t *layinc, const double *scale, const int32_t *nlayin, const double *emtemp,
+                     const double *laypress, const double *wave, const double *delg, const double *emissivity,
+                     const double *xfac, const double *solflux, const double *reflectance, const double *sol_ang,
+                     const double *emiss_ang, int ispace, double tsurf, int NWAVE, int NG, int NLAY, int NGAS,
+                     int NVMR, int NPAR, int NLAYMAX, int NPATH, double *spec, double *dspec, double *dtsurf,
+                     void *stream);
+
+/* ---- layer -> profile -> state vector ------------------------------------------------------
+ * Replaces map2pro + map2xvec (ForwardModel_0.py:5319-5424).  The host folds
+ * D[LAYINC[j,path],:] (DAM/DTE/DCO per parameter) with xmap into M[NPATH, NPAR*NLAYMAX, NX];
+ * this computes out[NWAVE,NPATH,NX] = sum_{k,j} dspec[NWAVE,path,k,j] * M[path,(k,j),x]. */
+int ansb200_jacobian_project(const double *dspec, const double *M, int NWAVE, int NPAR, int NLAYMAX,
+                             int NPATH, int NX, double *out, void *stream);
+
+/* ---- line-by-line absorption ---------------------------------------------------------------
+ * Replaces add_line_set_monochromatic_absorption (archnemesis/LineData_0.py:279-358) with the
+ * Voigt profile of lineshape/voigt_impl/voigt_scipy.py:8-52 (SciPy voigt_profile = Re w(z)).
+ *   nu, sw, e_lower, stim_ref [N]; broadening[3*M, N] rows (gamma, n, delta) per molecule;
+ *   mix[M]; pt[NPT,3] = (t_calc, p_calc, q_ratio) per state point; wn_grid[NWAVE] ascending.
+ * out[NPT,NWAVE] is ACCUMULATED into (like the reference). shape_id: 0 Voigt, 1 Lorentz, 2 Gaussian. */
+int ansb200_lbl_absorption(const double *wn_grid, int NWAVE, const double *nu, const double *sw,
+                           const double *e_lower, const double *stim_ref, const double *broadening,
+                           int N, const double *mix, int M, const double *pt, int NPT, double t_ref,
+                           double p_ref, double abundance, double mass, double s_floor,
+                           double wn_calc_window, double wn_approx_window, int shape_id, double *out,
+                           void *stream);
+
+/* Voigt profile exactly as the LBL kernel evaluates it (device arrays of length n; diagnostics). */
+int ansb200_voigt(const double *dwn, const double *alpha_d, const double *gamma_l, int n, double *out,
+                  void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANSB200_H */

@@ -1,0 +1,258 @@
+"""GPU parity tests: every CUDA entry point of libansb200.so against the CPU oracle on the same
+seeded inputs.  Tolerances: k-interp 1e-13 (exp/log differ by an ulp between CUDA and libm),
+overlap bit-exact given identical k, radiance/Jacobian 1e-9 (the BASELINE.json tolerance; the
+observed error is ~1e-13), Voigt 1e-12 against SciPy."""
+import numpy as np
+import pytest
+
+from tests.util import relerr, colerr, cpu
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+    from archnemesis_dist_b200 import ops, plan, synthetic
+    from oracle import oracle
+    return dict(torch=torch, ops=ops, plan=plan, syn=synthetic, orc=oracle)
+
+
+def _case(mods, **kw):
+    return mods["syn"].make_fm_case(**kw)
+
+
+@pytest.mark.parametrize("want_grad", [False, True])
+@pytest.mark.parametrize("zero_fraction", [0.0, 0.2])
+def test_kinterp_matches_oracle(mods, want_grad, zero_fraction):
+    ops, plan, orc = mods["ops"], mods["plan"], mods["orc"]
+    c = _case(mods, nwave=24, ng=20, ngas=5, nlay=30, npro=30, nx=10, seed=11, zero_fraction=zero_fraction)
+    tab = c["tab"]
+    press, temp = c["press"].copy(), c["temp"].copy()
+    press[0], press[-1], temp[3], temp[5] = 20.0, 1e-8, 50.0, 400.0   # clamp on all four sides
+    hp = plan.kinterp_plan(tab["PRESS"], tab["TEMP"], press, temp, want_grad)
+    T = ops.Table(tab["K"])
+    out = ops.kinterp(T, ops.DevicePlan(hp, want_grad), want_grad)
+    ref = orc.calc_k(tab["K"], tab["PRESS"], tab["TEMP"], press, temp, want_grad=want_grad)
+    if want_grad:
+        assert relerr(cpu(out[0]), ref[0]) < 1e-13
+        assert relerr(cpu(out[1]), ref[1]) < 1e-12
+    else:
+        assert relerr(cpu(out), ref) < 1e-13
+
+
+def test_kinterp_negative_and_mixed_corners(mods):
+    ops, plan, orc, syn = mods["ops"], mods["plan"], mods["orc"], mods["syn"]
+    tab = syn.make_ktable(6, 8, 6, 5, 3, seed=5)
+    K = tab["K"].copy()
+    rng = np.random.default_rng(0)
+    K[rng.uniform(size=K.shape) < 0.15] = 0.0          # mixed corners -> 0
+    K[:, :, :, :, 1] = -np.abs(K[:, :, :, :, 1])        # all corners <= 0 -> linear branch
+    press = np.exp(np.linspace(1.0, -12.0, 9))
+    temp = np.linspace(80.0, 280.0, 9)
+    hp = plan.kinterp_plan(tab["PRESS"], tab["TEMP"], press, temp, True)
+    k, d = ops.kinterp(ops.Table(K), ops.DevicePlan(hp, True), True)
+    kr, dr = orc.calc_k(K, tab["PRESS"], tab["TEMP"], press, temp, want_grad=True)
+    assert relerr(cpu(k), kr) < 1e-13 and relerr(cpu(d), dr) < 1e-12
+    assert (kr == 0).any() and (kr < 0).any()
+
+
+@pytest.mark.parametrize("ng,ngas", [(20, 6), (10, 3), (16, 2), (5, 4), (20, 1)])
+@pytest.mark.parametrize("want_grad", [False, True])
+def test_koverlap_bit_exact(mods, ng, ngas, want_grad):
+    ops, orc, syn, torch = mods["ops"], mods["orc"], mods["syn"], mods["torch"]
+    c = _case(mods, nwave=10, ng=ng, ngas=ngas, nlay=12, npro=12, nx=6, nvmr=max(ngas, 2), seed=100 + ng + ngas,
+              zero_fraction=0.15)
+    tab = c["tab"]
+    k, dkdT = orc.calc_k(tab["K"], tab["PRESS"], tab["TEMP"], c["press"], c["temp"], want_grad=True)
+    otab = ops.OverlapTables(tab["DELG"])
+    assert not otab.seq
+    kd, dd, am = ops.to_dev(k), ops.to_dev(dkdT), ops.to_dev(c["amount"])
+    if want_grad:
+        tau, dk = ops.koverlap(kd, am, otab, dkdT=dd)
+        rt, rd = orc.k_overlap(tab["DELG"], k, c["amount"], dkdT=dkdT)
+        assert np.array_equal(cpu(tau), rt)
+        assert np.array_equal(cpu(dk), rd)
+        tau2, dk2 = ops.koverlap(kd, am, otab, dkdT=dd, force_seq=True)
+        assert np.array_equal(cpu(tau2), rt) and np.array_equal(cpu(dk2), rd)
+    else:
+        tau = ops.koverlap(kd, am, otab)
+        assert np.array_equal(cpu(tau), orc.k_overlap(tab["DELG"], k, c["amount"]))
+
+
+def test_koverlap_float64_delg_and_ties(mods):
+    """float64 DELG (HDF5 tables) changes the bin edges; exact ties (gas far below another) keep tau exact."""
+    ops, orc = mods["ops"], mods["orc"]
+    c = _case(mods, nwave=6, ng=20, ngas=3, nlay=8, npro=8, nx=4, nvmr=3, seed=9)
+    tab = c["tab"]
+    k = orc.calc_k(tab["K"], tab["PRESS"], tab["TEMP"], c["press"], c["temp"])
+    k[:, :, :, 2] *= 1e-25      # a_i + b_j == a_i : whole rows tie
+    dg = tab["DELG"].astype(np.float64)
+    otab = ops.OverlapTables(dg)
+    tau = ops.koverlap(ops.to_dev(k), ops.to_dev(c["amount"]), otab)
+    assert relerr(cpu(tau), orc.k_overlap(dg, k, c["amount"])) < 1e-13
+
+
+@pytest.mark.parametrize("want_grad", [False, True])
+def test_gas_opacity_fused(mods, want_grad):
+    ops, plan, orc = mods["ops"], mods["plan"], mods["orc"]
+    c = _case(mods, nwave=12, ng=20, ngas=6, nlay=20, npro=20, nx=8, seed=21, zero_fraction=0.1)
+    tab = c["tab"]
+    hp = plan.kinterp_plan(tab["PRESS"], tab["TEMP"], c["press"], c["temp"], want_grad)
+    T = ops.Table(tab["K"])
+    dp = ops.DevicePlan(hp, want_grad)
+    otab = ops.OverlapTables(tab["DELG"])
+    am = ops.to_dev(c["amount"])
+    fused = ops.gas_opacity(T, dp, am, otab, want_grad)
+    # fused == unfused on the device, bit for bit
+    if want_grad:
+        k, d = ops.kinterp(T, dp, True)
+        tau, dk = ops.koverlap(k, am, otab, dkdT=d)
+        assert np.array_equal(cpu(fused[0]), cpu(tau)) and np.array_equal(cpu(fused[1]), cpu(dk))
+        kr, dr = orc.calc_k(tab["K"], tab["PRESS"], tab["TEMP"], c["press"], c["temp"], want_grad=True)
+        rt, rd = orc.k_overlap(tab["DELG"], kr, c["amount"], dkdT=dr)
+        assert relerr(cpu(fused[0]), rt) < 1e-11
+        assert colerr(cpu(fused[1]), rd) < 1e-10
+    else:
+        tau = ops.koverlap(ops.kinterp(T, dp, False), am, otab)
+        assert np.array_equal(cpu(fused), cpu(tau))
+        kr = orc.calc_k(tab["K"], tab["PRESS"], tab["TEMP"], c["press"], c["temp"])
+        assert relerr(cpu(fused), orc.k_overlap(tab["DELG"], kr, c["amount"])) < 1e-11
+
+
+def _radiance_inputs(mods, c, tau, dk):
+    ops, torch = mods["ops"], mods["torch"]
+    d = ops.to_dev
+    return dict(tau=d(tau), dk=d(dk) if dk is not None else None, gas_slot=d(c["gas_slot"], torch.int32),
+                taucia=d(c["taucon"]), dtaucon=d(c["dtaucon"]), layinc=d(c["LAYINC"], torch.int32), scale=d(c["SCALE"]),
+                nlayin=d(c["NLAYIN"], torch.int32), emtemp=d(c["EMTEMP"]), laypress=d(c["LAYPRESS"]),
+                wave=d(c["tab"]["WAVE"]), delg=d(c["tab"]["DELG"].astype(np.float64)), emissivity=d(c["EMISSIVITY"]),
+                xfac=d(c["xfac"]))
+
+
+@pytest.mark.parametrize("tsurf", [-1.0, 180.0])
+@pytest.mark.parametrize("want_grad", [False, True])
+def test_radiance_thermal(mods, tsurf, want_grad):
+    ops, orc = mods["ops"], mods["orc"]
+    c = _case(mods, nwave=14, ng=20, ngas=4, nlay=37, npro=37, nx=12, nvmr=6, ndust=1, seed=31, tsurf=tsurf)
+    c["xfac"] = np.linspace(0.5, 2.0, 14)
+    tab = c["tab"]
+    kr, dr = orc.calc_k(tab["K"], tab["PRESS"], tab["TEMP"], c["press"], c["temp"], want_grad=True)
+    tau, dk = orc.k_overlap(tab["DELG"], kr, c["amount"], dkdT=dr)
+    a = _radiance_inputs(mods, c, tau, dk if want_grad else None)
+    out = ops.radiance(ops.THERMAL, a["tau"], a["dk"], a["gas_slot"], a["taucia"], None, None,
+                       a["dtaucon"] if want_grad else None, a["layinc"], a["scale"], a["nlayin"], a["emtemp"],
+                       a["laypress"], a["wave"], a["delg"], a["emissivity"], a["xfac"], None, None, None, None,
+                       c["ISPACE"], tsurf, c["NVMR"], c["NPAR"], want_grad)
+    tl, tp, dtl = orc.assemble_opacity(tau, dk if want_grad else None, c["gas_slot"], c["NVMR"], c["NPAR"], c["taucon"],
+                                       c["dtaucon"], c["LAYINC"], c["SCALE"])
+    z = np.zeros(14)
+    S, dS, dT = orc.thermal_paths(c["ISPACE"], tab["WAVE"], tl, dtl, c["NVMR"], c["NLAYIN"], c["EMTEMP"], c["LAYPRESS"],
+                                  c["LAYINC"], tsurf, c["EMISSIVITY"], c["xfac"], z, z, np.array([100.0]),
+                                  np.array([10.0]))
+    dg = tab["DELG"]
+    if want_grad:
+        s_ref, d_ref, t_ref = orc.g_integrate(S, dS, dT, dg)
+        spec, dspec, dts = out
+        assert relerr(cpu(spec), s_ref) < 1e-12
+        got = np.transpose(cpu(dspec), (0, 2, 3, 1))     # -> (NWAVE,NPAR,NLAYIN,NPATH)
+        for kpar in range(c["NPAR"]):
+            assert colerr(got[:, kpar], d_ref[:, kpar]) < 1e-11, kpar
+        big = np.abs(d_ref) > 1e-6 * np.abs(d_ref).max()
+        assert relerr(got[big], d_ref[big]) < 1e-9
+        assert relerr(cpu(dts), t_ref) < 1e-12
+    else:
+        assert relerr(cpu(out), orc.g_integrate(S, None, None, dg)) < 1e-12
+
+
+@pytest.mark.parametrize("want_grad", [False, True])
+def test_radiance_transmission_multipath(mods, want_grad):
+    ops, orc, torch = mods["ops"], mods["orc"], mods["torch"]
+    c = _case(mods, nwave=9, ng=10, ngas=3, nlay=16, npro=16, nx=5, nvmr=4, seed=41)
+    rng = np.random.default_rng(3)
+    # three limb-like paths of different length (down and up again), zero padded like Path_0 does
+    nlm, npath = 24, 3
+    layinc = np.zeros((nlm, npath), np.int32)
+    scale = np.zeros((nlm, npath))
+    nlayin = np.array([24, 16, 6], np.int32)
+    for p, n in enumerate(nlayin):
+        half = n // 2
+        seq = list(range(15, 15 - half, -1))
+        layinc[:n, p] = seq + seq[::-1]
+        scale[:n, p] = rng.uniform(1.0, 30.0, n)
+    c.update(LAYINC=layinc, SCALE=scale, NLAYIN=nlayin, EMTEMP=np.zeros((nlm, npath)))
+    c["xfac"] = np.linspace(1.0, 3.0, 9)
+    tab = c["tab"]
+    kr, dr = orc.calc_k(tab["K"], tab["PRESS"], tab["TEMP"], c["press"], c["temp"], want_grad=True)
+    tau, dk = orc.k_overlap(tab["DELG"], kr, c["amount"], dkdT=dr)
+    tau *= 1e-3   # keep the transmissions away from underflow
+    dk *= 1e-3
+    a = _radiance_inputs(mods, c, tau, dk if want_grad else None)
+    out = ops.radiance(ops.TRANSMISSION, a["tau"], a["dk"], a["gas_slot"], a["taucia"], None, None,
+                       a["dtaucon"] if want_grad else None, a["layinc"], a["scale"], a["nlayin"], None, None, None,
+                       a["delg"], None, a["xfac"], None, None, None, None, 0, -1.0, c["NVMR"], c["NPAR"], want_grad)
+    tl, tp, dtl = orc.assemble_opacity(tau, dk if want_grad else None, c["gas_slot"], c["NVMR"], c["NPAR"], c["taucon"],
+                                       c["dtaucon"], layinc, scale)
+    S, dS = orc.transmission(tp, dtl, c["xfac"])
+    dg = tab["DELG"]
+    if want_grad:
+        s_ref, d_ref, _ = orc.g_integrate(S, dS, None, dg)
+        spec, dspec, _ = out
+        assert relerr(cpu(spec), s_ref) < 1e-12
+        got = np.transpose(cpu(dspec), (0, 2, 3, 1))
+        assert colerr(got, d_ref) < 1e-12
+    else:
+        assert relerr(cpu(out), orc.g_integrate(S, None, None, dg)) < 1e-12
+
+
+def test_jacobian_project(mods):
+    ops, plan, orc = mods["ops"], mods["plan"], mods["orc"]
+    c = _case(mods, nwave=50, ng=4, ngas=2, nlay=21, npro=33, nx=70, nvmr=5, ndust=2, seed=51)
+    rng = np.random.default_rng(8)
+    npath, nlm = 2, 21
+    layinc = np.stack([np.arange(20, -1, -1), np.r_[np.arange(20, 10, -1), np.zeros(11, int)]], axis=1).astype(np.int32)
+    nlayin = np.array([21, 10], np.int32)
+    dspec_ref = rng.normal(size=(50, c["NPAR"], nlm, npath))       # reference layout
+    dspec_ref[:, :, 10:, 1] = 0.0
+    xmap = c["xmap"].copy()
+    xmap[3, c["NVMR"] + 1, :] = 0.5      # a dust parameter too
+    M = plan.fold_projection(xmap, layinc, nlayin, c["DTE"], c["DAM"], c["DCO"], c["NVMR"], c["NDUST"])
+    out = ops.jacobian_project(ops.to_dev(np.transpose(dspec_ref, (0, 3, 1, 2))), ops.to_dev(M))
+    inc = orc.included_params(xmap)
+    d2 = orc.map2pro(dspec_ref, 50, c["NVMR"], c["NDUST"], c["NPRO"], npath, nlayin, layinc, c["DTE"], c["DAM"], c["DCO"],
+                     INCPAR=inc)
+    ref = orc.map2xvec(d2, xmap)
+    assert colerr(cpu(out), ref) < 1e-13
+
+
+def test_voigt_matches_scipy(mods):
+    import ctypes
+    from scipy.special import voigt_profile
+    from archnemesis_dist_b200 import _lib
+    ops, torch = mods["ops"], mods["torch"]
+    rng = np.random.default_rng(2)
+    n = 200000
+    dwn = np.concatenate([rng.uniform(-25, 25, n // 2), rng.normal(0, 0.01, n // 4), 10.0 ** rng.uniform(-8, 1.4, n // 4)])
+    ad = 10.0 ** rng.uniform(-4, -1.5, n)
+    gl = 10.0 ** rng.uniform(-6, 0.5, n)
+    dwn[:5] = [0.0, 25.0, -25.0, 1e-300, 24.999]
+    out = torch.empty(n, dtype=torch.float64, device="cuda")
+    d = ops.to_dev
+    a, b, g = d(dwn), d(ad), d(gl)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    _lib.check(_lib.load().ansb200_voigt(p(a), p(b), p(g), n, p(out), None))
+    ref = voigt_profile(dwn, ad / np.sqrt(2.0 * np.log(2.0)), gl)
+    assert relerr(cpu(out), ref) < 1e-12
+
+
+def test_lbl_absorption_matches_oracle(mods):
+    ops, orc, syn, torch = mods["ops"], mods["orc"], mods["syn"], mods["torch"]
+    from archnemesis_dist_b200 import lbl
+    wn = np.linspace(1000.0, 1010.0, 3001)
+    lines = syn.make_line_list(400, 1000.0, 1010.0, seed=4)
+    pts = [(200.0, 0.1, 1.3), (296.0, 1.0, 1.0), (120.0, 1e-4, 4.0)]
+    mix = np.array([0.05, 0.95])
+    out = lbl.lbl_absorption(wn, lines, pts, t_ref=296.0, p_ref=1.0, abundance=0.98, mass=28.0, mix=mix)
+    for i, (t, p, q) in enumerate(pts):
+        ref = orc.lbl_absorption(wn, lines, t, p, 296.0, 1.0, q, 0.98, 28.0, mix)
+        assert relerr(cpu(out[i]), ref) < 1e-11, i
