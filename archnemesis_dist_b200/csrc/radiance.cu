@@ -124,7 +124,7 @@ ans_radiance_kernel(RadParams P)
     double *sdts = sspec + NG;                            // [NG] dtsurf_g
     int *slay = reinterpret_cast<int *>(sdts + NG);      // [NLM]
 
-    const double wv = P.wave[iw];
+    const double wv = thermal ? P.wave[iw] : 0.0;
     const double xf = P.xfac ? P.xfac[iw] : 1.0;
     for (int j = threadIdx.x; j < n; j += RAD_THREADS) {
         const int l = P.layinc[(size_t)j * NPATH + ipath];
