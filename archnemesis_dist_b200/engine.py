@@ -1,0 +1,195 @@
+"""The hot path as one object: resident k-table + per-evaluation inputs -> spectrum and Jacobian.
+
+``HotPath`` is the public entry point of this package for callers that hold plain arrays (the
+benchmark, the GPU tests, the ``ForwardModel_0`` mix-in of ``forward_model.py``).  It strings the
+C-ABI calls of libansb200.so together on torch's current CUDA stream:
+
+    gas_opacity (k-interp + random overlap)  ->  radiance (+ layer Jacobian)  ->  jacobian_project
+
+Host arrays are staged through pinned memory; results come back as numpy arrays.  There is no CPU
+path: constructing a ``HotPath`` without a CUDA device raises.
+"""
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import ops as _ops
+from . import plan as _plan
+
+THERMAL, TRANSMISSION = 0, 1
+
+
+@dataclass
+class Evaluation:
+    """Host-side inputs of one CIRSrad evaluation (one atmosphere state, NPATH paths).
+
+    Names follow the reference objects they are read from:
+      press_atm, temp          LayerX.PRESS/101325, LayerX.TEMP            [NLAY]
+      amount                   LayerX.AMOUNT[:,IGAS]*1e-4 per active gas   [NGAS,NLAY]  (cm-2)
+      gas_slot                 AtmosphereX.locate_gas(ID,ISO) per active gas [NGAS]
+      taucia/taudust/tauray    continuum opacities                         [NWAVE,NLAY] or None
+      dtaucon                  d(continuum)/d(parameter)                   [NWAVE,NPAR,NLAY] or None
+      LAYINC, SCALE, EMTEMP    PathX                                       [NLAYMAX,NPATH]
+      NLAYIN                   PathX.NLAYIN                                [NPATH]
+      LAYPRESS                 LayerX.PRESS (Pa)                           [NLAY]
+    """
+    press_atm: np.ndarray
+    temp: np.ndarray
+    amount: np.ndarray
+    gas_slot: np.ndarray
+    NVMR: int
+    NPAR: int
+    LAYINC: np.ndarray
+    SCALE: np.ndarray
+    NLAYIN: np.ndarray
+    EMTEMP: Optional[np.ndarray] = None
+    LAYPRESS: Optional[np.ndarray] = None
+    taucia: Optional[np.ndarray] = None
+    taudust: Optional[np.ndarray] = None
+    tauray: Optional[np.ndarray] = None
+    dtaucon: Optional[np.ndarray] = None
+    mode: int = THERMAL
+    ISPACE: int = 0
+    TSURF: float = -1.0
+    EMISSIVITY: Optional[np.ndarray] = None
+    xfac: Optional[np.ndarray] = None
+    SOLFLUX: Optional[np.ndarray] = None
+    REFLECTANCE: Optional[np.ndarray] = None
+    SOL_ANG: Optional[np.ndarray] = None
+    EMISS_ANG: Optional[np.ndarray] = None
+    h2d_bytes: int = field(default=0, init=False)
+
+
+class _Stager:
+    """Pinned host staging + async H2D on the current stream; counts the bytes it moves."""
+
+    def __init__(self):
+        self.bytes = 0
+        self._pinned = {}
+
+    def __call__(self, name, a, dtype=torch.float64):
+        if a is None:
+            return None
+        npdt = np.float64 if dtype == torch.float64 else np.int32
+        a = np.ascontiguousarray(a, dtype=npdt)
+        slot = self._pinned.get(name)
+        if slot is None or slot[0].shape != a.shape or slot[0].dtype != dtype:
+            slot = [torch.empty(a.shape, dtype=dtype, pin_memory=True), None]
+            self._pinned[name] = slot
+        buf, ev = slot
+        if ev is not None:
+            ev.synchronize()          # the previous async copy out of this pinned buffer must be done
+        buf.numpy()[...] = a
+        self.bytes += a.nbytes
+        dev = buf.to("cuda", non_blocking=True)
+        slot[1] = torch.cuda.Event()
+        slot[1].record()
+        return dev
+
+
+class HotPath:
+    """Resident table + device operators for the correlated-k forward model and its Jacobian.
+
+    K      [NWAVE,NG,NP,NT,NGAS] float64 (SpectroscopyX.K);  PRESS (atm) / TEMP (K) / DELG / WAVE are
+           taken with the dtypes the live Spectroscopy object holds (float32 after a .kta read).
+    """
+
+    def __init__(self, K, PRESS, TEMP, DELG, WAVE, ops=_ops):
+        self.ops = ops
+        self.table = ops.Table(K)
+        self.NWAVE, self.NG, self.NP, self.NT, self.NGAS = (int(x) for x in K.shape)
+        self.PRESS = np.asarray(PRESS)
+        self.TEMP = np.asarray(TEMP)
+        self.DELG = np.asarray(DELG)
+        self.WAVE = np.asarray(WAVE, dtype=np.float64)
+        self.otab = ops.OverlapTables(self.DELG)
+        self.wave_d = ops.to_dev(self.WAVE)
+        self.delg_d = ops.to_dev(self.DELG.astype(np.float64))
+        self._stage = _Stager()
+        self.launches = 0
+
+    # -- host -> device ---------------------------------------------------------------------------
+    def stage(self, ev: Evaluation, return_grad, M=None):
+        """Copy one evaluation's inputs (pinned staging, async on the current stream) and build the
+        k-interp plan.  Returns a Staged object; ev.h2d_bytes records the bytes moved."""
+        st = self._stage
+        st.bytes = 0
+        i32 = torch.int32
+        hp = _plan.kinterp_plan(self.PRESS, self.TEMP, ev.press_atm, ev.temp, return_grad)
+        dev = {k: st("plan_" + k, v, i32 if v.dtype == np.int32 else torch.float64) for k, v in hp.items()}
+        s = Staged()
+        s.grad = return_grad
+        s.plan_host = hp
+        s.dplan = _DevPlan(dev, len(ev.press_atm))
+        s.amount = st("amount", ev.amount)
+        s.gas_slot = st("gas_slot", ev.gas_slot, i32)
+        s.taucia, s.taudust, s.tauray = st("taucia", ev.taucia), st("taudust", ev.taudust), st("tauray", ev.tauray)
+        s.dtaucon = st("dtaucon", ev.dtaucon) if return_grad else None
+        s.layinc, s.scale, s.nlayin = st("layinc", ev.LAYINC, i32), st("scale", ev.SCALE), st("nlayin", ev.NLAYIN, i32)
+        s.emtemp, s.laypress = st("emtemp", ev.EMTEMP), st("laypress", ev.LAYPRESS)
+        s.emissivity, s.xfac = st("emissivity", ev.EMISSIVITY), st("xfac", ev.xfac)
+        s.solflux, s.reflectance = st("solflux", ev.SOLFLUX), st("reflectance", ev.REFLECTANCE)
+        s.sol_ang, s.emiss_ang = st("sol_ang", ev.SOL_ANG), st("emiss_ang", ev.EMISS_ANG)
+        s.M = st("M", M) if M is not None else None
+        s.mode, s.ISPACE, s.TSURF, s.NVMR, s.NPAR = ev.mode, ev.ISPACE, ev.TSURF, ev.NVMR, ev.NPAR
+        ev.h2d_bytes = st.bytes
+        return s
+
+    # -- device stages ---------------------------------------------------------------------------
+    def gas_opacity(self, s, timers=None):
+        """calc_k[g] + k_overlap[g] fused on the device -> tau[NWAVE,NG,NLAY] (, dk[...,NGAS+1])."""
+        if timers is not None:
+            timers[0].record()
+        out = self.ops.gas_opacity(self.table, s.dplan, s.amount, self.otab, s.grad)
+        if timers is not None:
+            timers[1].record()
+        self.launches += 1
+        return out
+
+    def run(self, s, timers=None):
+        """Kernels only, inputs already resident: gas_opacity -> radiance (-> jacobian_project if s.M).
+        Device equivalent of ForwardModel_0.CIRSrad (archnemesis/ForwardModel_0.py:4376-4511) for the
+        thermal-emission and pure-transmission path types, followed by map2pro/map2xvec (:5319-5424)."""
+        go = self.gas_opacity(s, timers)
+        tau, dk = go if s.grad else (go, None)
+        out = self.ops.radiance(s.mode, tau, dk, s.gas_slot, s.taucia, s.taudust, s.tauray, s.dtaucon, s.layinc, s.scale,
+                                s.nlayin, s.emtemp, s.laypress, self.wave_d, self.delg_d, s.emissivity, s.xfac,
+                                s.solflux, s.reflectance, s.sol_ang, s.emiss_ang, s.ISPACE, s.TSURF, s.NVMR, s.NPAR,
+                                s.grad)
+        self.launches += 1
+        if not s.grad:
+            return out
+        spec, dspec, dtsurf = out
+        if s.M is None:
+            return spec, dspec, dtsurf
+        dx = self.ops.jacobian_project(dspec, s.M)
+        self.launches += 1
+        return spec, dx, dtsurf
+
+    # -- host-facing calls -------------------------------------------------------------------------
+    def cirsrad(self, ev: Evaluation, return_grad=False):
+        """spec[NWAVE,NPATH] (, dspec[NWAVE,NPATH,NPAR,NLAYMAX], dtsurf[NWAVE,NPATH]) as device tensors."""
+        return self.run(self.stage(ev, return_grad))
+
+    def forward_jacobian(self, ev: Evaluation, M):
+        """Spectrum and state-vector Jacobian; layer-space gradients never leave the device:
+        CIRSrad(return_grad=True) -> map2pro -> map2xvec of nemesisfmg (ForwardModel_0.py:694-714).
+        M = plan.fold_projection(...) [NPATH, NPAR*NLAYMAX, NX].  Returns device tensors
+        spec[NWAVE,NPATH], dspec_x[NWAVE,NPATH,NX], dtsurf[NWAVE,NPATH]."""
+        return self.run(self.stage(ev, True, M))
+
+    def close(self):
+        self.table.close()
+
+
+class Staged:
+    """Device-resident inputs of one evaluation (see HotPath.stage)."""
+
+
+class _DevPlan:
+    def __init__(self, dev, nlay):
+        self.NLAY = nlay
+        self.ip_lo, self.it_lo = dev["ip_lo"], dev["it_lo"]
+        self.w4, self.omv, self.vv, self.dudt = dev["w4"], dev["omv"], dev["vv"], dev["dudt"]
