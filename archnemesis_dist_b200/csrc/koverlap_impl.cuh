@@ -53,43 +53,142 @@ __device__ __forceinline__ double shfl_up_d(double v, int d)
     return __hiloint2double(hi, lo);
 }
 
-// Bitonic sort of 32*EPL (key, idx) pairs held blocked across the warp: element e = lane*EPL + r.
-template <int EPL>
+// Sorting network over 32*EPL (key, idx) pairs held blocked across the warp: element e = lane*EPL + r.
+//
+// Bitonic merge sort in its all-ascending form: the first stage of the merge of width k pairs e with
+// e ^ (k-1) (mirror image inside the block), the remaining stages pair e with e ^ j, j = k/4 .. 1,
+// and every comparator leaves the smaller element at the smaller index.  Inside a lane all
+// comparators are therefore static; across lanes the only run-time flag is "this lane holds the
+// smaller index".  EXACT selects the total order (key, idx); otherwise only keys are compared (a valid
+// ascending sequence, equal keys in network order) and the caller re-sorts exactly when it sees ties.
+// Compare/select is written in PTX (setp/selp) so that ptxas emits predicated selects, not branches.
+// Stages with k > EPL keep the k and j loops rolled so the code stays inside the instruction cache.
+template <bool EXACT>
+__device__ __forceinline__ void ov_ce(double &ka, int &ia, double &kb, int &ib)
+{
+    // afterwards (ka,ia) sorts before (kb,ib)
+    if (EXACT) {
+        asm("{\n\t.reg .pred lt, eq, il, sw;\n\t.reg .f64 t;\n\t.reg .s32 u;\n\t"
+            "setp.lt.f64 lt, %2, %0;\n\t"
+            "setp.eq.f64 eq, %2, %0;\n\t"
+            "setp.lt.s32 il, %3, %1;\n\t"
+            "and.pred eq, eq, il;\n\t"
+            "or.pred sw, lt, eq;\n\t"
+            "selp.f64 t, %2, %0, sw;\n\t"
+            "selp.f64 %2, %0, %2, sw;\n\t"
+            "mov.f64 %0, t;\n\t"
+            "selp.s32 u, %3, %1, sw;\n\t"
+            "selp.s32 %3, %1, %3, sw;\n\t"
+            "mov.s32 %1, u;\n\t}"
+            : "+d"(ka), "+r"(ia), "+d"(kb), "+r"(ib));
+    } else {
+        asm("{\n\t.reg .pred sw;\n\t.reg .f64 t;\n\t.reg .s32 u;\n\t"
+            "setp.lt.f64 sw, %2, %0;\n\t"
+            "selp.f64 t, %2, %0, sw;\n\t"
+            "selp.f64 %2, %0, %2, sw;\n\t"
+            "mov.f64 %0, t;\n\t"
+            "selp.s32 u, %3, %1, sw;\n\t"
+            "selp.s32 %3, %1, %3, sw;\n\t"
+            "mov.s32 %1, u;\n\t}"
+            : "+d"(ka), "+r"(ia), "+d"(kb), "+r"(ib));
+    }
+}
+
+// cross-lane comparator: (k,i) is mine, (pk,pi) the partner's; keep the smaller if keep_low else the larger
+template <bool EXACT>
+__device__ __forceinline__ void ov_ce_x(double &k, int &i, double pk, int pi, int keep_low)
+{
+    if (EXACT) {
+        asm("{\n\t.reg .pred lt, eq, il, kl, tk;\n\t"
+            "setp.lt.f64 lt, %2, %0;\n\t"
+            "setp.eq.f64 eq, %2, %0;\n\t"
+            "setp.lt.s32 il, %3, %1;\n\t"
+            "and.pred eq, eq, il;\n\t"
+            "or.pred lt, lt, eq;\n\t"          // partner sorts before mine (never equal: idx unique)
+            "setp.ne.s32 kl, %4, 0;\n\t"
+            "xor.pred tk, lt, kl;\n\t"
+            "not.pred tk, tk;\n\t"             // take = (lt == keep_low)
+            "selp.f64 %0, %2, %0, tk;\n\t"
+            "selp.s32 %1, %3, %1, tk;\n\t}"
+            : "+d"(k), "+r"(i) : "d"(pk), "r"(pi), "r"(keep_low));
+    } else {
+        asm("{\n\t.reg .pred lt, gt, kl, tk;\n\t"
+            "setp.lt.f64 lt, %2, %0;\n\t"
+            "setp.gt.f64 gt, %2, %0;\n\t"
+            "setp.ne.s32 kl, %4, 0;\n\t"
+            "and.pred lt, lt, kl;\n\t"
+            "not.pred kl, kl;\n\t"
+            "and.pred gt, gt, kl;\n\t"
+            "or.pred tk, lt, gt;\n\t"          // take = keep_low ? pk < k : pk > k  (equal keys: nobody moves)
+            "selp.f64 %0, %2, %0, tk;\n\t"
+            "selp.s32 %1, %3, %1, tk;\n\t}"
+            : "+d"(k), "+r"(i) : "d"(pk), "r"(pi), "r"(keep_low));
+    }
+}
+
+template <int EPL, bool EXACT>
+__device__ __forceinline__ void ov_intra_halfcleaners(double (&key)[EPL], int (&idx)[EPL], int jstart)
+{
+#pragma unroll
+    for (int j = jstart; j > 0; j >>= 1) {
+#pragma unroll
+        for (int r = 0; r < EPL; ++r)
+            if ((r & j) == 0) ov_ce<EXACT>(key[r], idx[r], key[r | j], idx[r | j]);
+    }
+}
+
+template <int EPL, bool EXACT>
 __device__ __forceinline__ void ov_bitonic_sort(double (&key)[EPL], int (&idx)[EPL], int lane)
 {
-    constexpr int N = 32 * EPL;
+    // runs inside one lane: k = 2 .. EPL
 #pragma unroll
-    for (int k = 2; k <= N; k <<= 1) {
+    for (int k = 2; k <= EPL; k <<= 1) {
 #pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j >= EPL) {
-                const int lm = j / EPL;
-                const bool lower = (lane & lm) == 0;
+        for (int r = 0; r < EPL; ++r) {
+            const int q = r ^ (k - 1);
+            if (r < q) ov_ce<EXACT>(key[r], idx[r], key[q], idx[q]);
+        }
+        ov_intra_halfcleaners<EPL, EXACT>(key, idx, k >> 2);
+    }
+    // merges across lanes: k = kl*EPL, kl = 2 .. 32
+#pragma unroll 1
+    for (int kl = 2; kl <= 32; kl <<= 1) {
+        {   // mirror stage: partner element = e ^ (k-1): lane ^ (kl-1), register EPL-1-r
+            const int keep_low = (lane & (kl >> 1)) == 0;
 #pragma unroll
-                for (int r = 0; r < EPL; ++r) {
-                    const bool up = (((lane * EPL + r) & k) == 0);
-                    const double pk = shfl_xor_d(key[r], lm);
-                    const int pi = __shfl_xor_sync(FULL, idx[r], lm);
-                    const bool partner_less = (pk < key[r]) || (pk == key[r] && pi < idx[r]);
-                    const bool take = (lower == up) ? partner_less : !partner_less;
-                    if (take) { key[r] = pk; idx[r] = pi; }
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < EPL; ++r) {
-                    if ((r & j) == 0) {
-                        const int q = r | j;
-                        const bool up = (((lane * EPL + r) & k) == 0);
-                        const bool gt = (key[r] > key[q]) || (key[r] == key[q] && idx[r] > idx[q]);
-                        if (gt == up) {
-                            const double tk = key[r]; key[r] = key[q]; key[q] = tk;
-                            const int ti = idx[r]; idx[r] = idx[q]; idx[q] = ti;
-                        }
-                    }
-                }
+            for (int r = 0; r < EPL / 2; ++r) {
+                const int q = EPL - 1 - r;
+                const double pkr = shfl_xor_d(key[q], kl - 1), pkq = shfl_xor_d(key[r], kl - 1);
+                const int pir = __shfl_xor_sync(FULL, idx[q], kl - 1), piq = __shfl_xor_sync(FULL, idx[r], kl - 1);
+                ov_ce_x<EXACT>(key[r], idx[r], pkr, pir, keep_low);
+                ov_ce_x<EXACT>(key[q], idx[q], pkq, piq, keep_low);
             }
         }
+#pragma unroll 1
+        for (int lm = kl >> 2; lm > 0; lm >>= 1) {   // half-cleaners across lanes: partner e ^ (lm*EPL)
+            const int keep_low = (lane & lm) == 0;
+#pragma unroll
+            for (int r = 0; r < EPL; ++r) {
+                const double pk = shfl_xor_d(key[r], lm);
+                const int pi = __shfl_xor_sync(FULL, idx[r], lm);
+                ov_ce_x<EXACT>(key[r], idx[r], pk, pi, keep_low);
+            }
+        }
+        ov_intra_halfcleaners<EPL, EXACT>(key, idx, EPL >> 1);
     }
+}
+
+// true if any two live neighbours of the sorted sequence carry equal keys
+template <int EPL>
+__device__ __forceinline__ bool ov_has_ties(const double (&key)[EPL], int lane)
+{
+    bool tie = false;
+#pragma unroll
+    for (int r = 0; r + 1 < EPL; ++r) tie |= (key[r] == key[r + 1]) & (key[r] != INFINITY);
+    const double nxt = __hiloint2double(__shfl_down_sync(FULL, __double2hiint(key[0]), 1),
+                                        __shfl_down_sync(FULL, __double2loint(key[0]), 1));
+    tie |= (lane < 31) & (key[EPL - 1] == nxt) & (nxt != INFINITY);
+    return __any_sync(FULL, tie);
 }
 
 // Per-warp shared-memory view.
@@ -114,7 +213,7 @@ __device__ __forceinline__ void ov_fold(const OvWarpSmem &s, const double *__res
     const int g1 = igas + 1;
     double key[EPL];
     int idx[EPL];
-    {
+    auto make_keys = [&]() {
         int e = lane * EPL;
         int i = e / NG, j = e - i * NG;
 #pragma unroll
@@ -129,8 +228,14 @@ __device__ __forceinline__ void ov_fold(const OvWarpSmem &s, const double *__res
             ++e;
             if (++j == NG) { j = 0; ++i; }
         }
+    };
+    make_keys();
+    ov_bitonic_sort<EPL, false>(key, idx, lane);
+    if (ov_has_ties<EPL>(key, lane)) {
+        // equal keys: order them by index like the oracle does (the reference's own order is unspecified)
+        make_keys();
+        ov_bitonic_sort<EPL, true>(key, idx, lane);
     }
-    ov_bitonic_sort<EPL>(key, idx, lane);
 
     // cumulative weight in sorted order
     double gd[EPL];
@@ -293,7 +398,7 @@ __device__ __forceinline__ void ov_fold(const OvWarpSmem &s, const double *__res
 }
 
 template <int EPL, int NPMAX, bool GRAD>
-__global__ void __launch_bounds__(OV_WARPS * 32)
+__global__ void __launch_bounds__(OV_WARPS * 32, 3)
 ans_koverlap_kernel(OvParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
