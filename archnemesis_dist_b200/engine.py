@@ -180,6 +180,11 @@ class HotPath:
         spec[NWAVE,NPATH], dspec_x[NWAVE,NPATH,NX], dtsurf[NWAVE,NPATH]."""
         return self.run(self.stage(ev, True, M))
 
+    @staticmethod
+    def to_host(t):
+        """Device tensor -> numpy array (synchronises the current stream)."""
+        return t.detach().cpu().numpy()
+
     def close(self):
         self.table.close()
 

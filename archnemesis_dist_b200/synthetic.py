@@ -1,7 +1,7 @@
 """Seeded synthetic k-tables, atmospheres and line lists of the shapes BASELINE.json names.
 
 The recipes are the ones SURVEY.md section 8d fixes for the benchmark configs.  Table values are
-rounded through float32 x 1e20 exactly as a ``.kta`` file stores them
+rounded through float32 exactly as a ``.kta`` round trip leaves them
 (archnemesis/Spectroscopy_0.py:67, :2844-2850), and PRESS/TEMP/DELG/G_ORD are float32 like the
 legacy reader leaves them (:2544-2559), so both the reference and this package see the same bits.
 """
@@ -30,8 +30,10 @@ def make_ktable(nwave, ng, npress, ntemp, ngas, seed, zero_fraction=0.0):
         # whole (wave, gas) columns without absorption, as real tables have outside bands
         dead = rng.uniform(size=(nwave, 1, 1, 1, ngas)) < zero_fraction
         K = np.where(dead, 0.0, K)
-    # .kta storage: float32(k * 1e20); reader returns float64(float32)/1e20
-    K = (K * 1.0e20).astype(np.float32).astype(np.float64) / 1.0e20
+    # .kta storage is float32(k * 1e20); read_ktable divides that float32 array by the Python float
+    # 1e20, which numpy evaluates in float32 (Spectroscopy_0.py:2844-2850), then widens: every table
+    # value is exactly float32-representable
+    K = ((K * 1.0e20).astype(np.float32) / np.float32(1.0e20)).astype(np.float64)
     wave = np.linspace(100.0, 100.0 + 0.25 * (nwave - 1), nwave)
     return dict(K=np.ascontiguousarray(K), PRESS=press, TEMP=temp, G_ORD=g_ord, DELG=del_g, WAVE=wave,
                 NWAVE=nwave, NG=ng, NP=npress, NT=ntemp, NGAS=ngas)

@@ -1,0 +1,261 @@
+"""TEST INFRASTRUCTURE: generate the golden vectors under tests/golden/ from the LIVE reference.
+
+Run in the build container only (needs /root/reference):   python -m oracle.make_golden
+
+Two fixture files are written (and committed, they are small):
+
+  tests/golden/stages.npz     inputs and outputs of every hot-path function of the reference called
+                              in isolation on small seeded arrays: Spectroscopy_0.calc_k / calc_kg,
+                              k_overlap / k_overlapg, calc_thermal_emission_spectrum[g], map2pro,
+                              map2xvec, add_line_set_monochromatic_absorption (numba + SciPy Voigt).
+  tests/golden/jupiter.npz    the Jupiter CIRS nadir deck of the reference's own test
+                              (tests/files/Jupiter_CIRS_nadir_thermal_emission, test_zzz_forward_models.py:155)
+                              run through the unmodified ForwardModel_0.nemesisfmg with synthetic
+                              .kta tables written by the reference's write_ktable (the real tables
+                              are absent, .MISSING_LARGE_BLOBS): every array CIRSrad consumed on a
+                              subset of wavenumber rows, and what CIRSrad / map2pro / map2xvec returned.
+
+The script also asserts that the CPU oracle reproduces the captured reference outputs, i.e. it is
+the pin of oracle/ against the reference.
+"""
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle.ref_import import import_reference, REFERENCE_ROOT  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+from archnemesis_dist_b200 import synthetic as syn  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+JUPITER_GASES = [(26, 0), (27, 0), (6, 1), (6, 2), (6, 3), (28, 0), (11, 0)]   # cirstest.kls order
+
+
+def rel(a, b):
+    d = np.abs(np.asarray(a) - np.asarray(b))
+    m = np.maximum(np.abs(a), np.abs(b))
+    m[m == 0] = 1.0
+    return float((d / m).max())
+
+
+def build_jupiter_deck(dst, nwave=60, vmin=5.0, delv=1.0, conv_lo=12.0, conv_hi=56.0):
+    """Copy the reference's Jupiter CIRS deck, write synthetic k-tables with the reference's own
+    writer and shrink the .spx to a few convolution points so the case runs in seconds."""
+    import_reference()
+    from archnemesis.Spectroscopy_0 import write_ktable
+    src = os.path.join(REFERENCE_ROOT, "tests", "files", "Jupiter_CIRS_nadir_thermal_emission")
+    shutil.rmtree(dst, ignore_errors=True)
+    shutil.copytree(src, dst)
+    os.chmod(dst, 0o755)
+    for f in os.listdir(dst):
+        os.chmod(os.path.join(dst, f), 0o644)
+    paths = []
+    for n, (gid, iso) in enumerate(JUPITER_GASES):
+        t = syn.make_ktable(nwave, 20, 8, 6, 1, seed=50 + n)
+        fn = os.path.join(dst, "gas%d_%d.kta" % (gid, iso))
+        write_ktable(fn, gid, iso, t["G_ORD"], t["DELG"], t["PRESS"], t["TEMP"], nwave, vmin, delv, 2.5, t["K"][..., 0])
+        paths.append(fn)
+    with open(os.path.join(dst, "cirstest.kls"), "w") as f:
+        f.write("\n".join(paths) + "\n")
+    lines = open(os.path.join(src, "cirstest.spx")).read().split("\n")
+    pts = [ln for ln in lines[4:] if ln.strip()]
+    sel = [p for p in pts if conv_lo <= float(p.split()[0]) <= conv_hi][::2]
+    with open(os.path.join(dst, "cirstest.spx"), "w") as f:
+        f.write("\n".join(lines[:1] + ["%10d" % len(sel)] + lines[2:4] + sel) + "\n")
+    return dst
+
+
+def load_jupiter(ans, deck):
+    cwd = os.getcwd()
+    os.chdir(deck)
+    try:
+        objs = ans.Files.read_input_files("cirstest")
+    finally:
+        os.chdir(cwd)
+    names = ["Atmosphere", "Measurement", "Spectroscopy", "Scatter", "Stellar", "Surface", "CIA", "Layer", "Variables"]
+    return dict(zip(names, objs[:9]))
+
+
+def make_forward_model(ans, cls, objs, deck):
+    return cls(runname=os.path.join(deck, "cirstest"), Atmosphere=objs["Atmosphere"], Surface=objs["Surface"],
+               Measurement=objs["Measurement"], Spectroscopy=objs["Spectroscopy"], Stellar=objs["Stellar"],
+               Scatter=objs["Scatter"], CIA=objs["CIA"], Layer=objs["Layer"], Variables=objs["Variables"])
+
+
+def golden_jupiter(ans):
+    from archnemesis_dist_b200.forward_model import B200HotPathMixin
+    fm_mod = sys.modules["archnemesis.ForwardModel_0"]   # the package attribute of that name is the class
+    deck = build_jupiter_deck(os.path.join(tempfile.mkdtemp(prefix="ansb200_"), "deck"))
+    objs = load_jupiter(ans, deck)
+    cap = {}
+
+    class Capture(fm_mod.ForwardModel_0):
+        def CIRSrad(self, return_grad=False):
+            out = super().CIRSrad(return_grad)
+            if return_grad:
+                cap["self"] = self
+                for nm in ("SpectroscopyX", "LayerX", "PathX", "AtmosphereX", "SurfaceX", "MeasurementX", "ScatterX"):
+                    cap[nm] = getattr(self, nm)     # nemesisfm[g] makes fresh copies per call: keep these
+                cap["out"] = out
+                # continuum terms exactly as the drop-in assembles them from the reference's routines
+                cap["cont"] = B200HotPathMixin._b200_continuum(self, True)
+                cia = self.calculate_vertical_cia_opacity(True)
+                ray = self.calc_tau_rayleigh(MakePlot=False)
+                dust = self.calc_tau_dust()
+                cap["raw"] = dict(TAUCIA=cia[0], dTAUCIA=cia[1], TAURAY=ray[0], dTAURAY=ray[1], TAUDUST1=dust[0],
+                                  TAUCLSCAT=dust[1], dTAUDUST1=dust[2], dTAUCLSCAT=dust[3])
+            return out
+
+    orig_m2x = fm_mod.map2xvec
+
+    def m2x(*a, **k):
+        r = orig_m2x(*a, **k)
+        cap["dSPEC1"] = r.copy()
+        cap["xmap"] = a[-1].copy()
+        return r
+
+    fm_mod.map2xvec = m2x
+    cwd = os.getcwd()
+    os.chdir(deck)
+    try:
+        FM = make_forward_model(ans, Capture, objs, deck)
+        SPECONV_fm = FM.nemesisfm()
+        SPECONV, dSPECONV = FM.nemesisfmg()
+    finally:
+        os.chdir(cwd)
+        fm_mod.map2xvec = orig_m2x
+    s = cap["self"]
+    sp, lay, path, atm = cap["SpectroscopyX"], cap["LayerX"], cap["PathX"], cap["AtmosphereX"]
+    SPECOUT, dSPECOUT, dTSURF = cap["out"]
+    TAUCIA, TAUDUST, TAURAY, dTAUCON = cap["cont"]
+    gas_slot = np.array([atm.locate_gas(sp.ID[i], sp.ISO[i]) for i in range(sp.NGAS)], np.int32)
+    amount = np.stack([lay.AMOUNT[:, g] * 1.0e-4 for g in gas_slot])
+
+    # ---- pin the oracle against what the reference just computed (all rows) -----------------------
+    NPAR = atm.NVMR + 2 + cap["ScatterX"].NDUST
+    k, dkdT = orc.calc_k(sp.K, sp.PRESS, sp.TEMP, lay.PRESS / 101325.0, lay.TEMP, want_grad=True)
+    tau, dk = orc.k_overlap(sp.DELG, k, amount, dkdT=dkdT)
+    t = tau + TAUCIA[:, None, :] + TAUDUST[:, None, :] + TAURAY[:, None, :]
+    z = np.zeros_like(TAUCIA)
+    tl, tp, dtl = orc.assemble_opacity(t, dk, gas_slot, atm.NVMR, NPAR, z, dTAUCON, path.LAYINC, path.SCALE)
+    emis = np.zeros(sp.NWAVE)
+    S, dS, dT = orc.thermal_paths(int(cap["MeasurementX"].ISPACE), sp.WAVE, tl, dtl, atm.NVMR, path.NLAYIN, path.EMTEMP,
+                                  lay.PRESS, path.LAYINC, float(cap["SurfaceX"].TSURF), emis, np.ones(sp.NWAVE))
+    o_spec, o_dspec, o_dts = orc.g_integrate(S, dS, dT, sp.DELG)
+    e1, e2 = rel(o_spec, SPECOUT), float(np.abs(o_dspec - dSPECOUT).max() / np.abs(dSPECOUT).max())
+    print("jupiter: oracle vs reference CIRSrad  spec %.2e  dspec(col) %.2e" % (e1, e2))
+    assert e1 < 1e-12 and e2 < 1e-12
+    inc = orc.included_params(cap["xmap"])
+    d2 = orc.map2pro(o_dspec, sp.NWAVE, atm.NVMR, atm.NDUST, atm.NP, path.NPATH, path.NLAYIN, path.LAYINC, lay.DTE,
+                     lay.DAM, lay.DCO, INCPAR=inc)
+    e3 = float(np.abs(orc.map2xvec(d2, cap["xmap"]) - cap["dSPEC1"]).max() / np.abs(cap["dSPEC1"]).max())
+    print("jupiter: oracle vs reference map2xvec %.2e" % e3)
+    assert e3 < 1e-12
+
+    rows = np.unique(np.linspace(0, sp.NWAVE - 1, 8).astype(int))
+    # read_ktable divides the float32 file values by 1e20 in float32 (Spectroscopy_0.py:2848): exact in f32
+    assert np.array_equal(sp.K.astype(np.float32).astype(np.float64), sp.K)
+    raw = cap["raw"]
+    out = dict(
+        rows=rows, K_f32=sp.K[rows].astype(np.float32), PRESS=sp.PRESS, TEMP=sp.TEMP, DELG=sp.DELG,
+        G_ORD=sp.G_ORD, WAVE=sp.WAVE[rows], ID=np.asarray(sp.ID), ISO=np.asarray(sp.ISO),
+        LAY_PRESS=lay.PRESS, LAY_TEMP=lay.TEMP, LAY_AMOUNT=lay.AMOUNT, LAY_TOTAM=lay.TOTAM, DTE=lay.DTE, DAM=lay.DAM,
+        DCO=lay.DCO, LAYINC=path.LAYINC, SCALE=path.SCALE, NLAYIN=path.NLAYIN, EMTEMP=path.EMTEMP,
+        IMOD=np.asarray(path.IMOD).astype(np.int64), SOL_ANG=np.asarray(path.SOL_ANG, float),
+        EMISS_ANG=np.asarray(path.EMISS_ANG, float), ATM_ID=np.asarray(atm.ID), ATM_ISO=np.asarray(atm.ISO),
+        NVMR=atm.NVMR, NDUST=atm.NDUST, NP=atm.NP, TSURF=float(cap["SurfaceX"].TSURF), ISPACE=int(cap["MeasurementX"].ISPACE),
+        IFORM=int(cap["MeasurementX"].IFORM), NX=s.Variables.NX, JSURF=int(s.Variables.JSURF), xmap=cap["xmap"],
+        TAUCIA=raw["TAUCIA"][rows], dTAUCIA=raw["dTAUCIA"][rows], TAURAY=raw["TAURAY"][rows],
+        dTAURAY=raw["dTAURAY"][rows], TAUDUST1=raw["TAUDUST1"][rows], TAUCLSCAT=raw["TAUCLSCAT"][rows],
+        dTAUDUST1=raw["dTAUDUST1"][rows], dTAUCLSCAT=raw["dTAUCLSCAT"][rows],
+        ref_SPECOUT=SPECOUT[rows], ref_dSPECOUT=dSPECOUT[rows], ref_dTSURF=dTSURF[rows], ref_dSPEC1=cap["dSPEC1"][rows],
+        ref_SPECONV=SPECONV, ref_dSPECONV=dSPECONV, ref_SPECONV_fm=SPECONV_fm,
+        gas_slot=gas_slot)
+    np.savez_compressed(os.path.join(GOLD, "jupiter.npz"), **out)
+    print("wrote jupiter.npz", os.path.getsize(os.path.join(GOLD, "jupiter.npz")) // 1024, "KiB")
+
+
+def golden_stages(ans):
+    from archnemesis.ForwardModel_0 import (k_overlap, k_overlapg, calc_thermal_emission_spectrum,
+                                            calc_thermal_emission_spectrumg, map2pro, map2xvec)
+    from archnemesis.LineData_0 import add_line_set_monochromatic_absorption
+    from archnemesis.lineshape import voigt
+    out = {}
+    # ---- k-interp + overlap -------------------------------------------------------------------------
+    c = syn.make_fm_case(nwave=5, ng=20, npress=6, ntemp=5, ngas=3, nlay=9, nvmr=4, ndust=1, npro=9, nx=7, seed=17,
+                         zero_fraction=0.2)
+    tab = c["tab"]
+    S = ans.Spectroscopy_0(ILBL=0)
+    for kk in ("K", "PRESS", "TEMP", "G_ORD", "DELG", "WAVE", "NWAVE", "NG", "NP", "NT", "NGAS"):
+        setattr(S, kk, tab[kk])
+    press, temp = c["press"].copy(), c["temp"].copy()
+    press[0], press[-1], temp[2], temp[4] = 20.0, 1e-8, 50.0, 400.0
+    k = S.calc_k(len(press), press, temp)
+    kg, dkdT = S.calc_kg(len(press), press, temp)
+    tau = k_overlap(tab["DELG"], k, c["amount"])
+    taug, dk = k_overlapg(tab["DELG"], kg, dkdT, c["amount"])
+    tau64 = k_overlap(tab["DELG"].astype(np.float64), k, c["amount"])
+    out.update(ko_seed=17, ko_press=press, ko_temp=temp, ko_amount=c["amount"], ko_k=k, ko_kg=kg, ko_dkdT=dkdT, ko_tau=tau,
+               ko_taug=taug, ko_dk=dk, ko_tau_f64delg=tau64)
+    # oracle pin
+    assert rel(orc.calc_k(tab["K"], tab["PRESS"], tab["TEMP"], press, temp), k) < 1e-15 * 4
+    assert np.array_equal(orc.k_overlap(tab["DELG"], k, c["amount"]), tau)
+    og = orc.k_overlap(tab["DELG"], kg, c["amount"], dkdT=dkdT)
+    assert np.array_equal(og[0], taug) and np.array_equal(og[1], dk)
+    # ---- thermal emission ---------------------------------------------------------------------------
+    tl, tp, dtl = orc.assemble_opacity(taug, dk, c["gas_slot"], c["NVMR"], c["NPAR"], c["taucon"], c["dtaucon"],
+                                       c["LAYINC"], c["SCALE"])
+    emt, emp = c["EMTEMP"][:, 0], c["LAYPRESS"][c["LAYINC"][:, 0]]
+    z = np.zeros(5)
+    em = np.full(5, 0.9)
+    t0 = np.ascontiguousarray(tl[:, :, :, 0])
+    d0 = np.ascontiguousarray(dtl[:, :, :, :, 0])
+    out.update(th_tau=t0, th_dtau=d0, th_emtemp=emt, th_empress=emp, th_wave=tab["WAVE"], th_nvmr=c["NVMR"])
+    for tag, ispace, wave, tsurf, emis in (("a", 0, tab["WAVE"], -1.0, z), ("b", 0, tab["WAVE"], 150.0, em),
+                                           ("c", 1, 1e4 / tab["WAVE"], 150.0, em)):
+        s = calc_thermal_emission_spectrum(ispace, wave, t0, None, emt, emp, tsurf, emis, z, z, 100.0, 10.0)
+        sg, dsg, dts = calc_thermal_emission_spectrumg(ispace, wave, t0, d0, c["NVMR"], emt, emp, tsurf, emis)
+        out.update({"th_%s_spec" % tag: s, "th_%s_specg" % tag: sg, "th_%s_dspec" % tag: dsg, "th_%s_dts" % tag: dts})
+        assert np.array_equal(orc.thermal(ispace, wave, t0, None, emt, emp, tsurf, emis, z, z, 100.0, 10.0), s)
+        o = orc.thermalg(ispace, wave, t0, d0, c["NVMR"], emt, emp, tsurf, emis)
+        assert np.array_equal(o[0], sg) and np.array_equal(o[1], dsg) and np.array_equal(o[2], dts)
+    # ---- map2pro / map2xvec -----------------------------------------------------------------------------
+    rng = np.random.default_rng(5)
+    dspec = rng.normal(size=(5, c["NPAR"], 9, 1))
+    inc = [i for i in range(c["NPAR"]) if np.mean(c["xmap"][:, i, :]) != 0.0]
+    d2 = map2pro(dspec, 5, c["NVMR"], c["NDUST"], c["NPRO"], 1, c["NLAYIN"], c["LAYINC"], c["DTE"], c["DAM"], c["DCO"],
+                 INCPAR=inc)
+    dx = map2xvec(d2, 5, c["NVMR"], c["NDUST"], c["NPRO"], 1, c["NX"], c["xmap"])
+    out.update(mp_dspec=dspec, mp_d2=d2, mp_dx=dx, mp_inc=np.array(inc))
+    # ---- line by line ---------------------------------------------------------------------------------------
+    wn = np.linspace(1000.0, 1004.0, 801)
+    lines = syn.make_line_list(60, 1000.0, 1004.0, seed=4, pad=30.0)
+    mix = np.array([0.05, 0.95])
+    pts = [(200.0, 0.1, 1.3), (296.0, 1.0, 1.0), (120.0, 1e-4, 4.0)]
+    res = []
+    for (tc, pc, q) in pts:
+        o = np.zeros(len(wn))
+        add_line_set_monochromatic_absorption(wn, voigt, tc, 296.0, pc, 1.0, q, 0.98, 28.0, mix, lines["broadening"],
+                                              lines["nu"], lines["sw"], lines["e_lower"], lines["stim_ref"], o)
+        res.append(o)
+        assert rel(orc.lbl_absorption(wn, lines, tc, pc, 296.0, 1.0, q, 0.98, 28.0, mix), o) < 1e-13
+    out.update(lbl_wn=wn, lbl_pts=np.array(pts), lbl_mix=mix, lbl_out=np.array(res),
+               **{"lbl_" + kk: v for kk, v in lines.items()})
+    np.savez_compressed(os.path.join(GOLD, "stages.npz"), **out)
+    print("wrote stages.npz", os.path.getsize(os.path.join(GOLD, "stages.npz")) // 1024, "KiB")
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    ans = import_reference()
+    golden_stages(ans)
+    golden_jupiter(ans)
+
+
+if __name__ == "__main__":
+    main()

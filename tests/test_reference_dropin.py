@@ -1,0 +1,64 @@
+"""CPU, needs the live reference: the drop-in class ForwardModel_B200 (forward_model.install) on the
+reference's own Jupiter CIRS nadir deck against the unmodified ForwardModel_0.  The device layer is
+replaced by the oracle-backed engine of tests/cpu_engine.py, so this exercises exactly the host
+logic of the drop-in: name rebinding, continuum assembly, surface terms, projection folding, the
+nemesisfmg override and the return layouts.  The CUDA kernels are checked against the same golden
+data in tests/test_gpu_golden.py."""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from tests.util import relerr, colerr
+
+pytestmark = pytest.mark.reference
+
+
+@pytest.fixture(scope="module")
+def jupiter():
+    from oracle.ref_import import import_reference
+    from oracle import make_golden as mg
+    ans = import_reference()
+    deck = mg.build_jupiter_deck(os.path.join(tempfile.mkdtemp(prefix="ansb200_t_"), "deck"))
+    return ans, deck, mg
+
+
+def test_install_rebinds_three_names_and_matches_reference(jupiter):
+    ans, deck, mg = jupiter
+    from archnemesis_dist_b200 import forward_model as fmod
+    from tests import cpu_engine
+    ref_cls = sys.modules["archnemesis.ForwardModel_0"].ForwardModel_0
+    objs = mg.load_jupiter(ans, deck)
+    cwd = os.getcwd()
+    os.chdir(deck)
+    try:
+        ref = mg.make_forward_model(ans, ref_cls, objs, deck)
+        S_ref, dS_ref = ref.nemesisfmg()
+        S0_ref = ref.nemesisfm()
+        cls = fmod.install(ans)
+        try:
+            assert ans.ForwardModel_0 is cls
+            assert sys.modules["archnemesis.ForwardModel_0"].ForwardModel_0 is cls
+            assert sys.modules["archnemesis.OptimalEstimation_0"].ForwardModel_0 is cls
+            assert issubclass(cls, ref_cls) and issubclass(cls, fmod.B200HotPathMixin)
+            cls.b200_engine = cpu_engine
+            fm = mg.make_forward_model(ans, ans.ForwardModel_0, objs, deck)
+            S, dS = fm.nemesisfmg()
+            S0 = fm.nemesisfm()          # inherited driver, overridden CIRSrad
+            # CIRSrad keeps the reference's return layout
+            spec, dspec, dts = fm.CIRSrad(return_grad=True)
+            assert dspec.shape == (fm.SpectroscopyX.NWAVE, fm.AtmosphereX.NVMR + 2 + fm.ScatterX.NDUST,
+                                   fm.PathX.NLAYIN.max(), fm.PathX.NPATH)
+            tg, dtg = fm.calculate_gaseous_line_opacity(True)
+        finally:
+            fmod.uninstall(ans)
+        assert ans.ForwardModel_0 is ref_cls
+        tg_ref, dtg_ref = ref_cls.calculate_gaseous_line_opacity(fm, True)
+    finally:
+        os.chdir(cwd)
+    assert relerr(S, S_ref) < 1e-12 and relerr(S0, S0_ref) < 1e-12
+    for ix in range(dS_ref.shape[2]):
+        assert colerr(dS[:, :, ix], dS_ref[:, :, ix]) < 1e-11, ix
+    assert relerr(tg, tg_ref) < 1e-13 and colerr(dtg, dtg_ref) < 1e-13
