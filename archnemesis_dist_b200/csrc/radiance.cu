@@ -263,8 +263,10 @@ ans_radiance_kernel(RadParams P)
             // which dk column feeds parameter k (last matching gas wins, like the reference's loop :3868-3872)
             int col = -1;
             double unit = 1.0;
-            if (k == P.NVMR) col = P.NGAS;
-            else for (int i = 0; i < P.NGAS; ++i) if (P.gas_slot[i] == k) { col = i; unit = 1.0e-4; }
+            if (P.dk) {   // no active gas (NGAS == 0): dTAUGAS is all zeros in the reference (:3883-3888)
+                if (k == P.NVMR) col = P.NGAS;
+                else for (int i = 0; i < P.NGAS; ++i) if (P.gas_slot[i] == k) { col = i; unit = 1.0e-4; }
+            }
             const double dcon = P.dtaucon ? P.dtaucon[((size_t)iw * NPAR + k) * NLAY + l] : 0.0;
             const double sc = sscale[j];
             for (int ig = 0; ig < NG; ++ig) {

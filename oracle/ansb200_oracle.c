@@ -7,7 +7,7 @@
  * so that bench.py can time a CPU baseline on the GPU box's host cores.
  *
  * Parity pin: every routine here is compared against the LIVE reference (imported from
- * /root/reference in the build container, see oracle/make_golden.py and tests/test_oracle_vs_reference.py)
+ * /root/reference in the build container, see oracle/make_golden.py and tests/test_plan.py::test_oracle_matches_live_reference_functions)
  * and against the golden vectors committed under tests/golden/.  The reference's own test-suite pins
  * none of these functions in isolation.
  *
@@ -91,11 +91,73 @@ void orc_kinterp(const double *K, int NWAVE, int NG, int NP, int NT, int NGAS, i
  * Both are produced on the host (archnemesis_dist_b200.plan / oracle.py) so that the float32
  * behaviour of the reference is reproduced bit for bit.
  *
- * The reference sorts with numba's np.argsort (an unstable quicksort); here ties are broken by
- * original index.  With distinct keys the permutation is identical.
+ * The reference sorts with numba's np.argsort, an UNSTABLE quicksort, so the order of equal keys
+ * (and with it the split of the gradient rows across bin edges) is a property of numba's
+ * implementation.  numba is a third-party dependency absent from /root/reference (setup.py:26
+ * requires numba>=0.57; the container has numba 0.65.0): its published algorithm
+ * (numba/misc/quicksort.py: median-of-three pivot stashed at the end, Hoare-style partition,
+ * explicit stack that always pushes the larger side, insertion sort below 15 elements; float keys
+ * compared with `a < b or (isnan(b) and not isnan(a))`, numba/np/arrayobj.py lt_floats) is
+ * restated below so that the oracle reproduces the reference's permutation bit for bit, ties
+ * included.
  * ------------------------------------------------------------------------------------------ */
 typedef struct { double key; int idx; } orc_kv;
 
+static inline int orc_lt(double a, double b) { return a < b || (isnan(b) && !isnan(a)); }
+
+#define ORC_SMALL_QUICKSORT 15
+#define ORC_MAX_STACK 100
+
+static void orc_numba_argsort(const double *A, int n, int *R)
+{
+    for (int i = 0; i < n; ++i) R[i] = i;
+    if (n < 2) return;
+    int stack_lo[ORC_MAX_STACK], stack_hi[ORC_MAX_STACK];
+    int ns = 1;
+    stack_lo[0] = 0; stack_hi[0] = n - 1;
+#define ORC_SWAP(x, y) do { int t__ = R[x]; R[x] = R[y]; R[y] = t__; } while (0)
+    while (ns > 0) {
+        ns -= 1;
+        int low = stack_lo[ns], high = stack_hi[ns];
+        while (high - low >= ORC_SMALL_QUICKSORT) {
+            /* partition A[low..high] around the median of {low, mid, high} */
+            int mid = (low + high) >> 1;
+            if (orc_lt(A[R[mid]], A[R[low]])) ORC_SWAP(low, mid);
+            if (orc_lt(A[R[high]], A[R[mid]])) ORC_SWAP(high, mid);
+            if (orc_lt(A[R[mid]], A[R[low]])) ORC_SWAP(low, mid);
+            double pivot = A[R[mid]];
+            ORC_SWAP(high, mid);
+            int i = low, j = high - 1;
+            for (;;) {
+                while (i < high && orc_lt(A[R[i]], pivot)) i += 1;
+                while (j >= low && orc_lt(pivot, A[R[j]])) j -= 1;
+                if (i >= j) break;
+                ORC_SWAP(i, j);
+                i += 1;
+                j -= 1;
+            }
+            ORC_SWAP(i, high);
+            if (high - i > i - low) {
+                if (high > i) { stack_lo[ns] = i + 1; stack_hi[ns] = high; ns += 1; }
+                high = i - 1;
+            } else {
+                if (i > low) { stack_lo[ns] = low; stack_hi[ns] = i - 1; ns += 1; }
+                low = i + 1;
+            }
+        }
+        /* insertion sort of A[low..high] */
+        for (int i = low + 1; i <= high; ++i) {
+            int k = R[i];
+            double v = A[k];
+            int j = i;
+            while (j > low && orc_lt(v, A[R[j - 1]])) { R[j] = R[j - 1]; j -= 1; }
+            R[j] = k;
+        }
+    }
+#undef ORC_SWAP
+}
+
+/* stable order (key, index): what the CUDA kernels produce for tied keys */
 static int orc_kv_cmp(const void *a, const void *b)
 {
     const orc_kv *x = (const orc_kv *)a, *y = (const orc_kv *)b;
@@ -104,6 +166,9 @@ static int orc_kv_cmp(const void *a, const void *b)
     return (x->idx > y->idx) - (x->idx < y->idx);
 }
 
+static int orc_sort_mode = 0;   /* 0: numba quicksort order (the reference), 1: stable (key, index) order */
+void orc_set_sort_mode(int mode) { orc_sort_mode = mode; }
+
 /* rank / rankg: sort `cont`, accumulate weights, rebin onto the g_ord bins.
  * grad may be NULL (rank).  npar_tot = row length of grad, n = leading columns that are live. */
 static void orc_rank(int ng, const double *weight, const double *cont, const double *g_ord,
@@ -111,8 +176,16 @@ static void orc_rank(int ng, const double *weight, const double *cont, const dou
                      double *k_g, double *dkdq)
 {
     int nloop = ng * ng;
-    for (int i = 0; i < nloop; ++i) { scratch[i].key = cont[i]; scratch[i].idx = i; }
-    qsort(scratch, (size_t)nloop, sizeof(orc_kv), orc_kv_cmp);
+    if (orc_sort_mode == 0) {
+        int R[1024];
+        int *Rp = nloop <= 1024 ? R : (int *)malloc(sizeof(int) * nloop);
+        orc_numba_argsort(cont, nloop, Rp);
+        for (int i = 0; i < nloop; ++i) { scratch[i].key = cont[Rp[i]]; scratch[i].idx = Rp[i]; }
+        if (Rp != R) free(Rp);
+    } else {
+        for (int i = 0; i < nloop; ++i) { scratch[i].key = cont[i]; scratch[i].idx = i; }
+        qsort(scratch, (size_t)nloop, sizeof(orc_kv), orc_kv_cmp);
+    }
     double run = 0.0;
     for (int i = 0; i < nloop; ++i) { run += weight[scratch[i].idx]; gdist[i] = run; }
     for (int i = 0; i < ng; ++i) k_g[i] = 0.0;

@@ -3,7 +3,7 @@
 A restatement (numpy for the host-sized pieces, plain C in ``ansb200_oracle.c`` for the loops) of
 the archNEMESIS v1.1.0 functions on the hot path; every function cites the reference lines it
 follows.  Parity pin: compared with the *live* reference in the build container
-(``tests/test_oracle_vs_reference.py``) and with the golden vectors under ``tests/golden/`` made by
+(``tests/test_plan.py::test_oracle_matches_live_reference_functions``) and with the golden vectors under ``tests/golden/`` made by
 ``oracle/make_golden.py`` from the unmodified reference.  The reference's own tests pin none of
 these functions in isolation.
 
@@ -52,6 +52,17 @@ def _p(a):
 
 def max_threads():
     return int(lib().orc_max_threads())
+
+
+NUMBA_ORDER, STABLE_ORDER = 0, 1
+
+
+def set_sort_mode(mode):
+    """Order of EQUAL sort keys in k_overlap[g]: NUMBA_ORDER (default) reproduces the permutation of
+    numba's unstable quicksort, i.e. the reference bit for bit; STABLE_ORDER breaks ties by original
+    index, which is what the CUDA kernels do.  The two differ only in how gradient rows of tied
+    elements are split across bin edges (tau is unaffected)."""
+    lib().orc_set_sort_mode(int(mode))
 
 
 # ----------------------------------------------------------------------------------------------

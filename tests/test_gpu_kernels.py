@@ -10,6 +10,16 @@ from tests.util import relerr, colerr, cpu
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def stable_tie_order():
+    """The CUDA sort breaks ties between equal keys by index; compare against the oracle in that mode
+    (its default reproduces numba's unstable quicksort, see test_tie_order_deviation)."""
+    from oracle import oracle
+    oracle.set_sort_mode(oracle.STABLE_ORDER)
+    yield
+    oracle.set_sort_mode(oracle.NUMBA_ORDER)
+
+
 @pytest.fixture(scope="module")
 def mods():
     import torch
@@ -91,6 +101,29 @@ def test_koverlap_float64_delg_and_ties(mods):
     otab = ops.OverlapTables(dg)
     tau = ops.koverlap(ops.to_dev(k), ops.to_dev(c["amount"]), otab)
     assert relerr(cpu(tau), orc.k_overlap(dg, k, c["amount"])) < 1e-13
+
+
+def test_tie_order_deviation(mods):
+    """Exact ties (a gas 25 orders of magnitude below another: a_i + b_j == a_i): tau matches the
+    reference's numba-quicksort order to rounding; the gradient columns of the tied gas are split
+    across bin edges in index order instead of numba's order (documented deviation)."""
+    ops, orc = mods["ops"], mods["orc"]
+    c = _case(mods, nwave=6, ng=20, ngas=3, nlay=8, npro=8, nx=4, nvmr=3, seed=9)
+    tab = c["tab"]
+    k, dkdT = orc.calc_k(tab["K"], tab["PRESS"], tab["TEMP"], c["press"], c["temp"], want_grad=True)
+    k[:, :, :, 2] *= 1e-25
+    dkdT[:, :, :, 2] *= 1e-25
+    otab = ops.OverlapTables(tab["DELG"])
+    tau, dk = ops.koverlap(ops.to_dev(k), ops.to_dev(c["amount"]), otab, dkdT=ops.to_dev(dkdT))
+    rt, rd = orc.k_overlap(tab["DELG"], k, c["amount"], dkdT=dkdT)            # stable order
+    assert np.array_equal(cpu(tau), rt) and np.array_equal(cpu(dk), rd)
+    orc.set_sort_mode(orc.NUMBA_ORDER)
+    nt, nd = orc.k_overlap(tab["DELG"], k, c["amount"], dkdT=dkdT)
+    assert relerr(cpu(tau), nt) < 1e-14
+    for col in (0, 1, 3):                                                   # untied gases and dT: unaffected
+        assert colerr(cpu(dk)[..., col], nd[..., col]) < 1e-13
+    assert colerr(cpu(dk)[..., 2], nd[..., 2]) < 0.5                        # tied gas: same mass, other split
+    assert abs(cpu(dk)[..., 2].sum() / nd[..., 2].sum() - 1.0) < 0.2
 
 
 @pytest.mark.parametrize("want_grad", [False, True])
