@@ -115,6 +115,8 @@ def test_jupiter_cirs_deck_golden():
     s1, d1 = fm.b200_forward_jacobian(g["xmap"])
     assert relerr(s1, g["ref_SPECOUT"]) < 1e-12
     for ix in range(d1.shape[2]):
-        assert colerr(d1[:, 0, ix], g["ref_dSPEC1"][:, 0, ix]) < 1e-11, ix
+        # 1e-9 is the BASELINE.json tolerance; the suffix-scan form of the Jacobian bracket cancels
+        # differently from the reference's O(N^2) recurrence: observed <= 2e-11
+        assert colerr(d1[:, 0, ix], g["ref_dSPEC1"][:, 0, ix]) < 1e-10, ix
     tg, dtg = fm.calculate_gaseous_line_opacity(True)
     assert tg.shape == (8, 20, 71) and dtg.shape == (8, 20, 13, 71)
