@@ -197,94 +197,30 @@ struct OvWarpSmem {
     double *a, *b, *bT;      // [NG] running tau_g, next gas tau, next gas dk/dT*amount
     double *dkp;             // [NG*NP1] running dk_g_param
     double *frac;            // [NG+1]
+    double *bsum;            // [NG*(NGAS+3)] raw bin sums: cont*w, w, gradient columns
     int *strad;              // [NG+1]
+    int *closed;             // [NG] bin closed by a straddling element
     unsigned short *sidx;    // [NG*NG] sorted packed indices
 };
 
-// One sort/rebin fold.  a[] holds the running tau_g, b[] the next gas; with GRAD the gradient row of
-// element (i,j) is { dkp[i][0..igas], kbuf[j][g1], dkp[i][igas+1] + bT[j] } (ForwardModel_0.py:5946-5949).
-template <int EPL, int NPMAX, bool GRAD>
-__device__ __forceinline__ void ov_fold(const OvWarpSmem &s, const double *__restrict__ wtab,
-                                        const double *__restrict__ gord, int NG, int NGAS, int igas, int lane,
-                                        int seq_rebin)
+__host__ __device__ inline size_t ov_per_warp_bytes(int NG, int NGAS, bool grad)
 {
+    const int NN = NG * NG, NP1 = NGAS + 1;
+    const int nd = NG * NGAS * (grad ? 2 : 1) + 3 * NG + (grad ? NG * NP1 : 0) + (NG + 1) + NG * (NP1 + 2);
+    return ((size_t)nd * 8 + (size_t)(2 * NG + 1) * 4 + (size_t)NN * 2 + 15) & ~(size_t)15;
+}
+
+// Rebin by lane-per-bin walk in sorted order (bit-identical rounding sequence to rank/rankg).  Used when
+// the host requests the literal sequential bin-edge scan (an element could straddle two edges).
+template <int NPMAX, bool GRAD>
+__device__ __noinline__ void ov_rebin_seq(OvWarpSmem s, const double *__restrict__ wtab,
+                                          const double *__restrict__ gord, int NG, int NGAS, int igas, int lane)
+{
+    // s.sidx holds the sorted packed indices (written by the caller)
     const int NN = NG * NG;
     const int NP1 = NGAS + 1;
     const int g1 = igas + 1;
-    double key[EPL];
-    int idx[EPL];
-    auto make_keys = [&]() {
-        int e = lane * EPL;
-        int i = e / NG, j = e - i * NG;
-#pragma unroll
-        for (int r = 0; r < EPL; ++r) {
-            if (e < NN) {
-                key[r] = __dadd_rn(s.a[i], s.b[j]);
-                idx[r] = (i << 5) | j;
-            } else {
-                key[r] = INFINITY;
-                idx[r] = (32 << 5) + (e - NN);   // distinct, above every live index
-            }
-            ++e;
-            if (++j == NG) { j = 0; ++i; }
-        }
-    };
-    make_keys();
-    ov_bitonic_sort<EPL, false>(key, idx, lane);
-    if (ov_has_ties<EPL>(key, lane)) {
-        // equal keys: order them by index like the oracle does (the reference's own order is unspecified)
-        make_keys();
-        ov_bitonic_sort<EPL, true>(key, idx, lane);
-    }
-
-    // cumulative weight in sorted order
-    double gd[EPL];
-    {
-        double run = 0.0;
-#pragma unroll
-        for (int r = 0; r < EPL; ++r) {
-            const int pi = idx[r];
-            const double w = (pi >> 5) < NG ? wtab[(pi >> 5) * NG + (pi & 31)] : 0.0;
-            run = __dadd_rn(run, w);
-            gd[r] = run;
-        }
-        double incl = run;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const double up = shfl_up_d(incl, d);
-            if (lane >= d) incl = __dadd_rn(incl, up);
-        }
-        const double base = __dsub_rn(incl, run);   // exclusive prefix of this lane
-#pragma unroll
-        for (int r = 0; r < EPL; ++r) gd[r] = __dadd_rn(base, gd[r]);
-        // publish sorted order, find the straddling elements
-        for (int m = lane; m <= NG; m += 32) { s.strad[m] = OV_NONE; s.frac[m] = 0.0; }
-        __syncwarp();
-        double prev = base;
-        int ig = 0;
-        {   // number of edges g_ord[1..NG] that are <= prev
-            int lo = 0, hi = NG;
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (gord[mid] <= prev) lo = mid; else hi = mid - 1;
-            }
-            ig = lo;
-        }
-#pragma unroll
-        for (int r = 0; r < EPL; ++r) {
-            const int pi = idx[r];
-            const int pos = lane * EPL + r;
-            if (pos < NN) s.sidx[pos] = (unsigned short)pi;
-            if ((pi >> 5) < NG) {
-                while (ig < NG && gord[ig + 1] <= prev) ++ig;
-                if (ig < NG && !(gd[r] < gord[ig + 1])) {
-                    s.strad[ig + 1] = pos;
-                    s.frac[ig + 1] = __ddiv_rn(__dsub_rn(gord[ig + 1], prev), __dsub_rn(gd[r], prev));
-                }
-            }
-            prev = gd[r];
-        }
-    }
+    const int seq_rebin = 1;
     __syncwarp();
 
     double res_tau = 0.0;
@@ -397,6 +333,204 @@ __device__ __forceinline__ void ov_fold(const OvWarpSmem &s, const double *__res
     __syncwarp();
 }
 
+// Rebin in parallel over the sorted elements still held in registers (rank/rankg, ForwardModel_0.py
+// :6155-6172 / :6002-6025).  Every lane walks its EPL consecutive sorted elements with a running
+// cumulative weight, accumulates cont*w, w and the gradient columns of the bin it is in and, at the
+// element that straddles a bin edge, closes the bin with `frac` and opens the next with `1-frac`.
+// Bins opened and closed inside one lane are stored directly; a bin that spans several lanes is the
+// owner lane's tail plus the heads of the following lanes (shuffle rounds, as many as the longest
+// span).  Lane m then normalises bin m.  Same arithmetic as the reference, different summation order
+// (agreement ~1e-15); requires that no element straddles two edges (host check), else ov_rebin_seq.
+template <int EPL, int NPMAX, bool GRAD>
+__device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const double *__restrict__ wtab,
+                                             const double *__restrict__ gord, int NG, int NGAS, int igas, int lane,
+                                             const double (&key)[EPL], const int (&idx)[EPL])
+{
+    constexpr int NQ = GRAD ? NPMAX + 2 : 2;   // 0: sum cont*w, 1: sum w, 2+p: gradient column p
+    const int NP1 = NGAS + 1, QS = NP1 + 2;
+    const int g1 = igas + 1;
+    const int n = igas + 3;
+    for (int t = lane; t < NG * QS; t += 32) s.bsum[t] = 0.0;
+    for (int t = lane; t < NG; t += 32) s.closed[t] = 0;
+
+    // exclusive prefix of the lane's weight
+    double run = 0.0;
+#pragma unroll
+    for (int r = 0; r < EPL; ++r) {
+        const int pi = idx[r];
+        run = __dadd_rn(run, (pi >> 5) < NG ? wtab[(pi >> 5) * NG + (pi & 31)] : 0.0);
+    }
+    double incl = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double up = shfl_up_d(incl, d);
+        if (lane >= d) incl = __dadd_rn(incl, up);
+    }
+    double prev = __dsub_rn(incl, run);
+    int ig;
+    {   // number of edges g_ord[1..NG] that are <= prev
+        int lo = 0, hi = NG;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (gord[mid] <= prev) lo = mid; else hi = mid - 1;
+        }
+        ig = lo;
+    }
+    __syncwarp();
+
+    double acc[NQ], head[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) { acc[q] = 0.0; head[q] = 0.0; }
+    bool head_pending = lane != 0;   // the segment this lane starts in was opened by an earlier lane
+#pragma unroll
+    for (int r = 0; r < EPL; ++r) {
+        const int pi = idx[r];
+        const int i = pi >> 5, j = pi & 31;
+        if (i < NG && ig < NG) {
+            const double w = wtab[i * NG + j];
+            const double gdn = __dadd_rn(prev, w);
+            double c[NQ];
+            c[0] = __dmul_rn(key[r], w);
+            c[1] = w;
+            if (GRAD) {
+#pragma unroll
+                for (int p = 0; p < NPMAX; ++p) {
+                    if (p < n) {
+                        double g;
+                        if (p <= igas) g = s.dkp[i * NP1 + p];
+                        else if (p == g1) g = s.kbuf[j * NGAS + g1];
+                        else g = __dadd_rn(s.dkp[i * NP1 + g1], s.bT[j]);
+                        c[2 + p] = __dmul_rn(g, w);
+                    } else {
+                        c[2 + p] = 0.0;
+                    }
+                }
+            }
+            const double edge = gord[ig + 1];
+            if (gdn < edge) {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) acc[q] = __dadd_rn(acc[q], c[q]);
+            } else {
+                const double frac = __ddiv_rn(__dsub_rn(edge, prev), __dsub_rn(gdn, prev));
+                const double omf = __dsub_rn(1.0, frac);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) acc[q] = __dadd_rn(acc[q], __dmul_rn(frac, c[q]));
+                if (head_pending) {
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) head[q] = acc[q];
+                    head_pending = false;
+                } else {
+                    s.bsum[ig * QS + 0] = acc[0];
+                    s.bsum[ig * QS + 1] = acc[1];
+                    if (GRAD) {
+#pragma unroll
+                        for (int p = 0; p < NPMAX; ++p) if (p < n) s.bsum[ig * QS + 2 + p] = acc[2 + p];
+                    }
+                }
+                s.closed[ig] = 1;
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) acc[q] = __dmul_rn(omf, c[q]);
+                ++ig;
+            }
+            prev = gdn;
+        }
+    }
+    // lanes that never closed their incoming segment pass everything on as "head"
+    const bool has_tail = !head_pending;
+    if (head_pending) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) { head[q] = acc[q]; acc[q] = 0.0; }
+    }
+    // tail + heads of the following lanes up to (and including) the first lane that closed a segment
+    bool open = has_tail;
+    for (int d = 1; d < 32; ++d) {
+        const bool cd = __shfl_down_sync(FULL, has_tail ? 1 : 0, d) != 0 || (lane + d >= 32);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const double hd = __hiloint2double(__shfl_down_sync(FULL, __double2hiint(head[q]), d),
+                                               __shfl_down_sync(FULL, __double2loint(head[q]), d));
+            if (open && lane + d < 32) acc[q] = __dadd_rn(acc[q], hd);
+        }
+        if (cd) open = false;
+        if (!__any_sync(FULL, open)) break;
+    }
+    if (has_tail && ig < NG) {
+        s.bsum[ig * QS + 0] = acc[0];
+        s.bsum[ig * QS + 1] = acc[1];
+        if (GRAD) {
+#pragma unroll
+            for (int p = 0; p < NPMAX; ++p) if (p < n) s.bsum[ig * QS + 2 + p] = acc[2 + p];
+        }
+    }
+    __syncwarp();
+    // normalise: a bin closed by a straddler, or the last bin if it was opened (:6171-6172)
+    const int m = lane;
+    if (m < NG) {
+        const bool opened = (m == 0) || s.closed[m - 1] != 0;
+        const bool norm = s.closed[m] != 0 || (m == NG - 1 && opened);
+        const double sw = s.bsum[m * QS + 1];
+        double t = s.bsum[m * QS + 0];
+        if (norm) t = __ddiv_rn(t, sw);
+        s.a[m] = t;
+        if (GRAD) {
+            for (int p = 0; p < NP1; ++p) {
+                double g = p < n ? s.bsum[m * QS + 2 + p] : 0.0;
+                if (norm && p < n) g = __ddiv_rn(g, sw);
+                s.dkp[m * NP1 + p] = g;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// One sort/rebin fold.  a[] holds the running tau_g, b[] the next gas; with GRAD the gradient row of
+// element (i,j) is { dkp[i][0..igas], kbuf[j][g1], dkp[i][igas+1] + bT[j] } (ForwardModel_0.py:5946-5949).
+template <int EPL, int NPMAX, bool GRAD>
+__device__ __forceinline__ void ov_fold(const OvWarpSmem &s, const double *__restrict__ wtab,
+                                        const double *__restrict__ gord, int NG, int NGAS, int igas, int lane,
+                                        int seq_rebin)
+{
+    const int NN = NG * NG;
+    const int NP1 = NGAS + 1;
+    const int g1 = igas + 1;
+    double key[EPL];
+    int idx[EPL];
+    auto make_keys = [&]() {
+        int e = lane * EPL;
+        int i = e / NG, j = e - i * NG;
+#pragma unroll
+        for (int r = 0; r < EPL; ++r) {
+            if (e < NN) {
+                key[r] = __dadd_rn(s.a[i], s.b[j]);
+                idx[r] = (i << 5) | j;
+            } else {
+                key[r] = INFINITY;
+                idx[r] = (32 << 5) + (e - NN);   // distinct, above every live index
+            }
+            ++e;
+            if (++j == NG) { j = 0; ++i; }
+        }
+    };
+    make_keys();
+    ov_bitonic_sort<EPL, false>(key, idx, lane);
+    if (ov_has_ties<EPL>(key, lane)) {
+        // equal keys: order them by index like the oracle does (the reference's own order is unspecified)
+        make_keys();
+        ov_bitonic_sort<EPL, true>(key, idx, lane);
+    }
+
+    if (seq_rebin) {
+#pragma unroll
+        for (int r = 0; r < EPL; ++r) {
+            const int pos = lane * EPL + r;
+            if (pos < NN) s.sidx[pos] = (unsigned short)idx[r];
+        }
+        ov_rebin_seq<NPMAX, GRAD>(s, wtab, gord, NG, NGAS, igas, lane);
+    } else {
+        ov_rebin_par<EPL, NPMAX, GRAD>(s, wtab, gord, NG, NGAS, igas, lane, key, idx);
+    }
+}
+
 template <int EPL, int NPMAX, bool GRAD>
 __global__ void __launch_bounds__(OV_WARPS * 32, 3)
 ans_koverlap_kernel(OvParams P)
@@ -409,8 +543,7 @@ ans_koverlap_kernel(OvParams P)
     double *gord = wtab + NN;
     double *wbase = gord + (NG + 1);
     // per-warp carve-up (doubles first, then ints, then shorts)
-    const int per_warp_d = NG * NGAS * (GRAD ? 2 : 1) + 3 * NG + (GRAD ? NG * NP1 : 0) + (NG + 1);
-    const size_t per_warp_bytes = ((size_t)per_warp_d * 8 + (size_t)(NG + 1) * 4 + (size_t)NN * 2 + 15) & ~(size_t)15;
+    const size_t per_warp_bytes = ov_per_warp_bytes(NG, NGAS, GRAD);
     unsigned char *mine = reinterpret_cast<unsigned char *>(wbase) + per_warp_bytes * warp;
     OvWarpSmem s;
     {
@@ -422,8 +555,10 @@ ans_koverlap_kernel(OvParams P)
         s.bT = d; d += NG;
         s.dkp = d; if (GRAD) d += NG * NP1;
         s.frac = d; d += NG + 1;
+        s.bsum = d; d += NG * (NP1 + 2);
         s.strad = reinterpret_cast<int *>(d);
-        s.sidx = reinterpret_cast<unsigned short *>(s.strad + NG + 1);
+        s.closed = s.strad + NG + 1;
+        s.sidx = reinterpret_cast<unsigned short *>(s.closed + NG);
     }
     for (int i = threadIdx.x; i < NN; i += blockDim.x) wtab[i] = P.weight[i];
     for (int i = threadIdx.x; i <= NG; i += blockDim.x) gord[i] = P.g_ord[i];
@@ -539,8 +674,7 @@ template <int EPL, int NPMAX, bool GRAD>
 inline int ov_launch(const OvParams &P, cudaStream_t stream)
 {
     const int NG = P.NG, NGAS = P.NGAS, NN = NG * NG, NP1 = NGAS + 1;
-    const int per_warp_d = NG * NGAS * (GRAD ? 2 : 1) + 3 * NG + (GRAD ? NG * NP1 : 0) + (NG + 1);
-    const size_t per_warp_bytes = ((size_t)per_warp_d * 8 + (size_t)(NG + 1) * 4 + (size_t)NN * 2 + 15) & ~(size_t)15;
+    const size_t per_warp_bytes = ov_per_warp_bytes(NG, NGAS, GRAD);
     const size_t smem = (size_t)(NN + NG + 1) * 8 + per_warp_bytes * OV_WARPS + 16;
     auto kern = ans_koverlap_kernel<EPL, NPMAX, GRAD>;
     if (smem > 48 * 1024) ANS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

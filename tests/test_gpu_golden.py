@@ -21,9 +21,13 @@ def test_stage_goldens_kinterp_overlap():
     assert relerr(cpu(ops.kinterp(T, ops.DevicePlan(hp0, False))), g["ko_k"]) < 1e-13
     otab = ops.OverlapTables(tab["DELG"])
     am = ops.to_dev(g["ko_amount"])
-    # reference k in, reference tau out: bit for bit
-    assert np.array_equal(cpu(ops.koverlap(ops.to_dev(g["ko_k"]), am, otab)), g["ko_tau"])
+    # reference k in, reference tau out: to rounding with the parallel rebin, bit for bit with the
+    # lane-per-bin walk that keeps the reference's summation order (force_seq)
+    assert relerr(cpu(ops.koverlap(ops.to_dev(g["ko_k"]), am, otab)), g["ko_tau"]) < 1e-13
+    assert np.array_equal(cpu(ops.koverlap(ops.to_dev(g["ko_k"]), am, otab, force_seq=True)), g["ko_tau"])
     t, dk = ops.koverlap(ops.to_dev(g["ko_kg"]), am, otab, dkdT=ops.to_dev(g["ko_dkdT"]))
+    assert relerr(cpu(t), g["ko_taug"]) < 1e-13 and colerr(cpu(dk), g["ko_dk"]) < 1e-13
+    t, dk = ops.koverlap(ops.to_dev(g["ko_kg"]), am, otab, dkdT=ops.to_dev(g["ko_dkdT"]), force_seq=True)
     assert np.array_equal(cpu(t), g["ko_taug"]) and np.array_equal(cpu(dk), g["ko_dk"])
     o64 = ops.OverlapTables(tab["DELG"].astype(np.float64))
     # float64 weights are not exactly summable: the warp scan rounds differently from the sequential cumsum
@@ -116,7 +120,7 @@ def test_jupiter_cirs_deck_golden():
     assert relerr(s1, g["ref_SPECOUT"]) < 1e-12
     for ix in range(d1.shape[2]):
         # 1e-9 is the BASELINE.json tolerance; the suffix-scan form of the Jacobian bracket cancels
-        # differently from the reference's O(N^2) recurrence: observed <= 2e-11
-        assert colerr(d1[:, 0, ix], g["ref_dSPEC1"][:, 0, ix]) < 1e-10, ix
+        # differently from the reference's O(N^2) recurrence: observed <= 2e-10 on the smallest columns
+        assert colerr(d1[:, 0, ix], g["ref_dSPEC1"][:, 0, ix]) < 1e-9, ix
     tg, dtg = fm.calculate_gaseous_line_opacity(True)
     assert tg.shape == (8, 20, 71) and dtg.shape == (8, 20, 13, 71)
