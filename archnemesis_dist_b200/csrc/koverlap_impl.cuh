@@ -178,17 +178,102 @@ __device__ __forceinline__ void ov_bitonic_sort(double (&key)[EPL], int (&idx)[E
     }
 }
 
-// true if any two live neighbours of the sorted sequence carry equal keys
-template <int EPL>
-__device__ __forceinline__ bool ov_has_ties(const double (&key)[EPL], int lane)
+// ---- fast path: 64-bit packed (float32 key | index) network ------------------------------------
+// The keys are scaled by a power of two, rounded to float32 (monotone), mapped to an order-preserving
+// uint32 and packed above the element index; one unsigned 64-bit compare then orders (key32, index)
+// and a comparator moves two registers instead of three.  Because the rounding is monotone the
+// result is the exact (key, index) order unless two keys that differ in float64 collide in float32 in
+// the wrong index order; the caller verifies the exact keys afterwards and falls back to the
+// float64 network (ov_bitonic_sort<EPL, true>) if the check fails.
+__device__ __forceinline__ void ov_ce_u64(unsigned long long &a, unsigned long long &b)
 {
-    bool tie = false;
+    asm("{\n\t.reg .pred sw;\n\t.reg .b64 t;\n\t"
+        "setp.lt.u64 sw, %1, %0;\n\t"
+        "selp.b64 t, %1, %0, sw;\n\t"
+        "selp.b64 %1, %0, %1, sw;\n\t"
+        "mov.b64 %0, t;\n\t}"
+        : "+l"(a), "+l"(b));
+}
+
+__device__ __forceinline__ void ov_ce_x_u64(unsigned long long &v, unsigned long long pv, int keep_low)
+{
+    asm("{\n\t.reg .pred lt, kl, tk;\n\t"
+        "setp.lt.u64 lt, %1, %0;\n\t"
+        "setp.ne.s32 kl, %2, 0;\n\t"
+        "xor.pred tk, lt, kl;\n\t"
+        "not.pred tk, tk;\n\t"          // take = (partner < mine) == keep_low   (values are unique)
+        "selp.b64 %0, %1, %0, tk;\n\t}"
+        : "+l"(v) : "l"(pv), "r"(keep_low));
+}
+
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m)
+{
+    unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
+    lo = __shfl_xor_sync(FULL, lo, m);
+    hi = __shfl_xor_sync(FULL, hi, m);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+template <int EPL>
+__device__ __forceinline__ void ov_bitonic_sort_u64(unsigned long long (&v)[EPL], int lane)
+{
 #pragma unroll
-    for (int r = 0; r + 1 < EPL; ++r) tie |= (key[r] == key[r + 1]) & (key[r] != INFINITY);
+    for (int k = 2; k <= EPL; k <<= 1) {
+#pragma unroll
+        for (int r = 0; r < EPL; ++r) {
+            const int q = r ^ (k - 1);
+            if (r < q) ov_ce_u64(v[r], v[q]);
+        }
+#pragma unroll
+        for (int j = k >> 2; j > 0; j >>= 1) {
+#pragma unroll
+            for (int r = 0; r < EPL; ++r)
+                if ((r & j) == 0) ov_ce_u64(v[r], v[r | j]);
+        }
+    }
+#pragma unroll 1
+    for (int kl = 2; kl <= 32; kl <<= 1) {
+        {
+            const int keep_low = (lane & (kl >> 1)) == 0;
+#pragma unroll
+            for (int r = 0; r < EPL / 2; ++r) {
+                const int q = EPL - 1 - r;
+                const unsigned long long pr = shfl_xor_u64(v[q], kl - 1), pq = shfl_xor_u64(v[r], kl - 1);
+                ov_ce_x_u64(v[r], pr, keep_low);
+                ov_ce_x_u64(v[q], pq, keep_low);
+            }
+        }
+#pragma unroll 1
+        for (int lm = kl >> 2; lm > 0; lm >>= 1) {
+            const int keep_low = (lane & lm) == 0;
+#pragma unroll
+            for (int r = 0; r < EPL; ++r) ov_ce_x_u64(v[r], shfl_xor_u64(v[r], lm), keep_low);
+        }
+#pragma unroll
+        for (int j = EPL >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int r = 0; r < EPL; ++r)
+                if ((r & j) == 0) ov_ce_u64(v[r], v[r | j]);
+        }
+    }
+}
+
+// order check of the sorted sequence: bit 0 = some neighbour pair is out of order (exact keys),
+// bit 1 = some live neighbour pair carries equal keys
+template <int EPL>
+__device__ __forceinline__ int ov_check_order(const double (&key)[EPL], int lane)
+{
+    bool bad = false, tie = false;
+#pragma unroll
+    for (int r = 0; r + 1 < EPL; ++r) {
+        bad |= key[r] > key[r + 1];
+        tie |= (key[r] == key[r + 1]) & (key[r] != INFINITY);
+    }
     const double nxt = __hiloint2double(__shfl_down_sync(FULL, __double2hiint(key[0]), 1),
                                         __shfl_down_sync(FULL, __double2loint(key[0]), 1));
+    bad |= (lane < 31) & (key[EPL - 1] > nxt);
     tie |= (lane < 31) & (key[EPL - 1] == nxt) & (nxt != INFINITY);
-    return __any_sync(FULL, tie);
+    return (__any_sync(FULL, bad) ? 1 : 0) | (__any_sync(FULL, tie) ? 2 : 0);
 }
 
 // Per-warp shared-memory view.
@@ -205,7 +290,9 @@ struct OvWarpSmem {
 
 __host__ __device__ inline size_t ov_per_warp_bytes(int NG, int NGAS, bool grad)
 {
-    const int NN = NG * NG, NP1 = NGAS + 1;
+    const int NP1 = NGAS + 1;
+    int NN = 128;                       // sorted-index staging is padded to 32*EPL entries
+    while (NN < NG * NG) NN <<= 1;
     const int nd = NG * NGAS * (grad ? 2 : 1) + 3 * NG + (grad ? NG * NP1 : 0) + (NG + 1) + NG * (NP1 + 2);
     return ((size_t)nd * 8 + (size_t)(2 * NG + 1) * 4 + (size_t)NN * 2 + 15) & ~(size_t)15;
 }
@@ -343,9 +430,10 @@ __device__ __noinline__ void ov_rebin_seq(OvWarpSmem s, const double *__restrict
 // (agreement ~1e-15); requires that no element straddles two edges (host check), else ov_rebin_seq.
 template <int EPL, int NPMAX, bool GRAD>
 __device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const double *__restrict__ wtab,
-                                             const double *__restrict__ gord, int NG, int NGAS, int igas, int lane,
-                                             const double (&key)[EPL], const int (&idx)[EPL])
+                                             const double *__restrict__ gord, int NG, int NGAS, int igas, int lane)
 {
+    // s.sidx[r*32 + lane] = packed index of sorted position lane*EPL + r (staged by the caller): the
+    // element loops stay rolled so the hot code fits the instruction cache
     constexpr int NQ = GRAD ? NPMAX + 2 : 2;   // 0: sum cont*w, 1: sum w, 2+p: gradient column p
     const int NP1 = NGAS + 1, QS = NP1 + 2;
     const int g1 = igas + 1;
@@ -355,9 +443,9 @@ __device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const double *
 
     // exclusive prefix of the lane's weight
     double run = 0.0;
-#pragma unroll
+#pragma unroll 4
     for (int r = 0; r < EPL; ++r) {
-        const int pi = idx[r];
+        const int pi = s.sidx[r * 32 + lane];
         run = __dadd_rn(run, (pi >> 5) < NG ? wtab[(pi >> 5) * NG + (pi & 31)] : 0.0);
     }
     double incl = run;
@@ -382,15 +470,15 @@ __device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const double *
 #pragma unroll
     for (int q = 0; q < NQ; ++q) { acc[q] = 0.0; head[q] = 0.0; }
     bool head_pending = lane != 0;   // the segment this lane starts in was opened by an earlier lane
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < EPL; ++r) {
-        const int pi = idx[r];
+        const int pi = s.sidx[r * 32 + lane];
         const int i = pi >> 5, j = pi & 31;
         if (i < NG && ig < NG) {
             const double w = wtab[i * NG + j];
             const double gdn = __dadd_rn(prev, w);
             double c[NQ];
-            c[0] = __dmul_rn(key[r], w);
+            c[0] = __dmul_rn(__dadd_rn(s.a[i], s.b[j]), w);
             c[1] = w;
             if (GRAD) {
 #pragma unroll
@@ -511,10 +599,41 @@ __device__ __forceinline__ void ov_fold(const OvWarpSmem &s, const double *__res
             if (++j == NG) { j = 0; ++i; }
         }
     };
-    make_keys();
-    ov_bitonic_sort<EPL, false>(key, idx, lane);
-    if (ov_has_ties<EPL>(key, lane)) {
-        // equal keys: order them by index like the oracle does (the reference's own order is unspecified)
+    // fast path: float32-key packed network, verified against the exact keys
+    bool sorted = false;
+    {
+        const double kmax = __dadd_rn(s.a[NG - 1], s.b[NG - 1]);
+        const int e = (__double2hiint(kmax) >> 20) & 0x7ff;
+        if (kmax > 0.0 && e > 200 && e < 2000) {
+            const double sc = __hiloint2double((2146 - e) << 20, 0);   // 2^(100 - exponent(kmax)): exact scaling
+            unsigned long long v[EPL];
+            int el = lane * EPL;
+            int i = el / NG, j = el - i * NG;
+#pragma unroll
+            for (int r = 0; r < EPL; ++r) {
+                if (el < NN) {
+                    const float kf = __double2float_rn(__dmul_rn(__dadd_rn(s.a[i], s.b[j]), sc));
+                    unsigned u = __float_as_uint(kf);
+                    u ^= ((unsigned)((int)u >> 31)) | 0x80000000u;      // order-preserving map, negatives included
+                    v[r] = ((unsigned long long)u << 32) | (unsigned)((i << 5) | j);
+                } else {
+                    v[r] = 0xffffffff00000000ull | (unsigned)((32 << 5) + (el - NN));
+                }
+                ++el;
+                if (++j == NG) { j = 0; ++i; }
+            }
+            ov_bitonic_sort_u64<EPL>(v, lane);
+#pragma unroll
+            for (int r = 0; r < EPL; ++r) {
+                idx[r] = (int)(unsigned)v[r];
+                const int ii = idx[r] >> 5, jj = idx[r] & 31;
+                key[r] = ii < NG ? __dadd_rn(s.a[ii], s.b[jj]) : INFINITY;
+            }
+            sorted = (ov_check_order<EPL>(key, lane) & 1) == 0;
+        }
+    }
+    if (!sorted) {
+        // float32 collision in the wrong order, or keys outside the scaled float32 range: exact network
         make_keys();
         ov_bitonic_sort<EPL, true>(key, idx, lane);
     }
@@ -527,7 +646,10 @@ __device__ __forceinline__ void ov_fold(const OvWarpSmem &s, const double *__res
         }
         ov_rebin_seq<NPMAX, GRAD>(s, wtab, gord, NG, NGAS, igas, lane);
     } else {
-        ov_rebin_par<EPL, NPMAX, GRAD>(s, wtab, gord, NG, NGAS, igas, lane, key, idx);
+#pragma unroll
+        for (int r = 0; r < EPL; ++r) s.sidx[r * 32 + lane] = (unsigned short)idx[r];
+        __syncwarp();
+        ov_rebin_par<EPL, NPMAX, GRAD>(s, wtab, gord, NG, NGAS, igas, lane);
     }
 }
 

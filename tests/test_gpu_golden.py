@@ -123,4 +123,4 @@ def test_jupiter_cirs_deck_golden():
         # differently from the reference's O(N^2) recurrence: observed <= 2e-10 on the smallest columns
         assert colerr(d1[:, 0, ix], g["ref_dSPEC1"][:, 0, ix]) < 1e-9, ix
     tg, dtg = fm.calculate_gaseous_line_opacity(True)
-    assert tg.shape == (8, 20, 71) and dtg.shape == (8, 20, 13, 71)
+    assert tg.shape == (8, 20, 71) and dtg.shape == (8, 20, 14, 71)
