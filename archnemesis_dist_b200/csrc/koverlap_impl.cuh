@@ -282,7 +282,8 @@ struct OvWarpSmem {
     double *a, *b, *bT;      // [NG] running tau_g, next gas tau, next gas dk/dT*amount
     double *dkp;             // [NG*NP1] running dk_g_param
     double *frac;            // [NG+1]
-    double *bsum;            // [NG*(NGAS+3)] raw bin sums: cont*w, w, gradient columns
+    double *bsum;            // [NG*(NGAS+3)] raw bin sums: cont*w, w, dT, gas columns
+    double *head;            // [32*QSH] per-lane partial sum of the bin a lane starts in (parallel rebin)
     int *strad;              // [NG+1]
     int *closed;             // [NG] bin closed by a straddling element
     unsigned short *sidx;    // [NG*NG] sorted packed indices
@@ -293,7 +294,8 @@ __host__ __device__ inline size_t ov_per_warp_bytes(int NG, int NGAS, bool grad)
     const int NP1 = NGAS + 1;
     int NN = 128;                       // sorted-index staging is padded to 32*EPL entries
     while (NN < NG * NG) NN <<= 1;
-    const int nd = NG * NGAS * (grad ? 2 : 1) + 3 * NG + (grad ? NG * NP1 : 0) + (NG + 1) + NG * (NP1 + 2);
+    const int nd = NG * NGAS * (grad ? 2 : 1) + 3 * NG + (grad ? NG * NP1 : 0) + (NG + 1) + NG * (NP1 + 2) +
+                   32 * ((NP1 + 2) | 1);
     return ((size_t)nd * 8 + (size_t)(2 * NG + 1) * 4 + (size_t)NN * 2 + 15) & ~(size_t)15;
 }
 
@@ -330,7 +332,7 @@ __device__ __noinline__ void ov_rebin_seq(OvWarpSmem s, const double *__restrict
                     double g;
                     if (p <= igas) g = s.dkp[i * NP1 + p];
                     else if (p == g1) g = s.kbuf[j * NGAS + g1];
-                    else g = __dadd_rn(s.dkp[i * NP1 + g1], s.bT[j]);
+                    else g = __dadd_rn(s.dkp[i * NP1 + NGAS], s.bT[j]);
                     gw[p] = __dmul_rn(g, w);
                 }
             }
@@ -414,30 +416,33 @@ __device__ __noinline__ void ov_rebin_seq(OvWarpSmem s, const double *__restrict
         s.a[m] = res_tau;
         if (GRAD) {
 #pragma unroll
-            for (int p = 0; p < NPMAX; ++p) if (p < NP1) s.dkp[m * NP1 + p] = (p < n) ? res_g[p] : 0.0;
+            for (int p = 0; p < NPMAX; ++p) {
+                if (p <= g1) s.dkp[m * NP1 + p] = res_g[p];            // gas columns
+                else if (p == g1 + 1) s.dkp[m * NP1 + NGAS] = res_g[p];   // temperature column
+            }
+            for (int p = g1 + 1; p < NGAS; ++p) s.dkp[m * NP1 + p] = 0.0;
         }
     }
     __syncwarp();
 }
 
-// Rebin in parallel over the sorted elements still held in registers (rank/rankg, ForwardModel_0.py
-// :6155-6172 / :6002-6025).  Every lane walks its EPL consecutive sorted elements with a running
-// cumulative weight, accumulates cont*w, w and the gradient columns of the bin it is in and, at the
-// element that straddles a bin edge, closes the bin with `frac` and opens the next with `1-frac`.
-// Bins opened and closed inside one lane are stored directly; a bin that spans several lanes is the
-// owner lane's tail plus the heads of the following lanes (shuffle rounds, as many as the longest
-// span).  Lane m then normalises bin m.  Same arithmetic as the reference, different summation order
+// Rebin in parallel over the sorted elements (rank/rankg, ForwardModel_0.py:6155-6172 / :6002-6025).
+// Every lane walks its EPL consecutive sorted elements (indices staged in shared memory so the loops
+// stay rolled and the hot code fits the instruction cache) with a running cumulative weight,
+// accumulates cont*w, w, the T column and the gas columns of the bin it is in and, at the element
+// that straddles a bin edge, closes the bin with `frac` and opens the next with `1-frac`.  A closed
+// partial sum goes to the lane's head slot if the bin was opened by an earlier lane, else straight to
+// the bin; a bin that spans several lanes is the owner lane's tail plus the heads of the following
+// lanes.  Lane m then normalises bin m.  Same arithmetic as the reference in another summation order
 // (agreement ~1e-15); requires that no element straddles two edges (host check), else ov_rebin_seq.
 template <int EPL, int NPMAX, bool GRAD>
 __device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const double *__restrict__ wtab,
                                              const double *__restrict__ gord, int NG, int NGAS, int igas, int lane)
 {
-    // s.sidx[r*32 + lane] = packed index of sorted position lane*EPL + r (staged by the caller): the
-    // element loops stay rolled so the hot code fits the instruction cache
-    constexpr int NQ = GRAD ? NPMAX + 2 : 2;   // 0: sum cont*w, 1: sum w, 2+p: gradient column p
-    const int NP1 = NGAS + 1, QS = NP1 + 2;
+    constexpr int NQ = GRAD ? NPMAX + 2 : 2;   // 0: sum cont*w, 1: sum w, 2: dT, 3+p: gas column p
+    const int NN = NG * NG;
+    const int NP1 = NGAS + 1, QS = NP1 + 2, QSH = QS | 1;
     const int g1 = igas + 1;
-    const int n = igas + 3;
     for (int t = lane; t < NG * QS; t += 32) s.bsum[t] = 0.0;
     for (int t = lane; t < NG; t += 32) s.closed[t] = 0;
 
@@ -466,10 +471,11 @@ __device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const double *
     }
     __syncwarp();
 
-    double acc[NQ], head[NQ];
+    double acc[NQ];
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) { acc[q] = 0.0; head[q] = 0.0; }
-    bool head_pending = lane != 0;   // the segment this lane starts in was opened by an earlier lane
+    for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
+    double *myhead = s.head + lane * QSH;
+    bool head_pending = lane != 0;   // the bin this lane starts in was opened by an earlier lane
 #pragma unroll 1
     for (int r = 0; r < EPL; ++r) {
         const int pi = s.sidx[r * 32 + lane];
@@ -481,17 +487,13 @@ __device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const double *
             c[0] = __dmul_rn(__dadd_rn(s.a[i], s.b[j]), w);
             c[1] = w;
             if (GRAD) {
+                c[2] = __dmul_rn(__dadd_rn(s.dkp[i * NP1 + NGAS], s.bT[j]), w);
+                const double kb = s.kbuf[j * NGAS + g1];
 #pragma unroll
-                for (int p = 0; p < NPMAX; ++p) {
-                    if (p < n) {
-                        double g;
-                        if (p <= igas) g = s.dkp[i * NP1 + p];
-                        else if (p == g1) g = s.kbuf[j * NGAS + g1];
-                        else g = __dadd_rn(s.dkp[i * NP1 + g1], s.bT[j]);
-                        c[2 + p] = __dmul_rn(g, w);
-                    } else {
-                        c[2 + p] = 0.0;
-                    }
+                for (int p = 0; p < NPMAX - 1; ++p) {
+                    // columns above g1 are still zero, so every gas column is processed alike
+                    const double g = (p < NGAS) ? ((p == g1) ? kb : s.dkp[i * NP1 + p]) : 0.0;
+                    c[3 + p] = __dmul_rn(g, w);
                 }
             }
             const double edge = gord[ig + 1];
@@ -501,53 +503,56 @@ __device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const double *
             } else {
                 const double frac = __ddiv_rn(__dsub_rn(edge, prev), __dsub_rn(gdn, prev));
                 const double omf = __dsub_rn(1.0, frac);
+                double *dst = head_pending ? myhead : s.bsum + ig * QS;
+                dst[0] = __dadd_rn(acc[0], __dmul_rn(frac, c[0]));
+                dst[1] = __dadd_rn(acc[1], __dmul_rn(frac, c[1]));
+                acc[0] = __dmul_rn(omf, c[0]);
+                acc[1] = __dmul_rn(omf, c[1]);
+                if (GRAD) {
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) acc[q] = __dadd_rn(acc[q], __dmul_rn(frac, c[q]));
-                if (head_pending) {
-#pragma unroll
-                    for (int q = 0; q < NQ; ++q) head[q] = acc[q];
-                    head_pending = false;
-                } else {
-                    s.bsum[ig * QS + 0] = acc[0];
-                    s.bsum[ig * QS + 1] = acc[1];
-                    if (GRAD) {
-#pragma unroll
-                        for (int p = 0; p < NPMAX; ++p) if (p < n) s.bsum[ig * QS + 2 + p] = acc[2 + p];
+                    for (int q = 2; q < NQ; ++q) {
+                        if (q < QS) dst[q] = __dadd_rn(acc[q], __dmul_rn(frac, c[q]));
+                        acc[q] = __dmul_rn(omf, c[q]);
                     }
                 }
+                head_pending = false;
                 s.closed[ig] = 1;
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) acc[q] = __dmul_rn(omf, c[q]);
                 ++ig;
             }
             prev = gdn;
         }
     }
-    // lanes that never closed their incoming segment pass everything on as "head"
+    // a lane that never closed the bin it started in passes everything on as its head
     const bool has_tail = !head_pending;
     if (head_pending) {
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) { head[q] = acc[q]; acc[q] = 0.0; }
-    }
-    // tail + heads of the following lanes up to (and including) the first lane that closed a segment
-    bool open = has_tail;
-    for (int d = 1; d < 32; ++d) {
-        const bool cd = __shfl_down_sync(FULL, has_tail ? 1 : 0, d) != 0 || (lane + d >= 32);
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            const double hd = __hiloint2double(__shfl_down_sync(FULL, __double2hiint(head[q]), d),
-                                               __shfl_down_sync(FULL, __double2loint(head[q]), d));
-            if (open && lane + d < 32) acc[q] = __dadd_rn(acc[q], hd);
-        }
-        if (cd) open = false;
-        if (!__any_sync(FULL, open)) break;
-    }
-    if (has_tail && ig < NG) {
-        s.bsum[ig * QS + 0] = acc[0];
-        s.bsum[ig * QS + 1] = acc[1];
+        myhead[0] = acc[0];
+        myhead[1] = acc[1];
         if (GRAD) {
 #pragma unroll
-            for (int p = 0; p < NPMAX; ++p) if (p < n) s.bsum[ig * QS + 2 + p] = acc[2 + p];
+            for (int q = 2; q < NQ; ++q) if (q < QS) myhead[q] = acc[q];
+        }
+    }
+    // lanes past the data count as closers so an open last bin stops there
+    const unsigned closers = __ballot_sync(FULL, has_tail || lane * EPL >= NN);
+    __syncwarp();
+    if (has_tail && ig < NG) {
+        // tail + heads of the following lanes up to (and including) the first lane that closed a bin
+        for (int l2 = lane + 1; l2 < 32 && l2 * EPL < NN; ++l2) {
+            const double *h = s.head + l2 * QSH;
+            acc[0] = __dadd_rn(acc[0], h[0]);
+            acc[1] = __dadd_rn(acc[1], h[1]);
+            if (GRAD) {
+#pragma unroll
+                for (int q = 2; q < NQ; ++q) if (q < QS) acc[q] = __dadd_rn(acc[q], h[q]);
+            }
+            if ((closers >> l2) & 1u) break;
+        }
+        double *dst = s.bsum + ig * QS;
+        dst[0] = acc[0];
+        dst[1] = acc[1];
+        if (GRAD) {
+#pragma unroll
+            for (int q = 2; q < NQ; ++q) if (q < QS) dst[q] = acc[q];
         }
     }
     __syncwarp();
@@ -556,23 +561,25 @@ __device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const double *
     if (m < NG) {
         const bool opened = (m == 0) || s.closed[m - 1] != 0;
         const bool norm = s.closed[m] != 0 || (m == NG - 1 && opened);
-        const double sw = s.bsum[m * QS + 1];
-        double t = s.bsum[m * QS + 0];
-        if (norm) t = __ddiv_rn(t, sw);
-        s.a[m] = t;
+        const double *src = s.bsum + m * QS;
+        const double sw = src[1];
+        s.a[m] = norm ? __ddiv_rn(src[0], sw) : src[0];
         if (GRAD) {
-            for (int p = 0; p < NP1; ++p) {
-                double g = p < n ? s.bsum[m * QS + 2 + p] : 0.0;
-                if (norm && p < n) g = __ddiv_rn(g, sw);
-                s.dkp[m * NP1 + p] = g;
+            s.dkp[m * NP1 + NGAS] = norm ? __ddiv_rn(src[2], sw) : src[2];
+            for (int p = 0; p < NGAS; ++p) {
+                const double g = src[3 + p];
+                s.dkp[m * NP1 + p] = (norm && p <= g1) ? __ddiv_rn(g, sw) : g;
             }
         }
     }
     __syncwarp();
 }
 
-// One sort/rebin fold.  a[] holds the running tau_g, b[] the next gas; with GRAD the gradient row of
-// element (i,j) is { dkp[i][0..igas], kbuf[j][g1], dkp[i][igas+1] + bT[j] } (ForwardModel_0.py:5946-5949).
+// One sort/rebin fold.  a[] holds the running tau_g, b[] the next gas.  Gradient storage: dkp[i][p] is
+// d tau_i / d amount_p for p < NGAS and dkp[i][NGAS] is d tau_i / dT at every stage (the reference keeps
+// the temperature column at index igas+1 and moves it one to the right per fold, ForwardModel_0.py
+// :5931, :5948; the values are the same).  The gradient row of element (i,j) is
+// { dkp[i][0..igas], kbuf[j][g1] } for the gases and dkp[i][NGAS] + bT[j] for T (:5946-5949).
 template <int EPL, int NPMAX, bool GRAD>
 __device__ __forceinline__ void ov_fold(const OvWarpSmem &s, const double *__restrict__ wtab,
                                         const double *__restrict__ gord, int NG, int NGAS, int igas, int lane,
@@ -654,7 +661,7 @@ __device__ __forceinline__ void ov_fold(const OvWarpSmem &s, const double *__res
 }
 
 template <int EPL, int NPMAX, bool GRAD>
-__global__ void __launch_bounds__(OV_WARPS * 32, 3)
+__global__ void __launch_bounds__(OV_WARPS * 32, 4)
 ans_koverlap_kernel(OvParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -678,6 +685,7 @@ ans_koverlap_kernel(OvParams P)
         s.dkp = d; if (GRAD) d += NG * NP1;
         s.frac = d; d += NG + 1;
         s.bsum = d; d += NG * (NP1 + 2);
+        s.head = d; d += 32 * ((NP1 + 2) | 1);
         s.strad = reinterpret_cast<int *>(d);
         s.closed = s.strad + NG + 1;
         s.sidx = reinterpret_cast<unsigned short *>(s.closed + NG);
@@ -733,13 +741,13 @@ ans_koverlap_kernel(OvParams P)
             if (first_neg) {
                 for (int i = lane; i < NG; i += 32) {
                     s.a[i] = __dmul_rn(KB(i, 1), am1);
-                    if (GRAD) { s.dkp[i * NP1 + 1] = KB(i, 1); s.dkp[i * NP1 + 2] = __dmul_rn(DB(i, 1), am1); }
+                    if (GRAD) { s.dkp[i * NP1 + 1] = KB(i, 1); s.dkp[i * NP1 + NGAS] = __dmul_rn(DB(i, 1), am1); }
                 }
                 __syncwarp();
             } else if (next_neg) {
                 for (int i = lane; i < NG; i += 32) {
                     s.a[i] = __dmul_rn(KB(i, 0), am0);
-                    if (GRAD) { s.dkp[i * NP1 + 0] = KB(i, 0); s.dkp[i * NP1 + 2] = __dmul_rn(DB(i, 0), am0); }
+                    if (GRAD) { s.dkp[i * NP1 + 0] = KB(i, 0); s.dkp[i * NP1 + NGAS] = __dmul_rn(DB(i, 0), am0); }
                 }
                 __syncwarp();
             } else {
@@ -748,7 +756,7 @@ ans_koverlap_kernel(OvParams P)
                     s.b[i] = __dmul_rn(KB(i, 1), am1);
                     if (GRAD) {
                         s.dkp[i * NP1 + 0] = KB(i, 0);
-                        s.dkp[i * NP1 + 1] = __dmul_rn(DB(i, 0), am0);
+                        s.dkp[i * NP1 + NGAS] = __dmul_rn(DB(i, 0), am0);
                         s.bT[i] = __dmul_rn(DB(i, 1), am1);
                     }
                 }
@@ -758,8 +766,8 @@ ans_koverlap_kernel(OvParams P)
             if (next_neg) {
                 if (GRAD) {
                     for (int i = lane; i < NG; i += 32) {
-                        s.dkp[i * NP1 + igas + 2] = s.dkp[i * NP1 + igas + 1];
-                        s.dkp[i * NP1 + igas + 1] = __dmul_rn(s.dkp[i * NP1 + igas + 1], 0.0);
+                        // reference: dk[:,igas+2] = dk[:,igas+1]; dk[:,igas+1] *= 0  (T column moves, gas column = 0*T)
+                        s.dkp[i * NP1 + g1] = __dmul_rn(s.dkp[i * NP1 + NGAS], 0.0);
                     }
                     __syncwarp();
                 }
@@ -767,7 +775,7 @@ ans_koverlap_kernel(OvParams P)
                 __syncwarp();
                 for (int i = lane; i < NG; i += 32) {
                     s.a[i] = __dmul_rn(KB(i, g1), am1);
-                    if (GRAD) { s.dkp[i * NP1 + g1] = KB(i, g1); s.dkp[i * NP1 + igas + 2] = __dmul_rn(DB(i, g1), am1); }
+                    if (GRAD) { s.dkp[i * NP1 + g1] = KB(i, g1); s.dkp[i * NP1 + NGAS] = __dmul_rn(DB(i, g1), am1); }
                 }
                 __syncwarp();
             } else {
