@@ -22,7 +22,7 @@
 #pragma once
 #include "kinterp.cuh"
 
-constexpr int OV_WARPS = 4;
+constexpr int OV_WARPS = 8;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int OV_NONE = 0x7fffffff;
 
@@ -581,7 +581,7 @@ __device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const double *
 // :5931, :5948; the values are the same).  The gradient row of element (i,j) is
 // { dkp[i][0..igas], kbuf[j][g1] } for the gases and dkp[i][NGAS] + bT[j] for T (:5946-5949).
 template <int EPL, int NPMAX, bool GRAD>
-__device__ __forceinline__ void ov_fold(const OvWarpSmem &s, const double *__restrict__ wtab,
+__device__ __forceinline__ void ov_sort_stage(const OvWarpSmem &s, const double *__restrict__ wtab,
                                         const double *__restrict__ gord, int NG, int NGAS, int igas, int lane,
                                         int seq_rebin)
 {
@@ -606,12 +606,39 @@ __device__ __forceinline__ void ov_fold(const OvWarpSmem &s, const double *__res
             if (++j == NG) { j = 0; ++i; }
         }
     };
-    // fast path: float32-key packed network, verified against the exact keys
+    // Trivial orders need no sort.  Row-major: the next gas is ascending and too weak to reach the next
+    // row, key(i,NG-1) <= key(i+1,0) (equal keys already sit in index order).  Column-major: the running
+    // opacity is ascending and too weak to reach the next column, key(NG-1,j) < key(0,j+1) (strict: an
+    // equal pair would be in the wrong index order).  Both tests use the exact keys.
     bool sorted = false;
     {
+        bool rowok = true, colok = true;
+        if (lane < NG - 1) {
+            const double b0 = s.b[0], bl = s.b[NG - 1], a0 = s.a[0], al = s.a[NG - 1];
+            rowok = (s.b[lane] <= s.b[lane + 1]) & (__dadd_rn(s.a[lane], bl) <= __dadd_rn(s.a[lane + 1], b0));
+            colok = (s.a[lane] <= s.a[lane + 1]) & (__dadd_rn(al, s.b[lane]) < __dadd_rn(a0, s.b[lane + 1]));
+        }
+        rowok = __all_sync(FULL, rowok);
+        colok = !rowok && __all_sync(FULL, colok);
+        if (rowok | colok) {
+            int el = lane * EPL;
+            int q = el / NG, rm = el - q * NG;      // el = q*NG + rm
+#pragma unroll
+            for (int r = 0; r < EPL; ++r) {
+                if (el < NN) idx[r] = rowok ? ((q << 5) | rm) : ((rm << 5) | q);
+                else idx[r] = (32 << 5) + (el - NN);
+                ++el;
+                if (++rm == NG) { rm = 0; ++q; }
+            }
+            sorted = true;
+        }
+    }
+    // fast path: float32-key packed network, verified against the exact keys
+    if (!sorted) {
         const double kmax = __dadd_rn(s.a[NG - 1], s.b[NG - 1]);
         const int e = (__double2hiint(kmax) >> 20) & 0x7ff;
-        if (kmax > 0.0 && e > 200 && e < 2000) {
+        // (vote: every lane holds the same value; this tells the compiler the branch is warp-uniform)
+        if (__all_sync(FULL, kmax > 0.0 && e > 200 && e < 2000)) {
             const double sc = __hiloint2double((2146 - e) << 20, 0);   // 2^(100 - exponent(kmax)): exact scaling
             unsigned long long v[EPL];
             int el = lane * EPL;
@@ -645,23 +672,32 @@ __device__ __forceinline__ void ov_fold(const OvWarpSmem &s, const double *__res
         ov_bitonic_sort<EPL, true>(key, idx, lane);
     }
 
+    // stage the sorted order for the rebin (blocked layout for the sequential walk, transposed for the
+    // parallel one)
     if (seq_rebin) {
 #pragma unroll
         for (int r = 0; r < EPL; ++r) {
             const int pos = lane * EPL + r;
             if (pos < NN) s.sidx[pos] = (unsigned short)idx[r];
         }
-        ov_rebin_seq<NPMAX, GRAD>(s, wtab, gord, NG, NGAS, igas, lane);
     } else {
 #pragma unroll
         for (int r = 0; r < EPL; ++r) s.sidx[r * 32 + lane] = (unsigned short)idx[r];
-        __syncwarp();
-        ov_rebin_par<EPL, NPMAX, GRAD>(s, wtab, gord, NG, NGAS, igas, lane);
     }
+    __syncwarp();
 }
 
 template <int EPL, int NPMAX, bool GRAD>
-__global__ void __launch_bounds__(OV_WARPS * 32, 4)
+__device__ __forceinline__ void ov_rebin(const OvWarpSmem &s, const double *__restrict__ wtab,
+                                         const double *__restrict__ gord, int NG, int NGAS, int igas, int lane,
+                                         int seq_rebin)
+{
+    if (seq_rebin) ov_rebin_seq<NPMAX, GRAD>(s, wtab, gord, NG, NGAS, igas, lane);
+    else ov_rebin_par<EPL, NPMAX, GRAD>(s, wtab, gord, NG, NGAS, igas, lane);
+}
+
+template <int EPL, int NPMAX, bool GRAD>
+__global__ void __launch_bounds__(OV_WARPS * 32, 2)
 ans_koverlap_kernel(OvParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -695,8 +731,9 @@ ans_koverlap_kernel(OvParams P)
     __syncthreads();
 
     const long long ncell = (long long)P.NWAVE * NLAY;
-    const long long cell = (long long)blockIdx.x * OV_WARPS + warp;
-    if (cell >= ncell) return;
+    long long cell = (long long)blockIdx.x * OV_WARPS + warp;
+    const bool live = cell < ncell;        // idle warps of the last CTA shadow the last cell (they join the barriers)
+    if (!live) cell = ncell - 1;
     const int iw = (int)(cell / NLAY);
     const int l = (int)(cell - (long long)iw * NLAY);
 
@@ -731,13 +768,16 @@ ans_koverlap_kernel(OvParams P)
 #define KB(g, gas) s.kbuf[(g) * NGAS + (gas)]
 #define DB(g, gas) s.dbuf[(g) * NGAS + (gas)]
     for (int igas = 0; igas < NGAS - 1; ++igas) {
+        // keep the CTA's warps in the same phase of the code: the hot path is larger than the
+        // instruction cache and warps that drift apart evict each other's lines
+        __syncthreads();
         const int g1 = igas + 1;
         const double am1 = __ldg(P.amount + (size_t)g1 * NLAY + l);
-        const bool next_neg = __dmul_rn(KB(NG - 1, g1), am1) <= 0.0;
+        const bool next_neg = __all_sync(FULL, __dmul_rn(KB(NG - 1, g1), am1) <= 0.0);   // uniform by construction
         bool do_fold = false;
         if (igas == 0) {
             const double am0 = __ldg(P.amount + l);
-            const bool first_neg = __dmul_rn(KB(NG - 1, 0), am0) <= 0.0;
+            const bool first_neg = __all_sync(FULL, __dmul_rn(KB(NG - 1, 0), am0) <= 0.0);
             if (first_neg) {
                 for (int i = lane; i < NG; i += 32) {
                     s.a[i] = __dmul_rn(KB(i, 1), am1);
@@ -771,7 +811,7 @@ ans_koverlap_kernel(OvParams P)
                     }
                     __syncwarp();
                 }
-            } else if (s.a[NG - 1] <= 0.0) {
+            } else if (__all_sync(FULL, s.a[NG - 1] <= 0.0)) {
                 __syncwarp();
                 for (int i = lane; i < NG; i += 32) {
                     s.a[i] = __dmul_rn(KB(i, g1), am1);
@@ -788,12 +828,13 @@ ans_koverlap_kernel(OvParams P)
         }
         if (do_fold) {
             __syncwarp();
-            ov_fold<EPL, NPMAX, GRAD>(s, wtab, gord, NG, NGAS, igas, lane, P.seq_rebin);
+            ov_sort_stage<EPL, NPMAX, GRAD>(s, wtab, gord, NG, NGAS, igas, lane, P.seq_rebin);
         }
+        if (do_fold) ov_rebin<EPL, NPMAX, GRAD>(s, wtab, gord, NG, NGAS, igas, lane, P.seq_rebin);
     }
 #undef KB
 #undef DB
-    for (int g = lane; g < NG; g += 32) {
+    for (int g = lane; live && g < NG; g += 32) {
         const size_t o = ((size_t)iw * NG + g) * NLAY + l;
         P.tau[o] = s.a[g];
         if (GRAD) for (int p = 0; p < NP1; ++p) P.dk[o * NP1 + p] = s.dkp[g * NP1 + p];
