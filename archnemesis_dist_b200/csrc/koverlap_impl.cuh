@@ -289,13 +289,23 @@ struct OvWarpSmem {
     unsigned short *sidx;    // [NG*NG] sorted packed indices
 };
 
+// head slots of the parallel rebin (32 lanes x QSH); the same region is the scratch of the tie-order
+// emulation (4 uint16 arrays of the padded sort length = that many doubles)
+__host__ __device__ inline int ov_head_doubles(int NG, int NGAS)
+{
+    int nnpad = 128;
+    while (nnpad < NG * NG) nnpad <<= 1;
+    const int h = 32 * ((NGAS + 3) | 1);
+    return h > nnpad ? h : nnpad;
+}
+
 __host__ __device__ inline size_t ov_per_warp_bytes(int NG, int NGAS, bool grad)
 {
     const int NP1 = NGAS + 1;
     int NN = 128;                       // sorted-index staging is padded to 32*EPL entries
     while (NN < NG * NG) NN <<= 1;
     const int nd = NG * NGAS * (grad ? 2 : 1) + 3 * NG + (grad ? NG * NP1 : 0) + (NG + 1) + NG * (NP1 + 2) +
-                   32 * ((NP1 + 2) | 1);
+                   ov_head_doubles(NG, NGAS);
     return ((size_t)nd * 8 + (size_t)(2 * NG + 1) * 4 + (size_t)NN * 2 + 15) & ~(size_t)15;
 }
 
@@ -575,6 +585,128 @@ __device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const double *
     __syncwarp();
 }
 
+// ---- order of EQUAL keys: numba's quicksort --------------------------------------------------------
+// The reference sorts with numba's np.argsort, an unstable quicksort (numba/misc/quicksort.py:
+// median-of-three pivot stashed at the end, Hoare partition, larger side pushed on an explicit stack,
+// insertion sort below 15 elements, `a < b or (isnan(b) and not isnan(a))` as the order).  Which of
+// several equal keys comes first is a property of that algorithm, and it decides how the gradient
+// rows of tied elements are split across bin edges.  When a fold has tied keys and gradients are
+// wanted, the same algorithm is replayed here by the whole warp so the permutation is the reference's:
+//   * the Hoare partition is data-parallel: the k-th element from the left that is not < pivot swaps
+//     with the k-th element from the right that is not > pivot while the former lies left of the
+//     latter; both lists come from one scan over the range, and the pivot's final slot follows;
+//   * disjoint ranges may be processed in any order, so small ranges are only recorded and the
+//     (stable) insertion sorts are done for all positions at once at the end.
+// Output: s.sidx[x] = packed (i,j) of sorted position x (blocked layout).
+__device__ __forceinline__ double ov_keyof(const OvWarpSmem &s, int pk)
+{
+    return __dadd_rn(s.a[pk >> 5], s.b[pk & 31]);
+}
+__device__ __forceinline__ bool ov_lt(double a, double b) { return a < b || (isnan(b) && !isnan(a)); }
+
+static __device__ __noinline__ void ov_numba_order(OvWarpSmem s, int NG, int lane)
+{
+    const int NN = NG * NG;
+    int nnpad = 128;
+    while (nnpad < NN) nnpad <<= 1;
+    unsigned short *R = s.sidx;
+    unsigned short *Lp = reinterpret_cast<unsigned short *>(s.head);
+    unsigned short *Rp = Lp + nnpad;
+    unsigned short *rlo = Rp + nnpad;
+    unsigned short *rhi = rlo + nnpad;
+    int *stk = s.strad;   // (low, high) pairs; depth <= log2(NN) because the larger side is pushed
+    for (int x = lane; x < NN; x += 32) {
+        R[x] = (unsigned short)(((x / NG) << 5) | (x % NG));
+        rlo[x] = (unsigned short)x;
+        rhi[x] = (unsigned short)x;
+    }
+    if (lane == 0) { stk[0] = 0; stk[1] = NN - 1; }
+    __syncwarp();
+    int ns = 1;
+    while (ns > 0) {
+        ns -= 1;
+        int low = stk[2 * ns], high = stk[2 * ns + 1];
+        __syncwarp();
+        while (high - low >= 15) {
+            const int mid = (low + high) >> 1;
+            if (lane == 0) {
+                unsigned short rl = R[low], rm = R[mid], rh = R[high], t;
+                if (ov_lt(ov_keyof(s, rm), ov_keyof(s, rl))) { t = rl; rl = rm; rm = t; }
+                if (ov_lt(ov_keyof(s, rh), ov_keyof(s, rm))) { t = rh; rh = rm; rm = t; }
+                if (ov_lt(ov_keyof(s, rm), ov_keyof(s, rl))) { t = rl; rl = rm; rm = t; }
+                R[low] = rl; R[mid] = rh; R[high] = rm;     // pivot (median) stashed at the end
+            }
+            __syncwarp();
+            const double pivot = ov_keyof(s, R[high]);
+            const int n = high - low;
+            const int ch = (n + 31) >> 5;
+            const int p0 = low + lane * ch, p1 = min(high, p0 + ch);
+            int nl = 0, nr = 0;
+            for (int p = p0; p < p1; ++p) {
+                const double v = ov_keyof(s, R[p]);
+                nl += !ov_lt(v, pivot);
+                nr += !ov_lt(pivot, v);
+            }
+            int il = nl, ir = nr;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int u = __shfl_up_sync(FULL, il, d), v = __shfl_down_sync(FULL, ir, d);
+                if (lane >= d) il += u;
+                if (lane + d < 32) ir += v;
+            }
+            const int totL = __shfl_sync(FULL, il, 31), totR = __shfl_sync(FULL, ir, 0);
+            int kl = il - nl, kr = ir - nr;
+            for (int p = p0; p < p1; ++p) if (!ov_lt(ov_keyof(s, R[p]), pivot)) Lp[kl++] = (unsigned short)p;
+            for (int p = p1 - 1; p >= p0; --p) if (!ov_lt(pivot, ov_keyof(s, R[p]))) Rp[kr++] = (unsigned short)p;
+            __syncwarp();
+            const int kmax = min(totL, totR);
+            int cnt = 0;
+            for (int k = lane; k < kmax; k += 32) cnt += Lp[k] < Rp[k];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
+            const int K = cnt;
+            int ifin;
+            if (K >= 1) ifin = (K < totL && Lp[K] < Rp[K - 1]) ? Lp[K] : Rp[K - 1];
+            else ifin = totL > 0 ? Lp[0] : high;
+            for (int k = lane; k < K; k += 32) {
+                const int x = Lp[k], y = Rp[k];
+                const unsigned short t = R[x]; R[x] = R[y]; R[y] = t;
+            }
+            __syncwarp();
+            if (lane == 0) { const unsigned short t = R[ifin]; R[ifin] = R[high]; R[high] = t; }
+            __syncwarp();
+            if (high - ifin > ifin - low) {
+                if (high > ifin) { if (lane == 0) { stk[2 * ns] = ifin + 1; stk[2 * ns + 1] = high; } ns += 1; }
+                high = ifin - 1;
+            } else {
+                if (ifin > low) { if (lane == 0) { stk[2 * ns] = low; stk[2 * ns + 1] = ifin - 1; } ns += 1; }
+                low = ifin + 1;
+            }
+            __syncwarp();
+        }
+        if (high > low)
+            for (int x = low + lane; x <= high; x += 32) { rlo[x] = (unsigned short)low; rhi[x] = (unsigned short)high; }
+        __syncwarp();
+    }
+    // stable insertion sort of every small range: rank inside the range
+    for (int x0 = 0; x0 < NN; x0 += 32) {
+        const int x = x0 + lane;
+        if (x < NN) {
+            const int lo = rlo[x], hi = rhi[x];
+            const double v = ov_keyof(s, R[x]);
+            int rank = 0;
+            for (int y = lo; y <= hi; ++y) {
+                const double u = ov_keyof(s, R[y]);
+                rank += ov_lt(u, v) || (y < x && !ov_lt(v, u));
+            }
+            Lp[lo + rank] = R[x];
+        }
+    }
+    __syncwarp();
+    for (int x = lane; x < NN; x += 32) R[x] = Lp[x];
+    __syncwarp();
+}
+
 // One sort/rebin fold.  a[] holds the running tau_g, b[] the next gas.  Gradient storage: dkp[i][p] is
 // d tau_i / d amount_p for p < NGAS and dkp[i][NGAS] is d tau_i / dT at every stage (the reference keeps
 // the temperature column at index igas+1 and moves it one to the right per fold, ForwardModel_0.py
@@ -672,6 +804,24 @@ __device__ __forceinline__ void ov_sort_stage(const OvWarpSmem &s, const double 
         ov_bitonic_sort<EPL, true>(key, idx, lane);
     }
 
+    if (GRAD) {
+        // equal keys: take the order numba's quicksort would produce (gradient rows of tied elements
+        // are split across bin edges in sort order; tau does not depend on it)
+#pragma unroll
+        for (int r = 0; r < EPL; ++r) {
+            const int ii = idx[r] >> 5, jj = idx[r] & 31;
+            key[r] = ii < NG ? __dadd_rn(s.a[ii], s.b[jj]) : INFINITY;
+        }
+        if (ov_check_order<EPL>(key, lane) & 2) {
+            ov_numba_order(s, NG, lane);
+#pragma unroll
+            for (int r = 0; r < EPL; ++r) {
+                const int pos = lane * EPL + r;
+                idx[r] = pos < NN ? (int)s.sidx[pos] : (32 << 5) + (pos - NN);
+            }
+            __syncwarp();
+        }
+    }
     // stage the sorted order for the rebin (blocked layout for the sequential walk, transposed for the
     // parallel one)
     if (seq_rebin) {
@@ -721,7 +871,7 @@ ans_koverlap_kernel(OvParams P)
         s.dkp = d; if (GRAD) d += NG * NP1;
         s.frac = d; d += NG + 1;
         s.bsum = d; d += NG * (NP1 + 2);
-        s.head = d; d += 32 * ((NP1 + 2) | 1);
+        s.head = d; d += ov_head_doubles(NG, NGAS);
         s.strad = reinterpret_cast<int *>(d);
         s.closed = s.strad + NG + 1;
         s.sidx = reinterpret_cast<unsigned short *>(s.closed + NG);

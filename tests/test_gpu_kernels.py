@@ -11,11 +11,11 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(autouse=True)
-def stable_tie_order():
-    """The CUDA sort breaks ties between equal keys by index; compare against the oracle in that mode
-    (its default reproduces numba's unstable quicksort, see test_tie_order_deviation)."""
+def reference_tie_order():
+    """The oracle's default reproduces numba's unstable quicksort for tied keys, like the kernels do when
+    gradients are requested (see test_tied_keys_follow_numba_order)."""
     from oracle import oracle
-    oracle.set_sort_mode(oracle.STABLE_ORDER)
+    oracle.set_sort_mode(oracle.NUMBA_ORDER)
     yield
     oracle.set_sort_mode(oracle.NUMBA_ORDER)
 
@@ -93,7 +93,8 @@ def test_koverlap_matches_oracle(mods, ng, ngas, want_grad):
     else:
         rt = orc.k_overlap(tab["DELG"], k, c["amount"])
         assert relerr(cpu(ops.koverlap(kd, am, otab)), rt) < 1e-13
-        assert np.array_equal(cpu(ops.koverlap(kd, am, otab, force_seq=True)), rt)
+        # (without gradients tied keys stay in index order: identical up to the rounding of equal terms)
+        assert relerr(cpu(ops.koverlap(kd, am, otab, force_seq=True)), rt) < 1e-14
 
 
 def test_koverlap_float64_delg_and_ties(mods):
@@ -109,10 +110,11 @@ def test_koverlap_float64_delg_and_ties(mods):
     assert relerr(cpu(tau), orc.k_overlap(dg, k, c["amount"])) < 1e-13
 
 
-def test_tie_order_deviation(mods):
-    """Exact ties (a gas 25 orders of magnitude below another: a_i + b_j == a_i): tau matches the
-    reference's numba-quicksort order to rounding; the gradient columns of the tied gas are split
-    across bin edges in index order instead of numba's order (documented deviation)."""
+def test_tied_keys_follow_numba_order(mods):
+    """Exact ties (a gas 25 orders of magnitude below another: a_i + b_j == a_i, whole rows of keys tie).
+    The reference's order of tied keys is whatever numba's unstable quicksort produces; the kernel replays
+    that algorithm (ov_numba_order), so even the gradient columns of the tied gas match the oracle in
+    its default NUMBA_ORDER mode -- bit for bit with the reference-order rebin (force_seq)."""
     ops, orc = mods["ops"], mods["orc"]
     c = _case(mods, nwave=6, ng=20, ngas=3, nlay=8, npro=8, nx=4, nvmr=3, seed=9)
     tab = c["tab"]
@@ -120,20 +122,20 @@ def test_tie_order_deviation(mods):
     k[:, :, :, 2] *= 1e-25
     dkdT[:, :, :, 2] *= 1e-25
     otab = ops.OverlapTables(tab["DELG"])
-    tau, dk = ops.koverlap(ops.to_dev(k), ops.to_dev(c["amount"]), otab, dkdT=ops.to_dev(dkdT))
-    rt, rd = orc.k_overlap(tab["DELG"], k, c["amount"], dkdT=dkdT)            # stable order
-    assert relerr(cpu(tau), rt) < 1e-13
-    for col in range(4):
-        assert colerr(cpu(dk)[..., col], rd[..., col]) < 1e-13
-    ts, ds = ops.koverlap(ops.to_dev(k), ops.to_dev(c["amount"]), otab, dkdT=ops.to_dev(dkdT), force_seq=True)
-    assert np.array_equal(cpu(ts), rt) and np.array_equal(cpu(ds), rd)
+    kd, dd, am = ops.to_dev(k), ops.to_dev(dkdT), ops.to_dev(c["amount"])
     orc.set_sort_mode(orc.NUMBA_ORDER)
     nt, nd = orc.k_overlap(tab["DELG"], k, c["amount"], dkdT=dkdT)
-    assert relerr(cpu(tau), nt) < 1e-14
-    for col in (0, 1, 3):                                                   # untied gases and dT: unaffected
-        assert colerr(cpu(dk)[..., col], nd[..., col]) < 1e-13
-    assert colerr(cpu(dk)[..., 2], nd[..., 2]) < 0.5                        # tied gas: same mass, other split
-    assert abs(cpu(dk)[..., 2].sum() / nd[..., 2].sum() - 1.0) < 0.2
+    orc.set_sort_mode(orc.STABLE_ORDER)
+    st, sd = orc.k_overlap(tab["DELG"], k, c["amount"], dkdT=dkdT)
+    assert colerr(sd[..., 2], nd[..., 2]) > 1e-6          # the two tie orders really differ for the tied gas
+    tau, dk = ops.koverlap(kd, am, otab, dkdT=dd)
+    assert relerr(cpu(tau), nt) < 1e-13
+    for col in range(4):
+        assert colerr(cpu(dk)[..., col], nd[..., col]) < 1e-13, col
+    ts, ds = ops.koverlap(kd, am, otab, dkdT=dd, force_seq=True)
+    assert np.array_equal(cpu(ts), nt) and np.array_equal(cpu(ds), nd)
+    # without gradients the tie order is irrelevant (equal keys contribute equally wherever they fall)
+    assert relerr(cpu(ops.koverlap(kd, am, otab)), nt) < 1e-13
 
 
 @pytest.mark.parametrize("want_grad", [False, True])
