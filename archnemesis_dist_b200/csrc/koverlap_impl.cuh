@@ -280,31 +280,39 @@ __device__ __forceinline__ int ov_check_order(const double (&key)[EPL], int lane
 struct OvWarpSmem {
     double *kbuf, *dbuf;     // [NG*NGAS] k and dk/dT of the cell
     double *a, *b, *bT;      // [NG] running tau_g, next gas tau, next gas dk/dT*amount
-    double *dkp;             // [NG*NP1] running dk_g_param
+    double *dkp;             // [NG*DS] running gradients: dT, gas columns (see ov_ds)
     double *frac;            // [NG+1]
-    double *bsum;            // [NG*(NGAS+3)] raw bin sums: cont*w, w, dT, gas columns
-    double *head;            // [32*QSH] per-lane partial sum of the bin a lane starts in (parallel rebin)
+    double *bsum;            // [NG*BS] raw bin sums (see ov_bs)
+    double *head;            // [32*BS] per-lane partial sum of the bin a lane starts in (parallel rebin)
     int *strad;              // [NG+1]
     int *closed;             // [NG] bin closed by a straddling element
     unsigned short *sidx;    // [NG*NG] sorted packed indices
 };
 
-// head slots of the parallel rebin (32 lanes x QSH); the same region is the scratch of the tie-order
+// Gradient storage (template NPMAX >= NGAS+1): row i of dkp is [ dT, gas 0 .. gas NPMAX-2 ] with the odd
+// stride DS = NPMAX+1 (bank-conflict free across rows); columns of gases not folded yet hold 0.  Raw bin
+// sums and head slots are rows of BS = (NPMAX+3)|1 doubles: cont*w, w, dT, gas 0 .. gas NPMAX-2, and the
+// column of the gas being folded (kept apart so that every gas column is processed alike).
+__host__ __device__ inline int ov_npmax(int NGAS) { return NGAS + 1 <= 4 ? 4 : (NGAS + 1 <= 8 ? 8 : 16); }
+__host__ __device__ inline int ov_ds(int npmax) { return npmax + 1; }
+__host__ __device__ inline int ov_bs(int npmax) { return (npmax + 3) | 1; }
+
+// head slots of the parallel rebin (32 lanes x BS); the same region is the scratch of the tie-order
 // emulation (4 uint16 arrays of the padded sort length = that many doubles)
 __host__ __device__ inline int ov_head_doubles(int NG, int NGAS)
 {
     int nnpad = 128;
     while (nnpad < NG * NG) nnpad <<= 1;
-    const int h = 32 * ((NGAS + 3) | 1);
+    const int h = 32 * ov_bs(ov_npmax(NGAS));
     return h > nnpad ? h : nnpad;
 }
 
 __host__ __device__ inline size_t ov_per_warp_bytes(int NG, int NGAS, bool grad)
 {
-    const int NP1 = NGAS + 1;
     int NN = 128;                       // sorted-index staging is padded to 32*EPL entries
     while (NN < NG * NG) NN <<= 1;
-    const int nd = NG * NGAS * (grad ? 2 : 1) + 3 * NG + (grad ? NG * NP1 : 0) + (NG + 1) + NG * (NP1 + 2) +
+    const int npm = ov_npmax(NGAS);
+    const int nd = NG * NGAS * (grad ? 2 : 1) + 3 * NG + (grad ? NG * ov_ds(npm) : 0) + (NG + 1) + NG * ov_bs(npm) +
                    ov_head_doubles(NG, NGAS);
     return ((size_t)nd * 8 + (size_t)(2 * NG + 1) * 4 + (size_t)NN * 2 + 15) & ~(size_t)15;
 }
@@ -317,7 +325,7 @@ __device__ __noinline__ void ov_rebin_seq(OvWarpSmem s, const double *__restrict
 {
     // s.sidx holds the sorted packed indices (written by the caller)
     const int NN = NG * NG;
-    const int NP1 = NGAS + 1;
+    constexpr int DS = NPMAX + 1;
     const int g1 = igas + 1;
     const int seq_rebin = 1;
     __syncwarp();
@@ -340,9 +348,9 @@ __device__ __noinline__ void ov_rebin_seq(OvWarpSmem s, const double *__restrict
             for (int p = 0; p < NPMAX; ++p) {
                 if (p < n) {
                     double g;
-                    if (p <= igas) g = s.dkp[i * NP1 + p];
+                    if (p <= igas) g = s.dkp[i * DS + 1 + p];
                     else if (p == g1) g = s.kbuf[j * NGAS + g1];
-                    else g = __dadd_rn(s.dkp[i * NP1 + NGAS], s.bT[j]);
+                    else g = __dadd_rn(s.dkp[i * DS], s.bT[j]);
                     gw[p] = __dmul_rn(g, w);
                 }
             }
@@ -427,10 +435,10 @@ __device__ __noinline__ void ov_rebin_seq(OvWarpSmem s, const double *__restrict
         if (GRAD) {
 #pragma unroll
             for (int p = 0; p < NPMAX; ++p) {
-                if (p <= g1) s.dkp[m * NP1 + p] = res_g[p];            // gas columns
-                else if (p == g1 + 1) s.dkp[m * NP1 + NGAS] = res_g[p];   // temperature column
+                if (p <= g1) s.dkp[m * DS + 1 + p] = res_g[p];       // gas columns
+                else if (p == g1 + 1) s.dkp[m * DS] = res_g[p];      // temperature column
             }
-            for (int p = g1 + 1; p < NGAS; ++p) s.dkp[m * NP1 + p] = 0.0;
+            for (int p = g1 + 1; p < NGAS; ++p) s.dkp[m * DS + 1 + p] = 0.0;
         }
     }
     __syncwarp();
@@ -449,11 +457,13 @@ template <int EPL, int NPMAX, bool GRAD>
 __device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const double *__restrict__ wtab,
                                              const double *__restrict__ gord, int NG, int NGAS, int igas, int lane)
 {
-    constexpr int NQ = GRAD ? NPMAX + 2 : 2;   // 0: sum cont*w, 1: sum w, 2: dT, 3+p: gas column p
+    // s.sidx[r*32 + lane] = packed index of sorted position lane*EPL + r (staged by the caller): the
+    // element loops stay rolled so the hot code fits the instruction cache
+    constexpr int NQ = GRAD ? NPMAX + 3 : 2;   // cont*w, w, dT, gas 0..NPMAX-2, column of the gas being folded
+    constexpr int DS = NPMAX + 1, BS = (NPMAX + 3) | 1;
     const int NN = NG * NG;
-    const int NP1 = NGAS + 1, QS = NP1 + 2, QSH = QS | 1;
     const int g1 = igas + 1;
-    for (int t = lane; t < NG * QS; t += 32) s.bsum[t] = 0.0;
+    for (int t = lane; t < NG * BS; t += 32) s.bsum[t] = 0.0;
     for (int t = lane; t < NG; t += 32) s.closed[t] = 0;
 
     // exclusive prefix of the lane's weight
@@ -484,7 +494,8 @@ __device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const double *
     double acc[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
-    double *myhead = s.head + lane * QSH;
+    double *myhead = s.head + lane * BS;
+    const double *kbcol = s.kbuf + g1;
     bool head_pending = lane != 0;   // the bin this lane starts in was opened by an earlier lane
 #pragma unroll 1
     for (int r = 0; r < EPL; ++r) {
@@ -497,33 +508,25 @@ __device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const double *
             c[0] = __dmul_rn(__dadd_rn(s.a[i], s.b[j]), w);
             c[1] = w;
             if (GRAD) {
-                c[2] = __dmul_rn(__dadd_rn(s.dkp[i * NP1 + NGAS], s.bT[j]), w);
-                const double kb = s.kbuf[j * NGAS + g1];
+                const double *row = s.dkp + i * DS;
+                c[2] = __dmul_rn(__dadd_rn(row[0], s.bT[j]), w);
 #pragma unroll
-                for (int p = 0; p < NPMAX - 1; ++p) {
-                    // columns above g1 are still zero, so every gas column is processed alike
-                    const double g = (p < NGAS) ? ((p == g1) ? kb : s.dkp[i * NP1 + p]) : 0.0;
-                    c[3 + p] = __dmul_rn(g, w);
-                }
+                for (int p = 0; p < NPMAX - 1; ++p) c[3 + p] = __dmul_rn(row[1 + p], w);   // unfolded gases are 0
+                c[NQ - 1] = __dmul_rn(kbcol[j * NGAS], w);
             }
             const double edge = gord[ig + 1];
             if (gdn < edge) {
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) acc[q] = __dadd_rn(acc[q], c[q]);
             } else {
+                // (gdn - prev is the element's weight; exact for float32-born weights)
                 const double frac = __ddiv_rn(__dsub_rn(edge, prev), __dsub_rn(gdn, prev));
                 const double omf = __dsub_rn(1.0, frac);
-                double *dst = head_pending ? myhead : s.bsum + ig * QS;
-                dst[0] = __dadd_rn(acc[0], __dmul_rn(frac, c[0]));
-                dst[1] = __dadd_rn(acc[1], __dmul_rn(frac, c[1]));
-                acc[0] = __dmul_rn(omf, c[0]);
-                acc[1] = __dmul_rn(omf, c[1]);
-                if (GRAD) {
+                double *dst = head_pending ? myhead : s.bsum + ig * BS;
 #pragma unroll
-                    for (int q = 2; q < NQ; ++q) {
-                        if (q < QS) dst[q] = __dadd_rn(acc[q], __dmul_rn(frac, c[q]));
-                        acc[q] = __dmul_rn(omf, c[q]);
-                    }
+                for (int q = 0; q < NQ; ++q) {
+                    dst[q] = __dadd_rn(acc[q], __dmul_rn(frac, c[q]));
+                    acc[q] = __dmul_rn(omf, c[q]);
                 }
                 head_pending = false;
                 s.closed[ig] = 1;
@@ -535,12 +538,8 @@ __device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const double *
     // a lane that never closed the bin it started in passes everything on as its head
     const bool has_tail = !head_pending;
     if (head_pending) {
-        myhead[0] = acc[0];
-        myhead[1] = acc[1];
-        if (GRAD) {
 #pragma unroll
-            for (int q = 2; q < NQ; ++q) if (q < QS) myhead[q] = acc[q];
-        }
+        for (int q = 0; q < NQ; ++q) myhead[q] = acc[q];
     }
     // lanes past the data count as closers so an open last bin stops there
     const unsigned closers = __ballot_sync(FULL, has_tail || lane * EPL >= NN);
@@ -548,22 +547,14 @@ __device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const double *
     if (has_tail && ig < NG) {
         // tail + heads of the following lanes up to (and including) the first lane that closed a bin
         for (int l2 = lane + 1; l2 < 32 && l2 * EPL < NN; ++l2) {
-            const double *h = s.head + l2 * QSH;
-            acc[0] = __dadd_rn(acc[0], h[0]);
-            acc[1] = __dadd_rn(acc[1], h[1]);
-            if (GRAD) {
+            const double *h = s.head + l2 * BS;
 #pragma unroll
-                for (int q = 2; q < NQ; ++q) if (q < QS) acc[q] = __dadd_rn(acc[q], h[q]);
-            }
+            for (int q = 0; q < NQ; ++q) acc[q] = __dadd_rn(acc[q], h[q]);
             if ((closers >> l2) & 1u) break;
         }
-        double *dst = s.bsum + ig * QS;
-        dst[0] = acc[0];
-        dst[1] = acc[1];
-        if (GRAD) {
+        double *dst = s.bsum + ig * BS;
 #pragma unroll
-            for (int q = 2; q < NQ; ++q) if (q < QS) dst[q] = acc[q];
-        }
+        for (int q = 0; q < NQ; ++q) dst[q] = acc[q];
     }
     __syncwarp();
     // normalise: a bin closed by a straddler, or the last bin if it was opened (:6171-6172)
@@ -571,14 +562,15 @@ __device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const double *
     if (m < NG) {
         const bool opened = (m == 0) || s.closed[m - 1] != 0;
         const bool norm = s.closed[m] != 0 || (m == NG - 1 && opened);
-        const double *src = s.bsum + m * QS;
+        const double *src = s.bsum + m * BS;
         const double sw = src[1];
         s.a[m] = norm ? __ddiv_rn(src[0], sw) : src[0];
         if (GRAD) {
-            s.dkp[m * NP1 + NGAS] = norm ? __ddiv_rn(src[2], sw) : src[2];
+            double *row = s.dkp + m * DS;
+            row[0] = norm ? __ddiv_rn(src[2], sw) : src[2];
             for (int p = 0; p < NGAS; ++p) {
-                const double g = src[3 + p];
-                s.dkp[m * NP1 + p] = (norm && p <= g1) ? __ddiv_rn(g, sw) : g;
+                const double g = (p == g1) ? src[NQ - 1] : src[3 + p];
+                row[1 + p] = (norm && p <= g1) ? __ddiv_rn(g, sw) : g;
             }
         }
     }
@@ -852,6 +844,7 @@ ans_koverlap_kernel(OvParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NG = P.NG, NGAS = P.NGAS, NLAY = P.NLAY, NN = NG * NG, NP1 = NGAS + 1;
+    constexpr int DS = NPMAX + 1, BS = (NPMAX + 3) | 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     double *wtab = reinterpret_cast<double *>(smem_raw);
@@ -868,9 +861,9 @@ ans_koverlap_kernel(OvParams P)
         s.a = d; d += NG;
         s.b = d; d += NG;
         s.bT = d; d += NG;
-        s.dkp = d; if (GRAD) d += NG * NP1;
+        s.dkp = d; if (GRAD) d += NG * DS;
         s.frac = d; d += NG + 1;
-        s.bsum = d; d += NG * (NP1 + 2);
+        s.bsum = d; d += NG * BS;
         s.head = d; d += ov_head_doubles(NG, NGAS);
         s.strad = reinterpret_cast<int *>(d);
         s.closed = s.strad + NG + 1;
@@ -912,7 +905,7 @@ ans_koverlap_kernel(OvParams P)
         }
     }
     for (int i = lane; i < NG; i += 32) s.a[i] = 0.0;
-    if (GRAD) for (int i = lane; i < NG * NP1; i += 32) s.dkp[i] = 0.0;
+    if (GRAD) for (int i = lane; i < NG * DS; i += 32) s.dkp[i] = 0.0;
     __syncwarp();
 
 #define KB(g, gas) s.kbuf[(g) * NGAS + (gas)]
@@ -931,13 +924,13 @@ ans_koverlap_kernel(OvParams P)
             if (first_neg) {
                 for (int i = lane; i < NG; i += 32) {
                     s.a[i] = __dmul_rn(KB(i, 1), am1);
-                    if (GRAD) { s.dkp[i * NP1 + 1] = KB(i, 1); s.dkp[i * NP1 + NGAS] = __dmul_rn(DB(i, 1), am1); }
+                    if (GRAD) { s.dkp[i * DS + 2] = KB(i, 1); s.dkp[i * DS] = __dmul_rn(DB(i, 1), am1); }
                 }
                 __syncwarp();
             } else if (next_neg) {
                 for (int i = lane; i < NG; i += 32) {
                     s.a[i] = __dmul_rn(KB(i, 0), am0);
-                    if (GRAD) { s.dkp[i * NP1 + 0] = KB(i, 0); s.dkp[i * NP1 + NGAS] = __dmul_rn(DB(i, 0), am0); }
+                    if (GRAD) { s.dkp[i * DS + 1] = KB(i, 0); s.dkp[i * DS] = __dmul_rn(DB(i, 0), am0); }
                 }
                 __syncwarp();
             } else {
@@ -945,8 +938,8 @@ ans_koverlap_kernel(OvParams P)
                     s.a[i] = __dmul_rn(KB(i, 0), am0);
                     s.b[i] = __dmul_rn(KB(i, 1), am1);
                     if (GRAD) {
-                        s.dkp[i * NP1 + 0] = KB(i, 0);
-                        s.dkp[i * NP1 + NGAS] = __dmul_rn(DB(i, 0), am0);
+                        s.dkp[i * DS + 1] = KB(i, 0);
+                        s.dkp[i * DS] = __dmul_rn(DB(i, 0), am0);
                         s.bT[i] = __dmul_rn(DB(i, 1), am1);
                     }
                 }
@@ -957,7 +950,7 @@ ans_koverlap_kernel(OvParams P)
                 if (GRAD) {
                     for (int i = lane; i < NG; i += 32) {
                         // reference: dk[:,igas+2] = dk[:,igas+1]; dk[:,igas+1] *= 0  (T column moves, gas column = 0*T)
-                        s.dkp[i * NP1 + g1] = __dmul_rn(s.dkp[i * NP1 + NGAS], 0.0);
+                        s.dkp[i * DS + 1 + g1] = __dmul_rn(s.dkp[i * DS], 0.0);
                     }
                     __syncwarp();
                 }
@@ -965,7 +958,7 @@ ans_koverlap_kernel(OvParams P)
                 __syncwarp();
                 for (int i = lane; i < NG; i += 32) {
                     s.a[i] = __dmul_rn(KB(i, g1), am1);
-                    if (GRAD) { s.dkp[i * NP1 + g1] = KB(i, g1); s.dkp[i * NP1 + NGAS] = __dmul_rn(DB(i, g1), am1); }
+                    if (GRAD) { s.dkp[i * DS + 1 + g1] = KB(i, g1); s.dkp[i * DS] = __dmul_rn(DB(i, g1), am1); }
                 }
                 __syncwarp();
             } else {
@@ -987,7 +980,10 @@ ans_koverlap_kernel(OvParams P)
     for (int g = lane; live && g < NG; g += 32) {
         const size_t o = ((size_t)iw * NG + g) * NLAY + l;
         P.tau[o] = s.a[g];
-        if (GRAD) for (int p = 0; p < NP1; ++p) P.dk[o * NP1 + p] = s.dkp[g * NP1 + p];
+        if (GRAD) {
+            for (int p = 0; p < NGAS; ++p) P.dk[o * NP1 + p] = s.dkp[g * DS + 1 + p];
+            P.dk[o * NP1 + NGAS] = s.dkp[g * DS];
+        }
     }
 }
 
