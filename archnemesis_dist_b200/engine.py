@@ -108,12 +108,12 @@ class HotPath:
         self.wave_d = ops.to_dev(self.WAVE)
         self.delg_d = ops.to_dev(self.DELG.astype(np.float64))
         self._stage = _Stager()
+        self._copy_stream = None
         self.launches = 0
 
     # -- host -> device ---------------------------------------------------------------------------
-    def stage(self, ev: Evaluation, return_grad, M=None):
-        """Copy one evaluation's inputs (pinned staging, async on the current stream) and build the
-        k-interp plan.  Returns a Staged object; ev.h2d_bytes records the bytes moved."""
+    def stage_opacity(self, ev: Evaluation, return_grad):
+        """Inputs of the gas-opacity kernel only (k-interp plan + amounts: a few KB)."""
         st = self._stage
         st.bytes = 0
         i32 = torch.int32
@@ -124,9 +124,16 @@ class HotPath:
         s.plan_host = hp
         s.dplan = _DevPlan(dev, len(ev.press_atm))
         s.amount = st("amount", ev.amount)
+        s.M = None
+        return s
+
+    def stage_radiance(self, s, ev: Evaluation, M=None):
+        """Inputs of the radiance / projection kernels (continuum terms, path, surface, M)."""
+        st = self._stage
+        i32 = torch.int32
         s.gas_slot = st("gas_slot", ev.gas_slot, i32)
         s.taucia, s.taudust, s.tauray = st("taucia", ev.taucia), st("taudust", ev.taudust), st("tauray", ev.tauray)
-        s.dtaucon = st("dtaucon", ev.dtaucon) if return_grad else None
+        s.dtaucon = st("dtaucon", ev.dtaucon) if s.grad else None
         s.layinc, s.scale, s.nlayin = st("layinc", ev.LAYINC, i32), st("scale", ev.SCALE), st("nlayin", ev.NLAYIN, i32)
         s.emtemp, s.laypress = st("emtemp", ev.EMTEMP), st("laypress", ev.LAYPRESS)
         s.emissivity, s.xfac = st("emissivity", ev.EMISSIVITY), st("xfac", ev.xfac)
@@ -136,6 +143,11 @@ class HotPath:
         s.mode, s.ISPACE, s.TSURF, s.NVMR, s.NPAR = ev.mode, ev.ISPACE, ev.TSURF, ev.NVMR, ev.NPAR
         ev.h2d_bytes = st.bytes
         return s
+
+    def stage(self, ev: Evaluation, return_grad, M=None):
+        """Copy one evaluation's inputs (pinned staging, async on the current stream) and build the
+        k-interp plan.  Returns a Staged object; ev.h2d_bytes records the bytes moved."""
+        return self.stage_radiance(self.stage_opacity(ev, return_grad), ev, M)
 
     # -- device stages ---------------------------------------------------------------------------
     def gas_opacity(self, s, timers=None):
@@ -152,7 +164,9 @@ class HotPath:
         """Kernels only, inputs already resident: gas_opacity -> radiance (-> jacobian_project if s.M).
         Device equivalent of ForwardModel_0.CIRSrad (archnemesis/ForwardModel_0.py:4376-4511) for the
         thermal-emission and pure-transmission path types, followed by map2pro/map2xvec (:5319-5424)."""
-        go = self.gas_opacity(s, timers)
+        return self.finish(s, self.gas_opacity(s, timers))
+
+    def finish(self, s, go):
         tau, dk = go if s.grad else (go, None)
         out = self.ops.radiance(s.mode, tau, dk, s.gas_slot, s.taucia, s.taudust, s.tauray, s.dtaucon, s.layinc, s.scale,
                                 s.nlayin, s.emtemp, s.laypress, self.wave_d, self.delg_d, s.emissivity, s.xfac,
@@ -169,16 +183,35 @@ class HotPath:
         return spec, dx, dtsurf
 
     # -- host-facing calls -------------------------------------------------------------------------
+    def _evaluate(self, ev: Evaluation, return_grad, M=None):
+        """stage -> kernels with the bulk of the host->device traffic (continuum terms, 36 MB at config 2)
+        hidden behind the gas-opacity kernel: that kernel needs only the plan and the amounts, so it is
+        launched first and the remaining inputs are staged on a side stream while it runs."""
+        s = self.stage_opacity(ev, return_grad)
+        go = self.gas_opacity(s)
+        main = torch.cuda.current_stream()
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+        with torch.cuda.stream(self._copy_stream):
+            self.stage_radiance(s, ev, M)
+            done = torch.cuda.Event()
+            done.record()
+        for t in vars(s).values():
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                t.record_stream(main)
+        main.wait_event(done)
+        return self.finish(s, go)
+
     def cirsrad(self, ev: Evaluation, return_grad=False):
         """spec[NWAVE,NPATH] (, dspec[NWAVE,NPATH,NPAR,NLAYMAX], dtsurf[NWAVE,NPATH]) as device tensors."""
-        return self.run(self.stage(ev, return_grad))
+        return self._evaluate(ev, return_grad)
 
     def forward_jacobian(self, ev: Evaluation, M):
         """Spectrum and state-vector Jacobian; layer-space gradients never leave the device:
         CIRSrad(return_grad=True) -> map2pro -> map2xvec of nemesisfmg (ForwardModel_0.py:694-714).
         M = plan.fold_projection(...) [NPATH, NPAR*NLAYMAX, NX].  Returns device tensors
         spec[NWAVE,NPATH], dspec_x[NWAVE,NPATH,NX], dtsurf[NWAVE,NPATH]."""
-        return self.run(self.stage(ev, True, M))
+        return self._evaluate(ev, True, M)
 
     @staticmethod
     def to_host(t):
