@@ -16,14 +16,24 @@ void ansb200_set_error(const char *fmt, ...)
 extern "C" const char *ansb200_last_error(void) { return g_err; }
 extern "C" int ansb200_version(void) { return 100; }
 
-// ln K tabulated once per table: positive entries get log(K); zero -> -inf; negative -> NaN so
-// that one non-finite corner routes the interpolation to the reference's linear / zero branches.
-__global__ void ans_table_log_kernel(const double *__restrict__ K, double *__restrict__ lnK, size_t n)
+// Table upload: the reference layout K[NWAVE,NG,NP,NT,NGAS] is re-ordered to plane-major
+// [NP*NT][NWAVE][NG][NGAS] and ln K is tabulated beside it: positive entries get log(K); zero -> -inf;
+// negative -> NaN so that one non-finite corner routes the interpolation to the reference's linear /
+// zero branches.  One thread per output element (coalesced writes, strided one-off reads).
+__global__ void ans_table_log_kernel(const double *__restrict__ Kin, double *__restrict__ K, double *__restrict__ lnK,
+                                     int NWAVE, int NG, int NPT, int NGAS)
 {
+    const size_t n = (size_t)NWAVE * NG * NPT * NGAS;
+    const size_t pairs = (size_t)NWAVE * NG;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        double v = K[i];
+        const size_t gas = i % NGAS;
+        const size_t rest = i / NGAS;
+        const size_t pair = rest % pairs;       // wave*NG + g
+        const size_t pt = rest / pairs;         // ip*NT + it
+        const double v = Kin[(pair * NPT + pt) * NGAS + gas];
+        K[i] = v;
         lnK[i] = v > 0.0 ? log(v) : (v == 0.0 ? -INFINITY : NAN);
     }
 }
@@ -39,27 +49,36 @@ extern "C" int ansb200_table_create(const double *K, int is_device, int NWAVE, i
     ansb200_table *t = new ansb200_table();
     t->NWAVE = NWAVE; t->NG = NG; t->NP = NP; t->NT = NT; t->NGAS = NGAS;
     t->K = nullptr; t->lnK = nullptr;
-    if (cudaMalloc(&t->K, n * sizeof(double)) != cudaSuccess || cudaMalloc(&t->lnK, n * sizeof(double)) != cudaSuccess) {
+    double *staging = nullptr;
+    if (cudaMalloc(&t->K, n * sizeof(double)) != cudaSuccess || cudaMalloc(&t->lnK, n * sizeof(double)) != cudaSuccess ||
+        (!is_device && cudaMalloc(&staging, n * sizeof(double)) != cudaSuccess)) {
         cudaGetLastError();
         if (t->K) cudaFree(t->K);
+        if (t->lnK) cudaFree(t->lnK);
         delete t;
-        ansb200_set_error("table_create: cudaMalloc of 2 x %zu bytes failed", n * sizeof(double));
+        ansb200_set_error("table_create: cudaMalloc of %d x %zu bytes failed", is_device ? 2 : 3, n * sizeof(double));
         return ANSB200_ENOMEM;
     }
-    cudaError_t e = cudaMemcpyAsync(t->K, K, n * sizeof(double),
-                                    is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream);
-    if (e != cudaSuccess) {
-        cudaFree(t->K); cudaFree(t->lnK); delete t;
-        ansb200_set_error("table_create: copy failed: %s", cudaGetErrorString(e));
-        return ANSB200_ECUDA;
+    const double *src = K;
+    cudaError_t e = cudaSuccess;
+    if (!is_device) {
+        e = cudaMemcpyAsync(staging, K, n * sizeof(double), cudaMemcpyHostToDevice, stream);
+        src = staging;
     }
-    int blocks = (int)((n + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    ans_table_log_kernel<<<blocks, 256, 0, stream>>>(t->K, t->lnK, n);
-    e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        int blocks = (int)((n + 255) / 256);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        ans_table_log_kernel<<<blocks, 256, 0, stream>>>(src, t->K, t->lnK, NWAVE, NG, NP * NT, NGAS);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && staging) {
+        e = cudaStreamSynchronize(stream);   // one-off upload: wait, then release the staging copy
+        cudaFree(staging);
+        staging = nullptr;
+    }
     if (e != cudaSuccess) {
-        cudaFree(t->K); cudaFree(t->lnK); delete t;
-        ansb200_set_error("table_create: log kernel launch failed: %s", cudaGetErrorString(e));
+        cudaFree(t->K); cudaFree(t->lnK); if (staging) cudaFree(staging); delete t;
+        ansb200_set_error("table_create: upload failed: %s", cudaGetErrorString(e));
         return ANSB200_ECUDA;
     }
     *out = t;

@@ -6,8 +6,8 @@
 #include "../../include/ansb200.h"
 
 struct ansb200_table {
-    double *K;    // [NWAVE,NG,NP,NT,NGAS] resident copy
-    double *lnK;  // same shape: log(K), -inf for K==0, NaN for K<0
+    double *K;    // resident copy, plane-major [NP*NT][NWAVE][NG][NGAS]
+    double *lnK;  // same layout: log(K), -inf for K==0, NaN for K<0
     int NWAVE, NG, NP, NT, NGAS;
 };
 

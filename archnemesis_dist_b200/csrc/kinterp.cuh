@@ -11,13 +11,17 @@ struct AnsLayerPlan {
     const double *w4, *omv, *vv, *dudt;
 };
 
+// Device table layout (api.cu): plane-major [NP*NT][NWAVE][NG][NGAS] -- one (p,T) plane is one contiguous
+// NWAVE*NG*NGAS run, so the NG*NGAS values a wavenumber needs from a plane are 960 contiguous bytes
+// (at 20 x 6) instead of twenty 48-byte pieces 14 KB apart in the reference's layout.
+// off00 addresses the (ip_lo, it_lo) corner; `plane` = NWAVE*NG*NGAS elements between consecutive T planes.
 template <bool GRAD>
 __device__ __forceinline__ void ans_kinterp_elem(const double *__restrict__ lnK, const double *__restrict__ K,
-                                                 size_t off00, int NT, int NGAS, double w0, double w1, double w2,
+                                                 size_t off00, int NT, size_t plane, double w0, double w1, double w2,
                                                  double w3, double omv, double v, double dudt, double &kout,
                                                  double &dkout)
 {
-    const size_t off01 = off00 + NGAS, off10 = off00 + (size_t)NT * NGAS, off11 = off10 + NGAS;
+    const size_t off01 = off00 + plane, off10 = off00 + (size_t)NT * plane, off11 = off10 + plane;
     double l00 = __ldg(lnK + off00), l01 = __ldg(lnK + off01), l10 = __ldg(lnK + off10), l11 = __ldg(lnK + off11);
     bool fast = isfinite(l00) && isfinite(l01) && isfinite(l10) && isfinite(l11);
     if (!fast) {

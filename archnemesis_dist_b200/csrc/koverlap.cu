@@ -11,10 +11,10 @@ __global__ void ans_koverlap_single_kernel(OvParams P)
         double kv, dv = 0.0;
         if (P.fused) {
             const size_t pair = o / P.NLAY;
-            const size_t slab = (size_t)P.NP * P.NT;
+            const size_t plane = (size_t)P.NWAVE * P.NG;          // NGAS == 1
             const double *w = P.plan.w4 + 4 * l;
-            ans_kinterp_elem<GRAD>(P.lnK, P.K, pair * slab + (size_t)P.plan.ip_lo[l] * P.NT + P.plan.it_lo[l], P.NT, 1,
-                                   w[0], w[1], w[2], w[3], GRAD ? P.plan.omv[l] : 0.0, GRAD ? P.plan.vv[l] : 0.0,
+            ans_kinterp_elem<GRAD>(P.lnK, P.K, ((size_t)P.plan.ip_lo[l] * P.NT + P.plan.it_lo[l]) * plane + pair, P.NT,
+                                   plane, w[0], w[1], w[2], w[3], GRAD ? P.plan.omv[l] : 0.0, GRAD ? P.plan.vv[l] : 0.0,
                                    GRAD ? P.plan.dudt[l] : 0.0, kv, dv);
         } else {
             kv = P.k[o];

@@ -882,17 +882,17 @@ ans_koverlap_kernel(OvParams P)
 
     // stage k (and dk/dT) of the cell
     if (P.fused) {
-        const size_t slab = (size_t)P.NP * P.NT * NGAS;
-        const size_t toff = ((size_t)__ldg(P.plan.ip_lo + l) * P.NT + __ldg(P.plan.it_lo + l)) * NGAS;
+        // plane-major table: the NG*NGAS values of this wavenumber in one (p,T) plane are contiguous
+        const size_t plane = (size_t)P.NWAVE * NG * NGAS;
+        const size_t toff = ((size_t)__ldg(P.plan.ip_lo + l) * P.NT + __ldg(P.plan.it_lo + l)) * plane +
+                            (size_t)iw * NG * NGAS;
         const double *w = P.plan.w4 + 4 * l;
         const double w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
         const double omv = GRAD ? __ldg(P.plan.omv + l) : 0.0, v = GRAD ? __ldg(P.plan.vv + l) : 0.0,
                      dudt = GRAD ? __ldg(P.plan.dudt + l) : 0.0;
         for (int e = lane; e < NG * NGAS; e += 32) {
-            const int g = e / NGAS, gas = e - g * NGAS;
             double kv, dv = 0.0;
-            ans_kinterp_elem<GRAD>(P.lnK, P.K, ((size_t)iw * NG + g) * slab + toff + gas, P.NT, NGAS, w0, w1, w2, w3,
-                                   omv, v, dudt, kv, dv);
+            ans_kinterp_elem<GRAD>(P.lnK, P.K, toff + e, P.NT, plane, w0, w1, w2, w3, omv, v, dudt, kv, dv);
             s.kbuf[e] = kv;
             if (GRAD) s.dbuf[e] = dv;
         }
