@@ -363,7 +363,14 @@ __device__ __noinline__ void ov_rebin_seq(OvWarpSmem s, const double *__restrict
         // most one bin, exactly like the reference loop.
         if (lane == 0) {
             for (int m = 0; m <= NG; ++m) { s.strad[m] = OV_NONE; s.frac[m] = 0.0; }
-            double run = 0.0, gprev = 0.0;
+            // gdist[iloop-1] wraps to the LAST cumulative weight when the very first element already
+            // reaches the first edge (python index -1, ForwardModel_0.py:6160 / :6009): start from the total
+            double gprev = 0.0;
+            for (int pos = 0; pos < NN; ++pos) {
+                const int pi = s.sidx[pos];
+                gprev = __dadd_rn(gprev, wtab[(pi >> 5) * NG + (pi & 31)]);
+            }
+            double run = 0.0;
             int ig = 0;
             for (int pos = 0; pos < NN && ig < NG; ++pos) {
                 const int pi = s.sidx[pos];

@@ -311,7 +311,8 @@ def run_b200(args, cfg):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = b_kio / (k_ms * 1e-3) / 1e9
         roof = dict(kernel="ans_koverlap_kernel (ansb200_gas_opacity: fused k-interp + random overlap, gradients)",
-                    bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=TRAFFIC,
+                    bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                    traffic=TRAFFIC if cfg["nwave"] == CFG["nwave"] else None,
                     peak_source="measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
                     algorithmic_bytes=b_kio, planes_touched=U, kernel_ms=k_ms, share_of_step=k_ms / ms_step)
         line = dict(metric=METRIC, value=value, unit="spectra/s", n_gpus=world, steps=K, warmup=args.warmup,
@@ -333,8 +334,10 @@ def run_b200(args, cfg):
         dist.destroy_process_group()
 
 
-# dram bytes per launch of the dominant kernel from the last `ncu --set full` capture (profiles/), or None
-TRAFFIC = None
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at config 2, from the
+# `ncu --set full` capture in profiles/r01_ncu_full_config2.txt (205.7 MB read = every touched table plane
+# once, 459.1 MB written; algorithmic B_kio is 715.5 MB, the remainder of the output was still in L2)
+TRAFFIC = 664.8e6
 
 
 def time_cpu_sampled(cfg, nsample):
