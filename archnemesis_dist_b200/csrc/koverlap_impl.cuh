@@ -178,84 +178,82 @@ __device__ __forceinline__ void ov_bitonic_sort(double (&key)[EPL], int (&idx)[E
     }
 }
 
-// ---- fast path: 64-bit packed (float32 key | index) network ------------------------------------
-// The keys are scaled by a power of two, rounded to float32 (monotone), mapped to an order-preserving
-// uint32 and packed above the element index; one unsigned 64-bit compare then orders (key32, index)
-// and a comparator moves two registers instead of three.  Because the rounding is monotone the
-// result is the exact (key, index) order unless two keys that differ in float64 collide in float32 in
-// the wrong index order; the caller verifies the exact keys afterwards and falls back to the
-// float64 network (ov_bitonic_sort<EPL, true>) if the check fails.
-__device__ __forceinline__ void ov_ce_u64(unsigned long long &a, unsigned long long &b)
-{
-    asm("{\n\t.reg .pred sw;\n\t.reg .b64 t;\n\t"
-        "setp.lt.u64 sw, %1, %0;\n\t"
-        "selp.b64 t, %1, %0, sw;\n\t"
-        "selp.b64 %1, %0, %1, sw;\n\t"
-        "mov.b64 %0, t;\n\t}"
-        : "+l"(a), "+l"(b));
-}
-
-__device__ __forceinline__ void ov_ce_x_u64(unsigned long long &v, unsigned long long pv, int keep_low)
-{
-    asm("{\n\t.reg .pred lt, kl, tk;\n\t"
-        "setp.lt.u64 lt, %1, %0;\n\t"
-        "setp.ne.s32 kl, %2, 0;\n\t"
-        "xor.pred tk, lt, kl;\n\t"
-        "not.pred tk, tk;\n\t"          // take = (partner < mine) == keep_low   (values are unique)
-        "selp.b64 %0, %1, %0, tk;\n\t}"
-        : "+l"(v) : "l"(pv), "r"(keep_low));
-}
-
-__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m)
-{
-    unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
-    lo = __shfl_xor_sync(FULL, lo, m);
-    hi = __shfl_xor_sync(FULL, hi, m);
-    return ((unsigned long long)hi << 32) | lo;
-}
-
+// ---- fast path: 32-bit packed (22-bit key | 10-bit index) network --------------------------------
+// The keys are scaled by a power of two and rounded to float32 (monotone); the top 22 bits of the
+// (positive) float32 pattern -- exponent and 14 mantissa bits -- are packed above the 10-bit element
+// index.  One unsigned min/max then orders (key22, index): a comparator is two instructions on one
+// register.  The order is exact except inside groups of keys that agree to 14 mantissa bits
+// (~0.5 pairs per fold at NG=20); the caller re-forms the exact float64 keys, repairs such groups with
+// odd-even transposition passes on (key, index) and falls back to the float64 network
+// (ov_bitonic_sort<EPL, true>) if a few passes do not suffice, so the result is always the exact order.
 template <int EPL>
-__device__ __forceinline__ void ov_bitonic_sort_u64(unsigned long long (&v)[EPL], int lane)
+__device__ __forceinline__ void ov_bitonic_sort_u32(unsigned (&v)[EPL], int lane)
 {
+#define OV_CE32(x, y) do { const unsigned lo__ = min(x, y), hi__ = max(x, y); x = lo__; y = hi__; } while (0)
 #pragma unroll
     for (int k = 2; k <= EPL; k <<= 1) {
 #pragma unroll
         for (int r = 0; r < EPL; ++r) {
             const int q = r ^ (k - 1);
-            if (r < q) ov_ce_u64(v[r], v[q]);
+            if (r < q) OV_CE32(v[r], v[q]);
         }
 #pragma unroll
         for (int j = k >> 2; j > 0; j >>= 1) {
 #pragma unroll
             for (int r = 0; r < EPL; ++r)
-                if ((r & j) == 0) ov_ce_u64(v[r], v[r | j]);
+                if ((r & j) == 0) OV_CE32(v[r], v[r | j]);
         }
     }
 #pragma unroll 1
     for (int kl = 2; kl <= 32; kl <<= 1) {
         {
-            const int keep_low = (lane & (kl >> 1)) == 0;
+            const bool keep_low = (lane & (kl >> 1)) == 0;
 #pragma unroll
             for (int r = 0; r < EPL / 2; ++r) {
                 const int q = EPL - 1 - r;
-                const unsigned long long pr = shfl_xor_u64(v[q], kl - 1), pq = shfl_xor_u64(v[r], kl - 1);
-                ov_ce_x_u64(v[r], pr, keep_low);
-                ov_ce_x_u64(v[q], pq, keep_low);
+                const unsigned pr = __shfl_xor_sync(FULL, v[q], kl - 1), pq = __shfl_xor_sync(FULL, v[r], kl - 1);
+                v[r] = keep_low ? min(v[r], pr) : max(v[r], pr);
+                v[q] = keep_low ? min(v[q], pq) : max(v[q], pq);
             }
         }
 #pragma unroll 1
         for (int lm = kl >> 2; lm > 0; lm >>= 1) {
-            const int keep_low = (lane & lm) == 0;
+            const bool keep_low = (lane & lm) == 0;
 #pragma unroll
-            for (int r = 0; r < EPL; ++r) ov_ce_x_u64(v[r], shfl_xor_u64(v[r], lm), keep_low);
+            for (int r = 0; r < EPL; ++r) {
+                const unsigned pv = __shfl_xor_sync(FULL, v[r], lm);
+                v[r] = keep_low ? min(v[r], pv) : max(v[r], pv);
+            }
         }
 #pragma unroll
         for (int j = EPL >> 1; j > 0; j >>= 1) {
 #pragma unroll
             for (int r = 0; r < EPL; ++r)
-                if ((r & j) == 0) ov_ce_u64(v[r], v[r | j]);
+                if ((r & j) == 0) OV_CE32(v[r], v[r | j]);
         }
     }
+#undef OV_CE32
+}
+
+// one odd-even transposition pass over the whole sequence on the exact (key, index) order
+template <int EPL>
+__device__ __forceinline__ void ov_fixup_pass(double (&key)[EPL], int (&idx)[EPL], int lane)
+{
+#pragma unroll
+    for (int r = 0; r + 1 < EPL; r += 2) ov_ce<true>(key[r], idx[r], key[r + 1], idx[r + 1]);
+#pragma unroll
+    for (int r = 1; r + 1 < EPL; r += 2) ov_ce<true>(key[r], idx[r], key[r + 1], idx[r + 1]);
+    // the pair that spans two lanes: my last element against the next lane's first
+    double nk = __hiloint2double(__shfl_down_sync(FULL, __double2hiint(key[0]), 1),
+                                 __shfl_down_sync(FULL, __double2loint(key[0]), 1));
+    int ni = __shfl_down_sync(FULL, idx[0], 1);
+    double pk = __hiloint2double(__shfl_up_sync(FULL, __double2hiint(key[EPL - 1]), 1),
+                                 __shfl_up_sync(FULL, __double2loint(key[EPL - 1]), 1));
+    int pi = __shfl_up_sync(FULL, idx[EPL - 1], 1);
+    if (lane == 31) { nk = key[EPL - 1]; ni = idx[EPL - 1]; }     // no neighbour: compare with itself (no-op)
+    if (lane == 0) { pk = key[0]; pi = idx[0]; }
+    ov_ce_x<true>(key[EPL - 1], idx[EPL - 1], nk, ni, 1);
+    ov_ce_x<true>(key[0], idx[0], pk, pi, 0);
 }
 
 // order check of the sorted sequence: bit 0 = some neighbour pair is out of order (exact keys),
@@ -771,34 +769,39 @@ __device__ __forceinline__ void ov_sort_stage(const OvWarpSmem &s, const double 
         // (vote: every lane holds the same value; this tells the compiler the branch is warp-uniform)
         if (__all_sync(FULL, kmax > 0.0 && e > 200 && e < 2000)) {
             const double sc = __hiloint2double((2146 - e) << 20, 0);   // 2^(100 - exponent(kmax)): exact scaling
-            unsigned long long v[EPL];
+            unsigned v[EPL];
             int el = lane * EPL;
             int i = el / NG, j = el - i * NG;
 #pragma unroll
             for (int r = 0; r < EPL; ++r) {
                 if (el < NN) {
+                    // positive keys only: the float32 bit pattern is then monotone (other keys end up misplaced
+                    // and are caught by the exact check below)
                     const float kf = __double2float_rn(__dmul_rn(__dadd_rn(s.a[i], s.b[j]), sc));
-                    unsigned u = __float_as_uint(kf);
-                    u ^= ((unsigned)((int)u >> 31)) | 0x80000000u;      // order-preserving map, negatives included
-                    v[r] = ((unsigned long long)u << 32) | (unsigned)((i << 5) | j);
+                    v[r] = ((__float_as_uint(kf) >> 9) << 10) | (unsigned)((i << 5) | j);
                 } else {
-                    v[r] = 0xffffffff00000000ull | (unsigned)((32 << 5) + (el - NN));
+                    v[r] = 0xffffffffu;           // padding: above every live element, index field marks it dead
                 }
                 ++el;
                 if (++j == NG) { j = 0; ++i; }
             }
-            ov_bitonic_sort_u64<EPL>(v, lane);
+            ov_bitonic_sort_u32<EPL>(v, lane);
 #pragma unroll
             for (int r = 0; r < EPL; ++r) {
-                idx[r] = (int)(unsigned)v[r];
+                idx[r] = (int)(v[r] & 1023u);
                 const int ii = idx[r] >> 5, jj = idx[r] & 31;
                 key[r] = ii < NG ? __dadd_rn(s.a[ii], s.b[jj]) : INFINITY;
             }
-            sorted = (ov_check_order<EPL>(key, lane) & 1) == 0;
+            int bad = ov_check_order<EPL>(key, lane) & 1;
+            for (int pass = 0; bad && pass < 6; ++pass) {
+                ov_fixup_pass<EPL>(key, idx, lane);
+                bad = ov_check_order<EPL>(key, lane) & 1;
+            }
+            sorted = !bad;
         }
     }
     if (!sorted) {
-        // float32 collision in the wrong order, or keys outside the scaled float32 range: exact network
+        // keys outside the scaled float32 range or a large group of near-equal keys: exact network
         make_keys();
         ov_bitonic_sort<EPL, true>(key, idx, lane);
     }
