@@ -278,6 +278,7 @@ __device__ __forceinline__ int ov_check_order(const double (&key)[EPL], int lane
 struct OvWarpSmem {
     double *kbuf, *dbuf;     // [NG*NGAS] k and dk/dT of the cell
     double *a, *b, *bT;      // [NG] running tau_g, next gas tau, next gas dk/dT*amount
+    double *colB;            // [NG*3] {b, bT, k of the gas being folded} packed per column for the rebin loop
     double *dkp;             // [NG*DS] running gradients: dT, gas columns (see ov_ds)
     double *frac;            // [NG+1]
     double *bsum;            // [NG*BS] raw bin sums (see ov_bs)
@@ -310,7 +311,7 @@ __host__ __device__ inline size_t ov_per_warp_bytes(int NG, int NGAS, bool grad)
     int NN = 128;                       // sorted-index staging is padded to 32*EPL entries
     while (NN < NG * NG) NN <<= 1;
     const int npm = ov_npmax(NGAS);
-    const int nd = NG * NGAS * (grad ? 2 : 1) + 3 * NG + (grad ? NG * ov_ds(npm) : 0) + (NG + 1) + NG * ov_bs(npm) +
+    const int nd = NG * NGAS * (grad ? 2 : 1) + 6 * NG + (grad ? NG * ov_ds(npm) : 0) + (NG + 1) + NG * ov_bs(npm) +
                    ov_head_doubles(NG, NGAS);
     return ((size_t)nd * 8 + (size_t)(2 * NG + 1) * 4 + (size_t)NN * 2 + 15) & ~(size_t)15;
 }
@@ -500,7 +501,17 @@ __device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const double *
 #pragma unroll
     for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
     double *myhead = s.head + lane * BS;
-    const double *kbcol = s.kbuf + g1;
+    if (GRAD) {
+        // per-row / per-column operands packed so that the loop below forms two base addresses per element:
+        // row i = [dT, gas columns, tau] (the spare slot of the dkp row), column j = [tau, dT part, k]
+        for (int t = lane; t < NG; t += 32) {
+            s.dkp[t * DS + NPMAX] = s.a[t];
+            s.colB[3 * t] = s.b[t];
+            s.colB[3 * t + 1] = s.bT[t];
+            s.colB[3 * t + 2] = s.kbuf[t * NGAS + g1];
+        }
+        __syncwarp();
+    }
     bool head_pending = lane != 0;   // the bin this lane starts in was opened by an earlier lane
 #pragma unroll 1
     for (int r = 0; r < EPL; ++r) {
@@ -510,14 +521,17 @@ __device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const double *
             const double w = wtab[i * NG + j];
             const double gdn = __dadd_rn(prev, w);
             double c[NQ];
-            c[0] = __dmul_rn(__dadd_rn(s.a[i], s.b[j]), w);
             c[1] = w;
             if (GRAD) {
                 const double *row = s.dkp + i * DS;
-                c[2] = __dmul_rn(__dadd_rn(row[0], s.bT[j]), w);
+                const double *col = s.colB + 3 * j;
+                c[0] = __dmul_rn(__dadd_rn(row[NPMAX], col[0]), w);
+                c[2] = __dmul_rn(__dadd_rn(row[0], col[1]), w);
 #pragma unroll
                 for (int p = 0; p < NPMAX - 1; ++p) c[3 + p] = __dmul_rn(row[1 + p], w);   // unfolded gases are 0
-                c[NQ - 1] = __dmul_rn(kbcol[j * NGAS], w);
+                c[NQ - 1] = __dmul_rn(col[2], w);
+            } else {
+                c[0] = __dmul_rn(__dadd_rn(s.a[i], s.b[j]), w);
             }
             const double edge = gord[ig + 1];
             if (gdn < edge) {
@@ -871,6 +885,7 @@ ans_koverlap_kernel(OvParams P)
         s.a = d; d += NG;
         s.b = d; d += NG;
         s.bT = d; d += NG;
+        s.colB = d; d += 3 * NG;
         s.dkp = d; if (GRAD) d += NG * DS;
         s.frac = d; d += NG + 1;
         s.bsum = d; d += NG * BS;
