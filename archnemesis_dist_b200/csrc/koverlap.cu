@@ -45,19 +45,22 @@ static int ov_run(OvParams &P, bool grad, cudaStream_t stream)
     const int NN = P.NG * P.NG;
     if (NN <= 128) return ov_dispatch_4(P, grad, stream);
     if (NN <= 256) return ov_dispatch_8(P, grad, stream);
+#ifdef OV_NG20
+    if (P.NG == 20) return ov_dispatch_16_ng20(P, grad, stream);
+#endif
     return ov_dispatch_16(P, grad, stream);
 }
 
 // The host checks (plan.overlap_tables) that no sorted element can straddle two bin edges; if it
 // can, bit 1 of want_grad requests the literal sequential bin-edge scan.
 extern "C" int ansb200_koverlap(const double *k, const double *dkdT, const double *amount, const double *weight,
-                                const double *g_ord, int NWAVE, int NG, int NLAY, int NGAS, int want_grad,
+                                const double *g_ord, const double *del_g, int NWAVE, int NG, int NLAY, int NGAS, int want_grad,
                                 double *tau, double *dk, void *stream_)
 {
     const bool grad = (want_grad & 1) != 0;
     ANS_REQUIRE(k && (!grad || dkdT), "koverlap: null k/dkdT");
     OvParams P{};
-    P.k = k; P.dkdT = dkdT; P.amount = amount; P.weight = weight; P.g_ord = g_ord;
+    P.k = k; P.dkdT = dkdT; P.amount = amount; P.weight = weight; P.g_ord = g_ord; P.del_g = del_g;
     P.NWAVE = NWAVE; P.NG = NG; P.NLAY = NLAY; P.NGAS = NGAS; P.tau = tau; P.dk = dk;
     P.fused = 0; P.seq_rebin = (want_grad & 2) ? 1 : 0;
     return ov_run(P, grad, (cudaStream_t)stream_);
@@ -65,8 +68,8 @@ extern "C" int ansb200_koverlap(const double *k, const double *dkdT, const doubl
 
 extern "C" int ansb200_gas_opacity(const ansb200_table *t, int NLAY, const int32_t *ip_lo, const int32_t *it_lo,
                                    const double *w4, const double *omv, const double *vv, const double *dudt,
-                                   const double *amount, const double *weight, const double *g_ord, int want_grad,
-                                   double *tau, double *dk, void *stream_)
+                                   const double *amount, const double *weight, const double *g_ord,
+                                   const double *del_g, int want_grad, double *tau, double *dk, void *stream_)
 {
     const bool grad = (want_grad & 1) != 0;
     ANS_REQUIRE(t && ip_lo && it_lo && w4, "gas_opacity: null pointer");
@@ -74,7 +77,7 @@ extern "C" int ansb200_gas_opacity(const ansb200_table *t, int NLAY, const int32
     OvParams P{};
     P.lnK = t->lnK; P.K = t->K; P.plan = AnsLayerPlan{ip_lo, it_lo, w4, omv, vv, dudt};
     P.NP = t->NP; P.NT = t->NT;
-    P.amount = amount; P.weight = weight; P.g_ord = g_ord;
+    P.amount = amount; P.weight = weight; P.g_ord = g_ord; P.del_g = del_g;
     P.NWAVE = t->NWAVE; P.NG = t->NG; P.NLAY = NLAY; P.NGAS = t->NGAS; P.tau = tau; P.dk = dk;
     P.fused = 1; P.seq_rebin = (want_grad & 2) ? 1 : 0;
     return ov_run(P, grad, (cudaStream_t)stream_);

@@ -22,8 +22,15 @@
 #pragma once
 #include "kinterp.cuh"
 
-constexpr int OV_WARPS = 8;
+#ifndef OV_NWARPS
+#define OV_NWARPS 8
+#endif
+constexpr int OV_WARPS = OV_NWARPS;
+#ifndef OV_MINB
+#define OV_MINB 2
+#endif
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int OV_CS = 6;   // doubles per column record {b, bT, k, -, -, -}: 3 sixteen-byte units, conflict-free mod 8
 constexpr int OV_NONE = 0x7fffffff;
 
 struct OvParams {
@@ -32,6 +39,7 @@ struct OvParams {
     AnsLayerPlan plan;
     int NP, NT;
     const double *amount, *weight, *g_ord;
+    const double *del_g;                    // [NG] quadrature weights (may be NULL): lets the kernel form del_g[i]*del_g[j] itself
     int NWAVE, NG, NLAY, NGAS;
     double *tau, *dk;
     int fused, seq_rebin;
@@ -274,13 +282,31 @@ __device__ __forceinline__ int ov_check_order(const double (&key)[EPL], int lane
     return (__any_sync(FULL, bad) ? 1 : 0) | (__any_sync(FULL, tie) ? 2 : 0);
 }
 
+// Weight of element (i,j).  The reference's table is del_g[i]*del_g[j] evaluated in del_g's dtype
+// (float32 on the .kta path).  A random lookup in the NG*NG table of doubles costs ~7 shared-memory
+// wavefronts per warp (bank conflicts) and was 28 % of the kernel's shared-memory traffic; two lookups in
+// the NG-entry float table are conflict-free (equal indices broadcast), and the float32 product is the
+// table entry bit for bit.  The CTA checks that at start-up (`f32`); otherwise (float64 del_g, or a
+// caller-made table) the table is used.
+struct OvWeight {
+    const double *wtab;
+    const float *dgf;
+    int NG;
+    bool f32;
+    __device__ __forceinline__ double operator()(int i, int j) const
+    {
+        if (f32) return (double)__fmul_rn(dgf[i], dgf[j]);
+        return wtab[i * NG + j];
+    }
+};
+
 // Per-warp shared-memory view.
 struct OvWarpSmem {
     double *kbuf, *dbuf;     // [NG*NGAS] k and dk/dT of the cell
     double *a, *b, *bT;      // [NG] running tau_g, next gas tau, next gas dk/dT*amount
-    double *colB;            // [NG*3] {b, bT, k of the gas being folded} packed per column for the rebin loop
-    double *dkp;             // [NG*DS] running gradients: dT, gas columns (see ov_ds)
-    double *frac;            // [NG+1]
+    double *colB;            // [NG*OV_CS] {b, bT, k of the gas being folded} packed per column for the rebin loop (16-byte aligned)
+    double *dkp;             // [NG*DS] rows [tau_i (copy made by the rebin), dT, gas columns] (see ov_ds); 16-byte aligned
+    double *frac, *gdn;      // [NG+1] cumulative weight before / after the straddler of every edge
     double *bsum;            // [NG*BS] raw bin sums (see ov_bs)
     double *head;            // [32*BS] per-lane partial sum of the bin a lane starts in (parallel rebin)
     int *strad;              // [NG+1]
@@ -288,32 +314,35 @@ struct OvWarpSmem {
     unsigned short *sidx;    // [NG*NG] sorted packed indices
 };
 
-// Gradient storage (template NPMAX >= NGAS+1): row i of dkp is [ dT, gas 0 .. gas NPMAX-2 ] with the odd
-// stride DS = NPMAX+1 (bank-conflict free across rows); columns of gases not folded yet hold 0.  Raw bin
+// Gradient storage (template NPMAX >= NGAS+1): row i of dkp is [ tau_i, dT, gas 0 .. gas NPMAX-2, - ] with the
+// even stride DS = NPMAX+2 (rows 16-byte aligned: the rebin loop reads them as double2; DS/2 is odd for
+// NPMAX = 8, so the 8 lanes of a 128-bit wavefront conflict only when their rows are equal mod 8);
+// columns of gases not folded yet hold 0.  Raw bin
 // sums and head slots are rows of BS = (NPMAX+3)|1 doubles: cont*w, w, dT, gas 0 .. gas NPMAX-2, and the
 // column of the gas being folded (kept apart so that every gas column is processed alike).
 __host__ __device__ inline int ov_npmax(int NGAS) { return NGAS + 1 <= 4 ? 4 : (NGAS + 1 <= 8 ? 8 : 16); }
-__host__ __device__ inline int ov_ds(int npmax) { return npmax + 1; }
+__host__ __device__ inline int ov_ds(int npmax) { return npmax + 2; }
 __host__ __device__ inline int ov_bs(int npmax) { return (npmax + 3) | 1; }
 
 // head slots of the parallel rebin (32 lanes x BS); the same region is the scratch of the tie-order
 // emulation (4 uint16 arrays of the padded sort length = that many doubles)
-__host__ __device__ inline int ov_head_doubles(int NG, int NGAS)
+__host__ __device__ inline int ov_head_doubles_np(int NG, int npmax)
 {
     int nnpad = 128;
     while (nnpad < NG * NG) nnpad <<= 1;
-    const int h = 32 * ov_bs(ov_npmax(NGAS));
+    const int h = 32 * ov_bs(npmax);
     return h > nnpad ? h : nnpad;
 }
+__host__ __device__ inline int ov_head_doubles(int NG, int NGAS) { return ov_head_doubles_np(NG, ov_npmax(NGAS)); }
 
 __host__ __device__ inline size_t ov_per_warp_bytes(int NG, int NGAS, bool grad)
 {
     int NN = 128;                       // sorted-index staging is padded to 32*EPL entries
     while (NN < NG * NG) NN <<= 1;
     const int npm = ov_npmax(NGAS);
-    const int nd = NG * NGAS * (grad ? 2 : 1) + 6 * NG + (grad ? NG * ov_ds(npm) : 0) + (NG + 1) + NG * ov_bs(npm) +
+    const int nd = NG * NGAS * (grad ? 2 : 1) + (3 + OV_CS) * NG + (grad ? NG * ov_ds(npm) : 0) + 2 * (NG + 1) + NG * ov_bs(npm) +
                    ov_head_doubles(NG, NGAS);
-    return ((size_t)nd * 8 + (size_t)(2 * NG + 1) * 4 + (size_t)NN * 2 + 15) & ~(size_t)15;
+    return ((size_t)nd * 8 + (size_t)(2 * NG + 2) * 4 + (size_t)NN * 2 + 15) & ~(size_t)15;
 }
 
 // Rebin by lane-per-bin walk in sorted order (bit-identical rounding sequence to rank/rankg).  Used when
@@ -324,7 +353,7 @@ __device__ __noinline__ void ov_rebin_seq(OvWarpSmem s, const double *__restrict
 {
     // s.sidx holds the sorted packed indices (written by the caller)
     const int NN = NG * NG;
-    constexpr int DS = NPMAX + 1;
+    constexpr int DS = NPMAX + 2;
     const int g1 = igas + 1;
     const int seq_rebin = 1;
     __syncwarp();
@@ -347,9 +376,9 @@ __device__ __noinline__ void ov_rebin_seq(OvWarpSmem s, const double *__restrict
             for (int p = 0; p < NPMAX; ++p) {
                 if (p < n) {
                     double g;
-                    if (p <= igas) g = s.dkp[i * DS + 1 + p];
+                    if (p <= igas) g = s.dkp[i * DS + 2 + p];
                     else if (p == g1) g = s.kbuf[j * NGAS + g1];
-                    else g = __dadd_rn(s.dkp[i * DS], s.bT[j]);
+                    else g = __dadd_rn(s.dkp[i * DS + 1], s.bT[j]);
                     gw[p] = __dmul_rn(g, w);
                 }
             }
@@ -441,10 +470,10 @@ __device__ __noinline__ void ov_rebin_seq(OvWarpSmem s, const double *__restrict
         if (GRAD) {
 #pragma unroll
             for (int p = 0; p < NPMAX; ++p) {
-                if (p <= g1) s.dkp[m * DS + 1 + p] = res_g[p];       // gas columns
-                else if (p == g1 + 1) s.dkp[m * DS] = res_g[p];      // temperature column
+                if (p <= g1) s.dkp[m * DS + 2 + p] = res_g[p];       // gas columns
+                else if (p == g1 + 1) s.dkp[m * DS + 1] = res_g[p];      // temperature column
             }
-            for (int p = g1 + 1; p < NGAS; ++p) s.dkp[m * DS + 1 + p] = 0.0;
+            for (int p = g1 + 1; p < NGAS; ++p) s.dkp[m * DS + 2 + p] = 0.0;
         }
     }
     __syncwarp();
@@ -452,32 +481,35 @@ __device__ __noinline__ void ov_rebin_seq(OvWarpSmem s, const double *__restrict
 
 // Rebin in parallel over the sorted elements (rank/rankg, ForwardModel_0.py:6155-6172 / :6002-6025).
 // Every lane walks its EPL consecutive sorted elements (indices staged in shared memory so the loops
-// stay rolled and the hot code fits the instruction cache) with a running cumulative weight,
-// accumulates cont*w, w, the T column and the gas columns of the bin it is in and, at the element
-// that straddles a bin edge, closes the bin with `frac` and opens the next with `1-frac`.  A closed
-// partial sum goes to the lane's head slot if the bin was opened by an earlier lane, else straight to
-// the bin; a bin that spans several lanes is the owner lane's tail plus the heads of the following
-// lanes.  Lane m then normalises bin m.  Same arithmetic as the reference in another summation order
-// (agreement ~1e-15); requires that no element straddles two edges (host check), else ov_rebin_seq.
+// stay rolled and the hot code fits the instruction cache) with a running cumulative weight and
+// accumulates cont*w, w, the T column and the gas columns of the elements that lie WHOLLY inside the
+// bin it is in.  The element that straddles a bin edge only closes the lane's partial sum (to the
+// lane's head slot if the bin was opened by an earlier lane, else straight to the bin) and leaves
+// (element, cumulative weight before / after) in the edge's slot: the straddle branch is divergent
+// (some lane takes it in most iterations), so it is kept to a handful of stores.  A bin that spans
+// several lanes is the owner lane's tail plus the heads of the following lanes.  Lane m finally adds
+// the (1-frac) part of the straddler that opens bin m and the frac part of the one that closes it
+// (frac and the products in the reference's rounding order) and normalises.  Same arithmetic as the
+// reference in another summation order (agreement ~1e-15); requires that no element straddles two
+// edges (host check), else ov_rebin_seq.
 template <int EPL, int NPMAX, bool GRAD>
-__device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const double *__restrict__ wtab,
+__device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const OvWeight &W,
                                              const double *__restrict__ gord, int NG, int NGAS, int igas, int lane)
 {
-    // s.sidx[r*32 + lane] = packed index of sorted position lane*EPL + r (staged by the caller): the
-    // element loops stay rolled so the hot code fits the instruction cache
+    // s.sidx[r*32 + lane] = packed index of sorted position lane*EPL + r (staged by the caller)
     constexpr int NQ = GRAD ? NPMAX + 3 : 2;   // cont*w, w, dT, gas 0..NPMAX-2, column of the gas being folded
-    constexpr int DS = NPMAX + 1, BS = (NPMAX + 3) | 1;
+    constexpr int DS = NPMAX + 2, BS = (NPMAX + 3) | 1;
     const int NN = NG * NG;
     const int g1 = igas + 1;
     for (int t = lane; t < NG * BS; t += 32) s.bsum[t] = 0.0;
-    for (int t = lane; t < NG; t += 32) s.closed[t] = 0;
+    for (int t = lane; t <= NG; t += 32) s.strad[t] = OV_NONE;
 
     // exclusive prefix of the lane's weight
     double run = 0.0;
 #pragma unroll 4
     for (int r = 0; r < EPL; ++r) {
         const int pi = s.sidx[r * 32 + lane];
-        run = __dadd_rn(run, (pi >> 5) < NG ? wtab[(pi >> 5) * NG + (pi & 31)] : 0.0);
+        run = __dadd_rn(run, (pi >> 5) < NG ? W(pi >> 5, pi & 31) : 0.0);
     }
     double incl = run;
 #pragma unroll
@@ -505,54 +537,62 @@ __device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const double *
         // per-row / per-column operands packed so that the loop below forms two base addresses per element:
         // row i = [dT, gas columns, tau] (the spare slot of the dkp row), column j = [tau, dT part, k]
         for (int t = lane; t < NG; t += 32) {
-            s.dkp[t * DS + NPMAX] = s.a[t];
-            s.colB[3 * t] = s.b[t];
-            s.colB[3 * t + 1] = s.bT[t];
-            s.colB[3 * t + 2] = s.kbuf[t * NGAS + g1];
+            s.dkp[t * DS] = s.a[t];
+            s.colB[OV_CS * t] = s.b[t];
+            s.colB[OV_CS * t + 1] = s.bT[t];
+            s.colB[OV_CS * t + 2] = s.kbuf[t * NGAS + g1];
         }
         __syncwarp();
     }
     bool head_pending = lane != 0;   // the bin this lane starts in was opened by an earlier lane
+    double edge = gord[ig < NG ? ig + 1 : NG];
+    // software pipeline: the index and weight of the next element are fetched while this one is summed
+    int pi = s.sidx[lane];
+    double w = (pi >> 5) < NG ? W(pi >> 5, pi & 31) : 0.0;
 #pragma unroll 1
     for (int r = 0; r < EPL; ++r) {
-        const int pi = s.sidx[r * 32 + lane];
         const int i = pi >> 5, j = pi & 31;
+        const double wc = w;
+        const int pn = s.sidx[(r + 1 < EPL ? r + 1 : r) * 32 + lane];
+        w = (pn >> 5) < NG ? W(pn >> 5, pn & 31) : 0.0;
         if (i < NG && ig < NG) {
-            const double w = wtab[i * NG + j];
-            const double gdn = __dadd_rn(prev, w);
-            double c[NQ];
-            c[1] = w;
-            if (GRAD) {
-                const double *row = s.dkp + i * DS;
-                const double *col = s.colB + 3 * j;
-                c[0] = __dmul_rn(__dadd_rn(row[NPMAX], col[0]), w);
-                c[2] = __dmul_rn(__dadd_rn(row[0], col[1]), w);
-#pragma unroll
-                for (int p = 0; p < NPMAX - 1; ++p) c[3 + p] = __dmul_rn(row[1 + p], w);   // unfolded gases are 0
-                c[NQ - 1] = __dmul_rn(col[2], w);
-            } else {
-                c[0] = __dmul_rn(__dadd_rn(s.a[i], s.b[j]), w);
-            }
-            const double edge = gord[ig + 1];
+            const double gdn = __dadd_rn(prev, wc);
             if (gdn < edge) {
+                acc[1] = __dadd_rn(acc[1], wc);
+                if (GRAD) {
+                    // row i = [tau_i, dT, gas columns] and column j = [b, bT, k, -] as double2; the pairs that
+                    // hold only gases not folded yet (all zero) are not loaded
+                    const double2 *row = reinterpret_cast<const double2 *>(s.dkp + i * DS);
+                    const double2 *col = reinterpret_cast<const double2 *>(s.colB + OV_CS * j);
+                    double2 rv[DS / 2];
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) acc[q] = __dadd_rn(acc[q], c[q]);
+                    for (int q = 0; q < DS / 2; ++q) rv[q] = (q == 0 || 2 * q - 2 <= igas) ? row[q] : make_double2(0.0, 0.0);
+                    const double2 c0 = col[0];
+                    const double ck = s.colB[OV_CS * j + 2];
+                    acc[0] = __fma_rn(__dadd_rn(rv[0].x, c0.x), wc, acc[0]);
+                    acc[2] = __fma_rn(__dadd_rn(rv[0].y, c0.y), wc, acc[2]);
+#pragma unroll
+                    for (int p = 0; p < NPMAX - 1; ++p)   // unfolded gases are 0
+                        acc[3 + p] = __fma_rn((p & 1) ? rv[1 + p / 2].y : rv[1 + p / 2].x, wc, acc[3 + p]);
+                    acc[NQ - 1] = __fma_rn(ck, wc, acc[NQ - 1]);
+                } else {
+                    acc[0] = __fma_rn(__dadd_rn(s.a[i], s.b[j]), wc, acc[0]);
+                }
             } else {
-                // (gdn - prev is the element's weight; exact for float32-born weights)
-                const double frac = __ddiv_rn(__dsub_rn(edge, prev), __dsub_rn(gdn, prev));
-                const double omf = __dsub_rn(1.0, frac);
+                // straddler of edge ig+1: close the partial sum, leave the element for lane ig / ig+1
                 double *dst = head_pending ? myhead : s.bsum + ig * BS;
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) {
-                    dst[q] = __dadd_rn(acc[q], __dmul_rn(frac, c[q]));
-                    acc[q] = __dmul_rn(omf, c[q]);
-                }
+                for (int q = 0; q < NQ; ++q) { dst[q] = acc[q]; acc[q] = 0.0; }
                 head_pending = false;
-                s.closed[ig] = 1;
                 ++ig;
+                s.strad[ig] = pi;
+                s.frac[ig] = prev;
+                s.gdn[ig] = gdn;
+                edge = gord[ig < NG ? ig + 1 : NG];
             }
             prev = gdn;
         }
+        pi = pn;
     }
     // a lane that never closed the bin it started in passes everything on as its head
     const bool has_tail = !head_pending;
@@ -576,20 +616,58 @@ __device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const double *
         for (int q = 0; q < NQ; ++q) dst[q] = acc[q];
     }
     __syncwarp();
-    // normalise: a bin closed by a straddler, or the last bin if it was opened (:6171-6172)
+    // lane m: bin m = whole elements + (1-frac) of the straddler of edge m + frac of the straddler of
+    // edge m+1; normalised if closed by a straddler, or if it is the last bin and was opened (:6171-6172)
     const int m = lane;
+    double res[NQ];
+    bool norm = false;
     if (m < NG) {
-        const bool opened = (m == 0) || s.closed[m - 1] != 0;
-        const bool norm = s.closed[m] != 0 || (m == NG - 1 && opened);
+        const int sp0 = m > 0 ? s.strad[m] : OV_NONE, sp1 = s.strad[m + 1];
+        const bool opened = (m == 0) || sp0 != OV_NONE;
+        norm = sp1 != OV_NONE || (m == NG - 1 && opened);
         const double *src = s.bsum + m * BS;
-        const double sw = src[1];
-        s.a[m] = norm ? __ddiv_rn(src[0], sw) : src[0];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) res[q] = src[q];
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const int sp = side == 0 ? sp0 : sp1;
+            if (sp != OV_NONE) {
+                const int e = m + side;
+                const double pv = s.frac[e], gd = s.gdn[e];
+                // (gd - pv is the element's weight; exact for float32-born weights)
+                const double frac = __ddiv_rn(__dsub_rn(gord[e], pv), __dsub_rn(gd, pv));
+                const double f = side == 0 ? __dsub_rn(1.0, frac) : frac;
+                const int i = sp >> 5, j = sp & 31;
+                const double w = W(i, j);
+                res[1] = __dadd_rn(res[1], __dmul_rn(f, w));
+                if (GRAD) {
+                    const double *row = s.dkp + i * DS;
+                    const double *col = s.colB + OV_CS * j;
+                    res[0] = __dadd_rn(res[0], __dmul_rn(f, __dmul_rn(__dadd_rn(row[0], col[0]), w)));
+                    res[2] = __dadd_rn(res[2], __dmul_rn(f, __dmul_rn(__dadd_rn(row[1], col[1]), w)));
+#pragma unroll
+                    for (int p = 0; p < NPMAX - 1; ++p)
+                        res[3 + p] = __dadd_rn(res[3 + p], __dmul_rn(f, __dmul_rn(row[2 + p], w)));
+                    res[NQ - 1] = __dadd_rn(res[NQ - 1], __dmul_rn(f, __dmul_rn(col[2], w)));
+                } else {
+                    res[0] = __dadd_rn(res[0], __dmul_rn(f, __dmul_rn(__dadd_rn(s.a[i], s.b[j]), w)));
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (m < NG) {
+        const double rs = norm ? __ddiv_rn(1.0, res[1]) : 1.0;
+        s.a[m] = __dmul_rn(res[0], rs);
         if (GRAD) {
             double *row = s.dkp + m * DS;
-            row[0] = norm ? __ddiv_rn(src[2], sw) : src[2];
-            for (int p = 0; p < NGAS; ++p) {
-                const double g = (p == g1) ? src[NQ - 1] : src[3 + p];
-                row[1 + p] = (norm && p <= g1) ? __ddiv_rn(g, sw) : g;
+            row[1] = __dmul_rn(res[2], rs);
+#pragma unroll
+            for (int p = 0; p < NPMAX - 1; ++p) {
+                if (p < NGAS) {
+                    const double g = (p == g1) ? res[NQ - 1] : res[3 + p];
+                    row[2 + p] = p <= g1 ? __dmul_rn(g, rs) : g;
+                }
             }
         }
     }
@@ -753,7 +831,8 @@ __device__ __forceinline__ void ov_sort_stage(const OvWarpSmem &s, const double 
     // row, key(i,NG-1) <= key(i+1,0) (equal keys already sit in index order).  Column-major: the running
     // opacity is ascending and too weak to reach the next column, key(NG-1,j) < key(0,j+1) (strict: an
     // equal pair would be in the wrong index order).  Both tests use the exact keys.
-    bool sorted = false;
+    bool sorted = false, keys_valid = false;
+    int chk = -1;
     {
         bool rowok = true, colok = true;
         if (lane < NG - 1) {
@@ -784,6 +863,7 @@ __device__ __forceinline__ void ov_sort_stage(const OvWarpSmem &s, const double 
         if (__all_sync(FULL, kmax > 0.0 && e > 200 && e < 2000)) {
             const double sc = __hiloint2double((2146 - e) << 20, 0);   // 2^(100 - exponent(kmax)): exact scaling
             unsigned v[EPL];
+            unsigned orb = 0u, mxb = 0u;
             int el = lane * EPL;
             int i = el / NG, j = el - i * NG;
 #pragma unroll
@@ -792,7 +872,10 @@ __device__ __forceinline__ void ov_sort_stage(const OvWarpSmem &s, const double 
                     // positive keys only: the float32 bit pattern is then monotone (other keys end up misplaced
                     // and are caught by the exact check below)
                     const float kf = __double2float_rn(__dmul_rn(__dadd_rn(s.a[i], s.b[j]), sc));
-                    v[r] = ((__float_as_uint(kf) >> 9) << 10) | (unsigned)((i << 5) | j);
+                    const unsigned kb = __float_as_uint(kf);
+                    orb |= kb;
+                    mxb = max(mxb, kb);
+                    v[r] = ((kb >> 9) << 10) | (unsigned)((i << 5) | j);
                 } else {
                     v[r] = 0xffffffffu;           // padding: above every live element, index field marks it dead
                 }
@@ -800,35 +883,64 @@ __device__ __forceinline__ void ov_sort_stage(const OvWarpSmem &s, const double 
                 if (++j == NG) { j = 0; ++i; }
             }
             ov_bitonic_sort_u32<EPL>(v, lane);
+            // If every key is a finite positive float and no two neighbours share their 22 key bits, the
+            // float32-rounded keys are strictly increasing, hence so are the exact keys (rounding is
+            // monotone): the order is exact and free of ties, no need to re-form the float64 keys.
+            bool dirty = (orb >> 31) != 0u || mxb >= 0x7f800000u;
 #pragma unroll
-            for (int r = 0; r < EPL; ++r) {
-                idx[r] = (int)(v[r] & 1023u);
-                const int ii = idx[r] >> 5, jj = idx[r] & 31;
-                key[r] = ii < NG ? __dadd_rn(s.a[ii], s.b[jj]) : INFINITY;
+            for (int r = 0; r + 1 < EPL; ++r) dirty |= ((v[r] | 1023u) >= v[r + 1]) & (v[r + 1] < 0xfffffc00u);
+            {
+                const unsigned nx = __shfl_down_sync(FULL, v[0], 1);
+                dirty |= (lane < 31) & ((v[EPL - 1] | 1023u) >= nx) & (nx < 0xfffffc00u);
             }
-            int bad = ov_check_order<EPL>(key, lane) & 1;
-            for (int pass = 0; bad && pass < 6; ++pass) {
-                ov_fixup_pass<EPL>(key, idx, lane);
-                bad = ov_check_order<EPL>(key, lane) & 1;
+#pragma unroll
+            for (int r = 0; r < EPL; ++r) idx[r] = (int)(v[r] & 1023u);
+            if (!__any_sync(FULL, dirty)) {
+                sorted = true;
+                chk = 0;
+            } else {
+#pragma unroll
+                for (int r = 0; r < EPL; ++r) {
+                    const int ii = idx[r] >> 5, jj = idx[r] & 31;
+                    key[r] = ii < NG ? __dadd_rn(s.a[ii], s.b[jj]) : INFINITY;
+                }
+                chk = ov_check_order<EPL>(key, lane);
+                for (int pass = 0; (chk & 1) && pass < 6; ++pass) {
+                    ov_fixup_pass<EPL>(key, idx, lane);
+                    chk = ov_check_order<EPL>(key, lane);
+                }
+                sorted = !(chk & 1);
+                keys_valid = sorted;
             }
-            sorted = !bad;
         }
     }
     if (!sorted) {
         // keys outside the scaled float32 range or a large group of near-equal keys: exact network
+#ifndef OV_NO_EXACT
         make_keys();
         ov_bitonic_sort<EPL, true>(key, idx, lane);
+        keys_valid = true;
+        chk = -1;
+#else
+        __trap();
+#endif
     }
 
     if (GRAD) {
         // equal keys: take the order numba's quicksort would produce (gradient rows of tied elements
-        // are split across bin edges in sort order; tau does not depend on it)
+        // are split across bin edges in sort order; tau does not depend on it).  The exact keys and
+        // the neighbour check of the fast path are reused when they are still valid.
+        if (chk < 0) {
+            if (!keys_valid) {
 #pragma unroll
-        for (int r = 0; r < EPL; ++r) {
-            const int ii = idx[r] >> 5, jj = idx[r] & 31;
-            key[r] = ii < NG ? __dadd_rn(s.a[ii], s.b[jj]) : INFINITY;
+                for (int r = 0; r < EPL; ++r) {
+                    const int ii = idx[r] >> 5, jj = idx[r] & 31;
+                    key[r] = ii < NG ? __dadd_rn(s.a[ii], s.b[jj]) : INFINITY;
+                }
+            }
+            chk = ov_check_order<EPL>(key, lane);
         }
-        if (ov_check_order<EPL>(key, lane) & 2) {
+        if (chk & 2) {
             ov_numba_order(s, NG, lane);
 #pragma unroll
             for (int r = 0; r < EPL; ++r) {
@@ -854,49 +966,72 @@ __device__ __forceinline__ void ov_sort_stage(const OvWarpSmem &s, const double 
 }
 
 template <int EPL, int NPMAX, bool GRAD>
-__device__ __forceinline__ void ov_rebin(const OvWarpSmem &s, const double *__restrict__ wtab,
+__device__ __forceinline__ void ov_rebin(const OvWarpSmem &s, const OvWeight &W,
                                          const double *__restrict__ gord, int NG, int NGAS, int igas, int lane,
                                          int seq_rebin)
 {
-    if (seq_rebin) ov_rebin_seq<NPMAX, GRAD>(s, wtab, gord, NG, NGAS, igas, lane);
-    else ov_rebin_par<EPL, NPMAX, GRAD>(s, wtab, gord, NG, NGAS, igas, lane);
+    if (seq_rebin) ov_rebin_seq<NPMAX, GRAD>(s, W.wtab, gord, NG, NGAS, igas, lane);
+    else ov_rebin_par<EPL, NPMAX, GRAD>(s, W, gord, NG, NGAS, igas, lane);
 }
 
-template <int EPL, int NPMAX, bool GRAD>
-__global__ void __launch_bounds__(OV_WARPS * 32, 2)
+// NGT > 0 fixes the number of g-ordinates at compile time (NG = 20 is what every NEMESIS k-table uses): the
+// per-warp shared-memory offsets and the row strides then fold into instruction immediates instead of
+// living in registers.  NGT = 0 is the general kernel.
+template <int EPL, int NPMAX, bool GRAD, int NGT>
+__global__ void __launch_bounds__(OV_WARPS * 32, OV_MINB)
 ans_koverlap_kernel(OvParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int NG = P.NG, NGAS = P.NGAS, NLAY = P.NLAY, NN = NG * NG, NP1 = NGAS + 1;
-    constexpr int DS = NPMAX + 1, BS = (NPMAX + 3) | 1;
+    const int NG = NGT > 0 ? NGT : P.NG;
+    const int NGAS = P.NGAS, NLAY = P.NLAY, NN = NG * NG, NP1 = NGAS + 1;
+    constexpr int DS = NPMAX + 2, BS = (NPMAX + 3) | 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     double *wtab = reinterpret_cast<double *>(smem_raw);
     double *gord = wtab + NN;
-    double *wbase = gord + (NG + 1);
+    float *dgf = reinterpret_cast<float *>(gord + NG + 1);
+    double *wbase = wtab + ((NN + NG + 2 + (NG + 1) / 2) & ~1);     // keeps the per-warp regions 16-byte aligned
     // per-warp carve-up (doubles first, then ints, then shorts)
     const size_t per_warp_bytes = ov_per_warp_bytes(NG, NGAS, GRAD);
     unsigned char *mine = reinterpret_cast<unsigned char *>(wbase) + per_warp_bytes * warp;
     OvWarpSmem s;
     {
         double *d = reinterpret_cast<double *>(mine);
-        s.kbuf = d; d += NG * NGAS;
-        s.dbuf = d; if (GRAD) d += NG * NGAS;
+        // (everything whose offset depends on the run-time NGAS comes last)
+        s.colB = d; d += OV_CS * NG;                       // (16-byte aligned: first in the region)
+        s.dkp = d; if (GRAD) d += NG * DS;
         s.a = d; d += NG;
         s.b = d; d += NG;
         s.bT = d; d += NG;
-        s.colB = d; d += 3 * NG;
-        s.dkp = d; if (GRAD) d += NG * DS;
         s.frac = d; d += NG + 1;
+        s.gdn = d; d += NG + 1;
         s.bsum = d; d += NG * BS;
-        s.head = d; d += ov_head_doubles(NG, NGAS);
+        s.head = d; d += ov_head_doubles_np(NG, NPMAX);
         s.strad = reinterpret_cast<int *>(d);
         s.closed = s.strad + NG + 1;
-        s.sidx = reinterpret_cast<unsigned short *>(s.closed + NG);
+        int nnpad = 128;
+        while (nnpad < NN) nnpad <<= 1;
+        s.sidx = reinterpret_cast<unsigned short *>(s.closed + NG + ((2 * NG + 1) & 1));   // (8-byte multiple of ints)
+        d = reinterpret_cast<double *>(s.sidx + nnpad);
+        s.kbuf = d; d += NG * NGAS;
+        s.dbuf = d;
     }
     for (int i = threadIdx.x; i < NN; i += blockDim.x) wtab[i] = P.weight[i];
     for (int i = threadIdx.x; i <= NG; i += blockDim.x) gord[i] = P.g_ord[i];
-    __syncthreads();
+    OvWeight W{wtab, dgf, NG, false};
+    {
+        // can del_g[i]*del_g[j] be formed on the fly as a float32 product?  (checked against the table)
+        bool ok = P.del_g != nullptr;
+        if (ok) {
+            for (int i = threadIdx.x; i < NG; i += blockDim.x) dgf[i] = (float)P.del_g[i];
+            for (int e = threadIdx.x; e < NN; e += blockDim.x) {
+                const int i = e / NG, j = e - i * NG;
+                const double di = P.del_g[i], dj = P.del_g[j];
+                ok = ok && (double)(float)di == di && (double)__fmul_rn((float)di, (float)dj) == P.weight[e];
+            }
+        }
+        W.f32 = __syncthreads_and(ok) != 0;
+    }
 
     const long long ncell = (long long)P.NWAVE * NLAY;
     long long cell = (long long)blockIdx.x * OV_WARPS + warp;
@@ -938,7 +1073,9 @@ ans_koverlap_kernel(OvParams P)
     for (int igas = 0; igas < NGAS - 1; ++igas) {
         // keep the CTA's warps in the same phase of the code: the hot path is larger than the
         // instruction cache and warps that drift apart evict each other's lines
+#ifndef OV_NO_FOLDBAR
         __syncthreads();
+#endif
         const int g1 = igas + 1;
         const double am1 = __ldg(P.amount + (size_t)g1 * NLAY + l);
         const bool next_neg = __all_sync(FULL, __dmul_rn(KB(NG - 1, g1), am1) <= 0.0);   // uniform by construction
@@ -949,13 +1086,13 @@ ans_koverlap_kernel(OvParams P)
             if (first_neg) {
                 for (int i = lane; i < NG; i += 32) {
                     s.a[i] = __dmul_rn(KB(i, 1), am1);
-                    if (GRAD) { s.dkp[i * DS + 2] = KB(i, 1); s.dkp[i * DS] = __dmul_rn(DB(i, 1), am1); }
+                    if (GRAD) { s.dkp[i * DS + 3] = KB(i, 1); s.dkp[i * DS + 1] = __dmul_rn(DB(i, 1), am1); }
                 }
                 __syncwarp();
             } else if (next_neg) {
                 for (int i = lane; i < NG; i += 32) {
                     s.a[i] = __dmul_rn(KB(i, 0), am0);
-                    if (GRAD) { s.dkp[i * DS + 1] = KB(i, 0); s.dkp[i * DS] = __dmul_rn(DB(i, 0), am0); }
+                    if (GRAD) { s.dkp[i * DS + 2] = KB(i, 0); s.dkp[i * DS + 1] = __dmul_rn(DB(i, 0), am0); }
                 }
                 __syncwarp();
             } else {
@@ -963,8 +1100,8 @@ ans_koverlap_kernel(OvParams P)
                     s.a[i] = __dmul_rn(KB(i, 0), am0);
                     s.b[i] = __dmul_rn(KB(i, 1), am1);
                     if (GRAD) {
-                        s.dkp[i * DS + 1] = KB(i, 0);
-                        s.dkp[i * DS] = __dmul_rn(DB(i, 0), am0);
+                        s.dkp[i * DS + 2] = KB(i, 0);
+                        s.dkp[i * DS + 1] = __dmul_rn(DB(i, 0), am0);
                         s.bT[i] = __dmul_rn(DB(i, 1), am1);
                     }
                 }
@@ -975,7 +1112,7 @@ ans_koverlap_kernel(OvParams P)
                 if (GRAD) {
                     for (int i = lane; i < NG; i += 32) {
                         // reference: dk[:,igas+2] = dk[:,igas+1]; dk[:,igas+1] *= 0  (T column moves, gas column = 0*T)
-                        s.dkp[i * DS + 1 + g1] = __dmul_rn(s.dkp[i * DS], 0.0);
+                        s.dkp[i * DS + 2 + g1] = __dmul_rn(s.dkp[i * DS + 1], 0.0);
                     }
                     __syncwarp();
                 }
@@ -983,7 +1120,7 @@ ans_koverlap_kernel(OvParams P)
                 __syncwarp();
                 for (int i = lane; i < NG; i += 32) {
                     s.a[i] = __dmul_rn(KB(i, g1), am1);
-                    if (GRAD) { s.dkp[i * DS + 1 + g1] = KB(i, g1); s.dkp[i * DS] = __dmul_rn(DB(i, g1), am1); }
+                    if (GRAD) { s.dkp[i * DS + 2 + g1] = KB(i, g1); s.dkp[i * DS + 1] = __dmul_rn(DB(i, g1), am1); }
                 }
                 __syncwarp();
             } else {
@@ -998,7 +1135,7 @@ ans_koverlap_kernel(OvParams P)
             __syncwarp();
             ov_sort_stage<EPL, NPMAX, GRAD>(s, wtab, gord, NG, NGAS, igas, lane, P.seq_rebin);
         }
-        if (do_fold) ov_rebin<EPL, NPMAX, GRAD>(s, wtab, gord, NG, NGAS, igas, lane, P.seq_rebin);
+        if (do_fold) ov_rebin<EPL, NPMAX, GRAD>(s, W, gord, NG, NGAS, igas, lane, P.seq_rebin);
     }
 #undef KB
 #undef DB
@@ -1006,19 +1143,19 @@ ans_koverlap_kernel(OvParams P)
         const size_t o = ((size_t)iw * NG + g) * NLAY + l;
         P.tau[o] = s.a[g];
         if (GRAD) {
-            for (int p = 0; p < NGAS; ++p) P.dk[o * NP1 + p] = s.dkp[g * DS + 1 + p];
-            P.dk[o * NP1 + NGAS] = s.dkp[g * DS];
+            for (int p = 0; p < NGAS; ++p) P.dk[o * NP1 + p] = s.dkp[g * DS + 2 + p];
+            P.dk[o * NP1 + NGAS] = s.dkp[g * DS + 1];
         }
     }
 }
 
-template <int EPL, int NPMAX, bool GRAD>
+template <int EPL, int NPMAX, bool GRAD, int NGT = 0>
 inline int ov_launch(const OvParams &P, cudaStream_t stream)
 {
     const int NG = P.NG, NGAS = P.NGAS, NN = NG * NG, NP1 = NGAS + 1;
     const size_t per_warp_bytes = ov_per_warp_bytes(NG, NGAS, GRAD);
-    const size_t smem = (size_t)(NN + NG + 1) * 8 + per_warp_bytes * OV_WARPS + 16;
-    auto kern = ans_koverlap_kernel<EPL, NPMAX, GRAD>;
+    const size_t smem = (size_t)((NN + NG + 2 + (NG + 1) / 2) & ~1) * 8 + per_warp_bytes * OV_WARPS + 16;
+    auto kern = ans_koverlap_kernel<EPL, NPMAX, GRAD, NGT>;
     if (smem > 48 * 1024) ANS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long ncell = (long long)P.NWAVE * P.NLAY;
     kern<<<ans_div_up(ncell, OV_WARPS), OV_WARPS * 32, smem, stream>>>(P);
@@ -1026,16 +1163,17 @@ inline int ov_launch(const OvParams &P, cudaStream_t stream)
     return ANSB200_OK;
 }
 
-template <int EPL>
+template <int EPL, int NGT = 0>
 int ov_dispatch_np(const OvParams &P, bool grad, cudaStream_t stream)
 {
-    if (!grad) return ov_launch<EPL, 1, false>(P, stream);
+    if (!grad) return ov_launch<EPL, 1, false, NGT>(P, stream);
     const int NP1 = P.NGAS + 1;
-    if (NP1 <= 4) return ov_launch<EPL, 4, true>(P, stream);
-    if (NP1 <= 8) return ov_launch<EPL, 8, true>(P, stream);
-    return ov_launch<EPL, 16, true>(P, stream);
+    if (NP1 <= 4) return ov_launch<EPL, 4, true, NGT>(P, stream);
+    if (NP1 <= 8) return ov_launch<EPL, 8, true, NGT>(P, stream);
+    return ov_launch<EPL, 16, true, NGT>(P, stream);
 }
 
 int ov_dispatch_4(const OvParams &P, bool grad, cudaStream_t stream);
 int ov_dispatch_8(const OvParams &P, bool grad, cudaStream_t stream);
 int ov_dispatch_16(const OvParams &P, bool grad, cudaStream_t stream);
+int ov_dispatch_16_ng20(const OvParams &P, bool grad, cudaStream_t stream);

@@ -108,6 +108,7 @@ class OverlapTables:
         w, g, seq = _plan.overlap_tables(del_g)
         self.weight = to_dev(w)
         self.g_ord = to_dev(g)
+        self.del_g = to_dev(np.asarray(del_g, dtype=np.float64))
         self.seq = seq
         self.NG = len(g) - 1
 
@@ -121,7 +122,7 @@ def koverlap(k, amount, otab, dkdT=None, force_seq=False):
     dk = torch.empty((NWAVE, NG, NLAY, NGAS + 1), dtype=torch.float64, device="cuda") if grad else None
     flag = int(grad) | (2 if (otab.seq or force_seq) else 0)
     _lib.check(_lib.load().ansb200_koverlap(_ptr(k), _ptr(dkdT), _ptr(amount), _ptr(otab.weight), _ptr(otab.g_ord),
-                                            NWAVE, NG, NLAY, NGAS, flag, _ptr(tau), _ptr(dk), _stream()))
+                                            _ptr(otab.del_g), NWAVE, NG, NLAY, NGAS, flag, _ptr(tau), _ptr(dk), _stream()))
     return (tau, dk) if grad else tau
 
 
@@ -135,7 +136,7 @@ def gas_opacity(table, dplan, amount, otab, want_grad=False, force_seq=False):
     flag = int(want_grad) | (2 if (otab.seq or force_seq) else 0)
     _lib.check(_lib.load().ansb200_gas_opacity(table.handle, NLAY, _ptr(dplan.ip_lo), _ptr(dplan.it_lo), _ptr(dplan.w4),
                                                _ptr(dplan.omv), _ptr(dplan.vv), _ptr(dplan.dudt), _ptr(amount),
-                                               _ptr(otab.weight), _ptr(otab.g_ord), flag, _ptr(tau), _ptr(dk),
+                                               _ptr(otab.weight), _ptr(otab.g_ord), _ptr(otab.del_g), flag, _ptr(tau), _ptr(dk),
                                                _stream()))
     return (tau, dk) if want_grad else tau
 

@@ -72,20 +72,22 @@ int ansb200_kinterp(const ansb200_table *t, int NLAY, const int32_t *ip_lo, cons
  * Replaces k_overlap + rank (archnemesis/ForwardModel_0.py:6029-6173) and k_overlapg + rankg
  * (:5842-6026).  weight[NG*NG] = del_g[i]*del_g[j] and g_ord[NG+1] = {0, cumsum(del_g)[..], 1}
  * are made on the host in del_g's own dtype (float32 on the .kta path) and widened.
+ * del_g[NG] (widened, may be NULL) lets the kernel form the products itself instead of looking them
+ * up; it is used only when it reproduces `weight` bit for bit (checked on the device).
  * amount[NGAS,NLAY] in cm-2.  Output tau[NWAVE,NG,NLAY]; if want_grad also
  * dk[NWAVE,NG,NLAY,NGAS+1] (d tau/d amount_gas ..., d tau/dT).
  * Ties between sort keys are broken by original index (the reference's numba quicksort leaves
  * their order unspecified). */
 int ansb200_koverlap(const double *k, const double *dkdT, const double *amount, const double *weight,
-                     const double *g_ord, int NWAVE, int NG, int NLAY, int NGAS, int want_grad,
+                     const double *g_ord, const double *del_g, int NWAVE, int NG, int NLAY, int NGAS, int want_grad,
                      double *tau, double *dk, void *stream);
 
 /* Fused k-interp + overlap: k_gas / dkgasdT never reach HBM.  Replaces the K_TABLES branch of
  * ForwardModel_0.calculate_gaseous_line_opacity (ForwardModel_0.py:3850-3877). */
 int ansb200_gas_opacity(const ansb200_table *t, int NLAY, const int32_t *ip_lo, const int32_t *it_lo,
                         const double *w4, const double *omv, const double *vv, const double *dudt,
-                        const double *amount, const double *weight, const double *g_ord, int want_grad,
-                        double *tau, double *dk, void *stream);
+                        const double *amount, const double *weight, const double *g_ord, const double *del_g,
+                        int want_grad, double *tau, double *dk, void *stream);
 
 /* ---- path radiance + layer-space Jacobian -------------------------------------------------
  * Replaces, for every path at once, the opacity assembly of calculate_layer_opacity

@@ -38,7 +38,7 @@ def test_argument_errors_are_reported_without_a_gpu():
     """EINVAL paths return before any CUDA call, so they can be checked on the CPU box."""
     from archnemesis_dist_b200 import _lib
     lib = _lib.load()
-    rc = lib.ansb200_koverlap(None, None, None, None, None, 1, 20, 1, 2, 0, None, None, None)
+    rc = lib.ansb200_koverlap(None, None, None, None, None, None, 1, 20, 1, 2, 0, None, None, None)
     assert rc == _lib.EINVAL
     with pytest.raises(ValueError):
         _lib.check(rc)

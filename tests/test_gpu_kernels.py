@@ -97,6 +97,29 @@ def test_koverlap_matches_oracle(mods, ng, ngas, want_grad):
         assert relerr(cpu(ops.koverlap(kd, am, otab, force_seq=True)), rt) < 1e-14
 
 
+@pytest.mark.parametrize("ng,ngas", [(20, 6), (16, 3), (7, 4)])
+def test_koverlap_non_monotone_gas(mods, ng, ngas):
+    """k(g) of one gas scrambled (not ascending in g): the shortcut orders (row-/column-major) must not
+    fire and the sort + rebin still match the oracle, with and without gradients."""
+    ops, orc = mods["ops"], mods["orc"]
+    c = _case(mods, nwave=12, ng=ng, ngas=ngas, nlay=10, npro=10, nx=4, nvmr=max(ngas, 2), seed=400 + ng)
+    tab = c["tab"]
+    k, dkdT = orc.calc_k(tab["K"], tab["PRESS"], tab["TEMP"], c["press"], c["temp"], want_grad=True)
+    perm = np.random.default_rng(5).permutation(ng)
+    k[:, :, :, 1] = k[:, :, :, 1][:, perm, :]
+    dkdT[:, :, :, 1] = dkdT[:, :, :, 1][:, perm, :]
+    otab = ops.OverlapTables(tab["DELG"])
+    kd, dd, am = ops.to_dev(k), ops.to_dev(dkdT), ops.to_dev(c["amount"])
+    rt, rd = orc.k_overlap(tab["DELG"], k, c["amount"], dkdT=dkdT)
+    t1, d1 = ops.koverlap(kd, am, otab, dkdT=dd)
+    assert relerr(cpu(t1), rt) < 1e-13
+    for col in range(rd.shape[-1]):
+        assert colerr(cpu(d1)[..., col], rd[..., col]) < 1e-13, col
+    t2, d2 = ops.koverlap(kd, am, otab, dkdT=dd, force_seq=True)
+    assert np.array_equal(cpu(t2), rt) and np.array_equal(cpu(d2), rd)
+    assert relerr(cpu(ops.koverlap(kd, am, otab)), orc.k_overlap(tab["DELG"], k, c["amount"])) < 1e-13
+
+
 def test_koverlap_float64_delg_and_ties(mods):
     """float64 DELG (HDF5 tables) changes the bin edges; exact ties (gas far below another) keep tau exact."""
     ops, orc = mods["ops"], mods["orc"]
