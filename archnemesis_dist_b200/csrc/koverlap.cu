@@ -45,9 +45,6 @@ static int ov_run(OvParams &P, bool grad, cudaStream_t stream)
     const int NN = P.NG * P.NG;
     if (NN <= 128) return ov_dispatch_4(P, grad, stream);
     if (NN <= 256) return ov_dispatch_8(P, grad, stream);
-#ifdef OV_NG20
-    if (P.NG == 20) return ov_dispatch_16_ng20(P, grad, stream);
-#endif
     return ov_dispatch_16(P, grad, stream);
 }
 

@@ -300,6 +300,9 @@ struct OvWeight {
     }
 };
 
+// Static-order tables: [order][RA | RB][NG*NG] + [order][NG] (+1 to stay even), see ov_static_setup
+__host__ __device__ inline int ov_static_doubles(int NG) { return (4 * NG * NG + 2 * NG + 1) & ~1; }
+
 // Per-warp shared-memory view.
 struct OvWarpSmem {
     double *kbuf, *dbuf;     // [NG*NGAS] k and dk/dT of the cell
@@ -796,6 +799,141 @@ static __device__ __noinline__ void ov_numba_order(OvWarpSmem s, int NG, int lan
     __syncwarp();
 }
 
+// ---- data-independent orders ----------------------------------------------------------------------
+// Row-major: the next gas is ascending and too weak to reach the next row, key(i,NG-1) <= key(i+1,0)
+// (equal keys already sit in index order).  Column-major: the running opacity is ascending and too weak
+// to reach the next column, key(NG-1,j) < key(0,j+1) (strict: an equal pair would be in the wrong index
+// order).  Both tests use the exact keys.  Returns 1 (row-major) / 2 (column-major) / 0, plus 4 if WANT_STRICT
+// and the whole key sequence is strictly increasing (no ties, so no question about the order of equal keys).
+template <bool WANT_STRICT>
+__device__ __forceinline__ int ov_trivial_order(const OvWarpSmem &s, int NG, int lane)
+{
+    bool rowok = true, colok = true;
+    if (lane < NG - 1) {
+        const double b0 = s.b[0], bl = s.b[NG - 1], a0 = s.a[0], al = s.a[NG - 1];
+        rowok = (s.b[lane] <= s.b[lane + 1]) & (__dadd_rn(s.a[lane], bl) <= __dadd_rn(s.a[lane + 1], b0));
+        colok = (s.a[lane] <= s.a[lane + 1]) & (__dadd_rn(al, s.b[lane]) < __dadd_rn(a0, s.b[lane + 1]));
+    }
+    rowok = __all_sync(FULL, rowok);
+    colok = !rowok && __all_sync(FULL, colok);
+    int ord = rowok ? 1 : (colok ? 2 : 0);
+    if (WANT_STRICT && ord) {
+        bool strict = true;
+        if (lane < NG) {
+            // row-major: lane i walks row i; column-major: lane j walks column j
+            const double mine = rowok ? s.a[lane] : s.b[lane];
+            const double *other = rowok ? s.b : s.a;
+            double kp = __dadd_rn(mine, other[0]);
+            for (int t = 1; t < NG; ++t) {
+                const double kn = __dadd_rn(mine, other[t]);
+                strict &= kp < kn;
+                kp = kn;
+            }
+            if (rowok && lane < NG - 1) strict &= kp < __dadd_rn(s.a[lane + 1], s.b[0]);
+        }
+        if (__all_sync(FULL, strict)) ord |= 4;
+    }
+    return ord;
+}
+
+// When the order of the NG*NG elements is row-major or column-major, the cumulative weights, the element
+// that straddles every bin edge and its `frac` depend on the quadrature only.  The rebin
+// (rank/rankg, ForwardModel_0.py:6155-6172 / :6002-6025) is then a fixed linear map:
+//     bin m = [ sum_i RA[i][m] x_i + sum_j RB[j][m] y_j ] / SW[m]
+// with RA[i][m] (RB[j][m]) the weight -- fractions included -- that row i (column j) contributes to bin m,
+// x_i the per-row operands (tau_i, dT_i, gas columns) and y_j the per-column ones (b_j, bT_j, k_j).
+// ov_static_setup builds the tables once per CTA by replaying the reference's loop over the fixed order
+// (thread (order, m) keeps the terms of bin m); `ok` is false if some bin would be left un-normalised
+// (degenerate quadrature), in which case the shortcut is not used.
+__device__ __forceinline__ bool ov_static_setup(double *stat, const double *wtab, const double *gord, int NG)
+{
+    const int NN = NG * NG;
+    for (int e = threadIdx.x; e < ov_static_doubles(NG); e += blockDim.x) stat[e] = 0.0;
+    __syncthreads();
+    bool ok = true;
+    if ((int)threadIdx.x < 2 * NG) {
+        const int o = threadIdx.x / NG, m = threadIdx.x - o * NG;
+        double *RA = stat + o * 2 * NN, *RB = RA + NN, *SW = stat + 4 * NN + o * NG;
+        double run = 0.0, sw = 0.0;
+        int ig = 0;
+        bool closed = false, opened = (m == 0);
+        for (int q = 0; q < NG && ig < NG; ++q) {
+            for (int r = 0; r < NG && ig < NG; ++r) {
+                const int i = o == 0 ? q : r, j = o == 0 ? r : q;
+                const double w = wtab[i * NG + j];
+                const double gdn = __dadd_rn(run, w);
+                double f = 0.0;
+                if (gdn < gord[ig + 1]) {
+                    if (ig == m) f = w;
+                } else {
+                    const double frac = __ddiv_rn(__dsub_rn(gord[ig + 1], run), __dsub_rn(gdn, run));
+                    if (ig == m) { f = __dmul_rn(frac, w); closed = true; }
+                    ++ig;
+                    if (ig == m) { f = __dmul_rn(__dsub_rn(1.0, frac), w); opened = true; }
+                }
+                if (f != 0.0) {
+                    RA[i * NG + m] = __dadd_rn(RA[i * NG + m], f);
+                    RB[j * NG + m] = __dadd_rn(RB[j * NG + m], f);
+                    sw = __dadd_rn(sw, f);
+                }
+                run = gdn;
+            }
+        }
+        SW[m] = sw;
+        ok = opened && (closed || m == NG - 1) && sw > 0.0;
+    }
+    return __syncthreads_and(ok) != 0;
+}
+
+template <int NPMAX, bool GRAD>
+__device__ __forceinline__ void ov_rebin_static(const OvWarpSmem &s, const double *__restrict__ stat, int ord,
+                                                int NG, int NGAS, int igas, int lane)
+{
+    constexpr int DS = NPMAX + 2;
+    const int NN = NG * NG, g1 = igas + 1, o = (ord & 3) - 1, m = lane;
+    const double *RA = stat + o * 2 * NN, *RB = RA + NN;
+    double ra_a = 0.0, rT = 0.0, rk = 0.0;
+    double rg[GRAD ? NPMAX - 1 : 1];
+#pragma unroll
+    for (int p = 0; p < (GRAD ? NPMAX - 1 : 1); ++p) rg[p] = 0.0;
+    if (m < NG) {
+#pragma unroll 2
+        for (int t = 0; t < NG; ++t) {
+            const double ra = RA[t * NG + m], rb = RB[t * NG + m];
+            ra_a = __fma_rn(ra, s.a[t], ra_a);
+            ra_a = __fma_rn(rb, s.b[t], ra_a);
+            if (GRAD) {
+                const double2 *row = reinterpret_cast<const double2 *>(s.dkp + t * DS);
+                rT = __fma_rn(ra, row[0].y, rT);
+                rT = __fma_rn(rb, s.bT[t], rT);
+                rk = __fma_rn(rb, s.kbuf[t * NGAS + g1], rk);
+#pragma unroll
+                for (int q = 1; q < DS / 2; ++q) {
+                    if (2 * q - 2 <= igas) {
+                        const double2 v = row[q];
+                        rg[2 * q - 2] = __fma_rn(ra, v.x, rg[2 * q - 2]);
+                        if (2 * q - 1 < NPMAX - 1) rg[2 * q - 1] = __fma_rn(ra, v.y, rg[2 * q - 1]);
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (m < NG) {
+        const double rs = __ddiv_rn(1.0, stat[4 * NN + o * NG + m]);
+        s.a[m] = __dmul_rn(ra_a, rs);
+        if (GRAD) {
+            double *row = s.dkp + m * DS;
+            row[1] = __dmul_rn(rT, rs);
+#pragma unroll
+            for (int p = 0; p < NPMAX - 1; ++p) {
+                if (p < NGAS) row[2 + p] = p <= igas ? __dmul_rn(rg[p], rs) : (p == g1 ? __dmul_rn(rk, rs) : 0.0);
+            }
+        }
+    }
+    __syncwarp();
+}
+
 // One sort/rebin fold.  a[] holds the running tau_g, b[] the next gas.  Gradient storage: dkp[i][p] is
 // d tau_i / d amount_p for p < NGAS and dkp[i][NGAS] is d tau_i / dT at every stage (the reference keeps
 // the temperature column at index igas+1 and moves it one to the right per fold, ForwardModel_0.py
@@ -804,7 +942,7 @@ static __device__ __noinline__ void ov_numba_order(OvWarpSmem s, int NG, int lan
 template <int EPL, int NPMAX, bool GRAD>
 __device__ __forceinline__ void ov_sort_stage(const OvWarpSmem &s, const double *__restrict__ wtab,
                                         const double *__restrict__ gord, int NG, int NGAS, int igas, int lane,
-                                        int seq_rebin)
+                                        int seq_rebin, int ord)
 {
     const int NN = NG * NG;
     const int NP1 = NGAS + 1;
@@ -827,21 +965,11 @@ __device__ __forceinline__ void ov_sort_stage(const OvWarpSmem &s, const double 
             if (++j == NG) { j = 0; ++i; }
         }
     };
-    // Trivial orders need no sort.  Row-major: the next gas is ascending and too weak to reach the next
-    // row, key(i,NG-1) <= key(i+1,0) (equal keys already sit in index order).  Column-major: the running
-    // opacity is ascending and too weak to reach the next column, key(NG-1,j) < key(0,j+1) (strict: an
-    // equal pair would be in the wrong index order).  Both tests use the exact keys.
+    // trivial orders (ov_trivial_order) need no sort
     bool sorted = false, keys_valid = false;
     int chk = -1;
     {
-        bool rowok = true, colok = true;
-        if (lane < NG - 1) {
-            const double b0 = s.b[0], bl = s.b[NG - 1], a0 = s.a[0], al = s.a[NG - 1];
-            rowok = (s.b[lane] <= s.b[lane + 1]) & (__dadd_rn(s.a[lane], bl) <= __dadd_rn(s.a[lane + 1], b0));
-            colok = (s.a[lane] <= s.a[lane + 1]) & (__dadd_rn(al, s.b[lane]) < __dadd_rn(a0, s.b[lane + 1]));
-        }
-        rowok = __all_sync(FULL, rowok);
-        colok = !rowok && __all_sync(FULL, colok);
+        const bool rowok = (ord & 3) == 1, colok = (ord & 3) == 2;
         if (rowok | colok) {
             int el = lane * EPL;
             int q = el / NG, rm = el - q * NG;      // el = q*NG + rm
@@ -916,14 +1044,10 @@ __device__ __forceinline__ void ov_sort_stage(const OvWarpSmem &s, const double 
     }
     if (!sorted) {
         // keys outside the scaled float32 range or a large group of near-equal keys: exact network
-#ifndef OV_NO_EXACT
         make_keys();
         ov_bitonic_sort<EPL, true>(key, idx, lane);
         keys_valid = true;
         chk = -1;
-#else
-        __trap();
-#endif
     }
 
     if (GRAD) {
@@ -974,23 +1098,20 @@ __device__ __forceinline__ void ov_rebin(const OvWarpSmem &s, const OvWeight &W,
     else ov_rebin_par<EPL, NPMAX, GRAD>(s, W, gord, NG, NGAS, igas, lane);
 }
 
-// NGT > 0 fixes the number of g-ordinates at compile time (NG = 20 is what every NEMESIS k-table uses): the
-// per-warp shared-memory offsets and the row strides then fold into instruction immediates instead of
-// living in registers.  NGT = 0 is the general kernel.
-template <int EPL, int NPMAX, bool GRAD, int NGT>
+template <int EPL, int NPMAX, bool GRAD>
 __global__ void __launch_bounds__(OV_WARPS * 32, OV_MINB)
 ans_koverlap_kernel(OvParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int NG = NGT > 0 ? NGT : P.NG;
-    const int NGAS = P.NGAS, NLAY = P.NLAY, NN = NG * NG, NP1 = NGAS + 1;
+    const int NG = P.NG, NGAS = P.NGAS, NLAY = P.NLAY, NN = NG * NG, NP1 = NGAS + 1;
     constexpr int DS = NPMAX + 2, BS = (NPMAX + 3) | 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     double *wtab = reinterpret_cast<double *>(smem_raw);
     double *gord = wtab + NN;
     float *dgf = reinterpret_cast<float *>(gord + NG + 1);
-    double *wbase = wtab + ((NN + NG + 2 + (NG + 1) / 2) & ~1);     // keeps the per-warp regions 16-byte aligned
+    double *stat = wtab + ((NN + NG + 2 + (NG + 1) / 2) & ~1);      // static-order rebin tables (ov_static_doubles)
+    double *wbase = stat + ov_static_doubles(NG);                   // keeps the per-warp regions 16-byte aligned
     // per-warp carve-up (doubles first, then ints, then shorts)
     const size_t per_warp_bytes = ov_per_warp_bytes(NG, NGAS, GRAD);
     unsigned char *mine = reinterpret_cast<unsigned char *>(wbase) + per_warp_bytes * warp;
@@ -1033,9 +1154,14 @@ ans_koverlap_kernel(OvParams P)
         W.f32 = __syncthreads_and(ok) != 0;
     }
 
+    // data-independent rebin of row-/column-major folds (not with the literal sequential scan)
+    const bool static_ok = ov_static_setup(stat, wtab, gord, NG) && !P.seq_rebin;
+
+    // persistent CTAs: every warp walks the (wavenumber, layer) cells with the grid's stride
     const long long ncell = (long long)P.NWAVE * NLAY;
-    long long cell = (long long)blockIdx.x * OV_WARPS + warp;
-    const bool live = cell < ncell;        // idle warps of the last CTA shadow the last cell (they join the barriers)
+    for (long long cell0 = (long long)blockIdx.x * OV_WARPS; cell0 < ncell; cell0 += (long long)gridDim.x * OV_WARPS) {
+    long long cell = cell0 + warp;
+    const bool live = cell < ncell;        // idle warps of the last round shadow the last cell (they join the barriers)
     if (!live) cell = ncell - 1;
     const int iw = (int)(cell / NLAY);
     const int l = (int)(cell - (long long)iw * NLAY);
@@ -1133,9 +1259,14 @@ ans_koverlap_kernel(OvParams P)
         }
         if (do_fold) {
             __syncwarp();
-            ov_sort_stage<EPL, NPMAX, GRAD>(s, wtab, gord, NG, NGAS, igas, lane, P.seq_rebin);
+            const int ord = ov_trivial_order<GRAD>(s, NG, lane);
+            if (static_ok && (ord & 3) && (!GRAD || (ord & 4))) {
+                ov_rebin_static<NPMAX, GRAD>(s, stat, ord, NG, NGAS, igas, lane);
+            } else {
+                ov_sort_stage<EPL, NPMAX, GRAD>(s, wtab, gord, NG, NGAS, igas, lane, P.seq_rebin, ord);
+                ov_rebin<EPL, NPMAX, GRAD>(s, W, gord, NG, NGAS, igas, lane, P.seq_rebin);
+            }
         }
-        if (do_fold) ov_rebin<EPL, NPMAX, GRAD>(s, W, gord, NG, NGAS, igas, lane, P.seq_rebin);
     }
 #undef KB
 #undef DB
@@ -1147,33 +1278,42 @@ ans_koverlap_kernel(OvParams P)
             P.dk[o * NP1 + NGAS] = s.dkp[g * DS + 1];
         }
     }
+    __syncwarp();
+    }   // cells
 }
 
-template <int EPL, int NPMAX, bool GRAD, int NGT = 0>
+template <int EPL, int NPMAX, bool GRAD>
 inline int ov_launch(const OvParams &P, cudaStream_t stream)
 {
     const int NG = P.NG, NGAS = P.NGAS, NN = NG * NG, NP1 = NGAS + 1;
     const size_t per_warp_bytes = ov_per_warp_bytes(NG, NGAS, GRAD);
-    const size_t smem = (size_t)((NN + NG + 2 + (NG + 1) / 2) & ~1) * 8 + per_warp_bytes * OV_WARPS + 16;
-    auto kern = ans_koverlap_kernel<EPL, NPMAX, GRAD, NGT>;
+    const size_t smem = (size_t)(((NN + NG + 2 + (NG + 1) / 2) & ~1) + ov_static_doubles(NG)) * 8 + per_warp_bytes * OV_WARPS + 16;
+    auto kern = ans_koverlap_kernel<EPL, NPMAX, GRAD>;
     if (smem > 48 * 1024) ANS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long ncell = (long long)P.NWAVE * P.NLAY;
-    kern<<<ans_div_up(ncell, OV_WARPS), OV_WARPS * 32, smem, stream>>>(P);
+    // persistent: as many CTAs as are resident at once (the occupancy API accounts for registers and smem)
+    int dev = 0, nsm = 148, per_sm = 1;
+    ANS_CUDA_CHECK(cudaGetDevice(&dev));
+    ANS_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    ANS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, OV_WARPS * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = ans_div_up(ncell, OV_WARPS);
+    if (grid > (long long)nsm * per_sm) grid = (long long)nsm * per_sm;
+    kern<<<(unsigned)grid, OV_WARPS * 32, smem, stream>>>(P);
     ANS_LAUNCH_CHECK();
     return ANSB200_OK;
 }
 
-template <int EPL, int NGT = 0>
+template <int EPL>
 int ov_dispatch_np(const OvParams &P, bool grad, cudaStream_t stream)
 {
-    if (!grad) return ov_launch<EPL, 1, false, NGT>(P, stream);
+    if (!grad) return ov_launch<EPL, 1, false>(P, stream);
     const int NP1 = P.NGAS + 1;
-    if (NP1 <= 4) return ov_launch<EPL, 4, true, NGT>(P, stream);
-    if (NP1 <= 8) return ov_launch<EPL, 8, true, NGT>(P, stream);
-    return ov_launch<EPL, 16, true, NGT>(P, stream);
+    if (NP1 <= 4) return ov_launch<EPL, 4, true>(P, stream);
+    if (NP1 <= 8) return ov_launch<EPL, 8, true>(P, stream);
+    return ov_launch<EPL, 16, true>(P, stream);
 }
 
 int ov_dispatch_4(const OvParams &P, bool grad, cudaStream_t stream);
 int ov_dispatch_8(const OvParams &P, bool grad, cudaStream_t stream);
 int ov_dispatch_16(const OvParams &P, bool grad, cudaStream_t stream);
-int ov_dispatch_16_ng20(const OvParams &P, bool grad, cudaStream_t stream);

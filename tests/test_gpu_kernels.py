@@ -120,6 +120,34 @@ def test_koverlap_non_monotone_gas(mods, ng, ngas):
     assert relerr(cpu(ops.koverlap(kd, am, otab)), orc.k_overlap(tab["DELG"], k, c["amount"])) < 1e-13
 
 
+@pytest.mark.parametrize("want_grad", [False, True])
+def test_koverlap_dominated_folds_static_orders(mods, want_grad):
+    """Folds whose order is data-independent: a next gas far weaker than the running opacity gives the
+    row-major order, a far stronger one the column-major order.  The kernel then applies the quadrature's
+    fixed rebin matrices (ov_rebin_static) instead of sorting; results must still match the oracle, and
+    the literal sequential rebin must stay bit-identical."""
+    ops, orc = mods["ops"], mods["orc"]
+    c = _case(mods, nwave=16, ng=20, ngas=5, nlay=9, npro=9, nx=4, nvmr=5, seed=77)
+    tab = c["tab"]
+    k, dkdT = orc.calc_k(tab["K"], tab["PRESS"], tab["TEMP"], c["press"], c["temp"], want_grad=True)
+    for gas, f in ((1, 1e-7), (2, 1e9), (3, 1e-9), (4, 1e11)):     # alternate weak / dominant gases
+        k[..., gas] *= f
+        dkdT[..., gas] *= f
+    otab = ops.OverlapTables(tab["DELG"])
+    kd, dd, am = ops.to_dev(k), ops.to_dev(dkdT), ops.to_dev(c["amount"])
+    if want_grad:
+        rt, rd = orc.k_overlap(tab["DELG"], k, c["amount"], dkdT=dkdT)
+        tau, dk = ops.koverlap(kd, am, otab, dkdT=dd)
+        assert relerr(cpu(tau), rt) < 1e-13
+        for col in range(rd.shape[-1]):
+            assert colerr(cpu(dk)[..., col], rd[..., col]) < 1e-13, col
+        ts, ds = ops.koverlap(kd, am, otab, dkdT=dd, force_seq=True)
+        assert np.array_equal(cpu(ts), rt) and np.array_equal(cpu(ds), rd)
+    else:
+        rt = orc.k_overlap(tab["DELG"], k, c["amount"])
+        assert relerr(cpu(ops.koverlap(kd, am, otab)), rt) < 1e-13
+
+
 def test_koverlap_float64_delg_and_ties(mods):
     """float64 DELG (HDF5 tables) changes the bin edges; exact ties (gas far below another) keep tau exact."""
     ops, orc = mods["ops"], mods["orc"]
