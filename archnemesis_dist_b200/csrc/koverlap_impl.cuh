@@ -32,6 +32,7 @@ constexpr int OV_WARPS = OV_NWARPS;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int OV_CS = 6;   // doubles per column record {b, bT, k, -, -, -}: 3 sixteen-byte units, conflict-free mod 8
 constexpr int OV_NONE = 0x7fffffff;
+constexpr unsigned OV_KEY_BASE = (227u - 62u) << 23;   // float32 pattern of 2^(100-62): origin of the packed sort keys
 
 struct OvParams {
     const double *k, *dkdT;                 // unfused source [NWAVE,NG,NLAY,NGAS]
@@ -187,9 +188,9 @@ __device__ __forceinline__ void ov_bitonic_sort(double (&key)[EPL], int (&idx)[E
 }
 
 // ---- fast path: 32-bit packed (22-bit key | 10-bit index) network --------------------------------
-// The keys are scaled by a power of two and rounded to float32 (monotone); the top 22 bits of the
-// (positive) float32 pattern -- exponent and 14 mantissa bits -- are packed above the 10-bit element
-// index.  One unsigned min/max then orders (key22, index): a comparator is two instructions on one
+// The keys are scaled by a power of two (kmax -> 2^100) and rounded to float32 (monotone); 6 exponent
+// bits relative to 2^(100-62) and 16 mantissa bits of the (positive) float32 pattern are packed above
+// the 10-bit element index.  One unsigned min/max then orders (key22, index): a comparator is two instructions on one
 // register.  The order is exact except inside groups of keys that agree to 14 mantissa bits
 // (~0.5 pairs per fold at NG=20); the caller re-forms the exact float64 keys, repairs such groups with
 // odd-even transposition passes on (key, index) and falls back to the float64 network
@@ -1003,7 +1004,11 @@ __device__ __forceinline__ void ov_sort_stage(const OvWarpSmem &s, const double 
                     const unsigned kb = __float_as_uint(kf);
                     orb |= kb;
                     mxb = max(mxb, kb);
-                    v[r] = ((kb >> 9) << 10) | (unsigned)((i << 5) | j);
+                    // 22 key bits = 6 exponent bits (kmax sits at 2^100: the 62 binades below it keep their own
+                    // exponent, anything smaller collapses to 0 and is then told apart by the exact check) and
+                    // 16 mantissa bits
+                    const unsigned kt = kb > OV_KEY_BASE ? kb - OV_KEY_BASE : 0u;
+                    v[r] = ((kt >> 7) << 10) | (unsigned)((i << 5) | j);
                 } else {
                     v[r] = 0xffffffffu;           // padding: above every live element, index field marks it dead
                 }
@@ -1014,7 +1019,9 @@ __device__ __forceinline__ void ov_sort_stage(const OvWarpSmem &s, const double 
             // If every key is a finite positive float and no two neighbours share their 22 key bits, the
             // float32-rounded keys are strictly increasing, hence so are the exact keys (rounding is
             // monotone): the order is exact and free of ties, no need to re-form the float64 keys.
-            bool dirty = (orb >> 31) != 0u || mxb >= 0x7f800000u;
+            // (a key beyond the 6-bit exponent range -- only possible when kmax is not the largest key -- or a
+            // negative / non-finite one makes the packed order meaningless: verify exactly)
+            bool dirty = (orb >> 31) != 0u || mxb >= OV_KEY_BASE + (64u << 23);
 #pragma unroll
             for (int r = 0; r + 1 < EPL; ++r) dirty |= ((v[r] | 1023u) >= v[r + 1]) & (v[r + 1] < 0xfffffc00u);
             {
@@ -1200,7 +1207,9 @@ ans_koverlap_kernel(OvParams P)
         // keep the CTA's warps in the same phase of the code: the hot path is larger than the
         // instruction cache and warps that drift apart evict each other's lines
 #ifndef OV_NO_FOLDBAR
-        __syncthreads();
+        // (measured at config 2: the gradient kernel loses 3 / 10 / 21 % with a barrier every 2nd / 4th /
+        // no fold; the smaller no-gradient kernel gains 4 % with one every 4th fold)
+        if (GRAD || (igas & 3) == 0) __syncthreads();
 #endif
         const int g1 = igas + 1;
         const double am1 = __ldg(P.amount + (size_t)g1 * NLAY + l);

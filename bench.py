@@ -90,7 +90,13 @@ def cpu_forward_jacobian(c, rows, nthreads):
 
 def time_cpu(c, nsample, steps, warmup):
     from oracle import oracle as orc
-    nthreads = max(1, min(orc.max_threads(), os.cpu_count() or 1))
+    # every host thread this process may use (torchrun exports OMP_NUM_THREADS=1: the explicit num_threads
+    # clause of the oracle's OpenMP loops is what counts, not the environment default)
+    try:
+        nthreads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        nthreads = os.cpu_count() or 1
+    nthreads = max(1, nthreads)
     nw = c["tab"]["NWAVE"]
     rows = np.unique(np.linspace(0, nw - 1, min(nsample, nw)).astype(int))
     times = []
@@ -193,6 +199,8 @@ def run_b200(args, cfg):
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     c = make_case(cfg, rank_seed=rank)
@@ -325,7 +333,7 @@ def run_b200(args, cfg):
                     e2e=dict(value=world * 1e3 / (e2e_ms / K), unit="spectra/s", h2d_bytes_per_step=h2d,
                              d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / K),
                     gpu_launches=launches, roofline=roof, clocks=clocks)
-        if not args.no_cpu_baseline and world >= 1:
+        if not args.no_cpu_baseline and world == 1:
             cb, _ = time_cpu_sampled(cfg, args.cpu_sample_waves)
             line["cpu_baseline"] = cb
         print(json.dumps(line))
