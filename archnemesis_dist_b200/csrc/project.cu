@@ -5,55 +5,102 @@
 // reference's parameter-inclusion rule :699-702) and xmap into one matrix per path,
 //     M[path, k*NLAYMAX + j, x] = sum_pro D_k[LAYINC[j,path], pro] * xmap[x, k, pro],
 // and this kernel is the skinny FP64 product out[w,path,:] = dspec[w,path,:] . M[path].
-// FP64 FMA pipe; nothing here is shaped for tensor cores (0.5 GFLOP at 4000 x 1000 x 60).
+// FP64 FMA pipe; nothing here is shaped for tensor cores (0.5 GFLOP at 4000 x 1000 x 60, 61 GFLOP for 64 limb
+// paths of 200 layers).
 #include "common.cuh"
 
-constexpr int PJ_BM = 32, PJ_BN = 64, PJ_BK = 16;
+// Tiling: a CTA owns 128 wavenumbers x 64 state-vector columns of one path and walks E = NPAR*NLAYMAX in
+// chunks of 16, double-buffered in shared memory.  Warp w owns the 8 columns [8w, 8w+8); lane l owns rows
+// 4l..4l+3, so a thread keeps a 4 x 8 micro-tile (32 FP64 accumulators) and per k reads its four A values
+// (two 128-bit loads, conflict-free) and the warp's eight B values (broadcast).  M is block-sparse -- a
+// state-vector element maps to the layers of ONE parameter (temperature, one gas, ...), so in a chunk of 16
+// rows of M most column groups are all zero: each warp tests its 16 x 8 block of the staged B tile
+// (ballot, warp-uniform) and skips the 512 FMAs per thread when it is empty.  At config 2 that leaves
+// ~1/NPAR of the dense flops; the dense rate is FP64-FMA-pipe bound.
+constexpr int PJ_BM = 128, PJ_BN = 64, PJ_BK = 16, PJ_THREADS = 256;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PJ_THREADS, 2)
 ans_project_kernel(const double *__restrict__ dspec, const double *__restrict__ M, int NWAVE, int E, int NPATH, int NX,
                    double *__restrict__ out)
 {
-    __shared__ double sA[PJ_BK][PJ_BM + 1];
-    __shared__ double sBm[PJ_BK][PJ_BN];
+    __shared__ __align__(16) double sA[2][PJ_BK][PJ_BM];      // [k][row]
+    __shared__ __align__(16) double sB[2][PJ_BK][PJ_BN];      // [k][col]
     const int ipath = blockIdx.z;
     const int w0 = blockIdx.x * PJ_BM, x0 = blockIdx.y * PJ_BN;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double *Mp = M + (size_t)ipath * E * NX;
-    double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    double acc[4][8];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[r][c] = 0.0;
+
+    // staging: A tile = 128 rows x 16 k (thread t: row t/2, 8 consecutive k -> one 64-byte run of dspec);
+    // B tile = 16 k x 64 columns (thread t: k = t/16, 4 consecutive columns)
+    const int ar = threadIdx.x >> 1, ak = (threadIdx.x & 1) * 8;
+    const int bk = threadIdx.x >> 4, bc = (threadIdx.x & 15) * 4;
+    const bool arow_ok = w0 + ar < NWAVE;
+    const double *arow = dspec + ((size_t)(arow_ok ? w0 + ar : 0) * NPATH + ipath) * E;
+    double ra[8], rb[4];
+    auto fetch = [&](int e0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int e = e0 + ak + q;
+            ra[q] = (arow_ok && e < E) ? __ldg(arow + e) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = e0 + bk, x = x0 + bc + q;
+            rb[q] = (e < E && x < NX) ? __ldg(Mp + (size_t)e * NX + x) : 0.0;
+        }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sA[buf][ak + q][ar] = ra[q];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sB[buf][bk][bc + q] = rb[q];
+    };
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    int buf = 0;
     for (int e0 = 0; e0 < E; e0 += PJ_BK) {
-        for (int t = threadIdx.x; t < PJ_BM * PJ_BK; t += 256) {
-            const int r = t / PJ_BK, c = t - r * PJ_BK;
-            const int w = w0 + r, e = e0 + c;
-            sA[c][r] = (w < NWAVE && e < E) ? dspec[((size_t)w * NPATH + ipath) * E + e] : 0.0;
-        }
-        for (int t = threadIdx.x; t < PJ_BK * PJ_BN; t += 256) {
-            const int r = t / PJ_BN, c = t - r * PJ_BN;
-            const int e = e0 + r, x = x0 + c;
-            sBm[r][c] = (e < E && x < NX) ? Mp[(size_t)e * NX + x] : 0.0;
-        }
-        __syncthreads();
+        const bool more = e0 + PJ_BK < E;
+        if (more) fetch(e0 + PJ_BK);            // global loads of the next chunk fly during the FMAs
+        // is this warp's 16 x 8 block of M empty?  (lane -> k = lane/2, 4 of the 8 columns)
+        const double *bq = &sB[buf][lane >> 1][warp * 8 + (lane & 1) * 4];
+        const bool nz = bq[0] != 0.0 || bq[1] != 0.0 || bq[2] != 0.0 || bq[3] != 0.0;
+        if (__any_sync(0xffffffffu, nz)) {
 #pragma unroll
-        for (int kk = 0; kk < PJ_BK; ++kk) {
-            const double a0 = sA[kk][ty * 2], a1 = sA[kk][ty * 2 + 1];
+            for (int kk = 0; kk < PJ_BK; ++kk) {
+                const double2 a01 = *reinterpret_cast<const double2 *>(&sA[buf][kk][lane * 4]);
+                const double2 a23 = *reinterpret_cast<const double2 *>(&sA[buf][kk][lane * 4 + 2]);
+                const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+                double bv[8];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const double b = sBm[kk][tx + 16 * c];
-                acc[0][c] += a0 * b;
-                acc[1][c] += a1 * b;
+                for (int c = 0; c < 8; c += 2) {
+                    const double2 b2 = *reinterpret_cast<const double2 *>(&sB[buf][kk][warp * 8 + c]);
+                    bv[c] = b2.x;
+                    bv[c + 1] = b2.y;
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[r][c] = fma(av[r], bv[c], acc[r][c]);
             }
         }
+        if (more) stash(buf ^ 1);
         __syncthreads();
+        buf ^= 1;
     }
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const int w = w0 + ty * 2 + r;
+    for (int r = 0; r < 4; ++r) {
+        const int w = w0 + lane * 4 + r;
         if (w >= NWAVE) continue;
+        double *o = out + ((size_t)w * NPATH + ipath) * NX + x0 + warp * 8;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int x = x0 + tx + 16 * c;
-            if (x < NX) out[((size_t)w * NPATH + ipath) * NX + x] = acc[r][c];
-        }
+        for (int c = 0; c < 8; ++c)
+            if (x0 + warp * 8 + c < NX) o[c] = acc[r][c];
     }
 }
 
@@ -65,7 +112,7 @@ extern "C" int ansb200_jacobian_project(const double *dspec, const double *M, in
     ANS_REQUIRE(NWAVE > 0 && NPAR > 0 && NLAYMAX > 0 && NPATH > 0 && NX > 0, "jacobian_project: bad shape");
     ANS_REQUIRE(NPATH <= 65535, "jacobian_project: NPATH too large");
     dim3 grid(ans_div_up(NWAVE, PJ_BM), ans_div_up(NX, PJ_BN), NPATH);
-    ans_project_kernel<<<grid, 256, 0, stream>>>(dspec, M, NWAVE, NPAR * NLAYMAX, NPATH, NX, out);
+    ans_project_kernel<<<grid, PJ_THREADS, 0, stream>>>(dspec, M, NWAVE, NPAR * NLAYMAX, NPATH, NX, out);
     ANS_LAUNCH_CHECK();
     return ANSB200_OK;
 }

@@ -6,7 +6,11 @@
 // unit scaling of :4244-4247, calculate_transmission_spectrum (:4104-4129) and the g-integration
 // of CIRSrad (:4504-4508).
 //
-// One CTA owns one (wavenumber, path).  Phase 0 tabulates the Planck function of the path's
+// One CTA owns one wavenumber and a subset of the paths (every NPG-th path), which it walks in sequence.
+// With several paths per CTA (limb / occultation: NPATH = 16..64) the wavenumber's tau and dk slabs
+// (NG*NLAY*(NGAS+2) doubles, 128 KB at 20 x 100 x 8) are staged in shared memory once and reused by every
+// path instead of being re-read through L2 (57 GB for 64 paths x 4000 wavenumbers).  Phase 0 tabulates the
+// Planck function of the path's
 // layers.  Phase 1: one warp per g-ordinate scans the path: lanes own contiguous layer chunks,
 // a multiplicative (gradient form, tr = trold*exp(-tau_j), :6446-6448) or additive (no-gradient
 // form, tr = exp(-sum tau), :6345-6346) warp scan gives the transmission to each layer, a reverse
@@ -14,14 +18,14 @@
 //     d spec / d q[k,j] = dtau[k,j] * D_j  +  [k == NVMR] * (T_{j-1} - T_j) * dB_j/dT
 //     D_j = T_j B_j - sum_{m>j} (T_{m-1} - T_m) B_m - T_N * radground
 // so only D[g][j] and the temperature term are kept (shared memory); the 5-D
-// (NWAVE,NG,NPAR,NLAYIN,NPATH) tensor of the reference never exists.  Phase 2: one thread per
-// (parameter, layer) pair forms dtau on the fly from dk / dtaucon, multiplies, applies xfac and
-// integrates over g with DELG, then nan_to_num.
+// (NWAVE,NG,NPAR,NLAYIN,NPATH) tensor of the reference never exists.  Phase 2: a warp per
+// (parameter, 32 path layers) forms dtau on the fly from dk / dtaucon against the pre-weighted
+// W[g][j] = D_j(g) SCALE_j DELG_g xfac, integrates over g, then nan_to_num; stores are contiguous in j.
 #include <float.h>
 #include "common.cuh"
 
-constexpr int RAD_THREADS = 256;
-constexpr int RAD_WARPS = RAD_THREADS / 32;
+constexpr int RAD_MAX_THREADS = 640;   // phase 1 is one warp per g-ordinate: NG warps (<= 20) when a CTA walks several paths
+                                       // with staged slabs (one CTA per SM), half as many for one path per CTA
 constexpr unsigned RFULL = 0xffffffffu;
 
 struct RadParams {
@@ -37,6 +41,8 @@ struct RadParams {
     int ispace;
     double tsurf;
     int NWAVE, NG, NLAY, NGAS, NVMR, NPAR, NLAYMAX, NPATH;
+    int NPG;      // path groups: CTA (iw, pg) walks paths pg, pg+NPG, ...
+    int stage;    // tau / dk slabs of the wavenumber staged in shared memory (several paths per CTA)
     double *spec, *dspec, *dtsurf;
 };
 
@@ -101,16 +107,17 @@ __device__ __forceinline__ double ans_nan_to_num(double v)
     return v;
 }
 
-__global__ void __launch_bounds__(RAD_THREADS)
+__global__ void __launch_bounds__(RAD_MAX_THREADS)
 ans_radiance_kernel(RadParams P)
 {
+    const int RAD_THREADS = blockDim.x, RAD_WARPS = blockDim.x >> 5;
     extern __shared__ __align__(16) unsigned char rad_smem[];
-    const int iw = blockIdx.x, ipath = blockIdx.y;
+    const int iw = blockIdx.x / P.NPG, pg = blockIdx.x - iw * P.NPG;
     const int NG = P.NG, NLAY = P.NLAY, NLM = P.NLAYMAX, NPATH = P.NPATH, NPAR = P.NPAR;
     const bool grad = (P.flags & ANSB200_RAD_GRAD) != 0;
     const bool thermal = (P.mode == 0);
-    const int n = P.nlayin[ipath];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int NP1 = P.NGAS + 1;
 
     // shared-memory carve-up
     double *sB = reinterpret_cast<double *>(rad_smem);   // [NLM] Planck
@@ -122,8 +129,39 @@ ans_radiance_kernel(RadParams P)
     double *sTT = sD + (grad ? (size_t)NG * NLM : 0);     // [NG][NLM]   (T_{j-1}-T_j) dB (grad, thermal)
     double *sspec = sTT + ((grad && thermal) ? (size_t)NG * NLM : 0);   // [NG] spec_g
     double *sdts = sspec + NG;                            // [NG] dtsurf_g
-    int *slay = reinterpret_cast<int *>(sdts + NG);      // [NLM]
+    double *sdelg = sdts + NG;                            // [NG] quadrature weights
+    double *stau = sdelg + NG;                            // [NG*NLAY]      staged tau slab  (P.stage)
+    double *sdk = stau + (P.stage ? (size_t)NG * NLAY : 0);                 // [NG*NLAY*NP1] staged dk slab (P.stage, grad)
+    int *slay = reinterpret_cast<int *>(sdk + ((P.stage && grad && P.dk) ? (size_t)NG * NLAY * NP1 : 0));   // [NLM]
+    int *scol = slay + NLM;                               // [NPAR] dk column feeding parameter k (-1: none)
 
+    // once per CTA: quadrature weights, the dk column of every parameter (last matching gas wins, like the
+    // reference's loop :3868-3872), and the wavenumber's tau / dk slabs when they are reused by several paths
+    for (int ig = threadIdx.x; ig < NG; ig += RAD_THREADS) sdelg[ig] = P.delg[ig];
+    if (grad) {
+        for (int k = threadIdx.x; k < NPAR; k += RAD_THREADS) {
+            int col = -1;
+            if (P.dk) {   // no active gas (NGAS == 0): dTAUGAS is all zeros in the reference (:3883-3888)
+                if (k == P.NVMR) col = P.NGAS;
+                else for (int i = 0; i < P.NGAS; ++i) if (P.gas_slot[i] == k) col = i;
+            }
+            scol[k] = col;
+        }
+    }
+    const double *tauw = P.tau + (size_t)iw * NG * NLAY;
+    const double *dkw = P.dk ? P.dk + (size_t)iw * NG * NLAY * NP1 : nullptr;
+    if (P.stage) {
+        for (int t = threadIdx.x; t < NG * NLAY; t += RAD_THREADS) stau[t] = tauw[t];
+        tauw = stau;
+        if (grad && P.dk) {
+            for (int t = threadIdx.x; t < NG * NLAY * NP1; t += RAD_THREADS) sdk[t] = dkw[t];
+            dkw = sdk;
+        }
+    }
+    __syncthreads();
+
+    for (int ipath = pg; ipath < NPATH; ipath += P.NPG) {
+    const int n = P.nlayin[ipath];
     const double wv = thermal ? P.wave[iw] : 0.0;
     const double xf = P.xfac ? P.xfac[iw] : 1.0;
     for (int j = threadIdx.x; j < n; j += RAD_THREADS) {
@@ -161,7 +199,7 @@ ans_radiance_kernel(RadParams P)
     const int CH = (n + 31) / 32;   // layers per lane
     double *myT = sT + (size_t)warp * (NLM + 1);   // myT[j+1] = transmission to the bottom of layer j, myT[0] = 1
     for (int ig = warp; ig < NG; ig += RAD_WARPS) {
-        const double *taug = P.tau + ((size_t)iw * NG + ig) * NLAY;
+        const double *taug = tauw + (size_t)ig * NLAY;
         const int j0 = lane * CH, j1 = min(n, j0 + CH);
         // local scan over this lane's chunk
         const bool prodform = thermal && grad;   // running product (gradient form) or running sum
@@ -197,7 +235,8 @@ ans_radiance_kernel(RadParams P)
             // transmission: spec_g = exp(-sum tau) [* xfac]; d/dq[k,j] = -spec_g * dtau[k,j]  (:4110-4126)
             const double sg = exp(-total) * xf;
             if (lane == 0) sspec[ig] = sg;
-            if (grad) for (int j = lane; j < n; j += 32) sD[(size_t)ig * NLM + j] = -sg;
+            // (weighted for phase 2: D_j(g) * SCALE_j * DELG_g; xfac is already inside spec_g)
+            if (grad) for (int j = lane; j < n; j += 32) sD[(size_t)ig * NLM + j] = -sg * sscale[j] * sdelg[ig];
             __syncwarp();
             continue;
         }
@@ -233,8 +272,9 @@ ans_radiance_kernel(RadParams P)
             double suffix = after + (ground ? Tn * radground : 0.0);
             for (int j = j1 - 1; j >= j0; --j) {
                 const double Tj = myT[j + 1], Tjm = myT[j];
-                sD[(size_t)ig * NLM + j] = Tj * sB[j] - suffix;
-                sTT[(size_t)ig * NLM + j] = (Tjm - Tj) * sdB[j];
+                // weighted for phase 2: D_j(g) * SCALE_j * DELG_g * xfac and (T_{j-1}-T_j) dB_j/dT * DELG_g * xfac
+                sD[(size_t)ig * NLM + j] = (Tj * sB[j] - suffix) * sscale[j] * (sdelg[ig] * xf);
+                sTT[(size_t)ig * NLM + j] = (Tjm - Tj) * sdB[j] * (sdelg[ig] * xf);
                 suffix += (Tjm - Tj) * sB[j];
             }
         }
@@ -242,46 +282,70 @@ ans_radiance_kernel(RadParams P)
     }
     __syncthreads();
 
-    // g-integration of the spectrum (:4504) and dTSURF (:4508)
-    if (threadIdx.x == 0) {
+    // g-integration of the spectrum (:4504) and dTSURF (:4508): warp 0, lanes over g
+    if (warp == 0) {
         double s = 0.0, d = 0.0;
-        for (int ig = 0; ig < NG; ++ig) { s += sspec[ig] * P.delg[ig]; if (thermal) d += sdts[ig] * P.delg[ig]; }
-        P.spec[(size_t)iw * NPATH + ipath] = s;
-        if (grad && thermal && P.dtsurf) P.dtsurf[(size_t)iw * NPATH + ipath] = d;
+        for (int ig = lane; ig < NG; ig += 32) { s += sspec[ig] * sdelg[ig]; if (thermal) d += sdts[ig] * sdelg[ig]; }
+        s = warp_sum(s);
+        d = warp_sum(d);
+        if (lane == 0) {
+            P.spec[(size_t)iw * NPATH + ipath] = s;
+            if (grad && thermal && P.dtsurf) P.dtsurf[(size_t)iw * NPATH + ipath] = d;
+        }
     }
-    if (!grad) return;
-
-    // Phase 2: layer-space gradients, g-integrated.  thread -> (j, k) with k fastest so that the
-    // NGAS+1 columns of one dk row are read by neighbouring threads.
-    const int NP1 = P.NGAS + 1;
+    if (grad) {
+    // Phase 2: layer-space gradients, g-integrated.  With W[g][j] = D_j(g) SCALE_j DELG_g xfac (phase 1),
+    //   d spec / d q[k,j] = unit_k sum_g W[g][j] dk[g, l_j, col_k]  +  dtaucon[k, l_j] sum_g W[g][j]
+    //                       (+ sum_g (T_{j-1}-T_j) dB_j/dT DELG_g xfac   for k = NVMR, thermal)
+    // i.e. the reference's (dgas + dcon) * SCALE * D * xfac summed over g with DELG (:3993, :4012, :6455-6476,
+    // :4244-4247, :4504-4507), regrouped so that the inner loop is two loads and one FMA.
+    // A warp takes one parameter k and 32 consecutive path layers j: the stores are contiguous in j and no
+    // per-element index division is needed.
     double *out = P.dspec + ((size_t)iw * NPATH + ipath) * NPAR * NLM;
-    for (int e = threadIdx.x; e < NPAR * NLM; e += RAD_THREADS) {
-        const int j = e / NPAR, k = e - j * NPAR;
+    const int nchunk = (NLM + 31) >> 5;
+    for (int item = warp; item < NPAR * nchunk; item += RAD_WARPS) {
+        const int k = item / nchunk, j = ((item - k * nchunk) << 5) + lane;
+        if (j >= NLM) continue;
         double acc = 0.0;
         if (j < n) {
             const int l = slay[j];
-            // which dk column feeds parameter k (last matching gas wins, like the reference's loop :3868-3872)
-            int col = -1;
-            double unit = 1.0;
-            if (P.dk) {   // no active gas (NGAS == 0): dTAUGAS is all zeros in the reference (:3883-3888)
-                if (k == P.NVMR) col = P.NGAS;
-                else for (int i = 0; i < P.NGAS; ++i) if (P.gas_slot[i] == k) { col = i; unit = 1.0e-4; }
+            const int col = scol[k];
+            const double *wp = sD + j;
+            double wsum = 0.0;
+            if (col >= 0) {
+                const double *dkp = dkw + (size_t)l * NP1 + col;
+                double a0 = 0.0, a1 = 0.0, w1 = 0.0;
+                int ig = 0;
+                for (; ig + 1 < NG; ig += 2) {
+                    const double wa = wp[(size_t)ig * NLM], wb = wp[(size_t)(ig + 1) * NLM];
+                    a0 = fma(wa, dkp[(size_t)ig * NLAY * NP1], a0);
+                    a1 = fma(wb, dkp[(size_t)(ig + 1) * NLAY * NP1], a1);
+                    wsum += wa;
+                    w1 += wb;
+                }
+                if (ig < NG) {
+                    const double wa = wp[(size_t)ig * NLM];
+                    a0 = fma(wa, dkp[(size_t)ig * NLAY * NP1], a0);
+                    wsum += wa;
+                }
+                wsum += w1;
+                acc = (a0 + a1) * (col < P.NGAS ? 1.0e-4 : 1.0);
+            } else if (P.dtaucon) {
+                for (int ig = 0; ig < NG; ++ig) wsum += wp[(size_t)ig * NLM];
             }
-            const double dcon = P.dtaucon ? P.dtaucon[((size_t)iw * NPAR + k) * NLAY + l] : 0.0;
-            const double sc = sscale[j];
-            for (int ig = 0; ig < NG; ++ig) {
-                double dgas = 0.0;
-                if (col >= 0) dgas = P.dk[(((size_t)iw * NG + ig) * NLAY + l) * NP1 + col] * unit;
-                const double tmp = (dgas + dcon) * sc;
-                double v = tmp * sD[(size_t)ig * NLM + j];
-                if (thermal && k == P.NVMR) v += sTT[(size_t)ig * NLM + j];
-                if (thermal) v *= xf;   // transmission: xfac already inside spec_g
-                acc += v * P.delg[ig];
+            if (P.dtaucon) acc = fma(P.dtaucon[((size_t)iw * NPAR + k) * NLAY + l], wsum, acc);
+            if (thermal && k == P.NVMR) {
+                double wt = 0.0;
+                for (int ig = 0; ig < NG; ++ig) wt += sTT[(size_t)ig * NLM + j];
+                acc += wt;
             }
             if (P.flags & ANSB200_RAD_NAN_TO_NUM) acc = ans_nan_to_num(acc);
         }
         out[(size_t)k * NLM + j] = acc;
     }
+    }
+    __syncthreads();   // the per-path arrays are reused by the CTA's next path
+    }   // paths
 }
 
 extern "C" int ansb200_radiance(int mode, unsigned flags, const double *tau, const double *dk, const int32_t *gas_slot,
@@ -312,14 +376,34 @@ extern "C" int ansb200_radiance(int mode, unsigned flags, const double *tau, con
     P.NWAVE = NWAVE; P.NG = NG; P.NLAY = NLAY; P.NGAS = NGAS; P.NVMR = NVMR; P.NPAR = NPAR; P.NLAYMAX = NLAYMAX;
     P.NPATH = NPATH; P.spec = spec; P.dspec = dspec; P.dtsurf = dtsurf;
     const bool thermal = mode == 0;
-    size_t nd = (size_t)4 * NLAYMAX + (size_t)RAD_WARPS * (NLAYMAX + 1) + (grad ? (size_t)NG * NLAYMAX : 0) +
-                ((grad && thermal) ? (size_t)NG * NLAYMAX : 0) + 2 * (size_t)NG;
-    size_t smem = nd * 8 + (size_t)NLAYMAX * 4 + 16;
-    ANS_REQUIRE(smem <= 227 * 1024, "radiance: NG*NLAYMAX too large for shared memory (%zu bytes)", smem);
-    if (smem > 48 * 1024)
-        ANS_CUDA_CHECK(cudaFuncSetAttribute(ans_radiance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(NWAVE, NPATH);
-    ans_radiance_kernel<<<grid, RAD_THREADS, smem, stream>>>(P);
+    auto base_bytes = [&](int nthreads) {
+        const size_t nd = (size_t)4 * NLAYMAX + (size_t)(nthreads / 32) * (NLAYMAX + 1) + (grad ? (size_t)NG * NLAYMAX : 0) +
+                          ((grad && thermal) ? (size_t)NG * NLAYMAX : 0) + 3 * (size_t)NG;
+        return nd * 8 + (size_t)(NLAYMAX + NPAR) * 4 + 16;
+    };
+    const int warps_n = NG < 4 ? 4 : (NG > RAD_MAX_THREADS / 32 ? RAD_MAX_THREADS / 32 : NG);
+    const int warps_1 = (warps_n + 1) / 2 < 4 ? 4 : (warps_n + 1) / 2;
+    const int RAD_THREADS_1 = 32 * warps_1, RAD_THREADS_N = 32 * warps_n;
+    size_t base = base_bytes(RAD_THREADS_1);
+    const size_t slab = ((size_t)NG * NLAY + ((grad && dk) ? (size_t)NG * NLAY * (NGAS + 1) : 0)) * 8;
+    ANS_REQUIRE(base <= 227 * 1024, "radiance: NG*NLAYMAX too large for shared memory (%zu bytes)", base);
+    // Several paths: one CTA per (wavenumber, path group) with the wavenumber's slabs staged once, as many
+    // groups as keep every SM busy (>= 4 paths per CTA so that the staging pays).  One path, or slabs that do
+    // not fit: one CTA per (wavenumber, path), slabs read through L2 (consecutive CTAs share the wavenumber).
+    int NPG = NPATH, stage = 0, nthreads = RAD_THREADS_1;
+    if (NPATH >= 4 && base_bytes(RAD_THREADS_N) + slab <= 227 * 1024) {
+        stage = 1;
+        nthreads = RAD_THREADS_N;
+        base = base_bytes(RAD_THREADS_N);
+        NPG = 1;
+        while ((long long)NWAVE * NPG < 2 * 148 && NPATH / (NPG * 2) >= 4) NPG *= 2;
+    }
+    P.NPG = NPG; P.stage = stage;
+    const size_t smem = base + (stage ? slab : 0);
+    ANS_CUDA_CHECK(cudaFuncSetAttribute(ans_radiance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
+    ANS_REQUIRE((long long)NWAVE * NPG < 2147483647LL, "radiance: NWAVE*NPATH too large");
+    ans_radiance_kernel<<<(unsigned)(NWAVE * NPG), nthreads, smem, stream>>>(P);
     ANS_LAUNCH_CHECK();
     return ANSB200_OK;
 }
