@@ -322,7 +322,8 @@ def run_b200(args, cfg):
                     bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                     traffic=TRAFFIC if cfg["nwave"] == CFG["nwave"] else None,
                     peak_source="measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
-                    algorithmic_bytes=b_kio, planes_touched=U, kernel_ms=k_ms, share_of_step=k_ms / ms_step)
+                    algorithmic_bytes=b_kio, planes_touched=U, kernel_ms=k_ms, share_of_step=k_ms / ms_step,
+                    ncu_utilisation=NCU_UTIL if cfg["nwave"] == CFG["nwave"] else None)
         line = dict(metric=METRIC, value=value, unit="spectra/s", n_gpus=world, steps=K, warmup=args.warmup,
                     ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                     data="synthetic",
@@ -343,9 +344,13 @@ def run_b200(args, cfg):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at config 2, from the
-# `ncu --set full` capture in profiles/r01_ncu_full_config2.txt (205.7 MB read = every touched table plane
-# once, 459.1 MB written; algorithmic B_kio is 715.5 MB, the remainder of the output was still in L2)
-TRAFFIC = 664.8e6
+# `ncu --set full` capture in profiles/r01_ncu_full_config2.txt (207.1 MB read = every touched table plane
+# once, 467.3 MB written; algorithmic B_kio is 715.5 MB, the remainder of the output was still in L2).
+# The same capture says what the kernel IS bound by (it is not HBM): issue slots 47 % busy with 16 resident
+# warps per SM stalled on fixed-latency dependencies, shared-memory data pipe 48 %, FP64 pipe 9 %.
+TRAFFIC = 674.4e6
+NCU_UTIL = dict(issue_slots_pct=47.3, smem_data_pipe_pct=47.6, fp64_pipe_pct=9.2, warps_active_pct=24.1,
+                source="profiles/r01_ncu_full_config2.txt (ncu --set full, not taken during the timed run)")
 
 
 def time_cpu_sampled(cfg, nsample):
