@@ -228,6 +228,34 @@ def golden_stages(ans):
         assert np.array_equal(orc.thermal(ispace, wave, t0, None, emt, emp, tsurf, emis, z, z, 100.0, 10.0), s)
         o = orc.thermalg(ispace, wave, t0, d0, c["NVMR"], emt, emp, tsurf, emis)
         assert np.array_equal(o[0], sg) and np.array_equal(o[1], dsg) and np.array_equal(o[2], dts)
+    # ---- transmission, several ragged limb paths (calculate_transmission_spectrum, :4104-4129) ----------------
+    import types
+    nlay = 9
+    tang = [1, 4, 6]                                   # tangent layers: path p sees layers above it, in and out
+    nlayin = np.array([2 * (nlay - t) for t in tang], np.int32)
+    nlm = int(nlayin.max())
+    layinc = np.zeros((nlm, 3), np.int32)
+    scale = np.zeros((nlm, 3))
+    for p_, t in enumerate(tang):
+        seq = list(range(nlay - 1, t - 1, -1)) + list(range(t, nlay))
+        layinc[:len(seq), p_] = seq
+        scale[:len(seq), p_] = 1.0 + 12.0 / (1.0 + np.abs(np.array(seq) - t))
+    # (rows past NLAYIN carry SCALE 0 and layer 0, like Path_0 pads them: zero opacity, zero gradient)
+    ttl, ttp, dttl = orc.assemble_opacity(taug * 1e-3, dk * 1e-3, c["gas_slot"], c["NVMR"], c["NPAR"], c["taucon"],
+                                          c["dtaucon"], layinc, scale)
+    stub = types.SimpleNamespace(SpectroscopyX=types.SimpleNamespace(NWAVE=5, NG=20),
+                                 MeasurementX=types.SimpleNamespace(IFORM=0), PathX=types.SimpleNamespace(NPATH=3))
+    tr_spec, tr_dspec = ans.ForwardModel_0.calculate_transmission_spectrum(stub, ttp, dttl, return_grad=True)
+    # g-integration exactly as CIRSrad does it (:4504-4507)
+    delg = tab["DELG"]
+    tr_s = np.tensordot(tr_spec, delg, axes=([1], [0]))
+    tr_d = np.nan_to_num(np.tensordot(tr_dspec, delg, axes=([1], [0])))
+    o_s, o_d = orc.transmission(ttp, dttl)
+    assert np.array_equal(o_s, tr_spec) and np.array_equal(o_d, tr_dspec)
+    og_s, og_d, _ = orc.g_integrate(o_s, o_d, None, delg)
+    assert np.array_equal(og_s, tr_s) and np.array_equal(og_d, tr_d)
+    out.update(tr_layinc=layinc, tr_scale=scale, tr_nlayin=nlayin, tr_tau=taug * 1e-3, tr_dk=dk * 1e-3,
+               tr_gas_slot=c["gas_slot"], tr_taucon=c["taucon"], tr_dtaucon=c["dtaucon"], tr_spec=tr_s, tr_dspec=tr_d)
     # ---- map2pro / map2xvec -----------------------------------------------------------------------------
     rng = np.random.default_rng(5)
     dspec = rng.normal(size=(5, c["NPAR"], 9, 1))

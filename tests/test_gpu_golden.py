@@ -68,6 +68,38 @@ def test_stage_goldens_thermal():
             assert relerr(cpu(s0)[:, 0], g["th_%s_spec" % tag][:, ig]) < 1e-12
 
 
+def test_stage_golden_transmission_limb_paths():
+    """Transmission mode over three ragged limb paths (staged-slab branch of the radiance kernel) against the
+    live reference's calculate_transmission_spectrum + CIRSrad g-integration, and the single-path branch
+    path by path."""
+    import torch
+    from archnemesis_dist_b200 import ops
+    g = load("stages.npz")
+    delg = stage_table()["tab"]["DELG"].astype(np.float64)
+    d = ops.to_dev
+    npar = g["tr_dtaucon"].shape[1]
+    nvmr = 4
+    args = (d(g["tr_tau"]), d(g["tr_dk"]), d(g["tr_gas_slot"], torch.int32), d(g["tr_taucon"]), None, None,
+            d(g["tr_dtaucon"]))
+    spec, dspec, _ = ops.radiance(ops.TRANSMISSION, *args, d(g["tr_layinc"], torch.int32), d(g["tr_scale"]),
+                                  d(g["tr_nlayin"], torch.int32), None, None, None, d(delg), None, None, None, None, None,
+                                  None, 0, -1.0, nvmr, npar, True)
+    got = np.transpose(cpu(dspec), (0, 2, 3, 1))       # [NWAVE,NPATH,NPAR,NLM] -> reference (NWAVE,NPAR,NLAYIN,NPATH)
+    assert relerr(cpu(spec), g["tr_spec"]) < 1e-13
+    assert colerr(got, g["tr_dspec"]) < 1e-13
+    for p in range(3):                                 # one path per launch: the un-staged branch
+        s1, d1, _ = ops.radiance(ops.TRANSMISSION, *args, d(np.ascontiguousarray(g["tr_layinc"][:, p:p + 1]), torch.int32),
+                                 d(np.ascontiguousarray(g["tr_scale"][:, p:p + 1])),
+                                 d(g["tr_nlayin"][p:p + 1], torch.int32), None, None, None, d(delg), None, None, None,
+                                 None, None, None, 0, -1.0, nvmr, npar, True)
+        assert relerr(cpu(s1)[:, 0], g["tr_spec"][:, p]) < 1e-13
+        assert colerr(cpu(d1)[:, 0], g["tr_dspec"][..., p]) < 1e-13
+    s0 = ops.radiance(ops.TRANSMISSION, d(g["tr_tau"]), None, None, d(g["tr_taucon"]), None, None, None,
+                      d(g["tr_layinc"], torch.int32), d(g["tr_scale"]), d(g["tr_nlayin"], torch.int32), None, None, None,
+                      d(delg), None, None, None, None, None, None, 0, -1.0, nvmr, npar, False)
+    assert relerr(cpu(s0), g["tr_spec"]) < 1e-13
+
+
 def test_stage_golden_projection_and_lbl():
     from archnemesis_dist_b200 import ops, plan, lbl
     g = load("stages.npz")

@@ -37,6 +37,17 @@ def test_thermal_stage_goldens():
         assert np.array_equal(ds, g["th_%s_dspec" % tag]) and np.array_equal(dt, g["th_%s_dts" % tag])
 
 
+def test_transmission_stage_golden():
+    """Three ragged limb paths through the live reference's calculate_transmission_spectrum
+    (ForwardModel_0.py:4104-4129) and CIRSrad's g-integration (:4504-4507)."""
+    g = load("stages.npz")
+    tl, tp, dtl = orc.assemble_opacity(g["tr_tau"], g["tr_dk"], g["tr_gas_slot"], 4, g["tr_dtaucon"].shape[1], g["tr_taucon"],
+                                       g["tr_dtaucon"], g["tr_layinc"], g["tr_scale"])
+    S, dS = orc.transmission(tp, dtl)
+    s, d, _ = orc.g_integrate(S, dS, None, stage_table()["tab"]["DELG"])
+    assert np.array_equal(s, g["tr_spec"]) and np.array_equal(d, g["tr_dspec"])
+
+
 def test_projection_stage_goldens():
     g = load("stages.npz")
     c = stage_table()
