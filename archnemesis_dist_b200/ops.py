@@ -180,3 +180,34 @@ def jacobian_project(dspec, M):
     _lib.check(_lib.load().ansb200_jacobian_project(_ptr(dspec), _ptr(M), NWAVE, NPAR, NLM, NPATH, NX, _ptr(out),
                                                     _stream()))
     return out
+
+
+class ConvOperator:
+    """Device copy of a plan.conv_operator (Measurement_0.conv / convg for k-tables)."""
+
+    def __init__(self, op):
+        self.mode, self.NCONV = int(op["mode"]), int(op["NCONV"])
+        self.row_start = to_dev(op["row_start"], torch.int32)
+        self.widx = to_dev(op["widx"], torch.int32)
+        self.wval = to_dev(op["wval"])
+        self.norm = to_dev(op["norm"])
+        self.np_lo = to_dev(op["np_lo"], torch.int32)
+        self.np_exact = to_dev(op["np_exact"], torch.int32)
+        self.xinfo = to_dev(op["xinfo"])
+
+
+def convolve(cop, block, col0_is_spectrum=True):
+    """Apply the instrument line shape to block[NWAVE, NCOL] (e.g. [spectrum | Jacobian columns]) ->
+    [NCONV, NCOL].  With col0_is_spectrum column 0 is evaluated like the reference's 1-D interpolation."""
+    _require_cuda()
+    if block.dim() != 2 or block.stride(1) != 1:
+        raise ValueError("convolve: block must be 2-D with unit column stride")
+    NWAVE, NCOL = block.shape
+    out = torch.empty((cop.NCONV, NCOL), dtype=torch.float64, device="cuda")
+    if not block.is_cuda or block.dtype != torch.float64:
+        raise ValueError("convolve: block must be a float64 device tensor")
+    _lib.check(_lib.load().ansb200_convolve(ctypes.c_void_p(block.data_ptr()), NWAVE, NCOL, block.stride(0), cop.mode,
+                                            int(bool(col0_is_spectrum)), _ptr(cop.row_start), _ptr(cop.widx),
+                                            _ptr(cop.wval), _ptr(cop.norm), _ptr(cop.np_lo), _ptr(cop.np_exact),
+                                            _ptr(cop.xinfo), cop.NCONV, _ptr(out), _stream()))
+    return out

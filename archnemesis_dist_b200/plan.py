@@ -136,3 +136,69 @@ def fold_projection(xmap, LAYINC, NLAYIN, DTE, DAM, DCO, NVMR, NDUST):
             # contribution of profile parameter p to state element x, driven by layer gradients of `src`
             M[ipath, src, 0:n, :] += D @ xmap[:, p, :].T
     return np.ascontiguousarray(M.reshape(NPATH, NPAR * NLM, NX))
+
+
+# ------------------------------------------------------------------------------------------------
+# Instrument line shape as a sparse operator on the wavenumber axis (Measurement_0.conv / convg,
+# archnemesis/Measurement_0.py:2288-2465 / :2467-2692), for the two modes convg supports with k-tables.
+# ------------------------------------------------------------------------------------------------
+CONV_INTERP, CONV_FILTER = 0, 1
+
+
+def conv_operator(Wave, VCONV, FWHM, NFIL=None, VFIL=None, AFIL=None):
+    """The convolution of one geometry as a sparse operator on the wavenumber axis.
+
+    FWHM == 0 (:2632-2640): ``scipy.interpolate.interp1d(Wave, y, axis=0)(VCONV)``.  SciPy (1.18) evaluates a
+    2-D y (the gradients) with ``idx = searchsorted(x, x_new).clip(1, n-1)`` and
+    ``(x_new-x_lo)/(x_hi-x_lo) * y_hi + (x_hi-x_new)/(x_hi-x_lo) * y_lo``: each row holds (hi, lo) with those
+    two weights, summed in that order.  A 1-D float64 y (the spectrum) is delegated to ``np.interp``, whose
+    kernel is ``slope = (y[j+1]-y[j])/(x[j+1]-x[j]); slope*(x_new-x[j]) + y[j]`` with x[j] <= x_new < x[j+1] and
+    y[j] itself on a knot: ``np_lo`` = j, ``np_exact`` marks the knots, ``xinfo`` = (x[j], x[j+1], x_new).
+    FWHM < 0 (:2642-2690): filter-weighted mean ``sum(f1*y)/sum(f1)`` over the calculation points between the
+    last one below VFIL[0] and the first one above VFIL[NFIL-1], ``f1 = np.interp(Wave[i], VFIL, AFIL)``, only
+    where f1 > 0, accumulated in ascending order; ``norm`` is that sum of f1.
+    FWHM > 0 with k-tables raises in the reference's convg (:2617-2619) and here."""
+    Wave = np.asarray(Wave, dtype=np.float64)
+    VCONV = np.asarray(VCONV, dtype=np.float64)
+    nconv = len(VCONV)
+    if FWHM > 0.0:
+        raise ValueError("conv_operator: FWHM>0 is not available for k-table Jacobians (Measurement_0.convg raises)")
+    if FWHM == 0.0:
+        if VCONV.min() < Wave[0] or VCONV.max() > Wave[-1]:
+            raise ValueError("A value in x_new is outside the interpolation range.")     # interp1d bounds_error
+        n = len(Wave)
+        idx = np.searchsorted(Wave, VCONV).clip(1, n - 1)
+        x_lo, x_hi = Wave[idx - 1], Wave[idx]
+        widx = np.stack([idx, idx - 1], axis=1).astype(np.int32).reshape(-1)
+        wval = np.stack([(VCONV - x_lo) / (x_hi - x_lo), (x_hi - VCONV) / (x_hi - x_lo)], axis=1).reshape(-1)
+        # np.interp bracket: x[j] <= x_new < x[j+1]; the last knot and exact hits return y[j]
+        j = np.searchsorted(Wave, VCONV, side="right") - 1
+        exact = (Wave[j.clip(0, n - 1)] == VCONV) | (j >= n - 1)
+        j = j.clip(0, n - 2)
+        j = np.where(exact & (VCONV == Wave[n - 1]), n - 1, j)
+        jn = np.minimum(j + 1, n - 1)
+        xinfo = np.stack([Wave[j], Wave[jn], VCONV], axis=1)
+        return dict(mode=CONV_INTERP, row_start=(2 * np.arange(nconv + 1)).astype(np.int32), widx=widx,
+                    wval=np.ascontiguousarray(wval), norm=np.ones(nconv), np_lo=j.astype(np.int32),
+                    np_exact=exact.astype(np.int32), xinfo=np.ascontiguousarray(xinfo), NCONV=nconv)
+    rows, vals, start, norm = [], [], [0], []
+    for ic in range(nconv):
+        nf = int(NFIL[ic])
+        xp = np.asarray(VFIL[0:nf, ic], dtype=np.float64)
+        yp = np.asarray(AFIL[0:nf, ic], dtype=np.float64)
+        lo = np.where(Wave < xp[0])[0]
+        hi = np.where(Wave > xp[nf - 1])[0]
+        i0, i1 = int(lo[len(lo) - 1]), int(hi[0])
+        tot = 0.0
+        for i in range(i0, i1 + 1):
+            f1 = float(np.interp(Wave[i], xp, yp))
+            if f1 > 0.0:
+                rows.append(i)
+                vals.append(f1)
+                tot = tot + f1
+        start.append(len(rows))
+        norm.append(tot)
+    return dict(mode=CONV_FILTER, row_start=np.asarray(start, np.int32), widx=np.asarray(rows, np.int32),
+                wval=np.asarray(vals, np.float64), norm=np.asarray(norm, np.float64),
+                np_lo=np.zeros(nconv, np.int32), np_exact=np.zeros(nconv, np.int32), xinfo=np.zeros((nconv, 3)),
+                NCONV=nconv)

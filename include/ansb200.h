@@ -123,6 +123,19 @@ int ansb200_radiance(int mode, unsigned flags, const double *tau, const double *
 int ansb200_jacobian_project(const double *dspec, const double *M, int NWAVE, int NPAR, int NLAYMAX,
                              int NPATH, int NX, double *out, void *stream);
 
+/* ---- instrument line shape -------------------------------------------------------------------
+ * Replaces Measurement_0.conv / convg for k-tables (archnemesis/Measurement_0.py:2288-2465,
+ * :2467-2692): mode 0 = FWHM == 0, scipy interp1d onto the convolution points (rows of two entries
+ * (hi, lo) with SciPy's weights; with col0_np_interp column 0 -- the spectrum -- is evaluated in
+ * np.interp's slope form from np_lo[NCONV], np_exact[NCONV], xinfo[NCONV,3] = (x_lo, x_hi, x_new));
+ * mode 1 = FWHM < 0, filter-weighted mean sum(wval*in)/norm over widx[row_start[c]:row_start[c+1]].
+ * The operator is built on the host (plan.conv_operator).  in[NWAVE, ld] (first NCOL columns used,
+ * e.g. [spectrum | Jacobian columns]) -> out[NCONV, NCOL].  Bit-identical to the reference. */
+int ansb200_convolve(const double *in, int NWAVE, int NCOL, int ld, int mode, int col0_np_interp,
+                     const int32_t *row_start, const int32_t *widx, const double *wval, const double *norm,
+                     const int32_t *np_lo, const int32_t *np_exact, const double *xinfo, int NCONV,
+                     double *out, void *stream);
+
 /* ---- line-by-line absorption ---------------------------------------------------------------
  * Replaces add_line_set_monochromatic_absorption (archnemesis/LineData_0.py:279-358) with the
  * Voigt profile of lineshape/voigt_impl/voigt_scipy.py:8-52 (SciPy voigt_profile = Re w(z)).

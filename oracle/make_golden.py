@@ -256,6 +256,36 @@ def golden_stages(ans):
     assert np.array_equal(og_s, tr_s) and np.array_equal(og_d, tr_d)
     out.update(tr_layinc=layinc, tr_scale=scale, tr_nlayin=nlayin, tr_tau=taug * 1e-3, tr_dk=dk * 1e-3,
                tr_gas_slot=c["gas_slot"], tr_taucon=c["taucon"], tr_dtaucon=c["dtaucon"], tr_spec=tr_s, tr_dspec=tr_d)
+    # ---- instrument line shape: Measurement_0.convg, FWHM == 0 and FWHM < 0 (:2467-2692) --------------------------
+    from archnemesis_dist_b200 import plan as b2plan
+    rng = np.random.default_rng(23)
+    cw = np.linspace(600.0, 640.0, 161)                      # calculation grid
+    cy = rng.uniform(0.5, 2.0, 161) * 1e-7
+    cg = rng.normal(size=(161, 5)) * 1e-9
+    vconv = np.sort(rng.uniform(603.0, 637.0, 11))
+    vconv[3], vconv[10] = cw[40], cw[160]                    # on a knot, and on the last knot
+    M0 = ans.Measurement_0(NGEOM=1, FWHM=0.0, NCONV=np.array([11], dtype="int32"))
+    M0.VCONV = vconv.reshape(11, 1)
+    y0, g0 = M0.convg(cw, cy, cg, IGEOM=0)
+    op0 = b2plan.conv_operator(cw, vconv, 0.0)
+    assert np.array_equal(orc.apply_conv(op0, cy), y0) and np.array_equal(orc.apply_conv(op0, cg), g0)
+    assert np.array_equal(M0.conv(cw, cy, IGEOM=0), y0)
+    vconv1 = np.clip(vconv, 604.0, 636.0)                    # the filters must stay inside the calculation grid
+    nfil = np.array([5, 7, 9, 4, 6, 8, 5, 7, 9, 6, 4], dtype="int32")
+    vfil = np.zeros((9, 11))
+    afil = np.zeros((9, 11))
+    for ic in range(11):
+        half = rng.uniform(0.6, 2.4)
+        vfil[:nfil[ic], ic] = np.linspace(vconv1[ic] - half, vconv1[ic] + half, nfil[ic])
+        afil[:nfil[ic], ic] = np.maximum(0.0, 1.0 - np.abs(np.linspace(-1.0, 1.0, nfil[ic])) ** 2) + 1e-3 * (ic % 3 == 0)
+    M1 = ans.Measurement_0(NGEOM=1, FWHM=-1.0, NCONV=np.array([11], dtype="int32"))
+    M1.VCONV, M1.NFIL, M1.VFIL, M1.AFIL = vconv1.reshape(11, 1), nfil, vfil, afil
+    y1, g1 = M1.convg(cw, cy, cg, IGEOM=0)
+    op1 = b2plan.conv_operator(cw, vconv1, -1.0, nfil, vfil, afil)
+    assert np.array_equal(orc.apply_conv(op1, cy), y1) and np.array_equal(orc.apply_conv(op1, cg), g1)
+    assert np.array_equal(M1.conv(cw, cy, IGEOM=0), y1)
+    out.update(cv_wave=cw, cv_y=cy, cv_grad=cg, cv_vconv=vconv, cv_vconv1=vconv1, cv_nfil=nfil, cv_vfil=vfil, cv_afil=afil,
+               cv_y0=y0, cv_g0=g0, cv_y1=y1, cv_g1=g1)
     # ---- map2pro / map2xvec -----------------------------------------------------------------------------
     rng = np.random.default_rng(5)
     dspec = rng.normal(size=(5, c["NPAR"], 9, 1))

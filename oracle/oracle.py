@@ -363,3 +363,32 @@ def lbl_absorption(wn_grid, lines, t_calc, p_calc, t_ref, p_ref, q_ratio, abunda
                              _p(nu), _p(sw), _p(el), _p(st), len(nu), ctypes.c_double(s_floor),
                              ctypes.c_double(wn_calc_window), ctypes.c_double(wn_approx_window), _p(out))
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# instrument line shape: Measurement_0.conv / convg for k-tables (Measurement_0.py:2288-2692)
+# ----------------------------------------------------------------------------------------------
+def apply_conv(op, y):
+    """Apply a conv operator (archnemesis_dist_b200.plan.conv_operator layout, host arrays) to y[NWAVE]
+    (spectrum) or y[NWAVE,NCOL] (gradients) in the reference's arithmetic.  Mode 0: np.interp's slope form for
+    a 1-D y, SciPy's two-weight form for a 2-D y; mode 1: sequential sum(f1*y)/sum(f1)."""
+    y = np.asarray(y, dtype=np.float64)
+    one_d = y.ndim == 1
+    y2 = y.reshape(len(y), -1)
+    out = np.zeros((op["NCONV"], y2.shape[1]))
+    rs, wi, wv = op["row_start"], op["widx"], op["wval"]
+    for c in range(op["NCONV"]):
+        if op["mode"] == 0 and one_d:
+            j = op["np_lo"][c]
+            x_lo, x_hi, x_new = op["xinfo"][c]
+            if op["np_exact"][c]:
+                out[c] = y2[j]
+            else:
+                slope = (y2[j + 1] - y2[j]) / (x_hi - x_lo)
+                out[c] = slope * (x_new - x_lo) + y2[j]
+        else:
+            acc = np.zeros(y2.shape[1])
+            for e in range(rs[c], rs[c + 1]):
+                acc = acc + wv[e] * y2[wi[e]]
+            out[c] = acc / op["norm"][c] if op["mode"] == 1 else acc
+    return out[:, 0] if one_d else out

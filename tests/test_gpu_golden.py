@@ -100,6 +100,26 @@ def test_stage_golden_transmission_limb_paths():
     assert relerr(cpu(s0), g["tr_spec"]) < 1e-13
 
 
+def test_stage_golden_convolve():
+    """ansb200_convolve on [spectrum | gradient columns] against Measurement_0.convg of the live reference:
+    bit-identical in both k-table modes, also through a strided view."""
+    import torch
+    from archnemesis_dist_b200 import ops, plan
+    g = load("stages.npz")
+    block = torch.from_numpy(np.concatenate([g["cv_y"][:, None], g["cv_grad"]], axis=1)).cuda()
+    for op, ys, gs in ((plan.conv_operator(g["cv_wave"], g["cv_vconv"], 0.0), g["cv_y0"], g["cv_g0"]),
+                       (plan.conv_operator(g["cv_wave"], g["cv_vconv1"], -1.0, g["cv_nfil"], g["cv_vfil"], g["cv_afil"]),
+                        g["cv_y1"], g["cv_g1"])):
+        out = cpu(ops.convolve(ops.ConvOperator(op), block))
+        assert np.array_equal(out[:, 0], ys) and np.array_equal(out[:, 1:], gs)
+        wide = torch.zeros((block.shape[0], 9), dtype=torch.float64, device="cuda")
+        wide[:, :6] = block
+        out2 = cpu(ops.convolve(ops.ConvOperator(op), wide[:, :6]))
+        assert np.array_equal(out2, out)
+        only_grad = cpu(ops.convolve(ops.ConvOperator(op), block[:, 1:].contiguous(), col0_is_spectrum=False))
+        assert np.array_equal(only_grad, gs)
+
+
 def test_stage_golden_projection_and_lbl():
     from archnemesis_dist_b200 import ops, plan, lbl
     g = load("stages.npz")

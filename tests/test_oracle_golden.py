@@ -48,6 +48,25 @@ def test_transmission_stage_golden():
     assert np.array_equal(s, g["tr_spec"]) and np.array_equal(d, g["tr_dspec"])
 
 
+def test_conv_operator_goldens():
+    """plan.conv_operator + oracle.apply_conv against the live reference's Measurement_0.convg / conv in
+    both k-table modes (FWHM == 0: interp1d, with points on a knot and on the last knot; FWHM < 0: filter
+    mean).  Bit-identical."""
+    from archnemesis_dist_b200 import plan
+    g = load("stages.npz")
+    op0 = plan.conv_operator(g["cv_wave"], g["cv_vconv"], 0.0)
+    assert np.array_equal(orc.apply_conv(op0, g["cv_y"]), g["cv_y0"])
+    assert np.array_equal(orc.apply_conv(op0, g["cv_grad"]), g["cv_g0"])
+    op1 = plan.conv_operator(g["cv_wave"], g["cv_vconv1"], -1.0, g["cv_nfil"], g["cv_vfil"], g["cv_afil"])
+    assert np.array_equal(orc.apply_conv(op1, g["cv_y"]), g["cv_y1"])
+    assert np.array_equal(orc.apply_conv(op1, g["cv_grad"]), g["cv_g1"])
+    import pytest
+    with pytest.raises(ValueError):
+        plan.conv_operator(g["cv_wave"], g["cv_vconv"], 0.5)                       # convg raises for FWHM > 0
+    with pytest.raises(ValueError):
+        plan.conv_operator(g["cv_wave"], np.array([599.0]), 0.0)                   # interp1d bounds_error
+
+
 def test_projection_stage_goldens():
     g = load("stages.npz")
     c = stage_table()
