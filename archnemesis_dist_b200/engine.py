@@ -213,6 +213,28 @@ class HotPath:
         spec[NWAVE,NPATH], dspec_x[NWAVE,NPATH,NX], dtsurf[NWAVE,NPATH]."""
         return self._evaluate(ev, True, M)
 
+    def forward_jacobian_conv(self, ev: Evaluation, M, conv_op, jsurf=-1, wgeom=1.0):
+        """forward_jacobian followed on the device by what nemesisfmg does with its result for one geometry
+        without averaging (ForwardModel_0.py:716-768): the surface-temperature column (dSPEC1[:,0,JSURF] =
+        dTSURF), the WGEOM weight, and the instrument line shape of Measurement_0.convg (k-tables, FWHM <= 0;
+        ``conv_op`` = ops.ConvOperator(plan.conv_operator(...))).  Returns one device tensor
+        [NCONV, 1+NX] = [SPECONV | dSPECONV]: the only array that has to travel back to the host."""
+        spec, dx, dtsurf = self._evaluate(ev, True, M)
+        nw, nx = dx.shape[0], dx.shape[2]
+        block = torch.empty((nw, nx + 1), dtype=torch.float64, device="cuda")
+        block[:, 0] = spec[:, 0]
+        block[:, 1:] = dx[:, 0, :]
+        if jsurf >= 0:
+            block[:, 1 + jsurf] = dtsurf[:, 0]
+        if wgeom != 1.0:
+            block *= float(wgeom)
+        self.launches += 1
+        return self.ops.convolve(conv_op, block)
+
+    def conv_operator(self, op):
+        """Device copy of a plan.conv_operator (kept by the caller for the life of a retrieval)."""
+        return self.ops.ConvOperator(op)
+
     @staticmethod
     def to_host(t):
         """Device tensor -> numpy array (synchronises the current stream)."""

@@ -242,6 +242,27 @@ class B200HotPathMixin:
             dSPEC1[:, 0, self.Variables.JSURF] = dTSURF[:, 0]      # :717-718
         return SPEC1, dSPEC1
 
+    def b200_device_conv_ok(self, IGEOM):
+        """Can the tail of nemesisfmg for this geometry (JSURF column, WGEOM weight, Measurement_0.convg) run on
+        the device?  One averaging point, no telluric transmission, spectral radiance units, k-tables with
+        FWHM <= 0 (the only modes the reference's convg supports with k-tables), and a path type on the device."""
+        M = self.Measurement
+        return (self._b200_mode() is not None and int(M.NAV[IGEOM]) == 1 and self.Telluric is None and
+                int(M.IFORM) != _IFORM_INTEGRATED_RADIANCE and int(self.Spectroscopy.ILBL) == _K_TABLES and
+                float(M.FWHM) <= 0.0 and self.PathX.NPATH == 1)
+
+    def b200_forward_jacobian_conv(self, xmap, IGEOM, wgeom):
+        """b200_forward_jacobian + the JSURF column + WGEOM + Measurement_0.convg (:716-768) with only
+        [NCONV, 1+NX] coming back from the device.  Returns SPECONV1[NCONV], dSPECONV1[NCONV,NX]."""
+        atm, lay, path, M = self.AtmosphereX, self.LayerX, self.PathX, self.Measurement
+        hp = self._b200_hotpath()
+        ev = self._b200_evaluation(self._b200_mode(), True)
+        Mx = _plan.fold_projection(xmap, path.LAYINC, path.NLAYIN, lay.DTE, lay.DAM, lay.DCO, atm.NVMR, atm.NDUST)
+        n = int(M.NCONV[IGEOM])
+        op = _plan.conv_operator(self.SpectroscopyX.WAVE, M.VCONV[0:n, IGEOM], float(M.FWHM), M.NFIL, M.VFIL, M.AFIL)
+        out = hp.to_host(hp.forward_jacobian_conv(ev, Mx, hp.conv_operator(op), int(self.Variables.JSURF), float(wgeom)))
+        return out[:, 0], out[:, 1:]
+
 
 class ArrayForwardModel(B200HotPathMixin):
     """The mix-in over plain namespaces: for hosts without the reference package.  `objects` maps
@@ -313,6 +334,7 @@ def make_forward_model_class(reference_cls):
                 NW = self.SpectroscopyX.NWAVE
                 SPEC = np.zeros(NW)
                 dSPEC = np.zeros((NW, self.Variables.NX))
+                conv_done = False
                 for IAV in range(M.NAV[IGEOM]):
                     self.select_Measurement(IGEOM, IAV)
                     self.AtmosphereX = deepcopy(self.Atmosphere)
@@ -333,6 +355,11 @@ def make_forward_model_class(reference_cls):
                     xmap = self.subprofretg()
                     self.LayerX.DUST_UNITS_FLAG = self.AtmosphereX.DUST_UNITS_FLAG
                     self.calc_pathg()
+                    if self.b200_device_conv_ok(IGEOM):
+                        # spectrum, Jacobian and the instrument line shape on the device: [NCONV, 1+NX] comes back
+                        S1, dS1 = self.b200_forward_jacobian_conv(xmap, IGEOM, M.WGEOM[IGEOM, IAV])
+                        conv_done = True
+                        break
                     SPEC1, dSPEC1 = self.b200_forward_jacobian(xmap)
                     if M.NAV[IGEOM] >= 1:
                         SPEC[:] = SPEC[:] + M.WGEOM[IGEOM, IAV] * SPEC1[:, 0]
@@ -340,6 +367,11 @@ def make_forward_model_class(reference_cls):
                     else:
                         SPEC[:] = SPEC1[:, 0]
                         dSPEC[:, :] = dSPEC1[:, 0, :]
+                if conv_done:
+                    n = M.NCONV[IGEOM]
+                    SPECONV[0:n, IGEOM] = S1[0:n]
+                    dSPECONV[0:n, IGEOM, :] = dS1[0:n, :]
+                    continue
                 if self.TelluricX is not None:
                     tmin, tmax = M.calc_wave_range(apply_doppler=False, IGEOM=IGEOM)
                     self.TelluricX.Spectroscopy.read_tables(wavemin=tmin, wavemax=tmax)

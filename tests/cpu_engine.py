@@ -73,6 +73,18 @@ class HotPath:
     def forward_jacobian(self, ev, M):
         return self.run(self.stage(ev, True, M))
 
+    def forward_jacobian_conv(self, ev, M, conv_op, jsurf=-1, wgeom=1.0):
+        spec, dx, dts = self.forward_jacobian(ev, M)
+        block = np.concatenate([spec[:, :1], dx[:, 0, :]], axis=1)
+        if jsurf >= 0:
+            block[:, 1 + jsurf] = dts[:, 0]
+        if wgeom != 1.0:
+            block = block * float(wgeom)
+        return np.concatenate([orc.apply_conv(conv_op, block[:, 0])[:, None], orc.apply_conv(conv_op, block[:, 1:])], axis=1)
+
+    def conv_operator(self, op):
+        return op
+
     @staticmethod
     def to_host(t):
         return np.asarray(t)

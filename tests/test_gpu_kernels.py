@@ -352,3 +352,39 @@ def test_lbl_absorption_matches_oracle(mods):
     for i, (t, p, q) in enumerate(pts):
         ref = orc.lbl_absorption(wn, lines, t, p, 296.0, 1.0, q, 0.98, 28.0, mix)
         assert relerr(cpu(out[i]), ref) < 1e-11, i
+
+
+@pytest.mark.parametrize("fwhm", [0.0, -1.0])
+def test_engine_forward_jacobian_conv(mods, fwhm):
+    """HotPath.forward_jacobian_conv (spectrum + Jacobian + JSURF column + WGEOM + instrument line shape on the
+    device, only [NCONV, 1+NX] returned) equals the same evaluation convolved on the host by the oracle's
+    restatement of Measurement_0.convg -- bit for bit, since the operator arithmetic is the reference's."""
+    from archnemesis_dist_b200 import engine
+    plan, orc = mods["plan"], mods["orc"]
+    c = _case(mods, nwave=40, ng=20, ngas=3, nlay=15, npro=15, nx=9, nvmr=4, seed=61, tsurf=160.0)
+    tab = c["tab"]
+    hp = engine.HotPath(tab["K"], tab["PRESS"], tab["TEMP"], tab["DELG"], tab["WAVE"])
+    ev = engine.Evaluation(press_atm=c["press"], temp=c["temp"], amount=c["amount"], gas_slot=c["gas_slot"],
+                           NVMR=c["NVMR"], NPAR=c["NPAR"], LAYINC=c["LAYINC"], SCALE=c["SCALE"], NLAYIN=c["NLAYIN"],
+                           EMTEMP=c["EMTEMP"], LAYPRESS=c["LAYPRESS"], taucia=c["taucon"], dtaucon=c["dtaucon"],
+                           TSURF=c["TSURF"], EMISSIVITY=c["EMISSIVITY"], xfac=c["xfac"])
+    M = plan.fold_projection(c["xmap"], c["LAYINC"], c["NLAYIN"], c["DTE"], c["DAM"], c["DCO"], c["NVMR"], c["NDUST"])
+    wave = tab["WAVE"]
+    vconv = np.linspace(wave[4], wave[-5], 7)          # filters of +-0.6 stay inside the 0.25-spaced grid
+    vconv[2] = wave[11]
+    if fwhm == 0.0:
+        op = plan.conv_operator(wave, vconv, 0.0)
+    else:
+        nfil = np.full(7, 5, np.int32)
+        vfil = np.stack([np.linspace(v - 0.6, v + 0.6, 5) for v in vconv], axis=1)
+        afil = np.tile(np.array([0.0, 0.5, 1.0, 0.5, 0.0])[:, None], (1, 7))
+        op = plan.conv_operator(wave, vconv, -1.0, nfil, vfil, afil)
+    jsurf, wgeom = 4, 0.75
+    out = cpu(hp.forward_jacobian_conv(ev, M, hp.conv_operator(op), jsurf, wgeom))
+    spec, dx, dts = (cpu(t) for t in hp.forward_jacobian(ev, M))
+    block = np.concatenate([spec[:, :1], dx[:, 0, :]], axis=1)
+    block[:, 1 + jsurf] = dts[:, 0]
+    block = block * wgeom
+    assert np.array_equal(out[:, 0], orc.apply_conv(op, block[:, 0]))
+    assert np.array_equal(out[:, 1:], orc.apply_conv(op, block[:, 1:]))
+    hp.close()
