@@ -73,3 +73,38 @@ def geometries(evaluate, n_geom):
     else:
         raise ValueError("fewer geometries than ranks: give every rank at least one geometry")
     return all_gather_rows(S, n_geom, dim=0), all_gather_rows(J, n_geom, dim=0)
+
+
+class WavenumberShard:
+    """Wavenumber sharding: every stage of the path is independent per wavenumber, so rank r
+    keeps only rows [lo, hi) of the k-table resident (1/R of the memory and of every kernel's work, nothing
+    duplicated -- unlike geometry sharding, which repeats the gas opacity on every rank) and the ranks'
+    [spectrum | Jacobian] row blocks are all-gathered.  The instrument line shape mixes neighbouring
+    wavenumbers, so it is applied after the gather (or through forward_jacobian_conv on the gathered block).
+
+    make_hotpath(K, PRESS, TEMP, DELG, WAVE) builds the rank's engine (engine.HotPath on the device)."""
+
+    def __init__(self, make_hotpath, K, PRESS, TEMP, DELG, WAVE, rank=None, world=None):
+        self.NWAVE = int(np.shape(K)[0])
+        self.lo, self.hi = my_chunk(self.NWAVE, rank, world)
+        if self.hi <= self.lo:
+            raise ValueError("fewer wavenumbers than ranks")
+        self.hotpath = make_hotpath(np.ascontiguousarray(K[self.lo:self.hi]), PRESS, TEMP, DELG,
+                                    np.ascontiguousarray(np.asarray(WAVE)[self.lo:self.hi]))
+
+    def slice_evaluation(self, ev):
+        """The rank's rows of the per-wavenumber inputs of an Evaluation (continuum terms, emissivity, ...)."""
+        import copy
+        e = copy.copy(ev)
+        for name in ("taucia", "taudust", "tauray", "dtaucon", "EMISSIVITY", "xfac", "SOLFLUX", "REFLECTANCE"):
+            a = getattr(ev, name)
+            if a is not None:
+                setattr(e, name, np.ascontiguousarray(np.asarray(a)[self.lo:self.hi]))
+        return e
+
+    def forward_jacobian(self, ev, M, to_tensor=None):
+        """spec[NWAVE,NPATH], dspec_x[NWAVE,NPATH,NX], dtsurf[NWAVE,NPATH] (full, on every rank)."""
+        out = self.hotpath.forward_jacobian(self.slice_evaluation(ev), M)
+        if to_tensor is not None:
+            out = tuple(to_tensor(o) for o in out)
+        return tuple(all_gather_rows(o, self.NWAVE, dim=0) for o in out)

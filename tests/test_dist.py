@@ -1,5 +1,5 @@
 """CPU, world_size 2 over gloo: the sharding + all-gather plumbing of archnemesis_dist_b200/dist.py
-(column sharding and geometry sharding) with the oracle-backed engine standing in for the device."""
+(column, geometry and wavenumber sharding) with the oracle-backed engine standing in for the device."""
 import os
 import socket
 
@@ -61,6 +61,12 @@ def _worker(rank, world, port, out_dir):
         for i in range(3):
             s, d, _ = hp.forward_jacobian(make_ev(scales[i]), M)
             assert np.array_equal(YN[i].numpy(), s[:, 0]) and np.array_equal(KK[i].numpy(), d[:, 0, :])
+        # (3) wavenumber sharding (NWAVE=3 over 2 ranks: ragged 2 + 1), two paths
+        ws = adist.WavenumberShard(cpu_engine.HotPath, tab["K"], tab["PRESS"], tab["TEMP"], tab["DELG"], tab["WAVE"])
+        got = ws.forward_jacobian(make_ev(1.0), M, to_tensor=t)
+        for a, b in zip(got, full):
+            # (the stand-in engine projects with einsum, whose blocking depends on the row count: compare to rounding)
+            assert a.shape == b.shape and np.abs(a.numpy() - b).max() <= 1e-13 * np.abs(b).max()
         open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
     finally:
         dist.destroy_process_group()
