@@ -231,6 +231,12 @@ class HotPath:
         self.launches += 1
         return self.ops.convolve(conv_op, block)
 
+    def project(self, dspec, M):
+        """Layer-space gradients still on the device x host-folded projection matrix -> dspec_x[NWAVE,NPATH,NX]
+        (map2pro + map2xvec, ForwardModel_0.py:5319-5424)."""
+        self.launches += 1
+        return self.ops.jacobian_project(dspec, self.ops.to_dev(M))
+
     def conv_operator(self, op):
         """Device copy of a plan.conv_operator (kept by the caller for the life of a retrieval)."""
         return self.ops.ConvOperator(op)

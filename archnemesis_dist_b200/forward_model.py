@@ -8,6 +8,10 @@ signatures and return shapes:
     calculate_gaseous_line_opacity(return_grad)      :3781-3891   (K_TABLES branch)
     calculate_layer_opacity(return_grad)             :3905-4016
     nemesisfmg() inner triple CIRSrad -> map2pro -> map2xvec       :694-718   (fused, see b200_forward_jacobian)
+    map2pro / map2xvec (module functions)            :5319-5424   (rebound by install(): CIRSrad's gradient stays on
+                                                     the device as a DeviceGradient and the projection is fused for
+                                                     every driver -- nemesisSOfmg :1188-1206, nemesisLfmg :1452-1470,
+                                                     process_IAV :2039-2059 -- without overriding them)
 
 It reads only the attributes the reference methods read (``SpectroscopyX``, ``LayerX``, ``PathX``,
 ``AtmosphereX``, ``SurfaceX``, ``MeasurementX``, ``ScatterX``, ``StellarX``, ``Variables``) and
@@ -69,6 +73,92 @@ class _TableCache:
 
 
 _TABLES = _TableCache()
+
+
+class DeviceGradient:
+    """What CIRSrad(return_grad=True) returns in place of dSPECOUT[NWAVE,NPAR,NLAYIN,NPATH] once install() is
+    active: the layer-space Jacobian stays on the device.  The reference's drivers (nemesisfmg, nemesisSOfmg,
+    nemesisLfmg, process_IAV) hand it straight to the module functions ``map2pro`` and ``map2xvec``
+    (ForwardModel_0.py:694-714, :1188-1206, :1452-1470, :2039-2059); install() rebinds those two names to
+    wrappers that recognise this object and run the fused projection on the device, so the 4-D array (64 MB
+    per path at config 2) never crosses PCIe.  Any other use -- indexing, numpy functions -- materialises it
+    through ``__array__`` in the reference's layout, so code that looks at dSPECOUT directly still works."""
+
+    def __init__(self, hotpath, dspec_dev, shape):
+        self._hp, self._dev, self.shape = hotpath, dspec_dev, tuple(shape)
+        self.ndim, self.dtype = 4, np.dtype(np.float64)
+        self._host = None
+
+    def materialise(self):
+        if self._host is None:
+            self._host = np.ascontiguousarray(np.transpose(self._hp.to_host(self._dev), (0, 2, 3, 1)))
+        return self._host
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.materialise()
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, idx):
+        return self.materialise()[idx]
+
+    def __len__(self):
+        return self.shape[0]
+
+
+class ProfileGradient:
+    """map2pro applied lazily to a DeviceGradient: remembers the layer->profile matrices so that map2xvec can
+    fold them with xmap into one projection (plan.fold_projection) and run it on the device."""
+
+    def __init__(self, grad, NVMR, NDUST, NPRO, NPATH, NLAYIN, LAYINC, DTE, DAM, DCO, INCPAR, fallback):
+        self.grad, self.args, self.INCPAR, self._fallback = grad, (NVMR, NDUST, NPRO, NPATH, NLAYIN, LAYINC, DTE, DAM, DCO), INCPAR, fallback
+        self.shape = (grad.shape[0], NVMR + 2 + NDUST, NPRO, NPATH)
+        self.ndim, self.dtype = 4, np.dtype(np.float64)
+        self._host = None
+
+    def materialise(self):
+        if self._host is None:
+            NVMR, NDUST, NPRO, NPATH, NLAYIN, LAYINC, DTE, DAM, DCO = self.args
+            self._host = self._fallback(self.grad.materialise(), self.grad.shape[0], NVMR, NDUST, NPRO, NPATH, NLAYIN,
+                                        LAYINC, DTE, DAM, DCO, INCPAR=self.INCPAR)
+        return self._host
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.materialise()
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, idx):
+        return self.materialise()[idx]
+
+    def __len__(self):
+        return self.shape[0]
+
+
+def make_fused_map_functions(ref_map2pro, ref_map2xvec):
+    """Wrappers for the module-level map2pro / map2xvec of archnemesis.ForwardModel_0 (:5319-5424): identical to
+    the reference for ordinary arrays; for a DeviceGradient they defer and then project on the device."""
+
+    def map2pro(dSPECIN, NWAVE, NVMR, NDUST, NPRO, NPATH, NLAYIN, LAYINC, DTE, DAM, DCO, INCPAR=[-1]):
+        if isinstance(dSPECIN, DeviceGradient):
+            return ProfileGradient(dSPECIN, NVMR, NDUST, NPRO, NPATH, NLAYIN, LAYINC, DTE, DAM, DCO, INCPAR, ref_map2pro)
+        return ref_map2pro(dSPECIN, NWAVE, NVMR, NDUST, NPRO, NPATH, NLAYIN, LAYINC, DTE, DAM, DCO, INCPAR=INCPAR)
+
+    def map2xvec(dSPECIN, NWAVE, NVMR, NDUST, NPRO, NPATH, NX, xmap):
+        if isinstance(dSPECIN, ProfileGradient):
+            pg = dSPECIN
+            nvmr, ndust, npro, npath, NLAYIN, LAYINC, DTE, DAM, DCO = pg.args
+            inc = list(pg.INCPAR)
+            # the fused matrix applies the reference's own inclusion rule (parameters whose xmap mean is non-zero,
+            # :699-702); any other INCPAR goes through the reference functions on the materialised array
+            if inc == _plan.included_params(xmap) and pg._host is None and pg.grad._host is None:
+                M = _plan.fold_projection(xmap, LAYINC, NLAYIN, DTE, DAM, DCO, nvmr, ndust)
+                hp = pg.grad._hp
+                return hp.to_host(hp.project(pg.grad._dev, M))
+            dSPECIN = pg.materialise()
+        return ref_map2xvec(np.asarray(dSPECIN), NWAVE, NVMR, NDUST, NPRO, NPATH, NX, xmap)
+
+    map2pro.__doc__ = (ref_map2pro.__doc__ or "") + "\n(archnemesis_dist_b200: defers for device-resident gradients)"
+    map2xvec.__doc__ = (ref_map2xvec.__doc__ or "") + "\n(archnemesis_dist_b200: fused projection on the device)"
+    return map2pro, map2xvec
 
 
 class B200HotPathMixin:
@@ -214,6 +304,10 @@ class B200HotPathMixin:
         if not return_grad:
             return hp.to_host(out)
         spec, dspec, dtsurf = out
+        if _INSTALLED.get("lazy_gradients") and hasattr(hp, "project"):
+            # (NWAVE, NPAR, NLAYIN, NPATH) like the reference, but still on the device: see DeviceGradient
+            nw, npath, npar, nlm = dspec.shape
+            return hp.to_host(spec), DeviceGradient(hp, dspec, (nw, npar, nlm, npath)), hp.to_host(dtsurf)
         return hp.to_host(spec), np.ascontiguousarray(np.transpose(hp.to_host(dspec), (0, 2, 3, 1))), hp.to_host(dtsurf)
 
     def b200_forward_jacobian(self, xmap):
@@ -412,6 +506,12 @@ def install(archnemesis=None):
     oe = sys.modules.get("archnemesis.OptimalEstimation_0")
     if oe is not None and hasattr(oe, "ForwardModel_0"):
         oe.ForwardModel_0 = cls
+    # the two module functions every driver calls by bare name after CIRSrad: with them
+    # rebound, nemesisSOfmg / nemesisLfmg / process_IAV get the fused device projection unchanged
+    if "map2pro" not in _INSTALLED:
+        _INSTALLED.update(map2pro=mod.map2pro, map2xvec=mod.map2xvec)
+    mod.map2pro, mod.map2xvec = make_fused_map_functions(_INSTALLED["map2pro"], _INSTALLED["map2xvec"])
+    _INSTALLED["lazy_gradients"] = True
     return cls
 
 
@@ -422,6 +522,10 @@ def uninstall(archnemesis=None):
         import archnemesis  # noqa: F811
     ref_cls = _INSTALLED.pop("reference")
     _INSTALLED.pop("cls", None)
+    _INSTALLED.pop("lazy_gradients", None)
+    if "map2pro" in _INSTALLED:
+        sys.modules["archnemesis.ForwardModel_0"].map2pro = _INSTALLED.pop("map2pro")
+        sys.modules["archnemesis.ForwardModel_0"].map2xvec = _INSTALLED.pop("map2xvec")
     sys.modules["archnemesis.ForwardModel_0"].ForwardModel_0 = ref_cls
     archnemesis.ForwardModel_0 = ref_cls
     oe = sys.modules.get("archnemesis.OptimalEstimation_0")

@@ -82,6 +82,10 @@ class HotPath:
             block = block * float(wgeom)
         return np.concatenate([orc.apply_conv(conv_op, block[:, 0])[:, None], orc.apply_conv(conv_op, block[:, 1:])], axis=1)
 
+    def project(self, dspec, M):
+        nwv, npath, npar, nlm = dspec.shape
+        return np.einsum("wpe,pex->wpx", np.asarray(dspec).reshape(nwv, npath, npar * nlm), M)
+
     def conv_operator(self, op):
         return op
 

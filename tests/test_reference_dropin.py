@@ -52,12 +52,23 @@ def test_install_rebinds_three_names_and_matches_reference(jupiter):
             assert dspec.shape == (fm.SpectroscopyX.NWAVE, fm.AtmosphereX.NVMR + 2 + fm.ScatterX.NDUST,
                                    fm.PathX.NLAYIN.max(), fm.PathX.NPATH)
             tg, dtg = fm.calculate_gaseous_line_opacity(True)
+            # the REFERENCE's own driver body on the drop-in instance: CIRSrad hands back a device-resident
+            # gradient, the rebound module functions map2pro / map2xvec defer and project it on the device --
+            # the route nemesisSOfmg / nemesisLfmg / process_IAV take without being overridden
+            mod = sys.modules["archnemesis.ForwardModel_0"]
+            assert mod.map2pro is not fmod._INSTALLED["map2pro"]
+            assert isinstance(dspec, fmod.DeviceGradient) and np.asarray(dspec).shape == dspec.shape
+            S_lazy, dS_lazy = ref_cls.nemesisfmg(fm)
         finally:
             fmod.uninstall(ans)
         assert ans.ForwardModel_0 is ref_cls
+        assert sys.modules["archnemesis.ForwardModel_0"].map2pro.__module__ == "archnemesis.ForwardModel_0"
         tg_ref, dtg_ref = ref_cls.calculate_gaseous_line_opacity(fm, True)
     finally:
         os.chdir(cwd)
+    assert relerr(S_lazy, S_ref) < 1e-12
+    for ix in range(dS_ref.shape[2]):
+        assert colerr(dS_lazy[:, :, ix], dS_ref[:, :, ix]) < 1e-11, ix
     assert relerr(S, S_ref) < 1e-12 and relerr(S0, S0_ref) < 1e-12
     for ix in range(dS_ref.shape[2]):
         assert colerr(dS[:, :, ix], dS_ref[:, :, ix]) < 1e-11, ix
