@@ -207,10 +207,30 @@ struct LblParams {
 
 #define ANS_C2_CGS (2.99792458E10 * 6.62607015E-27 / 1.380649E-16)
 
+// Voigt profile from per-line constants: inv_s2 = 1/(sigma sqrt 2), zimag = gamma/(sigma sqrt 2),
+// vnorm = 1/(sigma sqrt(2 pi)).  Within the +-25 cm-1 core window almost every pair has |z| > 4000 (sigma is
+// ~1e-3 cm-1), where the Faddeeva package's continued fraction is the closed form of its nu == 2 case:
+// one reciprocal instead of the five divisions of voigt_profile + w(z).  Everything else goes through the
+// general routine.  Differences from the division-by-division evaluation are a few ulp.
+__device__ __forceinline__ double ans_voigt_from_constants(double d, double inv_s2, double zimag, double vnorm)
+{
+    const double ispi = 0.56418958354775628694807945156;
+    const double x = fabs(d * inv_s2);
+    const double s = x + zimag;
+    if (s > 4000.0 && s <= 1.0e7) {
+        const double dr = x * x - zimag * zimag - 0.5, di = 2 * x * zimag;
+        const double denom = ispi * __drcp_rn(dr * dr + di * di);
+        return denom * (x * di - zimag * dr) * vnorm;
+    }
+    return ans_faddeeva_re(d * inv_s2, zimag) * vnorm;
+}
+
 __global__ void __launch_bounds__(LBL_THREADS)
 ans_lbl_kernel(LblParams P)
 {
-    __shared__ double s_nu[LBL_TILE], s_str[LBL_TILE], s_ad[LBL_TILE], s_gl[LBL_TILE], s_ac[LBL_TILE];
+    // per-line constants of the tile: shifted centre, abundance*strength, wing constant abundance*S*V(25)*25^2,
+    // and either the Voigt constants (fast) or (alpha_D, gamma_L) for the general line-shape routine
+    __shared__ double s_nu[LBL_TILE], s_A[LBL_TILE], s_W[LBL_TILE], s_c0[LBL_TILE], s_c1[LBL_TILE], s_c2[LBL_TILE];
     __shared__ unsigned char s_live[LBL_TILE];
     const int ipt = blockIdx.y;
     const double t_calc = P.pt[3 * ipt], p_calc = P.pt[3 * ipt + 1], q_ratio = P.pt[3 * ipt + 2];
@@ -231,45 +251,62 @@ ans_lbl_kernel(LblParams P)
     const double boltz = c2 * (t_calc - P.t_ref) / (t_calc * P.t_ref);
     const double t_ratio = P.t_ref / t_calc, p_ratio = p_calc / P.p_ref;
     const double cw2 = P.calc_win * P.calc_win;   // wn_calc_window_max**2.
+    const double SQRT_2LOG2 = 1.1774100225154747, INV_SQRT_2 = 0.707106781186547524401;
+    const double SQRT_2PI = 2.5066282746310002416123552393401042;
 
     for (int i0 = 0; i0 < P.N; i0 += LBL_TILE) {
         const int i = i0 + threadIdx.x;
         // derive the state-dependent parameters of one line per thread (LineData_0.py:123-226)
-        bool live = false;
+        unsigned char live = 0;
         if (threadIdx.x < LBL_TILE) {
-            double nus = 0, str = 0, ad = 0, gl = 0, ac = 0;
+            double nus = 0, A = 0, W = 0, k0 = 0, k1 = 0, k2 = 0;
             if (i < P.N) {
                 const double nui = P.nu[i];
-                str = P.sw[i] * ((1 - exp(-c2 * nui / t_calc)) / P.stim_ref[i]) * exp(boltz * P.e_lower[i]) * q_ratio;
-                double shift = 0;
+                const double str = P.sw[i] * ((1 - exp(-c2 * nui / t_calc)) / P.stim_ref[i]) * exp(boltz * P.e_lower[i]) * q_ratio;
+                double shift = 0, gl = 0;
                 for (int m = 0; m < P.M; ++m) {
                     gl += pow(t_ratio, P.broadening[(size_t)(3 * m + 1) * P.N + i]) * P.broadening[(size_t)(3 * m) * P.N + i] *
                           P.mix[m] * p_ratio;
                     shift += (p_ratio * P.broadening[(size_t)(3 * m + 2) * P.N + i]) * P.mix[m];
                 }
-                ad = dconst * nui * sqrt(t_calc / P.mass);
+                const double ad = dconst * nui * sqrt(t_calc / P.mass);
                 nus = nui + shift;
-                live = !(str < P.s_floor) && (wn_lo - nus < P.approx_win) && !(wn_hi - nus < -P.approx_win);
-                if (live) ac = ans_lineshape(P.shape_id, P.calc_win, ad, gl);
+                const bool in_reach = !(str < P.s_floor) && (wn_lo - nus < P.approx_win) && !(wn_hi - nus < -P.approx_win);
+                if (in_reach) {
+                    A = P.abundance * str;
+                    W = A * ans_lineshape(P.shape_id, P.calc_win, ad, gl) * cw2;
+                    const double sigma = ad / SQRT_2LOG2;
+                    if (P.shape_id == 0 && sigma > 0.0 && gl > 0.0) {
+                        live = 1;                                  // Voigt from constants
+                        k0 = INV_SQRT_2 / sigma;
+                        k1 = gl / sigma * INV_SQRT_2;
+                        k2 = 1.0 / sigma / SQRT_2PI;
+                    } else {
+                        live = 2;                                  // general line-shape routine
+                        k0 = ad;
+                        k1 = gl;
+                    }
+                }
             }
-            s_live[threadIdx.x] = live ? 1 : 0;
-            s_nu[threadIdx.x] = nus; s_str[threadIdx.x] = str; s_ad[threadIdx.x] = ad; s_gl[threadIdx.x] = gl;
-            s_ac[threadIdx.x] = ac;
+            s_live[threadIdx.x] = live;
+            s_nu[threadIdx.x] = nus; s_A[threadIdx.x] = A; s_W[threadIdx.x] = W;
+            s_c0[threadIdx.x] = k0; s_c1[threadIdx.x] = k1; s_c2[threadIdx.x] = k2;
         }
         const int any = __syncthreads_or(live ? 1 : 0);
         if (any) {
             const int cnt = min(LBL_TILE, P.N - i0);
             for (int li = 0; li < cnt; ++li) {
-                if (!s_live[li]) continue;
-                const double str = s_str[li], nus = s_nu[li], ad = s_ad[li], gl = s_gl[li], ac = s_ac[li];
+                const int kind = s_live[li];
+                if (!kind) continue;
+                const double nus = s_nu[li], A = s_A[li], W = s_W[li], k0 = s_c0[li], k1 = s_c1[li], k2 = s_c2[li];
 #pragma unroll
                 for (int q = 0; q < LBL_GP; ++q) {
                     const double d = wnj[q] - nus;
                     if (d >= P.approx_win || d < -P.approx_win) continue;
                     if (-P.calc_win <= d && d < P.calc_win)
-                        acc[q] += P.abundance * str * ans_lineshape(P.shape_id, d, ad, gl);
+                        acc[q] += A * (kind == 1 ? ans_voigt_from_constants(d, k0, k1, k2) : ans_lineshape(P.shape_id, d, k0, k1));
                     else
-                        acc[q] += P.abundance * str * ac * cw2 / (d * d);
+                        acc[q] += W * __drcp_rn(d * d);
                 }
             }
         }
