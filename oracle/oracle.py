@@ -392,3 +392,38 @@ def apply_conv(op, y):
                 acc = acc + wv[e] * y2[wi[e]]
             out[c] = acc / op["norm"][c] if op["mode"] == 1 else acc
     return out[:, 0] if one_d else out
+
+
+# ----------------------------------------------------------------------------------------------
+# optimal-estimation linear algebra: OptimalEstimation_0.py:545-720 (numpy restatement)
+# ----------------------------------------------------------------------------------------------
+def oe_gain_matrix(KK, SA, SE):
+    sa_kt = SA @ KK.T
+    M = KK @ sa_kt + SE
+    DD = np.linalg.solve(M.T, sa_kt.T).T
+    return DD, DD @ KK
+
+
+def oe_phiret(Y, YN, XN, XA, SE, SA):
+    b, d = YN - Y, XN - XA
+    if SE.shape == (1, 1):
+        meas = float(np.dot(b, b) / float(SE[0, 0]))
+    elif np.all(SE == np.diag(np.diagonal(SE))):
+        meas = float(np.dot(b / np.diagonal(SE), b))
+    else:
+        meas = float(b.T @ np.linalg.solve(SE, b))
+    apri = float(d.T @ np.linalg.solve(SA, d))
+    return meas / len(b), meas + apri
+
+
+def oe_next_xn(XA, XN, Y, YN, DD, AA):
+    return XA + (DD @ (Y - YN)) - (AA @ (XA - XN))
+
+
+def oe_serr(DD, AA, SA, SE, simple=False):
+    a = DD * SE[0, 0] if simple else DD @ SE
+    SM = a @ DD.T
+    b = AA.copy()
+    b[np.diag_indices_from(b)] -= 1.0
+    SN = (b @ SA) @ b.T
+    return SM, SN, SN + SM

@@ -388,3 +388,35 @@ def test_engine_forward_jacobian_conv(mods, fwhm):
     assert np.array_equal(out[:, 0], orc.apply_conv(op, block[:, 0]))
     assert np.array_equal(out[:, 1:], orc.apply_conv(op, block[:, 1:]))
     hp.close()
+
+
+def test_oe_algebra_on_device(mods):
+    """oe.calc_gain_matrix / calc_phiret / calc_next_xn / calc_serr (cuBLAS / cuSOLVER through torch.linalg) against
+    the numpy restatement of OptimalEstimation_0.py:545-720; tolerance scaled to the conditioning of the solve."""
+    from archnemesis_dist_b200 import oe
+    orc = mods["orc"]
+    rng = np.random.default_rng(11)
+    NY, NX = 300, 24
+    KK = rng.normal(size=(NY, NX))
+    A = rng.normal(size=(NX, NX))
+    SA = A @ A.T + NX * np.eye(NX)
+    Y, YN, XA, XN = rng.normal(size=NY), rng.normal(size=NY), rng.normal(size=NX), rng.normal(size=NX)
+    SE = np.diag(rng.uniform(0.5, 2.0, NY))
+    DD, AA = oe.calc_gain_matrix(KK, SA, SE)
+    rDD, rAA = orc.oe_gain_matrix(KK, SA, SE)
+    # two LU solves of the same NY x NY system (LAPACK on the host, cuSOLVER on the device) agree to
+    # eps * cond(M); everything downstream of DD inherits that
+    tol = 100 * np.finfo(float).eps * np.linalg.cond(KK @ SA @ KK.T + SE)
+    assert 1e-13 < tol < 1e-8
+    assert colerr(cpu(DD), rDD) < tol and colerr(cpu(AA), rAA) < tol
+    xn = oe.calc_next_xn(XA, XN, Y, YN, DD, AA)
+    assert colerr(cpu(xn), orc.oe_next_xn(XA, XN, Y, YN, rDD, rAA)) < tol
+    # SE diagonal, and the reference's (1,1) shorthand (phiret and calc_serr(simple=True); with a (1,1) SE the
+    # reference's gain matrix adds the scalar to EVERY element of kk sa kk^T, which is singular for NY > NX + 1)
+    for SE2, simple in ((SE, False), (np.array([[0.7]]), True)):
+        chisq, phi = oe.calc_phiret(Y, YN, XN, XA, SE2, SA)
+        rc, rp = orc.oe_phiret(Y, YN, XN, XA, SE2, SA)
+        assert abs(chisq - rc) < 1e-12 * abs(rc) and abs(phi - rp) < 1e-12 * abs(rp)
+        SM, SN, ST = oe.calc_serr(DD, AA, SA, SE2, simple=simple)
+        rSM, rSN, rST = orc.oe_serr(rDD, rAA, SA, SE2, simple=simple)
+        assert colerr(cpu(SM), rSM) < tol and colerr(cpu(SN), rSN) < tol and colerr(cpu(ST), rST) < tol

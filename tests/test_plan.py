@@ -92,3 +92,31 @@ def test_oracle_matches_live_reference_functions():
     tr, gr = fm.k_overlapg(tab["DELG"], kr, dr, c["amount"])
     to, go = orc.k_overlap(tab["DELG"], kr, c["amount"], dkdT=dr)
     assert np.array_equal(tr, to) and np.array_equal(gr, go)
+
+
+@pytest.mark.reference
+def test_oracle_oe_algebra_matches_live_reference():
+    """oracle.oe_* against OptimalEstimation_0.calc_gain_matrix / calc_phiret / calc_next_xn / calc_serr of the
+    live reference (OptimalEstimation_0.py:545-720) on a seeded problem."""
+    from oracle.ref_import import import_reference
+    from oracle import oracle as orc
+    ans = import_reference()
+    rng = np.random.default_rng(3)
+    NY, NX = 40, 9
+    OE = ans.OptimalEstimation_0(NX=NX, NY=NY)
+    OE.KK = rng.normal(size=(NY, NX))
+    A = rng.normal(size=(NX, NX))
+    OE.SA = A @ A.T + NX * np.eye(NX)
+    OE.SE = np.diag(rng.uniform(0.5, 2.0, NY))
+    OE.Y, OE.YN = rng.normal(size=NY), rng.normal(size=NY)
+    OE.XA, OE.XN = rng.normal(size=NX), rng.normal(size=NX)
+    OE.calc_gain_matrix()
+    DD, AA = orc.oe_gain_matrix(OE.KK, OE.SA, OE.SE)
+    assert np.array_equal(DD, OE.DD) and np.array_equal(AA, OE.AA)
+    OE.calc_phiret()
+    chisq, phi = orc.oe_phiret(OE.Y, OE.YN, OE.XN, OE.XA, OE.SE, OE.SA)
+    assert chisq == OE.CHISQ and phi == OE.PHI
+    assert np.array_equal(orc.oe_next_xn(OE.XA, OE.XN, OE.Y, OE.YN, OE.DD, OE.AA), OE.calc_next_xn())
+    OE.calc_serr()
+    SM, SN, ST = orc.oe_serr(OE.DD, OE.AA, OE.SA, OE.SE)
+    assert np.array_equal(SM, OE.SM) and np.array_equal(SN, OE.SN) and np.array_equal(ST, OE.ST)
