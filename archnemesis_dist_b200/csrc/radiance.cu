@@ -348,6 +348,124 @@ ans_radiance_kernel(RadParams P)
     }   // paths
 }
 
+// ---- transmission, many paths: one warp per path -----------------------------------------------------
+// calculate_transmission_spectrum (:4104-4129) is spec_g = exp(-sum_j tau_g[l_j] SCALE_j) (* xfac) and
+// d spec_g / d q[k,j] = -spec_g dtau_g[k, l_j] SCALE_j, so after the g-integration of CIRSrad (:4504-4507)
+//     d spec / d q[k,j] = -SCALE_j ( unit_k sum_g c_g dk[g, l_j, col_k] + dtaucon[k, l_j] sum_g c_g ),  c_g = spec_g DELG_g:
+// a path is described by NG numbers.  A CTA stages the wavenumber's tau / dk slabs and the continuum once and
+// each warp then walks its own paths with no CTA barrier: lanes sum the path's opacity per g (phase 1), then
+// sweep the (parameter, layer) outputs with consecutive lanes on consecutive layers (contiguous stores).
+// 5e3 warp instructions per (wavenumber, path) instead of 2.7e4 in the general kernel.
+constexpr int RADT_WARPS = 32;
+
+__global__ void __launch_bounds__(RADT_WARPS * 32)
+ans_transmission_paths_kernel(RadParams P)
+{
+    extern __shared__ __align__(16) unsigned char rad_smem[];
+    const int iw = blockIdx.x;
+    const int NG = P.NG, NLAY = P.NLAY, NLM = P.NLAYMAX, NPATH = P.NPATH, NPAR = P.NPAR, NP1 = P.NGAS + 1;
+    const bool grad = (P.flags & ANSB200_RAD_GRAD) != 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *stau = reinterpret_cast<double *>(rad_smem);          // [NG*NLAY] tau of the wavenumber
+    double *scon = stau + (size_t)NG * NLAY;                       // [NLAY] continuum (cia + dust + rayleigh)
+    double *sdelg = scon + NLAY;                                   // [NG]
+    double *sc = sdelg + NG;                                       // [RADT_WARPS][NG] c_g of the warp's current path
+    double *sdcon = sc + (size_t)RADT_WARPS * NG;                  // [NPAR*NLAY] dtaucon of the wavenumber (grad)
+    double *sdk = sdcon + ((grad && P.dtaucon) ? (size_t)NPAR * NLAY : 0);   // [NG*NLAY*NP1] dk of the wavenumber (grad)
+    int *scol = reinterpret_cast<int *>(sdk + ((grad && P.dk) ? (size_t)NG * NLAY * NP1 : 0));   // [NPAR]
+    const int nthr = blockDim.x;
+    for (int t = threadIdx.x; t < NG * NLAY; t += nthr) stau[t] = P.tau[(size_t)iw * NG * NLAY + t];
+    for (int l = threadIdx.x; l < NLAY; l += nthr) {
+        double c = 0.0;                                            // TAUCIA + TAUDUST + TAURAY in the reference's order (:3989)
+        if (P.taucia) c += P.taucia[(size_t)iw * NLAY + l];
+        if (P.taudust) c += P.taudust[(size_t)iw * NLAY + l];
+        if (P.tauray) c += P.tauray[(size_t)iw * NLAY + l];
+        scon[l] = c;
+    }
+    for (int g = threadIdx.x; g < NG; g += nthr) sdelg[g] = P.delg[g];
+    if (grad) {
+        if (P.dtaucon) for (int t = threadIdx.x; t < NPAR * NLAY; t += nthr) sdcon[t] = P.dtaucon[(size_t)iw * NPAR * NLAY + t];
+        if (P.dk) for (int t = threadIdx.x; t < NG * NLAY * NP1; t += nthr) sdk[t] = P.dk[(size_t)iw * NG * NLAY * NP1 + t];
+        for (int k = threadIdx.x; k < NPAR; k += nthr) {
+            int col = -1;
+            if (P.dk) {
+                if (k == P.NVMR) col = P.NGAS;
+                else for (int i = 0; i < P.NGAS; ++i) if (P.gas_slot[i] == k) col = i;
+            }
+            scol[k] = col;
+        }
+    }
+    __syncthreads();
+    const double xf = P.xfac ? P.xfac[iw] : 1.0;
+    double *myc = sc + (size_t)warp * NG;
+    for (int ipath = warp; ipath < NPATH; ipath += (nthr >> 5)) {
+        const int n = P.nlayin[ipath];
+        // phase 1: spec_g and c_g.  The lane's path layers (up to 8: NLAYMAX <= 256) stay in registers for all g.
+        constexpr int RQ = 8;
+        int lq[RQ];
+        double sq[RQ], cq[RQ];
+#pragma unroll
+        for (int q = 0; q < RQ; ++q) {
+            const int j = lane + 32 * q;
+            const bool ok = j < n;
+            lq[q] = ok ? P.layinc[(size_t)j * NPATH + ipath] : 0;
+            sq[q] = ok ? P.scale[(size_t)j * NPATH + ipath] : 0.0;
+            cq[q] = scon[lq[q]];
+        }
+        double spec = 0.0, csum = 0.0;
+        for (int g = 0; g < NG; ++g) {
+            const double *tg = stau + (size_t)g * NLAY;
+            double t = 0.0;
+#pragma unroll
+            for (int q = 0; q < RQ; ++q) t += (tg[lq[q]] + cq[q]) * sq[q];
+            for (int j = lane + 32 * RQ; j < n; j += 32) {          // (paths longer than 256 layers)
+                const int l = P.layinc[(size_t)j * NPATH + ipath];
+                t += (tg[l] + scon[l]) * P.scale[(size_t)j * NPATH + ipath];
+            }
+            t = warp_sum(t);
+            const double sg = exp(-t) * xf;
+            const double cg = sg * sdelg[g];
+            spec += cg;
+            csum += cg;
+            if (lane == 0) myc[g] = cg;
+        }
+        if (lane == 0) P.spec[(size_t)iw * NPATH + ipath] = spec;
+        __syncwarp();
+        if (grad) {
+            double *out = P.dspec + ((size_t)iw * NPATH + ipath) * NPAR * NLM;
+            for (int j0 = 0; j0 < NLM; j0 += 32) {
+                const int j = j0 + lane;
+                const bool live = j < n;
+                const int l = live ? P.layinc[(size_t)j * NPATH + ipath] : 0;
+                const double scl = live ? P.scale[(size_t)j * NPATH + ipath] : 0.0;
+                for (int k = 0; k < NPAR; ++k) {
+                    double v = 0.0;
+                    if (live) {
+                        const int col = scol[k];
+                        double a = 0.0;
+                        if (col >= 0) {
+                            const double *dkp = sdk + (size_t)l * NP1 + col;
+                            double a0 = 0.0, a1 = 0.0;
+                            int g = 0;
+                            for (; g + 1 < NG; g += 2) {
+                                a0 = fma(myc[g], dkp[(size_t)g * NLAY * NP1], a0);
+                                a1 = fma(myc[g + 1], dkp[(size_t)(g + 1) * NLAY * NP1], a1);
+                            }
+                            if (g < NG) a0 = fma(myc[g], dkp[(size_t)g * NLAY * NP1], a0);
+                            a = (a0 + a1) * (col < P.NGAS ? 1.0e-4 : 1.0);
+                        }
+                        if (P.dtaucon) a = fma(sdcon[(size_t)k * NLAY + l], csum, a);
+                        v = -(a * scl);
+                        if (P.flags & ANSB200_RAD_NAN_TO_NUM) v = ans_nan_to_num(v);
+                    }
+                    if (j < NLM) out[(size_t)k * NLM + j] = v;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 extern "C" int ansb200_radiance(int mode, unsigned flags, const double *tau, const double *dk, const int32_t *gas_slot,
                                 const double *taucia, const double *taudust, const double *tauray,
                                 const double *dtaucon, const int32_t *layinc, const double *scale,
@@ -390,6 +508,20 @@ extern "C" int ansb200_radiance(int mode, unsigned flags, const double *tau, con
     // Several paths: one CTA per (wavenumber, path group) with the wavenumber's slabs staged once, as many
     // groups as keep every SM busy (>= 4 paths per CTA so that the staging pays).  One path, or slabs that do
     // not fit: one CTA per (wavenumber, path), slabs read through L2 (consecutive CTAs share the wavenumber).
+    if (!thermal && NPATH >= 4) {
+        // transmission with several paths: warp-per-path kernel if the wavenumber's slabs fit in shared memory
+        const size_t nd_t = (size_t)NG * NLAY + NLAY + NG + (size_t)RADT_WARPS * NG + ((grad && dtaucon) ? (size_t)NPAR * NLAY : 0) +
+                            ((grad && dk) ? (size_t)NG * NLAY * (NGAS + 1) : 0);
+        const size_t smem_t = nd_t * 8 + (size_t)NPAR * 4 + 16;
+        if (smem_t <= 227 * 1024) {
+            ANS_CUDA_CHECK(cudaFuncSetAttribute(ans_transmission_paths_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)(smem_t > 48 * 1024 ? smem_t : 48 * 1024)));
+            int warps = NPATH < RADT_WARPS ? NPATH : RADT_WARPS;
+            ans_transmission_paths_kernel<<<(unsigned)NWAVE, warps * 32, smem_t, stream>>>(P);
+            ANS_LAUNCH_CHECK();
+            return ANSB200_OK;
+        }
+    }
     int NPG = NPATH, stage = 0, nthreads = RAD_THREADS_1;
     if (NPATH >= 4 && base_bytes(RAD_THREADS_N) + slab <= 227 * 1024) {
         stage = 1;
