@@ -1,21 +1,22 @@
-// koverlap.cu -- random-overlap gas mixing (k_overlap/rank, k_overlapg/rankg) on sm_100a.
+// koverlap_impl.cuh -- random-overlap gas mixing (k_overlap/rank, k_overlapg/rankg) on sm_100a.
 //
 // Reference: archnemesis/ForwardModel_0.py:6029-6173 (no gradients), :5842-6026 (gradients).
 //
-// Work decomposition: one warp owns one (wavenumber, layer) cell and folds the NGAS gases in
-// sequence exactly like the reference.  For every fold that needs the sort/rebin:
-//   1. the NG*NG keys  tau_i + k_j*amount  are formed in registers (EPL per lane, padded with +inf
-//      to 32*EPL), un-fused mul/add so the keys carry the reference's rounding;
-//   2. a register bitonic network (shuffles for the cross-lane stages) sorts (key, packed index)
-//      pairs -- total order, ties broken by index;
-//   3. the cumulative weight is a warp scan; every element finds its g-bin from the cumulative
-//      weight of its predecessor and the bin edges g_ord (host-made in del_g's dtype), and the
-//      element that straddles an edge publishes (position, frac) to shared memory;
-//   4. lane m (< NG) walks the sorted indices of bin m in order and accumulates
-//      cont*weight, weight and the gradient columns in the reference's order and rounding.
-// With identical k inputs the result is bit-identical to the reference whenever no element
-// straddles two bin edges (checked on the host: max weight < min bin width; otherwise the host
-// requests the literal sequential rebin, seq_rebin=1).
+// Work decomposition: persistent CTAs of OV_WARPS warps; one warp owns one (wavenumber, layer) cell at a
+// time and folds the NGAS gases in sequence exactly like the reference.  Per fold:
+//   0. row-/column-major key orders are data-independent: fixed rebin matrices (ov_rebin_static);
+//   1. otherwise the NG*NG keys  tau_i + k_j*amount  are packed as (22 key bits | 10 index bits) and
+//      sorted by a 32-bit min/max bitonic network in registers (EPL words per lane, padded to 32*EPL,
+//      shuffles for the cross-lane stages); the order is verified / repaired against the exact float64
+//      keys only when two neighbours share their key bits, and tied keys follow numba's quicksort
+//      (ov_numba_order) when gradients are wanted;
+//   2. the cumulative weight is a warp scan; every lane FMA-accumulates cont*w, w and the gradient
+//      columns of its EPL consecutive sorted elements, closing a partial sum at every element that
+//      straddles a bin edge; lane m assembles bin m (partial sums + the frac / 1-frac parts of its two
+//      straddlers) and normalises (ov_rebin_par).
+// With identical k inputs ov_rebin_par agrees with the reference to ~1e-15 (another summation order);
+// the literal sequential rebin (ov_rebin_seq: lane-per-bin walk in sorted order, requested by the host
+// when one element could straddle two bin edges, or by force_seq) is bit-identical to it.
 //
 // k and dk/dT of the cell come either from the arrays produced by ansb200_kinterp or, in the
 // fused entry point, straight from the resident ln K table (k_gas never touches HBM).
@@ -314,7 +315,7 @@ struct OvWarpSmem {
     double *bsum;            // [NG*BS] raw bin sums (see ov_bs)
     double *head;            // [32*BS] per-lane partial sum of the bin a lane starts in (parallel rebin)
     int *strad;              // [NG+1]
-    int *closed;             // [NG] bin closed by a straddling element
+    int *spare;              // [NG] (unused; keeps the int block an even count)
     unsigned short *sidx;    // [NG*NG] sorted packed indices
 };
 
@@ -1136,10 +1137,10 @@ ans_koverlap_kernel(OvParams P)
         s.bsum = d; d += NG * BS;
         s.head = d; d += ov_head_doubles_np(NG, NPMAX);
         s.strad = reinterpret_cast<int *>(d);
-        s.closed = s.strad + NG + 1;
+        s.spare = s.strad + NG + 1;
         int nnpad = 128;
         while (nnpad < NN) nnpad <<= 1;
-        s.sidx = reinterpret_cast<unsigned short *>(s.closed + NG + ((2 * NG + 1) & 1));   // (8-byte multiple of ints)
+        s.sidx = reinterpret_cast<unsigned short *>(s.spare + NG + ((2 * NG + 1) & 1));   // (8-byte multiple of ints)
         d = reinterpret_cast<double *>(s.sidx + nnpad);
         s.kbuf = d; d += NG * NGAS;
         s.dbuf = d;
