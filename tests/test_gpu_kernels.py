@@ -420,3 +420,102 @@ def test_oe_algebra_on_device(mods):
         SM, SN, ST = oe.calc_serr(DD, AA, SA, SE2, simple=simple)
         rSM, rSN, rST = orc.oe_serr(rDD, rAA, SA, SE2, simple=simple)
         assert colerr(cpu(SM), rSM) < tol and colerr(cpu(SN), rSN) < tol and colerr(cpu(ST), rST) < tol
+
+
+def _limb_paths(nlay, npath, nlm, rng, long_path=False):
+    """Ragged limb-like paths (down to a tangent layer and up again), zero padded like Path_0 pads them."""
+    layinc = np.zeros((nlm, npath), np.int32)
+    scale = np.zeros((nlm, npath))
+    nlayin = np.zeros(npath, np.int32)
+    for p in range(npath):
+        t = (p * (nlay - 2)) // npath
+        seq = list(range(nlay - 1, t - 1, -1)) + list(range(t, nlay))
+        if long_path and p == npath - 1:
+            seq = (seq * (nlm // len(seq) + 1))[:nlm]          # a path that revisits layers: more than 256 entries
+        n = min(len(seq), nlm)
+        nlayin[p] = n
+        layinc[:n, p] = seq[:n]
+        scale[:n, p] = rng.uniform(1.0, 20.0, n)
+    return layinc, scale, nlayin
+
+
+@pytest.mark.parametrize("want_grad", [False, True])
+@pytest.mark.parametrize("npath,nlm,long_path", [(7, 40, False), (5, 300, True), (40, 40, False)])
+def test_transmission_many_paths_warp_per_path_kernel(mods, want_grad, npath, nlm, long_path):
+    """NPATH >= 4 in transmission mode takes ans_transmission_paths_kernel (one warp per path on the staged
+    slabs, including more paths than warps and a path of more than 256 entries): against the oracle."""
+    ops, orc, torch = mods["ops"], mods["orc"], mods["torch"]
+    c = _case(mods, nwave=6, ng=20, ngas=3, nlay=18, npro=18, nx=5, nvmr=4, seed=43)
+    rng = np.random.default_rng(8)
+    layinc, scale, nlayin = _limb_paths(18, npath, nlm, rng, long_path)
+    c.update(LAYINC=layinc, SCALE=scale, NLAYIN=nlayin, EMTEMP=np.zeros((nlm, npath)))
+    c["xfac"] = np.linspace(1.0, 3.0, 6)
+    tab = c["tab"]
+    kr, dr = orc.calc_k(tab["K"], tab["PRESS"], tab["TEMP"], c["press"], c["temp"], want_grad=True)
+    tau, dk = orc.k_overlap(tab["DELG"], kr, c["amount"], dkdT=dr)
+    tau *= 2e-4
+    dk *= 2e-4
+    a = _radiance_inputs(mods, c, tau, dk if want_grad else None)
+    out = ops.radiance(ops.TRANSMISSION, a["tau"], a["dk"], a["gas_slot"], a["taucia"], None, None,
+                       a["dtaucon"] if want_grad else None, a["layinc"], a["scale"], a["nlayin"], None, None, None,
+                       a["delg"], None, a["xfac"], None, None, None, None, 0, -1.0, c["NVMR"], c["NPAR"], want_grad)
+    tl, tp, dtl = orc.assemble_opacity(tau, dk if want_grad else None, c["gas_slot"], c["NVMR"], c["NPAR"], c["taucon"],
+                                       c["dtaucon"], layinc, scale)
+    S, dS = orc.transmission(tp, dtl, c["xfac"])
+    dg = tab["DELG"]
+    if want_grad:
+        s_ref, d_ref, _ = orc.g_integrate(S, dS, None, dg)
+        spec, dspec, _ = out
+        assert relerr(cpu(spec), s_ref) < 1e-12
+        got = np.transpose(cpu(dspec), (0, 2, 3, 1))
+        assert colerr(got, d_ref) < 1e-12
+        for p in range(npath):                    # rows past NLAYIN are written as zeros
+            assert not np.any(got[:, :, nlayin[p]:, p])
+    else:
+        assert relerr(cpu(out), orc.g_integrate(S, None, None, dg)) < 1e-12
+
+
+@pytest.mark.parametrize("want_grad", [False, True])
+def test_thermal_many_limb_paths_staged_kernel(mods, want_grad):
+    """NPATH >= 4 in thermal mode: the CTA walks its paths on the staged tau / dk slabs (limb emission: no
+    ground term, layers seen twice)."""
+    ops, orc = mods["ops"], mods["orc"]
+    c = _case(mods, nwave=6, ng=20, ngas=3, nlay=18, npro=18, nx=5, nvmr=4, seed=47)
+    rng = np.random.default_rng(9)
+    npath, nlm = 6, 36
+    layinc, scale, nlayin = _limb_paths(18, npath, nlm, rng)
+    emtemp = np.zeros((nlm, npath))
+    for p in range(npath):
+        emtemp[:nlayin[p], p] = c["temp"][layinc[:nlayin[p], p]]
+    c.update(LAYINC=layinc, SCALE=scale, NLAYIN=nlayin, EMTEMP=emtemp)
+    c["xfac"] = np.linspace(0.5, 2.0, 6)
+    tab = c["tab"]
+    kr, dr = orc.calc_k(tab["K"], tab["PRESS"], tab["TEMP"], c["press"], c["temp"], want_grad=True)
+    tau, dk = orc.k_overlap(tab["DELG"], kr, c["amount"], dkdT=dr)
+    tau *= 2e-3
+    dk *= 2e-3
+    a = _radiance_inputs(mods, c, tau, dk if want_grad else None)
+    sol = ops.to_dev(np.full(npath, 100.0))
+    emi = ops.to_dev(np.full(npath, 10.0))
+    z6 = ops.to_dev(np.zeros(6))
+    out = ops.radiance(ops.THERMAL, a["tau"], a["dk"], a["gas_slot"], a["taucia"], None, None,
+                       a["dtaucon"] if want_grad else None, a["layinc"], a["scale"], a["nlayin"], a["emtemp"],
+                       a["laypress"], a["wave"], a["delg"], a["emissivity"], a["xfac"], None if want_grad else z6,
+                       None if want_grad else z6, None if want_grad else sol, None if want_grad else emi,
+                       c["ISPACE"], -1.0, c["NVMR"], c["NPAR"], want_grad)
+    tl, tp, dtl = orc.assemble_opacity(tau, dk if want_grad else None, c["gas_slot"], c["NVMR"], c["NPAR"], c["taucon"],
+                                       c["dtaucon"], layinc, scale)
+    z = np.zeros(6)
+    S, dS, dT = orc.thermal_paths(c["ISPACE"], tab["WAVE"], tl, dtl, c["NVMR"], nlayin, emtemp, c["LAYPRESS"], layinc,
+                                  -1.0, c["EMISSIVITY"], c["xfac"], z, z, np.full(npath, 100.0), np.full(npath, 10.0))
+    dg = tab["DELG"]
+    if want_grad:
+        s_ref, d_ref, t_ref = orc.g_integrate(S, dS, dT, dg)
+        spec, dspec, dts = out
+        assert relerr(cpu(spec), s_ref) < 1e-12
+        got = np.transpose(cpu(dspec), (0, 2, 3, 1))
+        for kpar in range(d_ref.shape[1]):
+            assert colerr(got[:, kpar], d_ref[:, kpar]) < 1e-11, kpar
+        assert relerr(cpu(dts), t_ref) < 1e-12
+    else:
+        assert relerr(cpu(out), orc.g_integrate(S, None, None, dg)) < 1e-12
