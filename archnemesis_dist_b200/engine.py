@@ -113,17 +113,33 @@ class HotPath:
 
     # -- host -> device ---------------------------------------------------------------------------
     def stage_opacity(self, ev: Evaluation, return_grad):
-        """Inputs of the gas-opacity kernel only (k-interp plan + amounts: a few KB)."""
+        """Inputs of the gas-opacity kernel only (k-interp plan + amounts: a few KB), packed into ONE pinned
+        buffer and one host->device copy so that the kernel can be launched after a single enqueue."""
         st = self._stage
         st.bytes = 0
-        i32 = torch.int32
         hp = _plan.kinterp_plan(self.PRESS, self.TEMP, ev.press_atm, ev.temp, return_grad)
-        dev = {k: st("plan_" + k, v, i32 if v.dtype == np.int32 else torch.float64) for k, v in hp.items()}
+        n = len(ev.press_atm)
+        amount = np.ascontiguousarray(ev.amount, dtype=np.float64)
+        ints = np.concatenate([hp["ip_lo"], hp["it_lo"]]).astype(np.int32)
+        if ints.size & 1:
+            ints = np.concatenate([ints, np.zeros(1, np.int32)])
+        parts = [hp["w4"].reshape(-1), hp["omv"], hp["vv"], hp["dudt"], amount.reshape(-1), ints.view(np.float64)]
+        packed = st("opacity_inputs", np.concatenate(parts))
+        off = 0
+
+        def take(count):
+            nonlocal off
+            v = packed[off:off + count]
+            off += count
+            return v
+        dev = dict(w4=take(4 * n).view(n, 4), omv=take(n), vv=take(n), dudt=take(n))
         s = Staged()
+        s.amount = take(amount.size).view(amount.shape)
+        iv = take(ints.size // 2).view(torch.int32)
+        dev["ip_lo"], dev["it_lo"] = iv[0:n], iv[n:2 * n]
         s.grad = return_grad
         s.plan_host = hp
-        s.dplan = _DevPlan(dev, len(ev.press_atm))
-        s.amount = st("amount", ev.amount)
+        s.dplan = _DevPlan(dev, n)
         s.M = None
         return s
 

@@ -21,6 +21,15 @@ def _bracket(grid, x):
     return i, None
 
 
+def _bracket_all(grid, x):
+    """_bracket for every layer at once: lo[n], clamped-to-first[n], clamped-to-last[n]."""
+    n = len(grid)
+    i = np.abs(grid[None, :] - x[:, None]).argmin(axis=1)
+    ge = grid[i] >= x
+    lo = np.where(ge, np.maximum(i - 1, 0), np.minimum(i, n - 2))
+    return lo, ge & (i == 0), (~ge) & (i == n - 1)
+
+
 def kinterp_plan(PRESS, TEMP, press, temp, grad):
     """Per-layer bracket indices and bilinear weights for calc_k (grad=False,
     Spectroscopy_0.py:2331-2389) or calc_kg (grad=True, :2176-2236).
@@ -29,47 +38,46 @@ def kinterp_plan(PRESS, TEMP, press, temp, grad):
     float64 after HDF5): numpy's scalar promotion then decides whether v, u and the four weight
     products are rounded to float32 before they multiply the float64 table -- that rounding is part
     of the reference's result, so it is reproduced here and the weights are widened afterwards.
+    The reference works layer by layer on scalars; here the layers are grouped by which of the two
+    coordinates is clamped to a grid edge (a clamped coordinate is a grid-dtype scalar, so v or u --
+    and, if both are clamped, the weight products -- are evaluated in the grid's dtype) and every
+    group is evaluated with arrays of exactly those dtypes: bit-identical to the scalar loop
+    (tests/test_plan.py against the oracle's scalar restatement), ~10x less host time per evaluation.
+    calc_k clamps the pressure and then takes the log, calc_kg takes the log first and replaces it by
+    log(PRESS[edge]): both end up with the log of a grid-dtype scalar when clamped.
     """
     PRESS = np.asarray(PRESS)
     TEMP = np.asarray(TEMP)
-    press = np.asarray(press)
-    temp = np.asarray(temp)
+    press = np.asarray(press, dtype=np.float64)
+    temp = np.asarray(temp, dtype=np.float64)
     n = len(press)
-    ip_lo = np.zeros(n, np.int32)
-    it_lo = np.zeros(n, np.int32)
+    ipl, p_first, p_last = _bracket_all(PRESS, press)
+    itl, t_first, t_last = _bracket_all(TEMP, temp)
+    pcl, tcl = p_first | p_last, t_first | t_last
+    plo, phi = np.log(PRESS[ipl]), np.log(PRESS[ipl + 1])            # grid dtype
+    tlo, thi = TEMP[itl], TEMP[itl + 1]
+    pedge = np.where(p_first, PRESS[0], PRESS[len(PRESS) - 1])        # grid dtype
+    tedge = np.where(t_first, TEMP[0], TEMP[len(TEMP) - 1])
     w4 = np.zeros((n, 4), np.float64)
     omv = np.zeros(n, np.float64)
     vv = np.zeros(n, np.float64)
-    dudt = np.zeros(n, np.float64)
-    for l in range(n):
-        press1 = press[l]
-        temp1 = temp[l]
-        ipl, pclamp = _bracket(PRESS, press1)
-        itl, tclamp = _bracket(TEMP, temp1)
-        if grad:
-            # calc_kg takes the log first and replaces it by log(PRESS[edge]) when clamped
-            lpress = np.log(press1) if pclamp is None else np.log(pclamp)
-        else:
-            # calc_k clamps the pressure, then takes the log
-            lpress = np.log(press1 if pclamp is None else pclamp)
-        if tclamp is not None:
-            temp1 = tclamp
-        plo = np.log(PRESS[ipl])
-        phi = np.log(PRESS[ipl + 1])
-        tlo = TEMP[itl]
-        thi = TEMP[itl + 1]
-        v = (lpress - plo) / (phi - plo)
-        u = (temp1 - tlo) / (thi - tlo)
-        ip_lo[l] = ipl
-        it_lo[l] = itl
-        w4[l, 0] = (1.0 - v) * (1.0 - u)
-        w4[l, 1] = v * (1.0 - u)
-        w4[l, 2] = v * u
-        w4[l, 3] = (1.0 - v) * u
-        omv[l] = 1.0 - v
-        vv[l] = v
-        dudt[l] = 1. / (thi - tlo)
-    return dict(ip_lo=ip_lo, it_lo=it_lo, w4=w4, omv=omv, vv=vv, dudt=dudt)
+    for pc in (False, True):
+        for tc in (False, True):
+            m = (pcl == pc) & (tcl == tc)
+            if not m.any():
+                continue
+            lp = np.log(pedge[m]) if pc else np.log(press[m])       # grid dtype if clamped, else float64
+            t1 = tedge[m] if tc else temp[m]
+            v = (lp - plo[m]) / (phi[m] - plo[m])
+            u = (t1 - tlo[m]) / (thi[m] - tlo[m])
+            w4[m, 0] = (1.0 - v) * (1.0 - u)
+            w4[m, 1] = v * (1.0 - u)
+            w4[m, 2] = v * u
+            w4[m, 3] = (1.0 - v) * u
+            omv[m] = 1.0 - v
+            vv[m] = v
+    dudt = (1. / (thi - tlo)).astype(np.float64)
+    return dict(ip_lo=ipl.astype(np.int32), it_lo=itl.astype(np.int32), w4=w4, omv=omv, vv=vv, dudt=dudt)
 
 
 def planes_touched(plan, NT):
