@@ -522,7 +522,14 @@ __device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const OvWeight
         const double up = shfl_up_d(incl, d);
         if (lane >= d) incl = __dadd_rn(incl, up);
     }
-    double prev = __dsub_rn(incl, run);
+    // Lane boundaries must be ONE number for both neighbours: the cumulative weight before lane L is lane L-1's
+    // inclusive scan value, and lane L-1 uses that same value as the cumulative weight of its last element
+    // (below).  With float32-born weights every sum is exact and this changes nothing; with float64 weights
+    // (HDF5 tables) a lane's own running sum and the scan differ by an ulp, and an edge lying between the two
+    // -- they coincide with the cumulative weight of whole rows in near row-major orders -- would get no
+    // straddler at all.
+    double prev = shfl_up_d(incl, 1);
+    if (lane == 0) prev = 0.0;
     int ig;
     {   // number of edges g_ord[1..NG] that are <= prev
         int lo = 0, hi = NG;
@@ -561,7 +568,7 @@ __device__ __forceinline__ void ov_rebin_par(const OvWarpSmem &s, const OvWeight
         const int pn = s.sidx[(r + 1 < EPL ? r + 1 : r) * 32 + lane];
         w = (pn >> 5) < NG ? W(pn >> 5, pn & 31) : 0.0;
         if (i < NG && ig < NG) {
-            const double gdn = __dadd_rn(prev, wc);
+            const double gdn = (r == EPL - 1) ? incl : __dadd_rn(prev, wc);
             if (gdn < edge) {
                 acc[1] = __dadd_rn(acc[1], wc);
                 if (GRAD) {
