@@ -21,3 +21,16 @@ def test_overlap_random_sweep(seed):
         # float64 quadrature weights are not exactly summable: the order of the cumulative sum shows at 1e-14
         assert r["tau"] < 2e-13 and r["tau_nograd"] < 2e-13, (desc, r)
         assert r["dk"] < 1e-11, (desc, r)
+
+
+@pytest.mark.parametrize("seed", [5, 99])
+def test_radiance_projection_random_sweep(seed):
+    """tools/stress_radiance.py: thermal / transmission, 1..33 nadir or ragged limb paths (one path per CTA, the
+    staged multi-path kernel and the warp-per-path transmission kernel), with and without gradients, surface,
+    dust / Rayleigh terms, wavelength space, followed by the projection onto the state vector."""
+    from tools import stress_radiance as sr
+    rng = np.random.default_rng(seed)
+    for case in range(16):
+        desc, e_s, e_d, e_x = sr.run_case(rng)
+        assert e_s < 1e-11, (desc, e_s)
+        assert e_d < 1e-10 and e_x < 1e-10, (desc, e_d, e_x)
