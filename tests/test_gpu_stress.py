@@ -34,3 +34,13 @@ def test_radiance_projection_random_sweep(seed):
         desc, e_s, e_d, e_x = sr.run_case(rng)
         assert e_s < 1e-11, (desc, e_s)
         assert e_d < 1e-10 and e_x < 1e-10, (desc, e_d, e_x)
+
+
+def test_lbl_random_sweep():
+    """tools/stress_lbl.py: pressures 1e-9..100 atm, temperatures 60..900 K, grids of 0.3..100 cm-1, windows, strength
+    floor, one or two broadeners, against the oracle's SciPy-Voigt restatement of add_line_set_monochromatic_absorption."""
+    from tools import stress_lbl as sl
+    rng = np.random.default_rng(3)
+    for case in range(8):
+        desc, e = sl.run_case(rng)
+        assert e < 1e-11, (desc, e)
