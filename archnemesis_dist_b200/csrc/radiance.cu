@@ -466,6 +466,198 @@ ans_transmission_paths_kernel(RadParams P)
     }
 }
 
+// ---- thermal emission with gradients, many paths: one warp per path ------------------------------------------
+// Same arithmetic as phase 1 / phase 2 of ans_radiance_kernel (gradient form tr = trold*exp(-tau_j), closed-form
+// D_j), reorganised so that a path never leaves its warp: lanes own contiguous chunks of up to TP_RQ path layers;
+// for every g the warp scans the path (chunk products, warp scan, reverse scan of the emission terms) and each
+// lane immediately adds W_j(g) dk[g, l_j, :] to the NGAS+1 running sums of its own layers, which stay in registers
+// across the g loop (TP_RQ * (TP_NC+1) doubles per lane).  No per-path [NG][NLAYIN] scratch, no CTA barrier after
+// the wavenumber's slabs are staged.  Used for NPATH >= 4, NLAYIN <= 32*TP_RQ, NGAS+1 <= TP_NC.
+constexpr int TP_RQ = 7;       // path layers per lane (224 per path)
+constexpr int TP_NC = 8;       // dk columns (NGAS + 1) kept per layer
+constexpr int TP_WARPS = 8;
+
+__global__ void __launch_bounds__(TP_WARPS * 32, 1)
+ans_thermal_paths_kernel(RadParams P)
+{
+    extern __shared__ __align__(16) unsigned char rad_smem[];
+    const int iw = blockIdx.x;
+    const int NG = P.NG, NLAY = P.NLAY, NLM = P.NLAYMAX, NPATH = P.NPATH, NPAR = P.NPAR, NP1 = P.NGAS + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nthr = blockDim.x;
+    double *stau = reinterpret_cast<double *>(rad_smem);          // [NG*NLAY]
+    double *scon = stau + (size_t)NG * NLAY;                       // [NLAY]
+    double *sdelg = scon + NLAY;                                   // [NG]
+    double *sdcon = sdelg + NG;                                    // [NPAR*NLAY]
+    double *sdk = sdcon + (P.dtaucon ? (size_t)NPAR * NLAY : 0);   // [NG*NLAY*TP_NC] (columns padded to TP_NC)
+    sdk += (sdk - stau) & 1;                                       // 16-byte aligned: rows are read as double2
+    double *spath = sdk + (size_t)NG * NLAY * TP_NC;               // per warp: B[NLM], dB[NLM], scale[NLM]
+    int *scol = reinterpret_cast<int *>(spath + (size_t)TP_WARPS * 3 * NLM);   // [NPAR]
+    int *slayw = scol + NPAR;                                      // per warp: layer index [NLM]
+    for (int t = threadIdx.x; t < NG * NLAY; t += nthr) stau[t] = P.tau[(size_t)iw * NG * NLAY + t];
+    for (int l = threadIdx.x; l < NLAY; l += nthr) {
+        double c = 0.0;
+        if (P.taucia) c += P.taucia[(size_t)iw * NLAY + l];
+        if (P.taudust) c += P.taudust[(size_t)iw * NLAY + l];
+        if (P.tauray) c += P.tauray[(size_t)iw * NLAY + l];
+        scon[l] = c;
+    }
+    for (int g = threadIdx.x; g < NG; g += nthr) sdelg[g] = P.delg[g];
+    if (P.dtaucon) for (int t = threadIdx.x; t < NPAR * NLAY; t += nthr) sdcon[t] = P.dtaucon[(size_t)iw * NPAR * NLAY + t];
+    for (int t = threadIdx.x; t < NG * NLAY * TP_NC; t += nthr) {
+        const int c = t % TP_NC, gl = t / TP_NC;
+        sdk[t] = c < NP1 ? P.dk[((size_t)iw * NG * NLAY + gl) * NP1 + c] : 0.0;
+    }
+    for (int k = threadIdx.x; k < NPAR; k += nthr) {
+        int col = -1;
+        if (k == P.NVMR) col = P.NGAS;
+        else for (int i = 0; i < P.NGAS; ++i) if (P.gas_slot[i] == k) col = i;
+        scol[k] = col;
+    }
+    __syncthreads();
+    const double wv = P.wave[iw];
+    const double xf = P.xfac ? P.xfac[iw] : 1.0;
+    double *sBw = spath + (size_t)warp * 3 * NLM, *sdBw = sBw + NLM, *sscw = sdBw + NLM;
+    int *slay = slayw + (size_t)warp * NLM;
+    const int tcol = P.NGAS;      // dk column of the temperature parameter
+    for (int ipath = warp; ipath < NPATH; ipath += (nthr >> 5)) {
+        const int n = P.nlayin[ipath];
+        for (int j = lane; j < n; j += 32) {
+            slay[j] = P.layinc[(size_t)j * NPATH + ipath];
+            sscw[j] = P.scale[(size_t)j * NPATH + ipath];
+            double bb, db;
+            ans_planckg(P.ispace, wv, P.emtemp[(size_t)j * NPATH + ipath], bb, db);
+            sBw[j] = bb;
+            sdBw[j] = db;
+        }
+        // limb / nadir test and ground term (:6353-6365, :6479-6494)
+        double radground = 0.0, dradground = 0.0;
+        bool ground = false;
+        if (n > 0) {
+            const int jh = n / 2 - 1;
+            const double p1 = P.laypress[P.layinc[(size_t)(jh >= 0 ? jh : n - 1) * NPATH + ipath]];
+            const double p2 = P.laypress[P.layinc[(size_t)(n - 1) * NPATH + ipath]];
+            ground = p2 > p1;
+            if (ground) {
+                if (P.tsurf <= 0.0) {
+                    ans_planckg(P.ispace, wv, P.emtemp[(size_t)(n - 1) * NPATH + ipath], radground, dradground);
+                } else {
+                    ans_planckg(P.ispace, wv, P.tsurf, radground, dradground);
+                    const double em = P.emissivity[iw];
+                    radground *= em;
+                    dradground *= em;
+                }
+            }
+        }
+        __syncwarp();
+        const int CH = (n + 31) / 32;
+        const int j0 = lane * CH, cnt = max(0, min(n, j0 + CH) - j0);
+        double acc[TP_RQ][TP_NC], wsum[TP_RQ];
+#pragma unroll
+        for (int q = 0; q < TP_RQ; ++q) {
+            wsum[q] = 0.0;
+#pragma unroll
+            for (int c = 0; c < TP_NC; ++c) acc[q][c] = 0.0;
+        }
+        double spec = 0.0, dts = 0.0;
+#pragma unroll 1
+        for (int g = 0; g < NG; ++g) {
+            const double *tg = stau + (size_t)g * NLAY;
+            // transmission to the bottom of each of the lane's layers: chunk products, then the warp scan
+            double Tq[TP_RQ];
+            double loc = 1.0;
+#pragma unroll
+            for (int q = 0; q < TP_RQ; ++q) {
+                if (q < cnt) {
+                    const int l = slay[j0 + q];
+                    loc *= exp(-((tg[l] + scon[l]) * sscw[j0 + q]));
+                }
+                Tq[q] = loc;
+            }
+            double incl = loc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double up = rshfl_up(incl, d);
+                if (lane >= d) incl *= up;
+            }
+            double base = rshfl_up(incl, 1);
+            if (lane == 0) base = 1.0;
+            const double Tn = rshfl_idx(incl, 31);
+            // emission terms E_j = (T_{j-1} - T_j) B_j, their sum and suffix sums
+            double esum = 0.0;
+#pragma unroll
+            for (int q = 0; q < TP_RQ; ++q) {
+                if (q < cnt) {
+                    Tq[q] *= base;
+                    const double Tm = q == 0 ? base : Tq[q > 0 ? q - 1 : 0];
+                    esum += (Tm - Tq[q]) * sBw[j0 + q];
+                }
+            }
+            double specg = warp_sum(esum);
+            if (ground) specg += Tn * radground;
+            const double dgx = sdelg[g] * xf;
+            spec += specg * xf * sdelg[g];
+            if (ground) dts += Tn * dradground * xf * sdelg[g];
+            double rincl = esum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double dn = rshfl_down(rincl, d);
+                if (lane + d < 32) rincl += dn;
+            }
+            double after = rshfl_down(rincl, 1);
+            if (lane == 31) after = 0.0;
+            double suffix = after + (ground ? Tn * radground : 0.0);
+#pragma unroll
+            for (int qq = 0; qq < TP_RQ; ++qq) {
+                constexpr int last = TP_RQ - 1;
+                const int q = last - qq;                 // (compile-time after unrolling: the lane's layers, last first)
+                if (q < cnt) {
+                    const int j = j0 + q;
+                    const double Tj = Tq[q], Tm = q == 0 ? base : Tq[q > 0 ? q - 1 : 0];
+                    const double W = (Tj * sBw[j] - suffix) * sscw[j] * dgx;
+                    const double TT = (Tm - Tj) * sdBw[j] * dgx;
+                    suffix += (Tm - Tj) * sBw[j];
+                    wsum[q] += W;
+                    const double2 *dkp = reinterpret_cast<const double2 *>(sdk + ((size_t)g * NLAY + slay[j]) * TP_NC);
+#pragma unroll
+                    for (int c2 = 0; c2 < TP_NC / 2; ++c2) {
+                        const double2 v = dkp[c2];
+                        acc[q][2 * c2] = fma(W, v.x, acc[q][2 * c2]);
+                        acc[q][2 * c2 + 1] = fma(W, v.y, acc[q][2 * c2 + 1]);
+                    }
+                    // (T_{j-1}-T_j) dB_j/dT belongs to the temperature parameter, whose dk column is NGAS
+#pragma unroll
+                    for (int c = 0; c < TP_NC; ++c) acc[q][c] += (c == tcol) ? TT : 0.0;
+                }
+            }
+        }
+        if (lane == 0) {
+            P.spec[(size_t)iw * NPATH + ipath] = spec;
+            if (P.dtsurf) P.dtsurf[(size_t)iw * NPATH + ipath] = dts;
+        }
+        // d spec / d q[k, j] = unit_k acc[j][col_k] + dtaucon[k, l_j] wsum[j]
+        double *out = P.dspec + ((size_t)iw * NPATH + ipath) * NPAR * NLM;
+#pragma unroll 1
+        for (int k = 0; k < NPAR; ++k) {
+            const int col = scol[k];
+            const double unit = (col >= 0 && col < P.NGAS) ? 1.0e-4 : 1.0;
+#pragma unroll
+            for (int q = 0; q < TP_RQ; ++q) {
+                if (q < cnt) {
+                    const int j = j0 + q;
+                    double v = 0.0;
+#pragma unroll
+                    for (int c = 0; c < TP_NC; ++c) v = (c == col) ? acc[q][c] * unit : v;
+                    if (P.dtaucon) v = fma(sdcon[(size_t)k * NLAY + slay[j]], wsum[q], v);
+                    if (P.flags & ANSB200_RAD_NAN_TO_NUM) v = ans_nan_to_num(v);
+                    out[(size_t)k * NLM + j] = v;
+                }
+            }
+            for (int j = n + lane; j < NLM; j += 32) out[(size_t)k * NLM + j] = 0.0;    // rows past NLAYIN
+        }
+        __syncwarp();
+    }
+}
+
 extern "C" int ansb200_radiance(int mode, unsigned flags, const double *tau, const double *dk, const int32_t *gas_slot,
                                 const double *taucia, const double *taudust, const double *tauray,
                                 const double *dtaucon, const int32_t *layinc, const double *scale,
@@ -518,6 +710,20 @@ extern "C" int ansb200_radiance(int mode, unsigned flags, const double *tau, con
                                                 (int)(smem_t > 48 * 1024 ? smem_t : 48 * 1024)));
             int warps = NPATH < RADT_WARPS ? NPATH : RADT_WARPS;
             ans_transmission_paths_kernel<<<(unsigned)NWAVE, warps * 32, smem_t, stream>>>(P);
+            ANS_LAUNCH_CHECK();
+            return ANSB200_OK;
+        }
+    }
+    if (thermal && grad && dk && NPATH >= 4 && NLAYMAX <= 32 * TP_RQ && NGAS + 1 <= TP_NC) {
+        // thermal emission with gradients over several paths: warp-per-path kernel if the slabs fit
+        const size_t nd_p = (size_t)NG * NLAY + NLAY + NG + (dtaucon ? (size_t)NPAR * NLAY : 0) +
+                            (size_t)NG * NLAY * TP_NC + (size_t)TP_WARPS * 3 * NLAYMAX + 1;
+        const size_t smem_p = nd_p * 8 + ((size_t)NPAR + (size_t)TP_WARPS * NLAYMAX) * 4 + 16;
+        if (smem_p <= 227 * 1024) {
+            ANS_CUDA_CHECK(cudaFuncSetAttribute(ans_thermal_paths_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)(smem_p > 48 * 1024 ? smem_p : 48 * 1024)));
+            const int warps = NPATH < TP_WARPS ? NPATH : TP_WARPS;
+            ans_thermal_paths_kernel<<<(unsigned)NWAVE, warps * 32, smem_p, stream>>>(P);
             ANS_LAUNCH_CHECK();
             return ANSB200_OK;
         }
