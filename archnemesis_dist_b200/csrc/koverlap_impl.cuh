@@ -30,6 +30,9 @@ constexpr int OV_WARPS = OV_NWARPS;
 #ifndef OV_MINB
 #define OV_MINB 2
 #endif
+#ifndef OV_MINB_NOGRAD
+#define OV_MINB_NOGRAD 3
+#endif
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int OV_CS = 6;   // doubles per column record {b, bT, k, -, -, -}: 3 sixteen-byte units, conflict-free mod 8
 constexpr int OV_NONE = 0x7fffffff;
@@ -331,22 +334,22 @@ __host__ __device__ inline int ov_bs(int npmax) { return (npmax + 3) | 1; }
 
 // head slots of the parallel rebin (32 lanes x BS); the same region is the scratch of the tie-order
 // emulation (4 uint16 arrays of the padded sort length = that many doubles)
-__host__ __device__ inline int ov_head_doubles_np(int NG, int npmax)
+// (only the gradient kernels replay numba's tie order, so only they need the scratch)
+__host__ __device__ inline int ov_head_doubles_np(int NG, int npmax, bool grad)
 {
     int nnpad = 128;
     while (nnpad < NG * NG) nnpad <<= 1;
     const int h = 32 * ov_bs(npmax);
-    return h > nnpad ? h : nnpad;
+    return (!grad || h > nnpad) ? h : nnpad;
 }
-__host__ __device__ inline int ov_head_doubles(int NG, int NGAS) { return ov_head_doubles_np(NG, ov_npmax(NGAS)); }
 
 __host__ __device__ inline size_t ov_per_warp_bytes(int NG, int NGAS, bool grad)
 {
     int NN = 128;                       // sorted-index staging is padded to 32*EPL entries
     while (NN < NG * NG) NN <<= 1;
-    const int npm = ov_npmax(NGAS);
+    const int npm = grad ? ov_npmax(NGAS) : 1;      // (the no-gradient kernels are instantiated with NPMAX = 1)
     const int nd = NG * NGAS * (grad ? 2 : 1) + (3 + OV_CS) * NG + (grad ? NG * ov_ds(npm) : 0) + 2 * (NG + 1) + NG * ov_bs(npm) +
-                   ov_head_doubles(NG, NGAS);
+                   ov_head_doubles_np(NG, npm, grad);
     return ((size_t)nd * 8 + (size_t)(2 * NG + 2) * 4 + (size_t)NN * 2 + 15) & ~(size_t)15;
 }
 
@@ -1114,7 +1117,7 @@ __device__ __forceinline__ void ov_rebin(const OvWarpSmem &s, const OvWeight &W,
 }
 
 template <int EPL, int NPMAX, bool GRAD>
-__global__ void __launch_bounds__(OV_WARPS * 32, OV_MINB)
+__global__ void __launch_bounds__(OV_WARPS * 32, GRAD ? OV_MINB : OV_MINB_NOGRAD)
 ans_koverlap_kernel(OvParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1142,7 +1145,7 @@ ans_koverlap_kernel(OvParams P)
         s.frac = d; d += NG + 1;
         s.gdn = d; d += NG + 1;
         s.bsum = d; d += NG * BS;
-        s.head = d; d += ov_head_doubles_np(NG, NPMAX);
+        s.head = d; d += ov_head_doubles_np(NG, NPMAX, GRAD);
         s.strad = reinterpret_cast<int *>(d);
         s.spare = s.strad + NG + 1;
         int nnpad = 128;
