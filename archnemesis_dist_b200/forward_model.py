@@ -337,13 +337,17 @@ class B200HotPathMixin:
         return SPEC1, dSPEC1
 
     def b200_device_conv_ok(self, IGEOM):
-        """Can the tail of nemesisfmg for this geometry (JSURF column, WGEOM weight, Measurement_0.convg) run on
-        the device?  One averaging point, no telluric transmission, spectral radiance units, k-tables with
-        FWHM <= 0 (the only modes the reference's convg supports with k-tables), and a path type on the device."""
+        """Can the tail of nemesisfmg for this geometry (JSURF column, WGEOM weight, Measurement_0.convg or
+        integrate_filterg) run on the device?  One averaging point, no telluric transmission, k-tables with
+        FWHM <= 0 (the only modes the reference's convg supports with k-tables; FWHM < 0 for integrated
+        radiances), and a path type on the device."""
         M = self.Measurement
-        return (self._b200_mode() is not None and int(M.NAV[IGEOM]) == 1 and self.Telluric is None and
-                int(M.IFORM) != _IFORM_INTEGRATED_RADIANCE and int(self.Spectroscopy.ILBL) == _K_TABLES and
-                float(M.FWHM) <= 0.0 and self.PathX.NPATH == 1)
+        if not (self._b200_mode() is not None and int(M.NAV[IGEOM]) == 1 and self.Telluric is None and
+                int(self.Spectroscopy.ILBL) == _K_TABLES and self.PathX.NPATH == 1):
+            return False
+        if int(M.IFORM) == _IFORM_INTEGRATED_RADIANCE:
+            return float(M.FWHM) < 0.0            # integrate_filterg raises for FWHM >= 0 (Measurement_0.py:2772)
+        return float(M.FWHM) <= 0.0
 
     def b200_forward_jacobian_conv(self, xmap, IGEOM, wgeom):
         """b200_forward_jacobian + the JSURF column + WGEOM + Measurement_0.convg (:716-768) with only
@@ -353,7 +357,11 @@ class B200HotPathMixin:
         ev = self._b200_evaluation(self._b200_mode(), True)
         Mx = _plan.fold_projection(xmap, path.LAYINC, path.NLAYIN, lay.DTE, lay.DAM, lay.DCO, atm.NVMR, atm.NDUST)
         n = int(M.NCONV[IGEOM])
-        op = _plan.conv_operator(self.SpectroscopyX.WAVE, M.VCONV[0:n, IGEOM], float(M.FWHM), M.NFIL, M.VFIL, M.AFIL)
+        if int(M.IFORM) == _IFORM_INTEGRATED_RADIANCE:
+            # integrate_filterg works on the Doppler-corrected grid (Measurement_0.py:2768)
+            op = _plan.filter_integral_operator(M.correct_doppler_shift(self.SpectroscopyX.WAVE), n, M.NFIL, M.VFIL, M.AFIL)
+        else:
+            op = _plan.conv_operator(self.SpectroscopyX.WAVE, M.VCONV[0:n, IGEOM], float(M.FWHM), M.NFIL, M.VFIL, M.AFIL)
         out = hp.to_host(hp.forward_jacobian_conv(ev, Mx, hp.conv_operator(op), int(self.Variables.JSURF), float(wgeom)))
         return out[:, 0], out[:, 1:]
 

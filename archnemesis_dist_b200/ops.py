@@ -194,6 +194,7 @@ class ConvOperator:
         self.np_lo = to_dev(op["np_lo"], torch.int32)
         self.np_exact = to_dev(op["np_exact"], torch.int32)
         self.xinfo = to_dev(op["xinfo"])
+        self.weighted_sum_only = bool(op.get("weighted_sum_only", False))
 
 
 def convolve(cop, block, col0_is_spectrum=True):
@@ -207,7 +208,8 @@ def convolve(cop, block, col0_is_spectrum=True):
     if not block.is_cuda or block.dtype != torch.float64:
         raise ValueError("convolve: block must be a float64 device tensor")
     _lib.check(_lib.load().ansb200_convolve(ctypes.c_void_p(block.data_ptr()), NWAVE, NCOL, block.stride(0), cop.mode,
-                                            int(bool(col0_is_spectrum)), _ptr(cop.row_start), _ptr(cop.widx),
+                                            int(bool(col0_is_spectrum) and not cop.weighted_sum_only), _ptr(cop.row_start),
+                                            _ptr(cop.widx),
                                             _ptr(cop.wval), _ptr(cop.norm), _ptr(cop.np_lo), _ptr(cop.np_exact),
                                             _ptr(cop.xinfo), cop.NCONV, _ptr(out), _stream()))
     return out

@@ -210,3 +210,33 @@ def conv_operator(Wave, VCONV, FWHM, NFIL=None, VFIL=None, AFIL=None):
                 wval=np.asarray(vals, np.float64), norm=np.asarray(norm, np.float64),
                 np_lo=np.zeros(nconv, np.int32), np_exact=np.zeros(nconv, np.int32), xinfo=np.zeros((nconv, 3)),
                 NCONV=nconv)
+
+
+def filter_integral_operator(Wave, NCONV, NFIL, VFIL, AFIL):
+    """Measurement_0.integrate_filter / integrate_filterg (archnemesis/Measurement_0.py:4079-4250; IFORM =
+    integrated radiance): ``np.trapz(y[i] * np.interp(Wave[i], VFIL, AFIL), Wave[i])`` over the calculation points
+    inside the filter, as rows of a weighted sum (no normalisation): the coefficient of y_i is
+    ``a_i * ((x_{i+1} - x_i) + (x_i - x_{i-1})) / 2`` with one-sided ends.  ``Wave`` is the Doppler-corrected grid
+    the reference passes (``correct_doppler_shift``).  Same sum as numba's trapz up to the order of the
+    additions (a few ulp)."""
+    Wave = np.asarray(Wave, dtype=np.float64)
+    rows, vals, start = [], [], [0]
+    for ic in range(int(NCONV)):
+        nf = int(NFIL[ic])
+        xp = np.asarray(VFIL[0:nf, ic], dtype=np.float64)
+        yp = np.asarray(AFIL[0:nf, ic], dtype=np.float64)
+        idx = np.where((Wave >= xp[0]) & (Wave <= xp[nf - 1]))[0]
+        if len(idx) >= 2:
+            x = Wave[idx]
+            a = np.interp(x, xp, yp)
+            d = np.diff(x)
+            c = np.zeros(len(idx))
+            c[:-1] += d / 2.0
+            c[1:] += d / 2.0
+            rows.extend(idx.tolist())
+            vals.extend((a * c).tolist())
+        start.append(len(rows))
+    n = int(NCONV)
+    return dict(mode=CONV_INTERP, row_start=np.asarray(start, np.int32), widx=np.asarray(rows, np.int32),
+                wval=np.asarray(vals, np.float64), norm=np.ones(n), np_lo=np.zeros(n, np.int32),
+                np_exact=np.zeros(n, np.int32), xinfo=np.zeros((n, 3)), NCONV=n, weighted_sum_only=True)

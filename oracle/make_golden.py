@@ -284,6 +284,12 @@ def golden_stages(ans):
     op1 = b2plan.conv_operator(cw, vconv1, -1.0, nfil, vfil, afil)
     assert np.array_equal(orc.apply_conv(op1, cy), y1) and np.array_equal(orc.apply_conv(op1, cg), g1)
     assert np.array_equal(M1.conv(cw, cy, IGEOM=0), y1)
+    # integrated radiance over the same filters: Measurement_0.integrate_filterg (:2742-2800, :4188-4250)
+    M1.V_DOPPLER = 0.0
+    yi, gi = M1.integrate_filterg(cw, cy, cg, IGEOM=0)
+    opi = b2plan.filter_integral_operator(cw, 11, nfil, vfil, afil)
+    assert rel(orc.apply_conv(opi, cy), yi) < 1e-14 and rel(orc.apply_conv(opi, cg), gi) < 1e-12
+    out.update(cv_yi=yi, cv_gi=gi)
     out.update(cv_wave=cw, cv_y=cy, cv_grad=cg, cv_vconv=vconv, cv_vconv1=vconv1, cv_nfil=nfil, cv_vfil=vfil, cv_afil=afil,
                cv_y0=y0, cv_g0=g0, cv_y1=y1, cv_g1=g1)
     # ---- map2pro / map2xvec -----------------------------------------------------------------------------

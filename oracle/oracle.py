@@ -378,7 +378,7 @@ def apply_conv(op, y):
     out = np.zeros((op["NCONV"], y2.shape[1]))
     rs, wi, wv = op["row_start"], op["widx"], op["wval"]
     for c in range(op["NCONV"]):
-        if op["mode"] == 0 and one_d:
+        if op["mode"] == 0 and one_d and not op.get("weighted_sum_only", False):
             j = op["np_lo"][c]
             x_lo, x_hi, x_new = op["xinfo"][c]
             if op["np_exact"][c]:

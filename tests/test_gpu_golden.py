@@ -118,6 +118,10 @@ def test_stage_golden_convolve():
         assert np.array_equal(out2, out)
         only_grad = cpu(ops.convolve(ops.ConvOperator(op), block[:, 1:].contiguous(), col0_is_spectrum=False))
         assert np.array_equal(only_grad, gs)
+    # integrated radiance (Measurement_0.integrate_filterg): weighted trapezoid sums, equal to rounding
+    opi = plan.filter_integral_operator(g["cv_wave"], 11, g["cv_nfil"], g["cv_vfil"], g["cv_afil"])
+    outi = cpu(ops.convolve(ops.ConvOperator(opi), block))
+    assert relerr(outi[:, 0], g["cv_yi"]) < 1e-14 and colerr(outi[:, 1:], g["cv_gi"]) < 1e-14
 
 
 def test_stage_golden_projection_and_lbl():

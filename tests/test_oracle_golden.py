@@ -60,6 +60,10 @@ def test_conv_operator_goldens():
     op1 = plan.conv_operator(g["cv_wave"], g["cv_vconv1"], -1.0, g["cv_nfil"], g["cv_vfil"], g["cv_afil"])
     assert np.array_equal(orc.apply_conv(op1, g["cv_y"]), g["cv_y1"])
     assert np.array_equal(orc.apply_conv(op1, g["cv_grad"]), g["cv_g1"])
+    # integrated radiance over the same filters (integrate_filterg): trapezoid sum, equal to rounding
+    opi = plan.filter_integral_operator(g["cv_wave"], 11, g["cv_nfil"], g["cv_vfil"], g["cv_afil"])
+    assert relerr(orc.apply_conv(opi, g["cv_y"]), g["cv_yi"]) < 1e-14
+    assert colerr(orc.apply_conv(opi, g["cv_grad"]), g["cv_gi"]) < 1e-14
     import pytest
     with pytest.raises(ValueError):
         plan.conv_operator(g["cv_wave"], g["cv_vconv"], 0.5)                       # convg raises for FWHM > 0
