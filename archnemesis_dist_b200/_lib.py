@@ -31,6 +31,7 @@ EXPORTS = {
     "ansb200_jacobian_project": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "ansb200_lbl_absorption": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _d, _d, _d, _d, _d, _d,
                                     _d, _i, _vp, _vp]),
+    "ansb200_lbl_table_opacity": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "ansb200_convolve": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "ansb200_voigt": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
 }

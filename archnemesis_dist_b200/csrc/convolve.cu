@@ -23,15 +23,15 @@ ans_convolve_kernel(const double *__restrict__ in, int NCOL, int ld, int mode, i
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= NCOL) return;
     double r;
-    if (mode == 0 && col0_np && col == 0) {
+    if (mode == 0 && (col0_np == 2 || (col0_np && col == 0))) {
         // np.interp: y[j] on a knot, else slope*(x - x[j]) + y[j]
         const int j = np_lo[c];
-        const double y0 = in[(size_t)j * ld];
+        const double y0 = in[(size_t)j * ld + col];
         if (np_exact[c]) {
             r = y0;
         } else {
             const double x_lo = xinfo[3 * c], x_hi = xinfo[3 * c + 1], x_new = xinfo[3 * c + 2];
-            const double slope = __ddiv_rn(__dsub_rn(in[(size_t)(j + 1) * ld], y0), __dsub_rn(x_hi, x_lo));
+            const double slope = __ddiv_rn(__dsub_rn(in[(size_t)(j + 1) * ld + col], y0), __dsub_rn(x_hi, x_lo));
             r = __dadd_rn(__dmul_rn(slope, __dsub_rn(x_new, x_lo)), y0);
         }
     } else {

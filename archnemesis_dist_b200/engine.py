@@ -94,10 +94,19 @@ class HotPath:
 
     K      [NWAVE,NG,NP,NT,NGAS] float64 (SpectroscopyX.K);  PRESS (atm) / TEMP (K) / DELG / WAVE are
            taken with the dtypes the live Spectroscopy object holds (float32 after a .kta read).
+           A 4-D K[NWAVE,NP,NT,NGAS] is a line-by-line table (ILBL = LINE_BY_LINE_TABLES, NG = 1, DELG = [1]):
+           the gas opacity then follows calc_klbl[g] and the plain sum over gases of the LBL branch of
+           calculate_gaseous_line_opacity (ForwardModel_0.py:3795-3815) instead of calc_k[g] + k_overlap[g];
+           everything downstream is shared.
     """
 
     def __init__(self, K, PRESS, TEMP, DELG, WAVE, ops=_ops):
         self.ops = ops
+        self.lbl_table = len(K.shape) == 4
+        if self.lbl_table:
+            K = K.reshape(K.shape[0], 1, K.shape[1], K.shape[2], K.shape[3])
+            if len(np.asarray(DELG)) != 1:
+                raise ValueError("a line-by-line table has one g-ordinate (DELG = [1.0])")
         self.table = ops.Table(K)
         self.NWAVE, self.NG, self.NP, self.NT, self.NGAS = (int(x) for x in K.shape)
         self.PRESS = np.asarray(PRESS)
@@ -117,6 +126,8 @@ class HotPath:
         buffer and one host->device copy so that the kernel can be launched after a single enqueue."""
         st = self._stage
         st.bytes = 0
+        if self.lbl_table:
+            return self._stage_lbl_opacity(ev, return_grad)
         hp = _plan.kinterp_plan(self.PRESS, self.TEMP, ev.press_atm, ev.temp, return_grad)
         n = len(ev.press_atm)
         amount = np.ascontiguousarray(ev.amount, dtype=np.float64)
@@ -141,6 +152,31 @@ class HotPath:
         s.plan_host = hp
         s.dplan = _DevPlan(dev, n)
         s.M = None
+        return s
+
+    def _stage_lbl_opacity(self, ev: Evaluation, return_grad):
+        """stage_opacity for a line-by-line table: plan.klbl_plan + amounts in one pinned buffer."""
+        st = self._stage
+        hp = _plan.klbl_plan(self.PRESS, self.TEMP, ev.press_atm, ev.temp, return_grad)
+        n = len(ev.press_atm)
+        amount = np.ascontiguousarray(ev.amount, dtype=np.float64)
+        parts = [hp["w4"].reshape(-1), hp["omv"], hp["vv"], hp["du1dt"], hp["du2dt"], amount.reshape(-1),
+                 hp["corner"].reshape(-1).view(np.float64)]
+        packed = st("opacity_inputs", np.concatenate(parts))
+        off = 0
+
+        def take(count):
+            nonlocal off
+            v = packed[off:off + count]
+            off += count
+            return v
+        s = Staged()
+        d = _LblDevPlan()
+        d.NLAY = n
+        d.w4, d.omv, d.vv, d.du1dt, d.du2dt = take(4 * n).view(n, 4), take(n), take(n), take(n), take(n)
+        s.amount = take(amount.size).view(amount.shape)
+        d.corner = take(2 * n).view(torch.int32)
+        s.grad, s.plan_host, s.dplan, s.M = return_grad, hp, d, None
         return s
 
     def stage_radiance(self, s, ev: Evaluation, M=None):
@@ -170,7 +206,10 @@ class HotPath:
         """calc_k[g] + k_overlap[g] fused on the device -> tau[NWAVE,NG,NLAY] (, dk[...,NGAS+1])."""
         if timers is not None:
             timers[0].record()
-        out = self.ops.gas_opacity(self.table, s.dplan, s.amount, self.otab, s.grad)
+        if self.lbl_table:
+            out = self.ops.lbl_table_opacity(self.table, s.dplan, s.amount, s.grad)
+        else:
+            out = self.ops.gas_opacity(self.table, s.dplan, s.amount, self.otab, s.grad)
         if timers is not None:
             timers[1].record()
         self.launches += 1
@@ -268,6 +307,10 @@ class HotPath:
 
 class Staged:
     """Device-resident inputs of one evaluation (see HotPath.stage)."""
+
+
+class _LblDevPlan:
+    """Device views of a plan.klbl_plan inside the packed staging buffer."""
 
 
 class _DevPlan:

@@ -35,6 +35,7 @@ from . import plan as _plan
 
 # enum values of the reference (archnemesis/enum/*.py) as plain ints so that nothing here imports it
 _K_TABLES = 0                 # SpectralCalculationModeEnum.K_TABLES
+_LBL_TABLES = 2               # SpectralCalculationModeEnum.LINE_BY_LINE_TABLES
 # PathCalcEnum is an IntFlag built with auto() (enum/path_calc_enum.py:3-25): bit = 1 << position
 _THERMAL_EMISSION = 1 << 6
 _MULTIPLE_SCATTERING = 1 << 8
@@ -161,6 +162,15 @@ def make_fused_map_functions(ref_map2pro, ref_map2xvec):
     return map2pro, map2xvec
 
 
+def _table_on_device(sp):
+    """k-tables [NWAVE,NG,NP,NT,NGAS] and in-memory line-by-line tables [NWAVE,NP,NT,NGAS] run on the device;
+    run-time line-by-line and tables read on line from HDF5 (K is None) stay on the reference."""
+    if sp.NGAS < 1 or sp.K is None:
+        return False
+    ilbl = int(sp.ILBL)
+    return (ilbl == _K_TABLES and np.ndim(sp.K) == 5) or (ilbl == _LBL_TABLES and np.ndim(sp.K) == 4)
+
+
 class B200HotPathMixin:
     """Overrides of the hot methods of ForwardModel_0.  `b200_engine` may be replaced (tests inject an
     oracle-backed engine to exercise the host logic without a GPU)."""
@@ -171,7 +181,7 @@ class B200HotPathMixin:
     def _b200_mode(self):
         """THERMAL / TRANSMISSION if this path type runs on the device, else None."""
         sp = self.SpectroscopyX
-        if int(sp.ILBL) != _K_TABLES or sp.NGAS < 1 or sp.K is None:
+        if not _table_on_device(sp):
             return None
         if getattr(self, "EmissionsX", None) is not None:
             return None
@@ -270,10 +280,11 @@ class B200HotPathMixin:
 
     # -- overridden reference methods ------------------------------------------------------------
     def calculate_gaseous_line_opacity(self, return_grad=False):
-        """K_TABLES branch of ForwardModel_0.calculate_gaseous_line_opacity (:3850-3877) on the device.
+        """K_TABLES (:3850-3877) and LINE_BY_LINE_TABLES (:3795-3815) branches of
+        ForwardModel_0.calculate_gaseous_line_opacity on the device.
         Returns numpy TAUGAS[NWAVE,NG,NLAY] and dTAUGAS[NWAVE,NG,NPAR,NLAY] like the reference."""
         sp = self.SpectroscopyX
-        if sp.NGAS < 1 or int(sp.ILBL) != _K_TABLES or sp.K is None:
+        if not _table_on_device(sp):
             return super().calculate_gaseous_line_opacity(return_grad)
         atm, lay = self.AtmosphereX, self.LayerX
         hp = self._b200_hotpath()
@@ -343,10 +354,12 @@ class B200HotPathMixin:
         radiances), and a path type on the device."""
         M = self.Measurement
         if not (self._b200_mode() is not None and int(M.NAV[IGEOM]) == 1 and self.Telluric is None and
-                int(self.Spectroscopy.ILBL) == _K_TABLES and self.PathX.NPATH == 1):
+                self.PathX.NPATH == 1):
             return False
         if int(M.IFORM) == _IFORM_INTEGRATED_RADIANCE:
             return float(M.FWHM) < 0.0            # integrate_filterg raises for FWHM >= 0 (Measurement_0.py:2772)
+        if int(self.Spectroscopy.ILBL) == _LBL_TABLES:
+            return True                           # lblconvg: analytic shapes (FWHM > 0), filters (< 0), np.interp (== 0)
         return float(M.FWHM) <= 0.0
 
     def b200_forward_jacobian_conv(self, xmap, IGEOM, wgeom):
@@ -356,14 +369,39 @@ class B200HotPathMixin:
         hp = self._b200_hotpath()
         ev = self._b200_evaluation(self._b200_mode(), True)
         Mx = _plan.fold_projection(xmap, path.LAYINC, path.NLAYIN, lay.DTE, lay.DAM, lay.DCO, atm.NVMR, atm.NDUST)
-        n = int(M.NCONV[IGEOM])
-        if int(M.IFORM) == _IFORM_INTEGRATED_RADIANCE:
-            # integrate_filterg works on the Doppler-corrected grid (Measurement_0.py:2768)
-            op = _plan.filter_integral_operator(M.correct_doppler_shift(self.SpectroscopyX.WAVE), n, M.NFIL, M.VFIL, M.AFIL)
-        else:
-            op = _plan.conv_operator(self.SpectroscopyX.WAVE, M.VCONV[0:n, IGEOM], float(M.FWHM), M.NFIL, M.VFIL, M.AFIL)
-        out = hp.to_host(hp.forward_jacobian_conv(ev, Mx, hp.conv_operator(op), int(self.Variables.JSURF), float(wgeom)))
+        cop = self._b200_conv_operator(hp, IGEOM)
+        out = hp.to_host(hp.forward_jacobian_conv(ev, Mx, cop, int(self.Variables.JSURF), float(wgeom)))
         return out[:, 0], out[:, 1:]
+
+    def _b200_conv_operator(self, hp, IGEOM):
+        """The line-shape operator of geometry IGEOM on the device, rebuilt only when the calculation grid or the
+        measurement's line-shape description changes (the analytic shapes cost NCONV x window-length libm calls)."""
+        M, WAVE = self.Measurement, np.asarray(self.SpectroscopyX.WAVE, dtype=np.float64)
+        n = int(M.NCONV[IGEOM])
+        integ = int(M.IFORM) == _IFORM_INTEGRATED_RADIANCE
+        lbl = int(self.Spectroscopy.ILBL) == _LBL_TABLES
+        vconv = np.asarray(M.VCONV[0:n, IGEOM], dtype=np.float64)
+        key = [IGEOM, integ, lbl, float(M.FWHM), int(getattr(M, "ISHAPE", 0) or 0), float(getattr(M, "V_DOPPLER", 0.0) or 0.0),
+               WAVE.tobytes(), vconv.tobytes()]
+        if float(M.FWHM) < 0.0:
+            key += [np.asarray(M.NFIL).tobytes(), np.asarray(M.VFIL).tobytes(), np.asarray(M.AFIL).tobytes()]
+        key = hash(tuple(key))
+        cache = self.__dict__.setdefault("_b200_conv_cache", {})
+        hit = cache.get(IGEOM)
+        if hit is not None and hit[0] == key and hit[1] is hp:
+            return hit[2]
+        if integ:
+            # integrate_filterg works on the Doppler-corrected grid (Measurement_0.py:2768)
+            op = _plan.filter_integral_operator(M.correct_doppler_shift(WAVE), n, M.NFIL, M.VFIL, M.AFIL)
+        elif lbl:
+            # lblconvg, also on the Doppler-corrected grid (Measurement_0.py:2222)
+            op = _plan.lbl_conv_operator(M.correct_doppler_shift(WAVE), vconv, float(M.FWHM), int(M.ISHAPE), M.NFIL, M.VFIL,
+                                         M.AFIL, grad=True)
+        else:
+            op = _plan.conv_operator(WAVE, vconv, float(M.FWHM), M.NFIL, M.VFIL, M.AFIL)
+        cop = hp.conv_operator(op)
+        cache[IGEOM] = (key, hp, cop)
+        return cop
 
 
 class ArrayForwardModel(B200HotPathMixin):

@@ -141,6 +141,34 @@ def gas_opacity(table, dplan, amount, otab, want_grad=False, force_seq=False):
     return (tau, dk) if want_grad else tau
 
 
+class LblDevicePlan:
+    """plan.klbl_plan uploaded to the device."""
+
+    def __init__(self, host_plan):
+        self.host = host_plan
+        self.NLAY = len(host_plan["corner"])
+        self.corner = to_dev(host_plan["corner"], torch.int32)
+        self.w4 = to_dev(host_plan["w4"])
+        self.omv, self.vv = to_dev(host_plan["omv"]), to_dev(host_plan["vv"])
+        self.du1dt, self.du2dt = to_dev(host_plan["du1dt"]), to_dev(host_plan["du2dt"])
+
+
+def lbl_table_opacity(table, dplan, amount, want_grad=False):
+    """calc_klbl[g] + the LBL-table branch of calculate_gaseous_line_opacity (ForwardModel_0.py:3795-3815):
+    tau[NWAVE,1,NLAY] (, dk[NWAVE,1,NLAY,NGAS+1]) from a resident NG = 1 table."""
+    _require_cuda()
+    NWAVE, NG, NP, NT, NGAS = table.shape
+    if NG != 1:
+        raise ValueError("lbl_table_opacity: the table must have NG = 1")
+    NLAY = dplan.NLAY
+    tau = torch.empty((NWAVE, 1, NLAY), dtype=torch.float64, device="cuda")
+    dk = torch.empty((NWAVE, 1, NLAY, NGAS + 1), dtype=torch.float64, device="cuda") if want_grad else None
+    _lib.check(_lib.load().ansb200_lbl_table_opacity(table.handle, NLAY, _ptr(dplan.corner), _ptr(dplan.w4), _ptr(dplan.omv),
+                                                     _ptr(dplan.vv), _ptr(dplan.du1dt), _ptr(dplan.du2dt), _ptr(amount),
+                                                     int(want_grad), _ptr(tau), _ptr(dk), _stream()))
+    return (tau, dk) if want_grad else tau
+
+
 THERMAL, TRANSMISSION = 0, 1
 
 
@@ -195,6 +223,7 @@ class ConvOperator:
         self.np_exact = to_dev(op["np_exact"], torch.int32)
         self.xinfo = to_dev(op["xinfo"])
         self.weighted_sum_only = bool(op.get("weighted_sum_only", False))
+        self.np_interp_all = bool(op.get("np_interp_all", False))       # lblconv / lblconvg with FWHM == 0
 
 
 def convolve(cop, block, col0_is_spectrum=True):
@@ -208,8 +237,7 @@ def convolve(cop, block, col0_is_spectrum=True):
     if not block.is_cuda or block.dtype != torch.float64:
         raise ValueError("convolve: block must be a float64 device tensor")
     _lib.check(_lib.load().ansb200_convolve(ctypes.c_void_p(block.data_ptr()), NWAVE, NCOL, block.stride(0), cop.mode,
-                                            int(bool(col0_is_spectrum) and not cop.weighted_sum_only), _ptr(cop.row_start),
-                                            _ptr(cop.widx),
-                                            _ptr(cop.wval), _ptr(cop.norm), _ptr(cop.np_lo), _ptr(cop.np_exact),
+                                            2 if cop.np_interp_all else int(bool(col0_is_spectrum) and not cop.weighted_sum_only),
+                                            _ptr(cop.row_start), _ptr(cop.widx), _ptr(cop.wval), _ptr(cop.norm), _ptr(cop.np_lo), _ptr(cop.np_exact),
                                             _ptr(cop.xinfo), cop.NCONV, _ptr(out), _stream()))
     return out

@@ -80,6 +80,58 @@ def kinterp_plan(PRESS, TEMP, press, temp, grad):
     return dict(ip_lo=ipl.astype(np.int32), it_lo=itl.astype(np.int32), w4=w4, omv=omv, vv=vv, dudt=dudt)
 
 
+def klbl_plan(PRESS, TEMP, press, temp, grad):
+    """Per-layer corner planes and weights for calc_klbl (grad=False, Spectroscopy_0.py:1800-1850) or
+    calc_klblg (grad=True, :1636-1684) on a line-by-line table K[NWAVE,NP,NT,NGAS].
+
+    The reference works on scalars with the grids' own dtypes (``np.log(self.PRESS)`` stays float32 after a
+    float32 read); every operation is repeated here on numpy scalars of those dtypes and widened at the end.
+    TEMP may be 2-D (pressure-dependent temperature grids, NT < 0): the two pressure levels then bracket the
+    temperature separately (it1/u1 on level ip, it2/u2 on level ip+1).  calc_klblg does not clamp ``it`` at
+    zero, so a layer sitting exactly on (or clamped to) the first temperature node indexes TEMP[-1] and
+    K[:, ip, -1]: the plan carries the wrapped plane numbers so that the device reads what the reference reads.
+    corner[NLAY,4] = ip*NT+it1, ip*NT+it1+1, (ip+1)*NT+it2, (ip+1)*NT+it2+1."""
+    LP = np.log(np.asarray(PRESS))
+    TEMP = np.asarray(TEMP)
+    press = np.asarray(press, dtype=np.float64)
+    temp = np.asarray(temp, dtype=np.float64)
+    n, npg, ntg = len(press), len(LP), TEMP.shape[-1]
+    pmin, pmax, tmin, tmax = np.min(LP), np.max(LP), np.min(TEMP), np.max(TEMP)
+    corner = np.zeros((n, 4), np.int32)
+    w4 = np.zeros((n, 4))
+    omv, vv, du1dt, du2dt = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
+
+    def bracket(T, t):
+        it = int(np.searchsorted(T, t)) - 1
+        if it < 0 and not grad:
+            it = 0
+        if it >= len(T) - 1:
+            it = len(T) - 2
+        return it, (t - T[it]) / (T[it + 1] - T[it]), 1. / (T[it + 1] - T[it])
+
+    for i in range(n):
+        p_l = np.log(press[i])
+        if p_l < pmin:
+            p_l = pmin
+        if p_l > pmax:
+            p_l = pmax
+        t_l = temp[i]
+        if t_l < tmin:
+            t_l = tmin
+        if t_l > tmax:
+            t_l = tmax
+        ip = min(max(int(np.searchsorted(LP, p_l)) - 1, 0), npg - 2)
+        v = (p_l - LP[ip]) / (LP[ip + 1] - LP[ip])
+        Tn, Tn2 = (TEMP[ip], TEMP[ip + 1]) if TEMP.ndim == 2 else (TEMP, TEMP)
+        it1, u1, d1 = bracket(Tn, t_l)
+        it2, u2, d2 = bracket(Tn2, t_l)
+        corner[i] = (ip * ntg + it1 % ntg, ip * ntg + (it1 + 1) % ntg,
+                     (ip + 1) * ntg + it2 % ntg, (ip + 1) * ntg + (it2 + 1) % ntg)
+        w4[i] = ((1.0 - v) * (1.0 - u1), v * (1.0 - u2), v * u2, (1.0 - v) * u1)
+        omv[i], vv[i], du1dt[i], du2dt[i] = 1.0 - v, v, d1, d2
+    return dict(corner=corner, w4=w4, omv=omv, vv=vv, du1dt=du1dt, du2dt=du2dt)
+
+
 def planes_touched(plan, NT):
     """Number of distinct (ip,it) table planes the plan references (U of SURVEY.md 8d)."""
     s = set()
@@ -240,3 +292,110 @@ def filter_integral_operator(Wave, NCONV, NFIL, VFIL, AFIL):
     return dict(mode=CONV_INTERP, row_start=np.asarray(start, np.int32), widx=np.asarray(rows, np.int32),
                 wval=np.asarray(vals, np.float64), norm=np.ones(n), np_lo=np.zeros(n, np.int32),
                 np_exact=np.zeros(n, np.int32), xinfo=np.zeros((n, 3)), NCONV=n, weighted_sum_only=True)
+
+
+ILS_SQUARE, ILS_TRIANGULAR, ILS_GAUSSIAN, ILS_HAMMING, ILS_HANNING = 0, 1, 2, 3, 4
+
+
+def lbl_conv_operator(Wave, VCONV, FWHM, ISHAPE=ILS_GAUSSIAN, NFIL=None, VFIL=None, AFIL=None, grad=True):
+    """Measurement_0.lblconv / lblconvg (archnemesis/Measurement_0.py:2125-2284 and the kernels :3335-4076) of one
+    geometry as a sparse operator on the (Doppler-corrected) calculation grid ``Wave``.
+
+    FWHM > 0: the analytic line shape ISHAPE of width FWHM around every convolution point: all calculation points
+      with v1 <= Wave <= v2 contribute ``f1`` where f1 > 0, in ascending order, and the sum is divided by sum(f1).
+      Square: v = vcen -+ FWHM/2 (v2 = v1 + FWHM), f1 = 1.  Triangular: +-FWHM, 1 - |dv|/FWHM.  Gaussian: sig =
+      0.5 FWHM / sqrt(ln 2), +-3 sig, exp(-(dv/sig)^2).  Hamming: the reference's apodised sinc,
+      a = 0.907/FWHM; the gradient kernels window it at +-FWHM (:3864-3866) while the spectrum-only kernel sets
+      v1 = v2 = vcen - 1.1 FWHM (:3389-3391) -- ``grad`` selects which one is reproduced.  Hanning has no weight in
+      the reference (f1 stays 0): the division by zero is raised here as ZeroDivisionError, like numba does.
+      ``grad`` also selects the arithmetic of the weights: the gradient kernels are numba-compiled (libm exp / sin
+      through ``math``, squares as products), the spectrum-only ``lblconv`` is plain Python on numpy scalars (its
+      @jit is commented out) and returns NaN instead of raising where no point carries weight.
+    FWHM < 0: the tabulated filter (VFIL, AFIL) of every convolution point, f1 = np.interp(Wave[i], VFIL, AFIL) for
+      VFIL[0] <= Wave[i] <= VFIL[NFIL-1].  (The k-table convg takes one extra point either side; lblconv does not.)
+    FWHM == 0: np.interp(VCONV, Wave, y) for the spectrum AND every gradient column (``np_interp_all``)."""
+    import math
+    Wave = np.asarray(Wave, dtype=np.float64)
+    VCONV = np.asarray(VCONV, dtype=np.float64)
+    nconv, n = len(VCONV), len(Wave)
+    if FWHM == 0.0:
+        # np.interp clamps outside the grid: the end values, flagged as exact hits
+        j = np.searchsorted(Wave, VCONV, side="right") - 1
+        below, above = VCONV < Wave[0], VCONV >= Wave[n - 1]
+        exact = below | above | (Wave[j.clip(0, n - 1)] == VCONV)
+        j = np.where(above, n - 1, j.clip(0, n - 2))
+        jn = np.minimum(j + 1, n - 1)
+        xinfo = np.stack([Wave[j], Wave[jn], VCONV], axis=1)
+        return dict(mode=CONV_INTERP, row_start=np.zeros(nconv + 1, np.int32), widx=np.zeros(1, np.int32),
+                    wval=np.zeros(1), norm=np.ones(nconv), np_lo=j.astype(np.int32), np_exact=exact.astype(np.int32),
+                    xinfo=np.ascontiguousarray(xinfo), NCONV=nconv, np_interp_all=True)
+    rows, vals, start, norm = [], [], [0], []
+    for ic in range(nconv):
+        vcen = VCONV[ic]
+        if FWHM > 0.0:
+            yfwhm = FWHM
+            if ISHAPE == ILS_SQUARE:
+                v1 = vcen - 0.5 * yfwhm
+                v2 = v1 + yfwhm
+            elif ISHAPE == ILS_TRIANGULAR:
+                v1, v2 = vcen - yfwhm, vcen + yfwhm
+            elif ISHAPE == ILS_GAUSSIAN:
+                sig = 0.5 * yfwhm / np.sqrt(np.log(2.0))
+                v1, v2 = vcen - 3. * sig, vcen + 3. * sig
+            elif ISHAPE == ILS_HAMMING:
+                v1, v2 = (vcen - yfwhm, vcen + yfwhm) if grad else (vcen - 1.1 * yfwhm, vcen - 1.1 * yfwhm)
+            else:
+                v1, v2 = vcen - 3. * yfwhm, vcen + 3. * yfwhm
+        else:
+            nf = int(NFIL[ic])
+            xp = np.asarray(VFIL[0:nf, ic], dtype=np.float64)
+            yp = np.asarray(AFIL[0:nf, ic], dtype=np.float64)
+            v1, v2 = xp[0], xp[nf - 1]
+        idx = np.where((Wave >= v1) & (Wave <= v2))[0]
+        x = Wave[idx]
+        if FWHM < 0.0:
+            f = np.interp(x, xp, yp)
+        elif ISHAPE == ILS_SQUARE:
+            f = np.ones(len(idx))
+        elif ISHAPE == ILS_TRIANGULAR:
+            f = 1.0 - np.abs(x - vcen) / yfwhm
+        elif ISHAPE == ILS_GAUSSIAN:
+            if grad:
+                # the compiled kernels: libm exp, and x**2.0 is a plain product (LLVM folds pow(x, 2) to x*x)
+                f = np.array([math.exp(-(((xi - vcen) / sig) * ((xi - vcen) / sig))) for xi in x.tolist()],
+                             dtype=np.float64)
+            else:
+                # the spectrum-only lblconv runs as plain Python (its @jit is commented out, :3334): numpy scalars
+                f = np.array([np.exp(-((xi - vcen) / sig) ** 2.0) for xi in x], dtype=np.float64)
+        elif ISHAPE == ILS_HAMMING:
+            a = 0.907 / yfwhm
+            f = np.zeros(len(idx))
+            for q, xi in enumerate(x.tolist() if grad else x):
+                k = xi - vcen
+                if k == 0.0:
+                    f[q] = a * 1.08
+                elif grad:
+                    num = a * (1.08 - (0.64 * (a * a) * (k * k))) * math.sin(2 * np.pi * a * k)
+                    den = (1 - 4 * (a * a) * (k * k)) * (2 * np.pi * a * k)
+                    f[q] = num / den
+                else:
+                    num = a * (1.08 - (0.64 * a**2 * k**2)) * np.sin(2 * np.pi * a * k)
+                    den = (1 - 4 * a**2 * k**2) * (2 * np.pi * a * k)
+                    f[q] = num / den
+        else:
+            f = np.zeros(len(idx))
+        keep = f > 0.0
+        tot = 0.0
+        for fv in f[keep].tolist():
+            tot = tot + fv
+        if tot == 0.0 and (grad or FWHM < 0.0):
+            # numba raises on the scalar 0/0; the plain-Python lblconv returns NaN (norm 0 and no entries: the kernel's 0/0)
+            raise ZeroDivisionError("lbl_conv_operator: no positive line-shape weight at convolution point %d" % ic)
+        rows.extend(idx[keep].tolist())
+        vals.extend(f[keep].tolist())
+        start.append(len(rows))
+        norm.append(tot)
+    return dict(mode=CONV_FILTER, row_start=np.asarray(start, np.int32), widx=np.asarray(rows, np.int32),
+                wval=np.asarray(vals, np.float64), norm=np.asarray(norm, np.float64),
+                np_lo=np.zeros(nconv, np.int32), np_exact=np.zeros(nconv, np.int32), xinfo=np.zeros((nconv, 3)),
+                NCONV=nconv)

@@ -116,6 +116,18 @@ int ansb200_radiance(int mode, unsigned flags, const double *tau, const double *
                      int NVMR, int NPAR, int NLAYMAX, int NPATH, double *spec, double *dspec, double *dtsurf,
                      void *stream);
 
+/* ---- gas opacity from line-by-line tables ------------------------------------------------------
+ * Replaces Spectroscopy_0.calc_klbl / calc_klblg (archnemesis/Spectroscopy_0.py:1768-1919, :1601-1765)
+ * and the LBL-table branch of calculate_gaseous_line_opacity (ForwardModel_0.py:3795-3815).  The table
+ * is created from K[NWAVE,NP,NT,NGAS] with NG = 1.  Host plan per layer (plan.klbl_plan): corner[NLAY,4]
+ * = plane numbers ip*NT+it of (ip,it1), (ip,it1+1), (ip+1,it2), (ip+1,it2+1); w4[NLAY,4] =
+ * (1-v)(1-u1), v(1-u2), v u2, (1-v)u1; omv = 1-v, vv = v, du1dt, du2dt (gradient only).
+ * amount[NGAS,NLAY] = LayerX.AMOUNT[:,IGAS]*1e-4.  tau[NWAVE,1,NLAY]; dk[NWAVE,1,NLAY,NGAS+1] with
+ * entry i = k_i (d tau/d amount_i before the 1e-4) and entry NGAS = d tau/dT, as ansb200_gas_opacity. */
+int ansb200_lbl_table_opacity(const ansb200_table *t, int NLAY, const int32_t *corner, const double *w4,
+                              const double *omv, const double *vv, const double *du1dt, const double *du2dt,
+                              const double *amount, int want_grad, double *tau, double *dk, void *stream);
+
 /* ---- layer -> profile -> state vector ------------------------------------------------------
  * Replaces map2pro + map2xvec (ForwardModel_0.py:5319-5424).  The host folds
  * D[LAYINC[j,path],:] (DAM/DTE/DCO per parameter) with xmap into M[NPATH, NPAR*NLAYMAX, NX];
@@ -127,8 +139,11 @@ int ansb200_jacobian_project(const double *dspec, const double *M, int NWAVE, in
  * Replaces Measurement_0.conv / convg for k-tables (archnemesis/Measurement_0.py:2288-2465,
  * :2467-2692): mode 0 = FWHM == 0, scipy interp1d onto the convolution points (rows of two entries
  * (hi, lo) with SciPy's weights; with col0_np_interp column 0 -- the spectrum -- is evaluated in
- * np.interp's slope form from np_lo[NCONV], np_exact[NCONV], xinfo[NCONV,3] = (x_lo, x_hi, x_new));
- * mode 1 = FWHM < 0, filter-weighted mean sum(wval*in)/norm over widx[row_start[c]:row_start[c+1]].
+ * np.interp's slope form from np_lo[NCONV], np_exact[NCONV], xinfo[NCONV,3] = (x_lo, x_hi, x_new);
+ * col0_np_interp = 2 evaluates EVERY column that way: Measurement_0.lblconv / lblconvg with FWHM == 0,
+ * :2176-2186, :2267-2284);
+ * mode 1 = FWHM < 0, filter-weighted mean sum(wval*in)/norm over widx[row_start[c]:row_start[c+1]]
+ * (also lblconv / lblconvg with FWHM > 0 or < 0, :3335-4076: plan.lbl_conv_operator).
  * The operator is built on the host (plan.conv_operator).  in[NWAVE, ld] (first NCOL columns used,
  * e.g. [spectrum | Jacobian columns]) -> out[NCONV, NCOL].  Bit-identical to the reference. */
 int ansb200_convolve(const double *in, int NWAVE, int NCOL, int ld, int mode, int col0_np_interp,

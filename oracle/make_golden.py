@@ -70,6 +70,38 @@ def build_jupiter_deck(dst, nwave=60, vmin=5.0, delv=1.0, conv_lo=12.0, conv_hi=
     return dst
 
 
+def build_jupiter_lbl_deck(dst, nwave=221, vmin=5.0, delv=0.25, conv_lo=12.0, conv_hi=52.0, fwhm=None):
+    """The same deck in line-by-line-table mode (ILBL = 2): synthetic .lta tables written with the reference's own
+    writer, a .lls list instead of the .kls, and optionally a positive FWHM in the .spx (Gaussian ILS through
+    the .sha file) so that lblconvg's analytic line shape is exercised."""
+    import_reference()
+    from archnemesis.Spectroscopy_0 import write_lbltable
+    dst = build_jupiter_deck(dst, conv_lo=conv_lo, conv_hi=conv_hi)
+    paths = []
+    for n, (gid, iso) in enumerate(JUPITER_GASES):
+        t = syn.make_ktable(nwave, 1, 8, 6, 1, seed=150 + n)
+        fn = os.path.join(dst, "gas%d_%d.lta" % (gid, iso))
+        write_lbltable(fn, 8, 6, gid, iso, t["PRESS"], t["TEMP"], nwave, vmin, delv, t["K"][:, 0, :, :, 0])
+        paths.append(fn)
+    with open(os.path.join(dst, "cirstest.lls"), "w") as f:
+        f.write("\n".join(paths) + "\n")
+    os.remove(os.path.join(dst, "cirstest.kls"))
+    inp = open(os.path.join(dst, "cirstest.inp")).read().split("\n")
+    inp[0] = "0 0 2\t\t\t! ISPACE, ISCAT, ILBL"
+    with open(os.path.join(dst, "cirstest.inp"), "w") as f:
+        f.write("\n".join(inp))
+    if fwhm is not None:
+        spx = open(os.path.join(dst, "cirstest.spx")).read().split("\n")
+        head = spx[0].split()
+        head[0] = "%.5f" % fwhm
+        spx[0] = "  ".join(head)
+        with open(os.path.join(dst, "cirstest.spx"), "w") as f:
+            f.write("\n".join(spx))
+        with open(os.path.join(dst, "cirstest.sha"), "w") as f:
+            f.write("2\n")
+    return dst
+
+
 def load_jupiter(ans, deck):
     cwd = os.getcwd()
     os.chdir(deck)
@@ -318,10 +350,102 @@ def golden_stages(ans):
     print("wrote stages.npz", os.path.getsize(os.path.join(GOLD, "stages.npz")) // 1024, "KiB")
 
 
+def golden_lbl_table(ans):
+    """Line-by-line tables: Spectroscopy_0.calc_klbl / calc_klblg, the LBL branch of
+    ForwardModel_0.calculate_gaseous_line_opacity, Measurement_0.lblconv / lblconvg -> lbl_table.npz."""
+    import types
+    from archnemesis_dist_b200 import plan as b2plan
+    out = {}
+    rng = np.random.default_rng(41)
+    for tag, ngas, gdt in (("a", 3, np.float32), ("b", 11, np.float64)):
+        nw, npg, ntg, nlay = 7, 5, 4, 10
+        K = np.exp(rng.uniform(-60.0, -40.0, size=(nw, npg, ntg, ngas)))
+        K[rng.uniform(size=K.shape) < 0.08] = 0.0                    # mixed corners -> zero
+        K[2, :, :, 0] = 0.0                                          # all four corners zero -> linear branch
+        K[4, :, :, 1] = -np.abs(rng.normal(size=(npg, ntg))) * 1e-30  # negative table values -> linear branch
+        PRESS = np.exp(np.linspace(np.log(1e-6), np.log(10.0), npg)).astype(gdt)
+        TEMP = np.linspace(80.0, 320.0, ntg).astype(gdt)
+        press = np.exp(rng.uniform(np.log(2e-6), np.log(5.0), nlay))
+        temp = rng.uniform(90.0, 310.0, nlay)
+        press[0], press[1], press[2] = 50.0, 1e-9, float(PRESS[2])   # clamped high / low, on a node
+        temp[3], temp[4], temp[5], temp[6] = 20.0, 500.0, float(TEMP[0]), float(TEMP[2])   # clamped, first node, a node
+        S = ans.Spectroscopy_0(ILBL=2)
+        S.K, S.PRESS, S.TEMP, S.NWAVE, S.NG, S.NP, S.NT, S.NGAS = K, PRESS, TEMP, nw, 1, npg, ntg, ngas
+        S.DELG = np.array([1.0])
+        S.ID, S.ISO = np.arange(1, ngas + 1), np.zeros(ngas, dtype=int)
+        k = S.calc_klbl(nlay, press, temp)
+        kg, dkdT = S.calc_klblg(nlay, press, temp)
+        nvmr = ngas + 2
+        slot = rng.permutation(nvmr)[:ngas]
+        AMOUNT = np.exp(rng.uniform(np.log(1e20), np.log(1e26), size=(nlay, nvmr)))
+        stub = types.SimpleNamespace(
+            SpectroscopyX=S, ScatterX=types.SimpleNamespace(NDUST=1),
+            LayerX=types.SimpleNamespace(NLAY=nlay, PRESS=press * 101325.0, TEMP=temp, AMOUNT=AMOUNT),
+            AtmosphereX=types.SimpleNamespace(NVMR=nvmr, locate_gas=lambda gid, iso: int(slot[int(gid) - 1])))
+        tau, _ = ans.ForwardModel_0.calculate_gaseous_line_opacity(stub, return_grad=False)
+        taug, dtau = ans.ForwardModel_0.calculate_gaseous_line_opacity(stub, return_grad=True)
+        # the layer pressures the reference interpolates at are LayerX.PRESS / 101325, not `press` itself
+        pl = stub.LayerX.PRESS / 101325.0
+        k, (kg, dkdT) = S.calc_klbl(nlay, pl, temp), S.calc_klblg(nlay, pl, temp)
+        assert np.array_equal(orc.calc_klbl(K, PRESS, TEMP, pl, temp), k)
+        o = orc.calc_klbl(K, PRESS, TEMP, pl, temp, want_grad=True)
+        assert np.array_equal(o[0], kg) and np.array_equal(o[1], dkdT)
+        amount = np.stack([AMOUNT[:, g] * 1.0e-4 for g in slot])
+        assert np.array_equal(orc.lbl_table_opacity(K, PRESS, TEMP, pl, temp, amount), tau)
+        ot, odk = orc.lbl_table_opacity(K, PRESS, TEMP, pl, temp, amount, want_grad=True)
+        assert np.array_equal(ot, taug)
+        for i, g in enumerate(slot):
+            assert np.array_equal(odk[:, :, :, i] * 1.0e-4, dtau[:, :, g, :])
+        assert np.array_equal(odk[:, :, :, ngas], dtau[:, :, nvmr, :])
+        out.update({"%s_K" % tag: K, "%s_PRESS" % tag: PRESS, "%s_TEMP" % tag: TEMP, "%s_press" % tag: pl,
+                    "%s_temp" % tag: temp, "%s_amount" % tag: amount, "%s_k" % tag: k, "%s_kg" % tag: kg,
+                    "%s_dkdT" % tag: dkdT, "%s_tau" % tag: tau, "%s_taug" % tag: taug, "%s_dk" % tag: odk})
+    # ---- lblconv / lblconvg (Measurement_0.py:2125-2284, kernels :3335-4076) -------------------------------------
+    cw = np.linspace(2000.0, 2004.0, 801)
+    cy = rng.uniform(0.5, 2.0, 801) * 1e-7
+    cg = rng.normal(size=(801, 4)) * 1e-9
+    vconv = np.sort(rng.uniform(2000.4, 2003.6, 9))
+    vconv[2] = cw[300]
+    out.update(lc_wave=cw, lc_y=cy, lc_grad=cg, lc_vconv=vconv)
+    for tag, fwhm, ishape in (("sq", 0.11, 0), ("tr", 0.09, 1), ("ga", 0.07, 2), ("ha", 0.10, 3), ("ip", 0.0, 2)):
+        M = ans.Measurement_0(NGEOM=1, FWHM=fwhm, ISHAPE=ishape, NCONV=np.array([9], dtype="int32"))
+        M.VCONV, M.V_DOPPLER = vconv.reshape(9, 1), 0.0
+        yg, gg = M.lblconvg(cw, cy, cg, IGEOM=0)
+        op = b2plan.lbl_conv_operator(cw, vconv, fwhm, ishape)
+        assert np.array_equal(orc.apply_conv(op, cy), yg), tag
+        assert np.array_equal(orc.apply_conv(op, cg), gg), tag
+        # the spectrum-only lblconv is plain Python (different exp / pow roundings; an empty Hamming window -> NaN)
+        op0 = b2plan.lbl_conv_operator(cw, vconv, fwhm, ishape, grad=False)
+        with np.errstate(all="ignore"):
+            y0 = M.lblconv(cw, cy, IGEOM=0)
+            assert np.array_equal(orc.apply_conv(op0, cy), y0, equal_nan=True), tag
+        out.update({"lc_%s_y" % tag: yg, "lc_%s_g" % tag: gg, "lc_%s_y0" % tag: y0, "lc_%s_fwhm" % tag: fwhm,
+                    "lc_%s_ishape" % tag: ishape})
+    nfil = np.array([5, 7, 9, 4, 6, 8, 5, 7, 9], dtype="int32")
+    vfil, afil = np.zeros((9, 9)), np.zeros((9, 9))
+    for ic in range(9):
+        half = rng.uniform(0.05, 0.3)
+        vfil[:nfil[ic], ic] = np.linspace(vconv[ic] - half, vconv[ic] + half, nfil[ic])
+        afil[:nfil[ic], ic] = np.maximum(0.0, 1.0 - np.abs(np.linspace(-1.0, 1.0, nfil[ic])) ** 2) + 1e-3 * (ic % 3 == 0)
+    M = ans.Measurement_0(NGEOM=1, FWHM=-1.0, NCONV=np.array([9], dtype="int32"))
+    M.VCONV, M.V_DOPPLER, M.NFIL, M.VFIL, M.AFIL = vconv.reshape(9, 1), 0.0, nfil, vfil, afil
+    yf, gf = M.lblconvg(cw, cy, cg, IGEOM=0)
+    op = b2plan.lbl_conv_operator(cw, vconv, -1.0, NFIL=nfil, VFIL=vfil, AFIL=afil)
+    assert np.array_equal(orc.apply_conv(op, cy), yf) and np.array_equal(orc.apply_conv(op, cg), gf)
+    assert np.array_equal(M.lblconv(cw, cy, IGEOM=0), yf)
+    out.update(lc_nfil=nfil, lc_vfil=vfil, lc_afil=afil, lc_fil_y=yf, lc_fil_g=gf)
+    np.savez_compressed(os.path.join(GOLD, "lbl_table.npz"), **out)
+    print("wrote lbl_table.npz", os.path.getsize(os.path.join(GOLD, "lbl_table.npz")) // 1024, "KiB")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ans = import_reference()
+    if "--lbl-table-only" in sys.argv:
+        golden_lbl_table(ans)
+        return
     golden_stages(ans)
+    golden_lbl_table(ans)
     golden_jupiter(ans)
 
 

@@ -149,6 +149,73 @@ def calc_k(K, PRESS, TEMP, press, temp, want_grad=False, nthreads=1):
 
 
 # ----------------------------------------------------------------------------------------------
+# line-by-line tables: Spectroscopy_0.calc_klbl (:1768-1919) / calc_klblg (:1601-1765) and the LBL-table
+# branch of calculate_gaseous_line_opacity (ForwardModel_0.py:3795-3815).  numpy restatement.
+# ----------------------------------------------------------------------------------------------
+def _klbl_bracket(T, t, clamp_low):
+    it = int(np.searchsorted(T, t)) - 1
+    if clamp_low and it < 0:          # calc_klbl clamps at the first node (:1838-1839); calc_klblg does not
+        it = 0
+    if it >= len(T) - 1:
+        it = len(T) - 2
+    return it
+
+
+def calc_klbl(K, PRESS, TEMP, press, temp, want_grad=False):
+    """K[NWAVE,NP,NT,NGAS] -> k[NWAVE,NLAY,NGAS] (, dkdT).  Python's negative index is kept where calc_klblg
+    lets ``it`` reach -1 (a layer on the first temperature node)."""
+    K = np.asarray(K, dtype=np.float64)
+    lnP = np.log(np.asarray(PRESS))
+    TEMP = np.asarray(TEMP)
+    nw, _, _, ngas = K.shape
+    nlay = len(press)
+    k = np.zeros((nw, nlay, ngas))
+    dkdT = np.zeros((nw, nlay, ngas)) if want_grad else None
+    for l in range(nlay):
+        pl = min(max(np.log(press[l]), np.min(lnP)), np.max(lnP))
+        tl = min(max(temp[l], np.min(TEMP)), np.max(TEMP))
+        ip = min(max(int(np.searchsorted(lnP, pl)) - 1, 0), len(lnP) - 2)
+        v = (pl - lnP[ip]) / (lnP[ip + 1] - lnP[ip])
+        Ta, Tb = (TEMP[ip], TEMP[ip + 1]) if TEMP.ndim == 2 else (TEMP, TEMP)
+        ia, ib = _klbl_bracket(Ta, tl, not want_grad), _klbl_bracket(Tb, tl, not want_grad)
+        ua, da = (tl - Ta[ia]) / (Ta[ia + 1] - Ta[ia]), 1. / (Ta[ia + 1] - Ta[ia])
+        ub, db = (tl - Tb[ib]) / (Tb[ib + 1] - Tb[ib]), 1. / (Tb[ib + 1] - Tb[ib])
+        c_lo1, c_lo2 = K[:, ip, ia, :], K[:, ip, ia + 1, :]
+        c_hi1, c_hi2 = K[:, ip + 1, ib, :], K[:, ip + 1, ib + 1, :]
+        pos = (c_lo1 > 0.0) & (c_lo2 > 0.0) & (c_hi1 > 0.0) & (c_hi2 > 0.0)
+        neg = (c_lo1 <= 0.0) & (c_lo2 <= 0.0) & (c_hi1 <= 0.0) & (c_hi2 <= 0.0)
+        for mask, f in ((pos, np.log), (neg, lambda a: a)):
+            a1, a2, b1, b2 = f(c_lo1[mask]), f(c_lo2[mask]), f(c_hi1[mask]), f(c_hi2[mask])
+            x = (1.0 - v) * (1.0 - ua) * a1 + v * (1.0 - ub) * b1 + v * ub * b2 + (1.0 - v) * ua * a2
+            kv = np.exp(x) if f is np.log else x
+            k[:, l, :][mask] = kv
+            if want_grad:
+                dx = -a1 * (1.0 - v) * da - b1 * v * db + b2 * v * db + a2 * (1.0 - v) * da
+                dkdT[:, l, :][mask] = kv * dx if f is np.log else dx
+    return (k, dkdT) if want_grad else k
+
+
+def lbl_table_opacity(K, PRESS, TEMP, press, temp, amount, want_grad=False):
+    """TAUGAS[NWAVE,1,NLAY] (, dk[NWAVE,1,NLAY,NGAS+1] = [k_i ..., dTAUGAS/dT]); amount[NGAS,NLAY] already
+    carries the 1e-4 (VLOSDENS).  ForwardModel_0.py:3803-3815: per-gas products, np.sum over the gas axis,
+    the temperature derivative as a running sum in gas order."""
+    out = calc_klbl(K, PRESS, TEMP, press, temp, want_grad)
+    k, dkdT = out if want_grad else (out, None)
+    nw, nlay, ngas = k.shape
+    per_gas = np.zeros((nw, 1, nlay, ngas))
+    for i in range(ngas):
+        per_gas[:, 0, :, i] = k[:, :, i] * amount[i]
+    tau = np.sum(per_gas, 3)
+    if not want_grad:
+        return tau
+    dk = np.zeros((nw, 1, nlay, ngas + 1))
+    for i in range(ngas):
+        dk[:, 0, :, i] = k[:, :, i]
+        dk[:, 0, :, ngas] = dk[:, 0, :, ngas] + dkdT[:, :, i] * amount[i]
+    return tau, dk
+
+
+# ----------------------------------------------------------------------------------------------
 # random overlap
 # ----------------------------------------------------------------------------------------------
 def overlap_tables(del_g):
@@ -371,14 +438,15 @@ def lbl_absorption(wn_grid, lines, t_calc, p_calc, t_ref, p_ref, q_ratio, abunda
 def apply_conv(op, y):
     """Apply a conv operator (archnemesis_dist_b200.plan.conv_operator layout, host arrays) to y[NWAVE]
     (spectrum) or y[NWAVE,NCOL] (gradients) in the reference's arithmetic.  Mode 0: np.interp's slope form for
-    a 1-D y, SciPy's two-weight form for a 2-D y; mode 1: sequential sum(f1*y)/sum(f1)."""
+    a 1-D y, SciPy's two-weight form for a 2-D y (np.interp for both when the operator says np_interp_all:
+    lblconv / lblconvg); mode 1: sequential sum(f1*y)/sum(f1)."""
     y = np.asarray(y, dtype=np.float64)
     one_d = y.ndim == 1
     y2 = y.reshape(len(y), -1)
     out = np.zeros((op["NCONV"], y2.shape[1]))
     rs, wi, wv = op["row_start"], op["widx"], op["wval"]
     for c in range(op["NCONV"]):
-        if op["mode"] == 0 and one_d and not op.get("weighted_sum_only", False):
+        if op["mode"] == 0 and (one_d or op.get("np_interp_all", False)) and not op.get("weighted_sum_only", False):
             j = op["np_lo"][c]
             x_lo, x_hi, x_new = op["xinfo"][c]
             if op["np_exact"][c]:

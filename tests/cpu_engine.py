@@ -17,6 +17,7 @@ class Staged:
 class HotPath:
     def __init__(self, K, PRESS, TEMP, DELG, WAVE, ops=None):
         self.K = np.asarray(K, dtype=np.float64)
+        self.lbl_table = self.K.ndim == 4
         self.PRESS, self.TEMP, self.DELG = np.asarray(PRESS), np.asarray(TEMP), np.asarray(DELG)
         self.WAVE = np.asarray(WAVE, dtype=np.float64)
         self.launches = 0
@@ -28,6 +29,8 @@ class HotPath:
 
     def gas_opacity(self, s, timers=None):
         ev = s.ev
+        if self.lbl_table:
+            return orc.lbl_table_opacity(self.K, self.PRESS, self.TEMP, ev.press_atm, ev.temp, ev.amount, s.grad)
         if s.grad:
             k, d = orc.calc_k(self.K, self.PRESS, self.TEMP, ev.press_atm, ev.temp, want_grad=True)
             return orc.k_overlap(self.DELG, k, ev.amount, dkdT=d)

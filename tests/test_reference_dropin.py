@@ -73,3 +73,42 @@ def test_install_rebinds_three_names_and_matches_reference(jupiter):
     for ix in range(dS_ref.shape[2]):
         assert colerr(dS[:, :, ix], dS_ref[:, :, ix]) < 1e-11, ix
     assert relerr(tg, tg_ref) < 1e-13 and colerr(dtg, dtg_ref) < 1e-13
+
+
+def test_line_by_line_table_deck_matches_reference():
+    """The same deck in LINE_BY_LINE_TABLES mode (synthetic .lta tables, Gaussian ILS of FWHM 1.5 cm-1): calc_klblg,
+    the gas sum, CIRSrad, the projection and lblconvg through the drop-in (device-side convolution route) against
+    the unmodified reference, plus the reference's own nemesisfmg body on the drop-in instance."""
+    from oracle.ref_import import import_reference
+    from oracle import make_golden as mg
+    from archnemesis_dist_b200 import forward_model as fmod
+    from tests import cpu_engine
+    ans = import_reference()
+    deck = mg.build_jupiter_lbl_deck(os.path.join(tempfile.mkdtemp(prefix="ansb200_l_"), "deck"), fwhm=1.5)
+    ref_cls = sys.modules["archnemesis.ForwardModel_0"].ForwardModel_0
+    objs = mg.load_jupiter(ans, deck)
+    assert int(objs["Spectroscopy"].ILBL) == 2
+    cwd = os.getcwd()
+    os.chdir(deck)
+    try:
+        ref = mg.make_forward_model(ans, ref_cls, objs, deck)
+        S_ref, dS_ref = ref.nemesisfmg()
+        cls = fmod.install(ans)
+        try:
+            cls.b200_engine = cpu_engine
+            fm = mg.make_forward_model(ans, ans.ForwardModel_0, objs, deck)
+            S, dS = fm.nemesisfmg()
+            assert fm._b200_mode() is not None and fm.b200_device_conv_ok(0)
+            assert fm._b200_hotpath().lbl_table
+            S_lazy, dS_lazy = ref_cls.nemesisfmg(fm)
+            tg, dtg = fm.calculate_gaseous_line_opacity(True)
+        finally:
+            fmod.uninstall(ans)
+        tg_ref, dtg_ref = ref_cls.calculate_gaseous_line_opacity(fm, True)
+    finally:
+        os.chdir(cwd)
+    assert np.array_equal(tg, tg_ref) and np.array_equal(dtg, dtg_ref)
+    assert relerr(S, S_ref) < 1e-13 and relerr(S_lazy, S_ref) < 1e-13
+    for ix in range(dS_ref.shape[2]):
+        assert colerr(dS[:, :, ix], dS_ref[:, :, ix]) < 1e-12, ix
+        assert colerr(dS_lazy[:, :, ix], dS_ref[:, :, ix]) < 1e-12, ix
