@@ -12,7 +12,9 @@
 // sums are kept un-fused and in the reference's order, so the result is bit-identical to it.
 #include "common.cuh"
 
-__global__ void __launch_bounds__(128)
+constexpr int CV_THREADS = 64;
+
+__global__ void __launch_bounds__(CV_THREADS)
 ans_convolve_kernel(const double *__restrict__ in, int NCOL, int ld, int mode, int col0_np,
                     const int32_t *__restrict__ row_start, const int32_t *__restrict__ widx,
                     const double *__restrict__ wval, const double *__restrict__ norm,
@@ -35,9 +37,23 @@ ans_convolve_kernel(const double *__restrict__ in, int NCOL, int ld, int mode, i
             r = __dadd_rn(__dmul_rn(slope, __dsub_rn(x_new, x_lo)), y0);
         }
     } else {
+        // the sum keeps the reference's order; the loads do not depend on it, so eight rows are fetched ahead of
+        // the adds (an analytic line shape spans hundreds of calculation points: a chain of dependent L2 round
+        // trips otherwise)
         double acc = 0.0;
-        for (int e = row_start[c]; e < row_start[c + 1]; ++e)
-            acc = __dadd_rn(acc, __dmul_rn(wval[e], in[(size_t)widx[e] * ld + col]));
+        int e = row_start[c];
+        const int e1 = row_start[c + 1];
+        for (; e + 8 <= e1; e += 8) {
+            double w[8], v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                w[q] = __ldg(wval + e + q);
+                v[q] = __ldg(in + (size_t)__ldg(widx + e + q) * ld + col);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc = __dadd_rn(acc, __dmul_rn(w[q], v[q]));
+        }
+        for (; e < e1; ++e) acc = __dadd_rn(acc, __dmul_rn(wval[e], in[(size_t)widx[e] * ld + col]));
         r = mode == 1 ? __ddiv_rn(acc, norm[c]) : acc;
     }
     out[(size_t)c * NCOL + col] = r;
@@ -54,8 +70,8 @@ extern "C" int ansb200_convolve(const double *in, int NWAVE, int NCOL, int ld, i
     ANS_REQUIRE(mode != 1 || norm, "convolve: the filter mean needs norm");
     ANS_REQUIRE(!(mode == 0 && col0_np_interp) || (np_lo && np_exact && xinfo), "convolve: np.interp form needs np_lo/np_exact/xinfo");
     ANS_REQUIRE(NWAVE > 0 && NCOL > 0 && ld >= NCOL && NCONV > 0 && NCONV <= 65535, "convolve: bad shape");
-    dim3 grid(ans_div_up(NCOL, 128), NCONV);
-    ans_convolve_kernel<<<grid, 128, 0, stream>>>(in, NCOL, ld, mode, col0_np_interp, row_start, widx, wval, norm, np_lo,
+    dim3 grid(ans_div_up(NCOL, CV_THREADS), NCONV);
+    ans_convolve_kernel<<<grid, CV_THREADS, 0, stream>>>(in, NCOL, ld, mode, col0_np_interp, row_start, widx, wval, norm, np_lo,
                                                   np_exact, xinfo, out);
     ANS_LAUNCH_CHECK();
     return ANSB200_OK;

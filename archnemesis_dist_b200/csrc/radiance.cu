@@ -714,7 +714,7 @@ extern "C" int ansb200_radiance(int mode, unsigned flags, const double *tau, con
             return ANSB200_OK;
         }
     }
-    if (thermal && grad && dk && NPATH >= 4 && NLAYMAX <= 32 * TP_RQ && NGAS + 1 <= TP_NC) {
+    if (thermal && grad && dk && (NPATH >= 4 || NG == 1) && NLAYMAX <= 32 * TP_RQ && NGAS + 1 <= TP_NC) {
         // thermal emission with gradients over several paths: warp-per-path kernel if the slabs fit
         const size_t nd_p = (size_t)NG * NLAY + NLAY + NG + (dtaucon ? (size_t)NPAR * NLAY : 0) +
                             (size_t)NG * NLAY * TP_NC + (size_t)TP_WARPS * 3 * NLAYMAX + 1;

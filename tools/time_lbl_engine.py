@@ -1,0 +1,74 @@
+#!/usr/bin/env python
+"""Line-by-line-table mode through the engine: one nadir thermal forward+Jacobian evaluation on a table of NWAVE
+monochromatic points (NG = 1), stage by stage with CUDA events, then end to end with the Gaussian ILS applied on the
+device (forward_jacobian_conv: only [NCONV, 1+NX] returns to the host)."""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from archnemesis_dist_b200 import engine, plan, synthetic as syn  # noqa: E402
+
+
+def main(nwave=100000, ngas=4, nlay=60, nx=60, nconv=400):
+    c = syn.make_fm_case(nwave=nwave, ng=1, ngas=ngas, nlay=nlay, npro=nlay, nx=nx, nvmr=ngas + 1, seed=5, tsurf=150.0)
+    tab = c["tab"]
+    K4 = np.ascontiguousarray(tab["K"][:, 0])
+    hp = engine.HotPath(K4, tab["PRESS"], tab["TEMP"], np.array([1.0]), tab["WAVE"])
+    ev = engine.Evaluation(press_atm=c["press"], temp=c["temp"], amount=c["amount"], gas_slot=c["gas_slot"],
+                           NVMR=c["NVMR"], NPAR=c["NPAR"], LAYINC=c["LAYINC"], SCALE=c["SCALE"], NLAYIN=c["NLAYIN"],
+                           EMTEMP=c["EMTEMP"], LAYPRESS=c["LAYPRESS"], taucia=c["taucon"], dtaucon=c["dtaucon"],
+                           TSURF=c["TSURF"], EMISSIVITY=c["EMISSIVITY"], xfac=c["xfac"])
+    M = plan.fold_projection(c["xmap"], c["LAYINC"], c["NLAYIN"], c["DTE"], c["DAM"], c["DCO"], c["NVMR"], c["NDUST"])
+    wave = tab["WAVE"]
+    step = wave[1] - wave[0]
+    vconv = np.linspace(wave[200], wave[-201], nconv)
+    t0 = time.perf_counter()
+    op = plan.lbl_conv_operator(wave, vconv, 40.0 * step, plan.ILS_GAUSSIAN)
+    t_op = (time.perf_counter() - t0) * 1e3
+    cop = hp.conv_operator(op)
+    sync = torch.cuda.synchronize
+    for _ in range(3):
+        hp.forward_jacobian_conv(ev, M, cop, 2, 1.0)
+    sync()
+    ev_ = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    s = hp.stage(ev, True, M)
+    sync()
+    reps = 5
+    acc = np.zeros(4)
+    for _ in range(reps):
+        ev_[0].record()
+        go = hp.gas_opacity(s)
+        ev_[1].record()
+        out = hp.ops.radiance(s.mode, go[0], go[1], s.gas_slot, s.taucia, s.taudust, s.tauray, s.dtaucon, s.layinc, s.scale,
+                              s.nlayin, s.emtemp, s.laypress, hp.wave_d, hp.delg_d, s.emissivity, s.xfac, s.solflux,
+                              s.reflectance, s.sol_ang, s.emiss_ang, s.ISPACE, s.TSURF, s.NVMR, s.NPAR, True)
+        ev_[2].record()
+        dx = hp.ops.jacobian_project(out[1], s.M)
+        ev_[3].record()
+        block = torch.cat([out[0][:, :1], dx[:, 0, :]], dim=1)
+        hp.ops.convolve(cop, block)
+        ev_[4].record()
+        sync()
+        acc += [ev_[i].elapsed_time(ev_[i + 1]) for i in range(4)]
+    acc /= reps
+    print("LBL table NWAVE=%d NLAY=%d NGAS=%d NX=%d NCONV=%d (%d operator entries, built in %.0f ms on the host)"
+          % (nwave, nlay, ngas, nx, nconv, len(op["widx"]), t_op))
+    for name, v in zip(("lbl_table_opacity (calc_klblg + gas sum)", "radiance + layer Jacobian", "projection",
+                        "block assembly + lblconvg"), acc):
+        print("  %-45s %8.3f ms" % (name, v))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        o = hp.to_host(hp.forward_jacobian_conv(ev, M, cop, 2, 1.0))
+    print("  %-45s %8.3f ms  (h2d %.1f MB, d2h %.2f MB)" % ("end to end, host arrays in / [NCONV,1+NX] out",
+                                                             (time.perf_counter() - t0) * 1e3 / reps,
+                                                             ev.h2d_bytes / 1e6, o.nbytes / 1e6))
+    hp.close()
+
+
+if __name__ == "__main__":
+    main()
