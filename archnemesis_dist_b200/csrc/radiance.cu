@@ -691,8 +691,9 @@ extern "C" int ansb200_radiance(int mode, unsigned flags, const double *tau, con
                           ((grad && thermal) ? (size_t)NG * NLAYMAX : 0) + 3 * (size_t)NG;
         return nd * 8 + (size_t)(NLAYMAX + NPAR) * 4 + 16;
     };
-    const int warps_n = NG < 4 ? 4 : (NG > RAD_MAX_THREADS / 32 ? RAD_MAX_THREADS / 32 : NG);
-    const int warps_1 = (warps_n + 1) / 2 < 4 ? 4 : (warps_n + 1) / 2;
+    const int warps_min = NG == 1 ? 2 : 4;      // line-by-line tables: one g-ordinate, many small CTAs
+    const int warps_n = NG < 4 ? warps_min : (NG > RAD_MAX_THREADS / 32 ? RAD_MAX_THREADS / 32 : NG);
+    const int warps_1 = (warps_n + 1) / 2 < warps_min ? warps_min : (warps_n + 1) / 2;
     const int RAD_THREADS_1 = 32 * warps_1, RAD_THREADS_N = 32 * warps_n;
     size_t base = base_bytes(RAD_THREADS_1);
     const size_t slab = ((size_t)NG * NLAY + ((grad && dk) ? (size_t)NG * NLAY * (NGAS + 1) : 0)) * 8;
@@ -714,7 +715,7 @@ extern "C" int ansb200_radiance(int mode, unsigned flags, const double *tau, con
             return ANSB200_OK;
         }
     }
-    if (thermal && grad && dk && (NPATH >= 4 || NG == 1) && NLAYMAX <= 32 * TP_RQ && NGAS + 1 <= TP_NC) {
+    if (thermal && grad && dk && NPATH >= 4 && NLAYMAX <= 32 * TP_RQ && NGAS + 1 <= TP_NC) {
         // thermal emission with gradients over several paths: warp-per-path kernel if the slabs fit
         const size_t nd_p = (size_t)NG * NLAY + NLAY + NG + (dtaucon ? (size_t)NPAR * NLAY : 0) +
                             (size_t)NG * NLAY * TP_NC + (size_t)TP_WARPS * 3 * NLAYMAX + 1;

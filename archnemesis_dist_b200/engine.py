@@ -64,6 +64,7 @@ class Evaluation:
 
 class _Stager:
     """Pinned host staging + async H2D on the current stream; counts the bytes it moves."""
+    CHUNK_BYTES = 16 << 20
 
     def __init__(self):
         self.bytes = 0
@@ -81,9 +82,20 @@ class _Stager:
         buf, ev = slot
         if ev is not None:
             ev.synchronize()          # the previous async copy out of this pinned buffer must be done
-        buf.numpy()[...] = a
         self.bytes += a.nbytes
-        dev = buf.to("cuda", non_blocking=True)
+        if a.nbytes < self.CHUNK_BYTES:
+            buf.numpy()[...] = a
+            dev = buf.to("cuda", non_blocking=True)
+        else:
+            # large inputs (line-by-line grids: continuum terms of 1e5 wavenumbers): the copy into pinned memory
+            # is split over torch's host threads and pipelined against the DMA chunk by chunk
+            src, pin = torch.from_numpy(a).view(-1), buf.view(-1)
+            dev = torch.empty(a.shape, dtype=dtype, device="cuda")
+            dflat = dev.view(-1)
+            step = self.CHUNK_BYTES // a.itemsize
+            for i in range(0, src.numel(), step):
+                pin[i:i + step].copy_(src[i:i + step])
+                dflat[i:i + step].copy_(pin[i:i + step], non_blocking=True)
         slot[1] = torch.cuda.Event()
         slot[1].record()
         return dev
