@@ -67,6 +67,21 @@ def _worker(rank, world, port, out_dir):
         for a, b in zip(got, full):
             # (the stand-in engine projects with einsum, whose blocking depends on the row count: compare to rounding)
             assert a.shape == b.shape and np.abs(a.numpy() - b).max() <= 1e-13 * np.abs(b).max()
+        # (4) the same on a line-by-line table (4-D K, NG = 1): 5 wavenumbers over 2 ranks
+        cl = syn.make_fm_case(nwave=5, ng=1, ngas=2, nlay=8, nvmr=3, npro=8, nx=7, seed=6)
+        tl = cl["tab"]
+        K4, one = np.ascontiguousarray(tl["K"][:, 0]), np.array([1.0])
+        evl = engine.Evaluation(press_atm=cl["press"], temp=cl["temp"], amount=cl["amount"], gas_slot=cl["gas_slot"],
+                                NVMR=cl["NVMR"], NPAR=cl["NPAR"], LAYINC=cl["LAYINC"], SCALE=cl["SCALE"],
+                                NLAYIN=cl["NLAYIN"], EMTEMP=cl["EMTEMP"], LAYPRESS=cl["LAYPRESS"], taucia=cl["taucon"],
+                                dtaucon=cl["dtaucon"], TSURF=cl["TSURF"], EMISSIVITY=cl["EMISSIVITY"], xfac=cl["xfac"])
+        Ml = plan.fold_projection(cl["xmap"], cl["LAYINC"], cl["NLAYIN"], cl["DTE"], cl["DAM"], cl["DCO"], cl["NVMR"],
+                                  cl["NDUST"])
+        full_l = cpu_engine.HotPath(K4, tl["PRESS"], tl["TEMP"], one, tl["WAVE"]).forward_jacobian(evl, Ml)
+        wsl = adist.WavenumberShard(cpu_engine.HotPath, K4, tl["PRESS"], tl["TEMP"], one, tl["WAVE"])
+        assert wsl.hotpath.lbl_table and wsl.hotpath.K.shape[0] == (3 if rank == 0 else 2)
+        for a, b in zip(wsl.forward_jacobian(evl, Ml, to_tensor=t), full_l):
+            assert a.shape == b.shape and np.abs(a.numpy() - b).max() <= 1e-13 * np.abs(b).max()
         open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
     finally:
         dist.destroy_process_group()

@@ -37,7 +37,7 @@ def test_lbl_table_opacity_goldens(tag):
     assert np.array_equal(dk[..., :ngas][z], g[tag + "_dk"][..., :ngas][z])
 
 
-@pytest.mark.parametrize("ngas", [1, 4, 9])
+@pytest.mark.parametrize("ngas", [1, 2, 4, 6, 9, 16])
 def test_lbl_table_opacity_matches_oracle(ngas):
     from oracle import oracle as orc
     rng = np.random.default_rng(100 + ngas)
