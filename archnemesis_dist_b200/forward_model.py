@@ -52,8 +52,8 @@ _SQ_CM_TO_SQ_METER = 1.0e-4
 class _TableCache:
     """Device-resident tables keyed on the identity of the host K array (plus shape): the
     reference re-reads and re-allocates its tables on every nemesisfm[g] call
-    (ForwardModel_0.py:652-654); `install()` wraps read_tables so the same host array -- and with it
-    the device copy -- is reused when (LOCATION, wavemin, wavemax) repeat."""
+    (ForwardModel_0.py:652-654); `install()` memoises read_tables (make_cached_read_tables) so the same
+    host array -- and with it the device copy -- is reused when the files, wavemin and wavemax repeat."""
 
     def __init__(self, capacity=4):
         self.capacity = capacity
@@ -74,6 +74,58 @@ class _TableCache:
 
 
 _TABLES = _TableCache()
+
+
+def make_cached_read_tables(ref_read_tables, capacity=4):
+    """Spectroscopy_0.read_tables (archnemesis/Spectroscopy_0.py:1448-1528) memoised on what it depends on.
+
+    Every nemesisfm[g] / nemesisSOfm[g] / nemesisLfm[g] call deep-copies the Spectroscopy object and re-reads the
+    ``.kta`` / ``.lta`` files of every active gas from disk (ForwardModel_0.py:652-654; 7-8 s per call on the real
+    Jupiter tables).  The outcome is a pure function of the table files, the header grid and the
+    requested range, so it is kept: a repeat call installs the SAME (read-only) WAVE and K arrays on the new copy,
+    and since the device table cache (_TableCache) is keyed on the identity of K, the resident device table is
+    reused as well -- no disk read, no host re-assembly, no re-upload.  The key holds the files' size and mtime, so
+    an edited table is read again.  Run-time line-by-line, on-line HDF5 tables and objects without LOCATION go
+    straight to the reference method."""
+    import os
+    cache = []      # [(key, WAVE, K)]
+
+    def stamp(path):
+        for cand in (path, path + ".kta", path + ".lta", path + ".h5"):
+            try:
+                st = os.stat(cand)
+                return (cand, st.st_size, st.st_mtime_ns)
+            except OSError:
+                continue
+        return (path, None, None)
+
+    def read_tables(self, wavemin=0., wavemax=1.0e10, wavedelta=1.0):
+        ilbl = int(self.ILBL)
+        if ilbl not in (_K_TABLES, _LBL_TABLES) or self.LOCATION is None or getattr(self, "ONLINE", False):
+            return ref_read_tables(self, wavemin=wavemin, wavemax=wavemax, wavedelta=wavedelta)
+        if self.WAVE is None:
+            self.read_header()
+        W = np.asarray(self.WAVE)
+        key = (ilbl, tuple(stamp(str(f)) for f in self.LOCATION), float(wavemin), float(wavemax),
+               len(W), float(W[0]) if len(W) else 0.0, float(W[-1]) if len(W) else 0.0,
+               int(self.NG), int(self.NP), int(self.NT), int(self.NGAS))
+        for k, wave, K in cache:
+            if k == key:
+                self.WAVE, self.NWAVE, self.K = wave, len(wave), K
+                read_tables.hits += 1
+                return None
+        out = ref_read_tables(self, wavemin=wavemin, wavemax=wavemax, wavedelta=wavedelta)
+        if isinstance(self.K, np.ndarray) and isinstance(self.WAVE, np.ndarray):
+            self.K.setflags(write=False)          # shared between evaluations from now on
+            self.WAVE.setflags(write=False)
+            cache.append((key, self.WAVE, self.K))
+            del cache[:-capacity]
+        return out
+
+    read_tables.hits = 0
+    read_tables.cache = cache
+    read_tables.__doc__ = (ref_read_tables.__doc__ or "") + "\n(archnemesis_dist_b200: memoised, see make_cached_read_tables)"
+    return read_tables
 
 
 class DeviceGradient:
@@ -558,6 +610,11 @@ def install(archnemesis=None):
         _INSTALLED.update(map2pro=mod.map2pro, map2xvec=mod.map2xvec)
     mod.map2pro, mod.map2xvec = make_fused_map_functions(_INSTALLED["map2pro"], _INSTALLED["map2xvec"])
     _INSTALLED["lazy_gradients"] = True
+    # table residency across evaluations: read_tables memoised on the Spectroscopy class
+    spec_mod = sys.modules.get("archnemesis.Spectroscopy_0")
+    if spec_mod is not None and "read_tables" not in _INSTALLED:
+        _INSTALLED["read_tables"] = spec_mod.Spectroscopy_0.read_tables
+        spec_mod.Spectroscopy_0.read_tables = make_cached_read_tables(_INSTALLED["read_tables"])
     return cls
 
 
@@ -572,6 +629,8 @@ def uninstall(archnemesis=None):
     if "map2pro" in _INSTALLED:
         sys.modules["archnemesis.ForwardModel_0"].map2pro = _INSTALLED.pop("map2pro")
         sys.modules["archnemesis.ForwardModel_0"].map2xvec = _INSTALLED.pop("map2xvec")
+    if "read_tables" in _INSTALLED:
+        sys.modules["archnemesis.Spectroscopy_0"].Spectroscopy_0.read_tables = _INSTALLED.pop("read_tables")
     sys.modules["archnemesis.ForwardModel_0"].ForwardModel_0 = ref_cls
     archnemesis.ForwardModel_0 = ref_cls
     oe = sys.modules.get("archnemesis.OptimalEstimation_0")

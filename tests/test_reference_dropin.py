@@ -59,8 +59,21 @@ def test_install_rebinds_three_names_and_matches_reference(jupiter):
             assert mod.map2pro is not fmod._INSTALLED["map2pro"]
             assert isinstance(dspec, fmod.DeviceGradient) and np.asarray(dspec).shape == dspec.shape
             S_lazy, dS_lazy = ref_cls.nemesisfmg(fm)
+            # table residency: read_tables is memoised while installed -- the second evaluation re-uses the very
+            # same host K (no disk read) and therefore the same resident engine table
+            spec_cls = sys.modules["archnemesis.Spectroscopy_0"].Spectroscopy_0
+            rt = spec_cls.read_tables
+            assert rt is not fmod._INSTALLED["read_tables"] and rt.hits >= 2
+            K_first, hp_first = fm.SpectroscopyX.K, fm._b200_hotpath()
+            hits = rt.hits
+            S_again, dS_again = fm.nemesisfmg()
+            assert rt.hits == hits + 1 and fm.SpectroscopyX.K is K_first and fm._b200_hotpath() is hp_first
+            assert not K_first.flags.writeable
+            assert np.array_equal(S_again, S) and np.array_equal(dS_again, dS)
         finally:
             fmod.uninstall(ans)
+        assert sys.modules["archnemesis.Spectroscopy_0"].Spectroscopy_0.read_tables.__name__ == "read_tables"
+        assert not hasattr(sys.modules["archnemesis.Spectroscopy_0"].Spectroscopy_0.read_tables, "hits")
         assert ans.ForwardModel_0 is ref_cls
         assert sys.modules["archnemesis.ForwardModel_0"].map2pro.__module__ == "archnemesis.ForwardModel_0"
         tg_ref, dtg_ref = ref_cls.calculate_gaseous_line_opacity(fm, True)
