@@ -691,7 +691,7 @@ extern "C" int ansb200_radiance(int mode, unsigned flags, const double *tau, con
                           ((grad && thermal) ? (size_t)NG * NLAYMAX : 0) + 3 * (size_t)NG;
         return nd * 8 + (size_t)(NLAYMAX + NPAR) * 4 + 16;
     };
-    const int warps_min = NG == 1 ? 2 : 4;      // line-by-line tables: one g-ordinate, many small CTAs
+    const int warps_min = NG == 1 ? 1 : 4;      // line-by-line tables: one g-ordinate, many small CTAs
     const int warps_n = NG < 4 ? warps_min : (NG > RAD_MAX_THREADS / 32 ? RAD_MAX_THREADS / 32 : NG);
     const int warps_1 = (warps_n + 1) / 2 < warps_min ? warps_min : (warps_n + 1) / 2;
     const int RAD_THREADS_1 = 32 * warps_1, RAD_THREADS_N = 32 * warps_n;
