@@ -212,16 +212,19 @@ struct LblParams {
 // ~1e-3 cm-1), where the Faddeeva package's continued fraction is the closed form of its nu == 2 case:
 // one reciprocal instead of the five divisions of voigt_profile + w(z).  Everything else goes through the
 // general routine.  Differences from the division-by-division evaluation are a few ulp.
-__device__ __forceinline__ double ans_voigt_from_constants(double d, double inv_s2, double zimag, double vnorm)
+__device__ __forceinline__ double ans_voigt_far(double x, double zimag, double vnorm)
 {
     const double ispi = 0.56418958354775628694807945156;
+    const double dr = x * x - zimag * zimag - 0.5, di = 2 * x * zimag;
+    const double denom = ispi * __drcp_rn(dr * dr + di * di);
+    return denom * (x * di - zimag * dr) * vnorm;
+}
+
+__device__ __forceinline__ double ans_voigt_from_constants(double d, double inv_s2, double zimag, double vnorm)
+{
     const double x = fabs(d * inv_s2);
     const double s = x + zimag;
-    if (s > 4000.0 && s <= 1.0e7) {
-        const double dr = x * x - zimag * zimag - 0.5, di = 2 * x * zimag;
-        const double denom = ispi * __drcp_rn(dr * dr + di * di);
-        return denom * (x * di - zimag * dr) * vnorm;
-    }
+    if (s > 4000.0 && s <= 1.0e7) return ans_voigt_far(x, zimag, vnorm);
     return ans_faddeeva_re(d * inv_s2, zimag) * vnorm;
 }
 
@@ -286,6 +289,19 @@ ans_lbl_kernel(LblParams P)
                         k0 = ad;
                         k1 = gl;
                     }
+                    // The CTA spans wn_lo..wn_hi (2 cm-1 at a 0.002 cm-1 grid), so almost every line treats all of
+                    // the CTA's points alike.  d = wn - nus is monotone in wn (also after rounding), so the two end
+                    // points classify every point in between exactly as the per-pair tests would:
+                    //   3  every point in the 1/dnu^2 wing (calc_win <= |d| < approx_win)
+                    //   4  every point in the core window with |z| in the Faddeeva closed-form range
+                    // Those tiles run branch-free loops below; anything else keeps the per-pair tests.
+                    const double d_lo = wn_lo - nus, d_hi = wn_hi - nus;
+                    if ((d_lo >= P.calc_win && d_hi < P.approx_win) || (d_hi < -P.calc_win && d_lo >= -P.approx_win)) {
+                        live = 3;
+                    } else if (live == 1 && -P.calc_win <= d_lo && d_hi < P.calc_win && (d_lo > 0.0 || d_hi < 0.0)) {
+                        const double near = d_lo > 0.0 ? d_lo : -d_hi, far = d_lo > 0.0 ? d_hi : -d_lo;
+                        if (fabs(near * k0) + k1 > 4000.0 && fabs(far * k0) + k1 <= 1.0e7) live = 4;
+                    }
                 }
             }
             s_live[threadIdx.x] = live;
@@ -299,12 +315,28 @@ ans_lbl_kernel(LblParams P)
                 const int kind = s_live[li];
                 if (!kind) continue;
                 const double nus = s_nu[li], A = s_A[li], W = s_W[li], k0 = s_c0[li], k1 = s_c1[li], k2 = s_c2[li];
+                if (kind == 3) {
+#pragma unroll
+                    for (int q = 0; q < LBL_GP; ++q) {
+                        const double d = wnj[q] - nus;
+                        acc[q] += W * __drcp_rn(d * d);
+                    }
+                    continue;
+                }
+                if (kind == 4) {
+#pragma unroll
+                    for (int q = 0; q < LBL_GP; ++q) {
+                        const double d = wnj[q] - nus;
+                        acc[q] += A * ans_voigt_far(fabs(d * k0), k1, k2);
+                    }
+                    continue;
+                }
 #pragma unroll
                 for (int q = 0; q < LBL_GP; ++q) {
                     const double d = wnj[q] - nus;
                     if (d >= P.approx_win || d < -P.approx_win) continue;
                     if (-P.calc_win <= d && d < P.calc_win)
-                        acc[q] += A * (kind == 1 ? ans_voigt_from_constants(d, k0, k1, k2) : ans_lineshape(P.shape_id, d, k0, k1));
+                        acc[q] += A * (kind != 2 ? ans_voigt_from_constants(d, k0, k1, k2) : ans_lineshape(P.shape_id, d, k0, k1));
                     else
                         acc[q] += W * __drcp_rn(d * d);
                 }
