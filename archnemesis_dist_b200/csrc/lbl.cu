@@ -31,6 +31,19 @@ __device__ __forceinline__ double ans_sinh_taylor(double x)
     return x * (1 + (x * x) * (0.1666666666666666666667 + 0.00833333333333333333333 * (x * x)));
 }
 
+// 1/x for normal, finite x (the pair loop: squared distances and |z|^4-sized denominators): the hardware seed
+// (>= 20 bits) and two Newton steps, <= 1 ulp, without the special-case handling and final rounding fix-up of
+// __drcp_rn (half its instructions).
+__device__ __forceinline__ double ans_rcp_fast(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
 // Re w(x + i y) for y >= 0 (the Voigt function), following the published Faddeeva-package
 // algorithm at relerr = DBL_EPSILON.
 __device__ double ans_faddeeva_re(double xin, double y)
@@ -68,12 +81,13 @@ __device__ double ans_faddeeva_re(double xin, double y)
         const double c0 = 3.9, c1 = 11.398, c2 = 0.08254, c3 = 0.1421, c4 = 0.2023;
         double nu = floor(c0 + c1 / (c2 * x + c3 * ya + c4));
         double wr = xs, wi = ya;
+        // |w|^2 >= x^2 + y^2 > 36 here: the reciprocal helper applies (<= 1 ulp per step of a contracting recurrence)
         for (nu = 0.5 * (nu - 1); nu > 0.4; nu -= 0.5) {
-            const double denom = nu / (wr * wr + wi * wi);
+            const double denom = nu * ans_rcp_fast(wr * wr + wi * wi);
             wr = xs - wr * denom;
             wi = ya + wi * denom;
         }
-        const double denom = ispi / (wr * wr + wi * wi);
+        const double denom = ispi * ans_rcp_fast(wr * wr + wi * wi);
         return denom * wi;
     }
 
@@ -216,7 +230,7 @@ __device__ __forceinline__ double ans_voigt_far(double x, double zimag, double v
 {
     const double ispi = 0.56418958354775628694807945156;
     const double dr = x * x - zimag * zimag - 0.5, di = 2 * x * zimag;
-    const double denom = ispi * __drcp_rn(dr * dr + di * di);
+    const double denom = ispi * ans_rcp_fast(dr * dr + di * di);
     return denom * (x * di - zimag * dr) * vnorm;
 }
 
@@ -233,7 +247,7 @@ ans_lbl_kernel(LblParams P)
 {
     // per-line constants of the tile: shifted centre, abundance*strength, wing constant abundance*S*V(25)*25^2,
     // and either the Voigt constants (fast) or (alpha_D, gamma_L) for the general line-shape routine
-    __shared__ double s_nu[LBL_TILE], s_A[LBL_TILE], s_W[LBL_TILE], s_c0[LBL_TILE], s_c1[LBL_TILE], s_c2[LBL_TILE];
+    __shared__ double2 s_nw[LBL_TILE], s_a0[LBL_TILE], s_12[LBL_TILE];     // (nus, W), (A, c0), (c1, c2): 16-byte reads
     __shared__ unsigned char s_live[LBL_TILE];
     const int ipt = blockIdx.y;
     const double t_calc = P.pt[3 * ipt], p_calc = P.pt[3 * ipt + 1], q_ratio = P.pt[3 * ipt + 2];
@@ -305,8 +319,9 @@ ans_lbl_kernel(LblParams P)
                 }
             }
             s_live[threadIdx.x] = live;
-            s_nu[threadIdx.x] = nus; s_A[threadIdx.x] = A; s_W[threadIdx.x] = W;
-            s_c0[threadIdx.x] = k0; s_c1[threadIdx.x] = k1; s_c2[threadIdx.x] = k2;
+            s_nw[threadIdx.x] = make_double2(nus, W);
+            s_a0[threadIdx.x] = make_double2(A, k0);
+            s_12[threadIdx.x] = make_double2(k1, k2);
         }
         const int any = __syncthreads_or(live ? 1 : 0);
         if (any) {
@@ -314,15 +329,18 @@ ans_lbl_kernel(LblParams P)
             for (int li = 0; li < cnt; ++li) {
                 const int kind = s_live[li];
                 if (!kind) continue;
-                const double nus = s_nu[li], A = s_A[li], W = s_W[li], k0 = s_c0[li], k1 = s_c1[li], k2 = s_c2[li];
+                const double2 nw = s_nw[li];
+                const double nus = nw.x, W = nw.y;
                 if (kind == 3) {
 #pragma unroll
                     for (int q = 0; q < LBL_GP; ++q) {
                         const double d = wnj[q] - nus;
-                        acc[q] += W * __drcp_rn(d * d);
+                        acc[q] += W * ans_rcp_fast(d * d);
                     }
                     continue;
                 }
+                const double2 a0 = s_a0[li], c12 = s_12[li];
+                const double A = a0.x, k0 = a0.y, k1 = c12.x, k2 = c12.y;
                 if (kind == 4) {
 #pragma unroll
                     for (int q = 0; q < LBL_GP; ++q) {
@@ -338,7 +356,7 @@ ans_lbl_kernel(LblParams P)
                     if (-P.calc_win <= d && d < P.calc_win)
                         acc[q] += A * (kind != 2 ? ans_voigt_from_constants(d, k0, k1, k2) : ans_lineshape(P.shape_id, d, k0, k1));
                     else
-                        acc[q] += W * __drcp_rn(d * d);
+                        acc[q] += W * ans_rcp_fast(d * d);
                 }
             }
         }
