@@ -95,6 +95,54 @@ def klbl_plan(PRESS, TEMP, press, temp, grad):
     TEMP = np.asarray(TEMP)
     press = np.asarray(press, dtype=np.float64)
     temp = np.asarray(temp, dtype=np.float64)
+    if TEMP.ndim == 1:
+        return _klbl_plan_grouped(LP, TEMP, press, temp, grad)
+    return _klbl_plan_scalar(LP, TEMP, press, temp, grad)
+
+
+def _klbl_plan_grouped(LP, TEMP, press, temp, grad):
+    """klbl_plan for a single temperature grid, all layers at once.  A clamped coordinate is a grid-dtype scalar in
+    the reference, so v or u -- and, if both are clamped, the weight products -- are evaluated in the grid's dtype:
+    the layers are grouped by which coordinates are clamped and every group is evaluated with arrays of exactly
+    those dtypes (same device as kinterp_plan; bit-identical to the scalar loop, tests/test_lbl_table.py)."""
+    n, npg, ntg = len(press), len(LP), len(TEMP)
+    pmin, pmax, tmin, tmax = np.min(LP), np.max(LP), np.min(TEMP), np.max(TEMP)
+    lp = np.log(press)
+    p_lo, p_hi = lp < pmin, lp > pmax
+    t_lo, t_hi = temp < tmin, temp > tmax
+    pcl, tcl = p_lo | p_hi, t_lo | t_hi
+    pedge = np.where(p_lo, pmin, pmax)                       # grid dtype
+    tedge = np.where(t_lo, tmin, tmax)
+    corner = np.zeros((n, 4), np.int32)
+    w4 = np.zeros((n, 4))
+    omv, vv, du = np.zeros(n), np.zeros(n), np.zeros(n)
+    for pc in (False, True):
+        for tc in (False, True):
+            m = (pcl == pc) & (tcl == tc)
+            if not m.any():
+                continue
+            p_l = pedge[m] if pc else lp[m]
+            t_l = tedge[m] if tc else temp[m]
+            ip = np.clip(np.searchsorted(LP, p_l) - 1, 0, npg - 2)
+            v = (p_l - LP[ip]) / (LP[ip + 1] - LP[ip])
+            it = np.searchsorted(TEMP, t_l) - 1
+            if not grad:
+                it = np.maximum(it, 0)
+            it = np.minimum(it, ntg - 2)                     # it = -1 survives with gradients: Python's index wrap
+            u = (t_l - TEMP[it]) / (TEMP[it + 1] - TEMP[it])
+            d = 1. / (TEMP[it + 1] - TEMP[it])
+            lo, hi = it % ntg, (it + 1) % ntg
+            corner[m] = np.stack([ip * ntg + lo, ip * ntg + hi, (ip + 1) * ntg + lo, (ip + 1) * ntg + hi], axis=1)
+            w4[m, 0] = (1.0 - v) * (1.0 - u)
+            w4[m, 1] = v * (1.0 - u)
+            w4[m, 2] = v * u
+            w4[m, 3] = (1.0 - v) * u
+            omv[m], vv[m], du[m] = 1.0 - v, v, d
+    return dict(corner=corner, w4=w4, omv=omv, vv=vv, du1dt=du, du2dt=du.copy())
+
+
+def _klbl_plan_scalar(LP, TEMP, press, temp, grad):
+    """klbl_plan layer by layer on numpy scalars, literally as the reference does it (any TEMP layout)."""
     n, npg, ntg = len(press), len(LP), TEMP.shape[-1]
     pmin, pmax, tmin, tmax = np.min(LP), np.max(LP), np.min(TEMP), np.max(TEMP)
     corner = np.zeros((n, 4), np.int32)
