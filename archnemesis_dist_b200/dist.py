@@ -2,7 +2,7 @@
 NVLink for the single exchange step.
 
 The path shards three independent ways with no data-path collective until the end:
-state-vector columns, geometries / paths, and wavenumbers.  Rank r takes the r-th contiguous chunk,
+state-vector columns, geometries / paths, and wavenumbers (plus the (p,T) grid of the line-by-line generation).  Rank r takes the r-th contiguous chunk,
 split exactly like the reference splits its joblib workers (archnemesis/ForwardModel_0.py:2322-2330:
 ``base = n // R`` with the first ``n % R`` chunks one longer), computes it against a full replica of
 the k-table, and one ``all_gather`` assembles YN / KK on every rank for the (replicated, tiny)
@@ -73,6 +73,18 @@ def geometries(evaluate, n_geom):
     else:
         raise ValueError("fewer geometries than ranks: give every rank at least one geometry")
     return all_gather_rows(S, n_geom, dim=0), all_gather_rows(J, n_geom, dim=0)
+
+
+def pt_grid(absorption, pts, **kw):
+    """(p,T)-grid sharding of the line-by-line cross-section generation (BASELINE config 3; the reference's
+    calc_lbltable farms chunks of the grid out the same way, Spectroscopy_0.py:3124-3336): every state point is an
+    independent slice of the launch, so rank r evaluates its contiguous chunk of `pts` with the full line list and
+    the k[NPT, NWAVE] rows are all-gathered.  `absorption(pts_chunk)` returns the chunk's [n, NWAVE] tensor."""
+    pts = np.asarray(pts, dtype=np.float64).reshape(-1, 3)
+    lo, hi = my_chunk(len(pts))
+    if hi <= lo:
+        raise ValueError("fewer (p,T) points than ranks")
+    return all_gather_rows(absorption(pts[lo:hi], **kw), len(pts), dim=0)
 
 
 class WavenumberShard:

@@ -82,6 +82,17 @@ def _worker(rank, world, port, out_dir):
         assert wsl.hotpath.lbl_table and wsl.hotpath.K.shape[0] == (3 if rank == 0 else 2)
         for a, b in zip(wsl.forward_jacobian(evl, Ml, to_tensor=t), full_l):
             assert a.shape == b.shape and np.abs(a.numpy() - b).max() <= 1e-13 * np.abs(b).max()
+        # (5) (p,T)-grid sharding of the line-by-line generation: 5 state points over 2 ranks (3 + 2)
+        from oracle import oracle as orc
+        wn = np.linspace(1000.0, 1001.0, 41)
+        lines = syn.make_line_list(12, 1000.0, 1001.0, seed=3, pad=5.0)
+        mix = np.array([0.1, 0.9])
+        pts = [(200.0, 0.1, 1.0), (296.0, 1.0, 1.1), (150.0, 1e-3, 0.9), (250.0, 0.5, 1.0), (120.0, 1e-4, 2.0)]
+
+        def absorb(chunk):
+            return t(np.stack([orc.lbl_absorption(wn, lines, tc, pc, 296.0, 1.0, q, 1.0, 28.0, mix) for tc, pc, q in chunk]))
+        grid = adist.pt_grid(absorb, pts)
+        assert grid.shape == (5, 41) and np.array_equal(grid.numpy(), absorb(np.asarray(pts)).numpy())
         open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
     finally:
         dist.destroy_process_group()
