@@ -9,6 +9,13 @@ from .ops import _ptr, _require_cuda, _stream, to_dev
 SHAPE_IDS = {"voigt": 0, "lorentz": 1, "gaussian": 2}
 
 
+def resident_lines(lines):
+    """Upload a line list once: dict of device tensors accepted by lbl_absorption in place of the host arrays
+    (a 10^6-line list is 80 MB; generating a (p,T) grid launch by launch should not re-send it)."""
+    _require_cuda()
+    return {k: to_dev(lines[k]) for k in ("nu", "sw", "e_lower", "stim_ref", "broadening")}
+
+
 def lbl_absorption(wn_grid, lines, pts, t_ref, p_ref, abundance, mass, mix, s_floor=0.0, wn_calc_window=25.0,
                    wn_approx_window=75.0, shape="voigt", out=None):
     """wn_grid[NWAVE] ascending; lines: dict(nu, sw, e_lower, stim_ref [N], broadening [3*M,N]) -- the rows of

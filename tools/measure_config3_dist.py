@@ -29,8 +29,12 @@ pts = [(float(temps[(3 * i) % 15]), float(press[(7 * i + 5) % 20]), 1.0) for i i
 mix = np.array([0.1, 0.9])
 
 
+dev_lines = lbl.resident_lines(lines)
+wn_d = torch.from_numpy(wn).cuda()
+
+
 def step():
-    return adist.pt_grid(lambda chunk: lbl.lbl_absorption(wn, lines, chunk, 296.0, 1.0, 1.0, 28.0, mix), pts)
+    return adist.pt_grid(lambda chunk: lbl.lbl_absorption(wn_d, dev_lines, chunk, 296.0, 1.0, 1.0, 28.0, mix), pts)
 
 
 step()
