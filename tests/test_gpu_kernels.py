@@ -352,6 +352,27 @@ def test_lbl_absorption_matches_oracle(mods):
     for i, (t, p, q) in enumerate(pts):
         ref = orc.lbl_absorption(wn, lines, t, p, 296.0, 1.0, q, 0.98, 28.0, mix)
         assert relerr(cpu(out[i]), ref) < 1e-11, i
+    # a device-resident line list gives the same launch
+    again = lbl.lbl_absorption(torch.from_numpy(wn).cuda(), lbl.resident_lines(lines), pts, t_ref=296.0, p_ref=1.0,
+                               abundance=0.98, mass=28.0, mix=mix)
+    assert torch.equal(again, out)
+
+
+def test_lbl_uniform_window_classes_match_per_pair_tests(mods):
+    """Lines whose 25 / 75 cm-1 windows end inside a CTA's 1024 grid points take the per-pair tests, all others the
+    branch-free loops: a wide, coarse grid (every CTA spans 40 cm-1, so most lines are mixed) and a narrow, fine one
+    (every line uniform) against the oracle, plus window edges that fall exactly on grid points."""
+    orc, syn = mods["orc"], mods["syn"]
+    from archnemesis_dist_b200 import lbl
+    mix = np.array([0.2, 0.8])
+    for wn in (np.linspace(900.0, 1100.0, 5121), np.linspace(1000.0, 1000.5, 2049)):
+        lines = syn.make_line_list(300, wn[0], wn[-1], seed=9, pad=80.0)
+        lines["nu"][:4] = [wn[100] - 25.0, wn[200] + 25.0, wn[300] - 75.0, wn[50] + 75.0]   # edges on grid points
+        pts = [(220.0, 0.3, 1.0), (90.0, 2e-5, 1.5)]
+        out = lbl.lbl_absorption(wn, lines, pts, t_ref=296.0, p_ref=1.0, abundance=1.0, mass=44.0, mix=mix)
+        for i, (t, p, q) in enumerate(pts):
+            ref = orc.lbl_absorption(wn, lines, t, p, 296.0, 1.0, q, 1.0, 44.0, mix)
+            assert relerr(cpu(out[i]), ref) < 1e-11, (len(wn), i)
 
 
 @pytest.mark.parametrize("fwhm", [0.0, -1.0])
