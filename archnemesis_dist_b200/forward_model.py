@@ -260,14 +260,17 @@ class B200HotPathMixin:
         NWAVE, NLAY = self.SpectroscopyX.NWAVE, self.LayerX.NLAY
         NVMR, NDUST = self.AtmosphereX.NVMR, self.ScatterX.NDUST
         dTAUCON = np.zeros((NWAVE, NVMR + 2 + NDUST, NLAY)) if return_grad else None
+        touched = False      # no contribution at all: hand None to the engine instead of NWAVE*NPAR*NLAY zeros
         TAUCIA, dTAUCIA = self.calculate_vertical_cia_opacity(return_grad)
         if return_grad and dTAUCIA is not None:
+            touched = True
             dTAUCON[:, 0:NVMR, :] = dTAUCON[:, 0:NVMR, :] + np.transpose(
                 np.transpose(dTAUCIA[:, :, 0:NVMR], axes=(2, 0, 1)) / (self.LayerX.TOTAM.T), axes=(1, 0, 2))
             dTAUCON[:, NVMR, :] = dTAUCON[:, NVMR, :] + dTAUCIA[:, :, NVMR]
         TAURAY, dTAURAY = self.calc_tau_rayleigh(MakePlot=False)
         self.LayerX.TAURAY = TAURAY
         if return_grad and (dTAURAY is not None):
+            touched = touched or NVMR > 0
             for i in range(NVMR):
                 dTAUCON[:, i, :] = dTAUCON[:, i, :] + dTAURAY[:, :]
         TAUDUST1, TAUCLSCAT, dTAUDUST1, dTAUCLSCAT = self.calc_tau_dust()
@@ -277,9 +280,12 @@ class B200HotPathMixin:
         self.LayerX.TAUSCAT = np.sum(TAUCLSCAT, 2)
         self.LayerX.TAUCLSCAT = TAUCLSCAT
         if return_grad:
+            touched = touched or NDUST > 0
             for i in range(NDUST):
                 dTAUCON[:, NVMR + 1 + i, :] = dTAUCON[:, NVMR + 1 + i, :] + dTAUDUST1[:, :, i]
-        return TAUCIA, TAUDUST, TAURAY, dTAUCON
+        if hasattr(self, "CIAX") and self.CIAX is None:
+            TAUCIA = None                 # calculate_vertical_cia_opacity returned zeros (:3894-3896)
+        return TAUCIA, TAUDUST, TAURAY, (dTAUCON if touched else None)
 
     def _b200_surface_terms(self, mode):
         """xfac, EMISSIVITY, SOLFLUX, REFLECTANCE as calculate_thermal_emission_spectrum
