@@ -89,7 +89,7 @@ class _Stager:
         else:
             # large inputs (line-by-line grids: continuum terms of 1e5 wavenumbers): the copy into pinned memory
             # is split over torch's host threads and pipelined against the DMA chunk by chunk
-            src, pin = torch.from_numpy(a).view(-1), buf.view(-1)
+            src, pin = torch.from_numpy(a if a.flags.writeable else a.copy()).view(-1), buf.view(-1)
             dev = torch.empty(a.shape, dtype=dtype, device="cuda")
             dflat = dev.view(-1)
             step = self.CHUNK_BYTES // a.itemsize

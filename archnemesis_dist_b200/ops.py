@@ -33,7 +33,10 @@ def to_dev(a, dtype=torch.float64):
     if isinstance(a, torch.Tensor):
         return a.to(device="cuda", dtype=dtype).contiguous()
     npdt = {torch.float64: np.float64, torch.int32: np.int32}[dtype]
-    return torch.from_numpy(np.ascontiguousarray(a, dtype=npdt)).cuda()
+    h = np.ascontiguousarray(a, dtype=npdt)
+    if not h.flags.writeable:           # e.g. the memoised, shared WAVE grid: torch refuses read-only views
+        h = h.copy()
+    return torch.from_numpy(h).cuda()
 
 
 class Table:
