@@ -303,6 +303,55 @@ ans_radiance_kernel(RadParams P)
     // per-element index division is needed.
     double *out = P.dspec + ((size_t)iw * NPATH + ipath) * NPAR * NLM;
     const int nchunk = (NLM + 31) >> 5;
+    if (NG == 1) {
+        // One g-ordinate (line-by-line tables): an item is one dk load, one dtaucon load, two FMAs and a store, and a
+        // CTA is a single warp, so the items' global loads would run one round trip after another.  Four items are
+        // fetched before any of them is finished (same arithmetic as the general loop below with NG = 1).
+        const int nitem = NPAR * nchunk;
+        for (int item0 = warp * 4; item0 < nitem; item0 += RAD_WARPS * 4) {
+            double dkv[4], dcv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int item = item0 + u;
+                const int k = item / nchunk, j = ((item - k * nchunk) << 5) + lane;
+                dkv[u] = 0.0;
+                dcv[u] = 0.0;
+                if (item < nitem && j < n) {
+                    const int l = slay[j], col = scol[k];
+                    if (col >= 0) dkv[u] = dkw[(size_t)l * NP1 + col];
+                    if (P.dtaucon) dcv[u] = P.dtaucon[((size_t)iw * NPAR + k) * NLAY + l];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int item = item0 + u;
+                const int k = item / nchunk, j = ((item - k * nchunk) << 5) + lane;
+                if (item >= nitem || j >= NLM) continue;
+                double acc = 0.0;
+                if (j < n) {
+                    const int col = scol[k];
+                    const double wa = sD[j];
+                    double wsum = 0.0;
+                    if (col >= 0) {
+                        const double a0 = fma(wa, dkv[u], 0.0);
+                        wsum += wa;
+                        wsum += 0.0;
+                        acc = (a0 + 0.0) * (col < P.NGAS ? 1.0e-4 : 1.0);
+                    } else if (P.dtaucon) {
+                        wsum += wa;
+                    }
+                    if (P.dtaucon) acc = fma(dcv[u], wsum, acc);
+                    if (thermal && k == P.NVMR) {
+                        double wt = 0.0;
+                        wt += sTT[j];
+                        acc += wt;
+                    }
+                    if (P.flags & ANSB200_RAD_NAN_TO_NUM) acc = ans_nan_to_num(acc);
+                }
+                out[(size_t)k * NLM + j] = acc;
+            }
+        }
+    } else
     for (int item = warp; item < NPAR * nchunk; item += RAD_WARPS) {
         const int k = item / nchunk, j = ((item - k * nchunk) << 5) + lane;
         if (j >= NLM) continue;
@@ -311,6 +360,8 @@ ans_radiance_kernel(RadParams P)
             const int l = slay[j];
             const int col = scol[k];
             const double *wp = sD + j;
+            // issued before the g loop so that its latency overlaps the dk loads
+            const double dcon = P.dtaucon ? P.dtaucon[((size_t)iw * NPAR + k) * NLAY + l] : 0.0;
             double wsum = 0.0;
             if (col >= 0) {
                 const double *dkp = dkw + (size_t)l * NP1 + col;
@@ -333,7 +384,7 @@ ans_radiance_kernel(RadParams P)
             } else if (P.dtaucon) {
                 for (int ig = 0; ig < NG; ++ig) wsum += wp[(size_t)ig * NLM];
             }
-            if (P.dtaucon) acc = fma(P.dtaucon[((size_t)iw * NPAR + k) * NLAY + l], wsum, acc);
+            if (P.dtaucon) acc = fma(dcon, wsum, acc);
             if (thermal && k == P.NVMR) {
                 double wt = 0.0;
                 for (int ig = 0; ig < NG; ++ig) wt += sTT[(size_t)ig * NLM + j];
