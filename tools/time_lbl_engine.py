@@ -19,7 +19,20 @@ def main(nwave=100000, ngas=4, nlay=60, nx=60, nconv=400):
     tab = c["tab"]
     K4 = np.ascontiguousarray(tab["K"][:, 0])
     hp = engine.HotPath(K4, tab["PRESS"], tab["TEMP"], np.array([1.0]), tab["WAVE"])
-    ev = engine.Evaluation(press_atm=c["press"], temp=c["temp"], amount=c["amount"], gas_slot=c["gas_slot"],
+    npath = int(os.environ.get("LIMB_PATHS", "0"))
+    if npath:
+        # solar-occultation shape (the reference's mars_solocc example: ILBL = 2, one path per tangent height)
+        nlm = 2 * nlay
+        layinc, scale, nlayin = np.zeros((nlm, npath), np.int32), np.zeros((nlm, npath)), np.zeros(npath, np.int32)
+        for p in range(npath):
+            t = (p * (nlay - 2)) // npath
+            seq = list(range(nlay - 1, t - 1, -1)) + list(range(t, nlay))
+            nlayin[p] = len(seq)
+            layinc[:len(seq), p] = seq
+            scale[:len(seq), p] = 1.0 + 20.0 / (1.0 + np.abs(np.array(seq) - t))
+        c["LAYINC"], c["SCALE"], c["NLAYIN"], c["EMTEMP"] = layinc, scale, nlayin, c["temp"][layinc]
+    ev = engine.Evaluation(mode=engine.TRANSMISSION if npath else engine.THERMAL,
+                           press_atm=c["press"], temp=c["temp"], amount=c["amount"], gas_slot=c["gas_slot"],
                            NVMR=c["NVMR"], NPAR=c["NPAR"], LAYINC=c["LAYINC"], SCALE=c["SCALE"], NLAYIN=c["NLAYIN"],
                            EMTEMP=c["EMTEMP"], LAYPRESS=c["LAYPRESS"], taucia=c["taucon"], dtaucon=c["dtaucon"],
                            TSURF=c["TSURF"], EMISSIVITY=c["EMISSIVITY"], xfac=c["xfac"])
@@ -57,11 +70,14 @@ def main(nwave=100000, ngas=4, nlay=60, nx=60, nconv=400):
         sync()
         samples.append([ev_[i].elapsed_time(ev_[i + 1]) for i in range(4)])
     acc = np.median(np.array(samples), axis=0)
-    print("LBL table NWAVE=%d NLAY=%d NGAS=%d NX=%d NCONV=%d (%d operator entries, built in %.0f ms on the host)"
-          % (nwave, nlay, ngas, nx, nconv, len(op["widx"]), t_op))
+    print("LBL table NWAVE=%d NLAY=%d NGAS=%d NX=%d NCONV=%d %s(%d operator entries, built in %.0f ms on the host)"
+          % (nwave, nlay, ngas, nx, nconv, ("%d limb paths, transmission " % npath) if npath else "", len(op["widx"]), t_op))
     for name, v in zip(("lbl_table_opacity (calc_klblg + gas sum)", "radiance + layer Jacobian", "projection",
                         "block assembly + lblconvg"), acc):
         print("  %-45s %8.3f ms (median of %d)" % (name, v, reps))
+    if npath:
+        hp.close()
+        return          # the convolved end-to-end route is per geometry (one path); the stages above are the point here
     t0 = time.perf_counter()
     for _ in range(reps):
         o = hp.to_host(hp.forward_jacobian_conv(ev, M, cop, 2, 1.0))
