@@ -19,6 +19,8 @@ from . import ops as _ops
 from . import plan as _plan
 
 THERMAL, TRANSMISSION = 0, 1
+_PINNED_OUT = {}                  # (shape, dtype) -> pinned host buffer of HotPath.to_host
+_PINNED_OUT_MAX = 64 << 20
 
 
 @dataclass
@@ -310,8 +312,20 @@ class HotPath:
 
     @staticmethod
     def to_host(t):
-        """Device tensor -> numpy array (synchronises the current stream)."""
-        return t.detach().cpu().numpy()
+        """Device tensor -> numpy array (synchronises the current stream).  Results up to 64 MB go through a cached
+        pinned buffer (one DMA, then a host copy out of it) instead of a pageable-memory copy."""
+        t = t.detach()
+        if not t.is_cuda or t.numel() == 0 or t.numel() * t.element_size() > _PINNED_OUT_MAX:
+            return t.cpu().numpy()
+        key = (tuple(t.shape), t.dtype)
+        buf = _PINNED_OUT.get(key)
+        if buf is None:
+            if len(_PINNED_OUT) >= 16:
+                _PINNED_OUT.clear()
+            buf = _PINNED_OUT[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        buf.copy_(t.contiguous(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return buf.numpy().copy()
 
     def close(self):
         self.table.close()
