@@ -105,3 +105,25 @@ def test_wide_quadrature_uses_sequential_rebin():
     tau, dk = ops.koverlap(ops.to_dev(k), ops.to_dev(c["amount"]), otab, dkdT=ops.to_dev(d))
     rt, rd = orc.k_overlap(dg, k, c["amount"], dkdT=d)
     assert np.array_equal(cpu(tau), rt) and np.array_equal(cpu(dk), rd)
+
+
+def test_stager_chunked_upload_round_trips():
+    """Large per-evaluation inputs are copied into pinned memory and sent chunk by chunk (engine._Stager): ragged
+    last chunk, int32 payloads, read-only sources and buffer re-use between evaluations."""
+    import torch
+    from archnemesis_dist_b200.engine import _Stager
+    st = _Stager()
+    st.CHUNK_BYTES = 1 << 20
+    rng = np.random.default_rng(2)
+    a = rng.normal(size=(701, 13, 97))                     # 7.07 MB: seven chunks, the last one ragged
+    d = st("x", a)
+    assert torch.equal(d.cpu(), torch.from_numpy(a)) and st.bytes == a.nbytes
+    b = rng.normal(size=a.shape)
+    b.setflags(write=False)
+    d2 = st("x", b)                                        # same slot: waits for the first copy, then overwrites
+    assert torch.equal(d2.cpu(), torch.from_numpy(b.copy())) and torch.equal(d.cpu(), torch.from_numpy(a))
+    i = rng.integers(-5, 5, size=(300001,)).astype(np.int32)
+    di = st("i", i, torch.int32)
+    assert di.dtype == torch.int32 and torch.equal(di.cpu(), torch.from_numpy(i))
+    small = rng.normal(size=(17, 3))
+    assert torch.equal(st("s", small).cpu(), torch.from_numpy(small))
