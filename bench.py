@@ -8,9 +8,17 @@ projection (ansb200_jacobian_project) [-> NCCL all-gather of the KK rows when N 
 Weak scaling: every rank evaluates its own geometry (atmosphere state seeded by rank) against a
 full replica of the table and the ranks' [spectrum | Jacobian] blocks are all-gathered.
 
+After the timed loops rank 0 checks the numbers it timed: the [spectrum | Jacobian] rows of the timed case are
+compared with the CPU oracle on the same rows (all NWAVE rows at N = 1, where that pass is also the
+`cpu_baseline`; 64 strided rows at N > 1) -> `parity`, and the process exits non-zero above 1e-9.
+
+Extra keys (not part of the headline): at N = 1 `extra` carries BASELINE configs 3, 4 and 5 (line-by-line
+generation, 64 limb / occultation paths, NX = 1000); at N > 1 `strong` carries the strong-scaling figures of one
+config-2 evaluation and of the 64-path config 4 under wavenumber sharding (dist.WavenumberShard).
+
 Prints ONE JSON line (see DESIGN.md "Measurement").  `--impl reference` times the CPU oracle port
 of the reference path on the host cores instead (the reference itself is pure Python + numba and
-is not present on the GPU box).
+is not present on the GPU box): every step is one pass over all NWAVE wavenumbers of the same case.
 """
 import argparse
 import json
@@ -38,8 +46,10 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nwave", type=int, default=CFG["nwave"], help="override NWAVE (experiments only)")
     ap.add_argument("--nx", type=int, default=CFG["nx"])
-    ap.add_argument("--cpu-sample-waves", type=int, default=256)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-rows", type=int, default=0,
+                    help="rows compared with the CPU oracle after the timed loop (0: every row at N=1, 64 at N>1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the full CPU pass (parity on 64 rows only)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config 3/4/5 and strong-scaling extras")
     ap.add_argument("--stage-times", action="store_true", help="also print per-kernel times to stderr")
     return ap.parse_args()
 
@@ -50,85 +60,127 @@ def workload_name(cfg):
                                              cfg["nvmr"] + 2 + cfg["ndust"], cfg["nx"], cfg["npress"], cfg["ntemp"]))
 
 
-def make_case(cfg, rank_seed=0, nwave=None):
+def make_case(cfg, nwave=None):
+    """The synthetic config-2 case (SURVEY.md 8d recipe, seeded): table + rank 0's atmosphere."""
     from archnemesis_dist_b200 import synthetic
-    c = synthetic.make_fm_case(nwave=nwave or cfg["nwave"], ng=cfg["ng"], npress=cfg["npress"], ntemp=cfg["ntemp"],
-                               ngas=cfg["ngas"], nlay=cfg["nlay"], nvmr=cfg["nvmr"], ndust=cfg["ndust"],
-                               npro=cfg["npro"], nx=cfg["nx"], seed=cfg["seed"])
-    if rank_seed:
-        # another geometry / atmosphere state on the same table: perturb T, amounts and the viewing angle
-        rng = np.random.default_rng(1000 + rank_seed)
-        c["temp"] = c["temp"] + rng.uniform(-3.0, 3.0, size=c["temp"].shape)
-        c["amount"] = c["amount"] * 10.0 ** rng.uniform(-0.2, 0.2, size=c["amount"].shape)
-        c["SCALE"] = np.full_like(c["SCALE"], 1.0 / np.cos(np.deg2rad(5.0 + 5.0 * rank_seed)))
-        c["EMTEMP"] = c["temp"][c["LAYINC"][:, 0]].reshape(-1, 1).copy()
+    return synthetic.make_fm_case(nwave=nwave or cfg["nwave"], ng=cfg["ng"], npress=cfg["npress"], ntemp=cfg["ntemp"],
+                                  ngas=cfg["ngas"], nlay=cfg["nlay"], nvmr=cfg["nvmr"], ndust=cfg["ndust"],
+                                  npro=cfg["npro"], nx=cfg["nx"], seed=cfg["seed"])
+
+
+def perturb_case(c0, rank_seed):
+    """Rank r's geometry / atmosphere state on the same table: T, amounts and the viewing angle perturbed."""
+    if not rank_seed:
+        return c0
+    c = dict(c0)
+    rng = np.random.default_rng(1000 + rank_seed)
+    c["temp"] = c0["temp"] + rng.uniform(-3.0, 3.0, size=c0["temp"].shape)
+    c["amount"] = c0["amount"] * 10.0 ** rng.uniform(-0.2, 0.2, size=c0["amount"].shape)
+    c["SCALE"] = np.full_like(c0["SCALE"], 1.0 / np.cos(np.deg2rad(5.0 + 5.0 * rank_seed)))
+    c["EMTEMP"] = c["temp"][c0["LAYINC"][:, 0]].reshape(-1, 1).copy()
     return c
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference path, on a bounded sample of wavenumbers
+# CPU arm: the oracle port of the reference path on the host cores
 # ------------------------------------------------------------------------------------------------
+def config_dict(cfg, world):
+    """The `config` object of the JSON line; identical in the B200 arm and in the reference arm."""
+    plane_mb = cfg["nwave"] * cfg["ng"] * cfg["ngas"] * 8 / 1e6
+    return dict(workload=workload_name(cfg),
+                sharding=("one geometry per rank, table replicated, NCCL all-gather of [spectrum|Jacobian] rows"
+                          if world > 1 else "single GPU"),
+                l2="per-step working set (~50 touched table planes of %.1f MB each + %.0f MB of tau/dk) exceeds the "
+                   "126 MB L2; no explicit flush" % (plane_mb, cfg["nwave"] * cfg["ng"] * cfg["nlay"] * 8 * (2 + cfg["ngas"]) / 1e6))
+
+
+def host_threads():
+    # every host thread this process may use (torchrun exports OMP_NUM_THREADS=1: the explicit num_threads
+    # clause of the oracle's OpenMP loops is what counts, not the environment default)
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, n)
+
+
 def cpu_forward_jacobian(c, rows, nthreads):
     """The reference chain calc_kg -> k_overlapg -> layer opacity -> thermal_g -> g-sum -> map2pro ->
-    map2xvec (oracle restatement) on the wavenumber rows `rows` of case c."""
+    map2xvec (oracle restatement) on the wavenumber rows `rows` of case c (None: every row)."""
     from oracle import oracle as orc
     tab = c["tab"]
-    K = np.ascontiguousarray(tab["K"][rows])
-    k, dkdT = orc.calc_k(K, tab["PRESS"], tab["TEMP"], c["press"], c["temp"], want_grad=True, nthreads=nthreads)
+    sl = (lambda a: a) if rows is None else (lambda a: np.ascontiguousarray(a[rows]))
+    n = tab["NWAVE"] if rows is None else len(rows)
+    k, dkdT = orc.calc_k(sl(tab["K"]), tab["PRESS"], tab["TEMP"], c["press"], c["temp"], want_grad=True, nthreads=nthreads)
     tau, dk = orc.k_overlap(tab["DELG"], k, c["amount"], dkdT=dkdT, nthreads=nthreads)
-    tl, tp, dtl = orc.assemble_opacity(tau, dk, c["gas_slot"], c["NVMR"], c["NPAR"], c["taucon"][rows],
-                                       c["dtaucon"][rows], c["LAYINC"], c["SCALE"])
-    S, dS, dT = orc.thermal_paths(c["ISPACE"], tab["WAVE"][rows], tl, dtl, c["NVMR"], c["NLAYIN"], c["EMTEMP"],
-                                  c["LAYPRESS"], c["LAYINC"], c["TSURF"], c["EMISSIVITY"][rows], c["xfac"][rows],
+    del k, dkdT
+    tl, tp, dtl = orc.assemble_opacity(tau, dk, c["gas_slot"], c["NVMR"], c["NPAR"], sl(c["taucon"]),
+                                       sl(c["dtaucon"]), c["LAYINC"], c["SCALE"])
+    del tau, dk
+    S, dS, dT = orc.thermal_paths(c["ISPACE"], sl(tab["WAVE"]), tl, dtl, c["NVMR"], c["NLAYIN"], c["EMTEMP"],
+                                  c["LAYPRESS"], c["LAYINC"], c["TSURF"], sl(c["EMISSIVITY"]), sl(c["xfac"]),
                                   nthreads=nthreads)
+    del tl, dtl
     spec, dspec, dts = orc.g_integrate(S, dS, dT, tab["DELG"])
+    del S, dS
     inc = orc.included_params(c["xmap"])
-    d2 = orc.map2pro(dspec, len(rows), c["NVMR"], c["NDUST"], c["NPRO"], 1, c["NLAYIN"], c["LAYINC"], c["DTE"], c["DAM"],
+    d2 = orc.map2pro(dspec, n, c["NVMR"], c["NDUST"], c["NPRO"], 1, c["NLAYIN"], c["LAYINC"], c["DTE"], c["DAM"],
                      c["DCO"], INCPAR=inc)
     return spec, orc.map2xvec(d2, c["xmap"])
 
 
-def time_cpu(c, nsample, steps, warmup):
-    from oracle import oracle as orc
-    # every host thread this process may use (torchrun exports OMP_NUM_THREADS=1: the explicit num_threads
-    # clause of the oracle's OpenMP loops is what counts, not the environment default)
-    try:
-        nthreads = len(os.sched_getaffinity(0))
-    except AttributeError:
-        nthreads = os.cpu_count() or 1
-    nthreads = max(1, nthreads)
+CPU_BLOCK = 500        # wavenumbers per oracle call: bounds the host memory of the layer-space intermediates
+
+
+def cpu_full_pass(c, nthreads):
+    """One evaluation of the whole case on the host cores (blocks of CPU_BLOCK wavenumbers, every wavenumber
+    done).  Returns seconds, spec[NWAVE,1], dx[NWAVE,1,NX]."""
     nw = c["tab"]["NWAVE"]
-    rows = np.unique(np.linspace(0, nw - 1, min(nsample, nw)).astype(int))
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        cpu_forward_jacobian(c, rows, nthreads)
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    t = statistics.mean(times)
-    full = t * nw / len(rows)          # the path is independent per wavenumber: scale to the whole spectrum
-    return dict(value=1.0 / full, unit="spectra/s", cores=nthreads, kind="port",
-                sample="%d of %d wavenumbers (every layer, g-ordinate, gas and state element), oracle C port with "
-                       "OpenMP over wavenumbers, scaled by NWAVE/sample; %.2f s per sample pass" % (len(rows), nw, t)), t
+    specs, jacs = [], []
+    t0 = time.perf_counter()
+    for lo in range(0, nw, CPU_BLOCK):
+        s, x = cpu_forward_jacobian(c, np.arange(lo, min(nw, lo + CPU_BLOCK)), nthreads)
+        specs.append(s)
+        jacs.append(x)
+    dt = time.perf_counter() - t0
+    return dt, np.concatenate(specs), np.concatenate(jacs)
+
+
+def cpu_baseline_dict(seconds, nthreads, nw, passes):
+    return dict(value=1.0 / seconds, unit="spectra/s", cores=nthreads, kind="port",
+                sample="all %d wavenumbers of the timed case (every layer, g-ordinate, gas and state element), oracle C "
+                       "port of the reference path with OpenMP over wavenumbers; %.2f s per pass, %d pass(es) timed, "
+                       "nothing extrapolated" % (nw, seconds, passes))
 
 
 def run_reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    nsample = args.cpu_sample_waves
-    c = make_case(cfg, nwave=max(nsample, 8))      # the sample is generated directly (same recipe, seed)
-    cb, t = time_cpu(c, nsample, args.steps, args.warmup)
-    # c holds only the sample rows; scale to the full NWAVE of the workload
-    value = 1.0 / (t * cfg["nwave"] / c["tab"]["NWAVE"])
-    cb["value"] = value
-    cb["sample"] = cb["sample"].replace("of %d wavenumbers" % c["tab"]["NWAVE"], "of %d wavenumbers" % cfg["nwave"])
+    nthreads = host_threads()
+    c = make_case(cfg)                     # the case rank 0 of the B200 arm times
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, _, _ = cpu_full_pass(c, nthreads)
+        if i >= args.warmup:
+            times.append(dt)
+    t = statistics.mean(times)
+    value = 1.0 / t
+    cb = cpu_baseline_dict(t, nthreads, cfg["nwave"], len(times))
     line = dict(impl="reference", metric=METRIC, value=value, unit="spectra/s", n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=1e3 / value, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f64", data="synthetic", config=dict(workload=workload_name(cfg)), cpu_baseline=cb,
+                warmup=args.warmup, ms_per_step=1e3 * t, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f64", data="synthetic", config=config_dict(cfg, args.gpus), cpu_baseline=cb,
                 e2e=dict(value=value, unit="spectra/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
+
+
+def parity_of(spec, dx, s_ref, x_ref):
+    """max relative spectrum error and max Jacobian error relative to each state-vector column's largest entry."""
+    e_s = float(np.abs(spec - s_ref).max() / np.abs(s_ref).max())
+    cm = np.abs(x_ref).max(axis=(0, 1))
+    cm[cm == 0] = 1.0
+    e_x = float((np.abs(dx - x_ref).max(axis=(0, 1)) / cm).max())
+    return e_s, e_x
 
 
 # ------------------------------------------------------------------------------------------------
@@ -187,10 +239,70 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def make_evaluation(c, **kw):
+    from archnemesis_dist_b200 import engine
+    a = dict(press_atm=c["press"], temp=c["temp"], amount=c["amount"], gas_slot=c["gas_slot"], NVMR=c["NVMR"],
+             NPAR=c["NPAR"], LAYINC=c["LAYINC"], SCALE=c["SCALE"], NLAYIN=c["NLAYIN"], EMTEMP=c["EMTEMP"],
+             LAYPRESS=c["LAYPRESS"], taucia=c["taucon"], dtaucon=c["dtaucon"], mode=engine.THERMAL,
+             ISPACE=c["ISPACE"], TSURF=c["TSURF"], EMISSIVITY=c["EMISSIVITY"], xfac=c["xfac"])
+    a.update(kw)
+    return engine.Evaluation(**a)
+
+
+def fold_M(c):
+    from archnemesis_dist_b200 import plan
+    return plan.fold_projection(c["xmap"], c["LAYINC"], c["NLAYIN"], c["DTE"], c["DAM"], c["DCO"], c["NVMR"], c["NDUST"])
+
+
+def limb_case(c, npath):
+    """BASELINE config 4 on the atmosphere of case c: `npath` limb / occultation paths, path g sees the layers
+    above its tangent layer twice (NLAYIN up to 2 NLAY), padded like Path_0 pads them."""
+    nlay = len(c["press"])
+    d = dict(c)
+    nlm = 2 * nlay
+    layinc = np.zeros((nlm, npath), np.int32)
+    scale = np.zeros((nlm, npath))
+    emtemp = np.zeros((nlm, npath))
+    nlayin = np.zeros(npath, np.int32)
+    for g in range(npath):
+        t = (g * (nlay - 2)) // npath
+        seq = np.array(list(range(nlay - 1, t - 1, -1)) + list(range(t, nlay)))
+        n = len(seq)
+        nlayin[g] = n
+        layinc[:n, g] = seq
+        scale[:n, g] = 1.0 + 20.0 / (1.0 + np.abs(seq - t))
+        emtemp[:n, g] = c["temp"][seq]
+    d.update(LAYINC=layinc, SCALE=scale, NLAYIN=nlayin, EMTEMP=emtemp)
+    return d
+
+
+def cpu_limb_rows(c4, rows, transmission, nthreads):
+    """Oracle chain for the multi-path case on the wavenumber rows `rows` (parity of the extras)."""
+    from oracle import oracle as orc
+    tab = c4["tab"]
+    K = np.ascontiguousarray(tab["K"][rows])
+    k, dkdT = orc.calc_k(K, tab["PRESS"], tab["TEMP"], c4["press"], c4["temp"], want_grad=True, nthreads=nthreads)
+    tau, dk = orc.k_overlap(tab["DELG"], k, c4["amount"], dkdT=dkdT, nthreads=nthreads)
+    tl, tp, dtl = orc.assemble_opacity(tau, dk, c4["gas_slot"], c4["NVMR"], c4["NPAR"], c4["taucon"][rows],
+                                       c4["dtaucon"][rows], c4["LAYINC"], c4["SCALE"])
+    if transmission:
+        S, dS = orc.transmission(tp, dtl, c4["xfac"][rows])
+        dT = None
+    else:
+        S, dS, dT = orc.thermal_paths(c4["ISPACE"], tab["WAVE"][rows], tl, dtl, c4["NVMR"], c4["NLAYIN"], c4["EMTEMP"],
+                                      c4["LAYPRESS"], c4["LAYINC"], c4["TSURF"], c4["EMISSIVITY"][rows],
+                                      c4["xfac"][rows], nthreads=nthreads)
+    spec, dspec, _ = orc.g_integrate(S, dS, dT, tab["DELG"])
+    npath = c4["LAYINC"].shape[1]
+    d2 = orc.map2pro(dspec, len(rows), c4["NVMR"], c4["NDUST"], c4["NPRO"], npath, c4["NLAYIN"], c4["LAYINC"], c4["DTE"],
+                     c4["DAM"], c4["DCO"], INCPAR=orc.included_params(c4["xmap"]))
+    return spec, orc.map2xvec(d2, c4["xmap"])
+
+
 def run_b200(args, cfg):
     import torch
     import torch.distributed as dist
-    from archnemesis_dist_b200 import engine, plan
+    from archnemesis_dist_b200 import dist as adist, engine, plan
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -203,15 +315,12 @@ def run_b200(args, cfg):
             os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    c = make_case(cfg, rank_seed=rank)
+    c0 = make_case(cfg)                              # the table and rank 0's atmosphere
+    c = perturb_case(c0, rank)
     tab = c["tab"]
     hp = engine.HotPath(tab["K"], tab["PRESS"], tab["TEMP"], tab["DELG"], tab["WAVE"])
-    ev = engine.Evaluation(press_atm=c["press"], temp=c["temp"], amount=c["amount"], gas_slot=c["gas_slot"],
-                           NVMR=c["NVMR"], NPAR=c["NPAR"], LAYINC=c["LAYINC"], SCALE=c["SCALE"], NLAYIN=c["NLAYIN"],
-                           EMTEMP=c["EMTEMP"], LAYPRESS=c["LAYPRESS"], taucia=c["taucon"], dtaucon=c["dtaucon"],
-                           mode=engine.THERMAL, ISPACE=c["ISPACE"], TSURF=c["TSURF"], EMISSIVITY=c["EMISSIVITY"],
-                           xfac=c["xfac"])
-    M = plan.fold_projection(c["xmap"], c["LAYINC"], c["NLAYIN"], c["DTE"], c["DAM"], c["DCO"], c["NVMR"], c["NDUST"])
+    ev = make_evaluation(c)
+    M = fold_M(c)
     NW, NX = cfg["nwave"], cfg["nx"]
     gathered = torch.empty((world, NW, NX + 1), dtype=torch.float64, device="cuda") if world > 1 else None
     block = torch.empty((NW, NX + 1), dtype=torch.float64, device="cuda")
@@ -225,6 +334,9 @@ def run_b200(args, cfg):
         return spec, dx
 
     host_out = torch.empty((NW, NX + 1), dtype=torch.float64, pin_memory=True)
+    # the assembled YN / KK rows are wanted on ONE host (the optimal-estimation update runs once): rank 0 reads the
+    # gathered block back, the other ranks keep their device copy
+    host_all = torch.empty((world, NW, NX + 1), dtype=torch.float64, pin_memory=True) if world > 1 and rank == 0 else None
 
     def step_e2e():
         spec, dx, _ = hp.forward_jacobian(ev, M)          # public API: host arrays in
@@ -232,15 +344,13 @@ def run_b200(args, cfg):
             block[:, 0] = spec[:, 0]
             block[:, 1:] = dx[:, 0, :]
             dist.all_gather_into_tensor(gathered, block)
-        if world > 1:
-            host_all.copy_(gathered, non_blocking=True)
+            if rank == 0:
+                host_all.copy_(gathered, non_blocking=True)
         else:
             # one contiguous [NWAVE, 1+NX] device block, one DMA into pinned memory (strided D2H copies go
             # through a bounce buffer and a second launch each)
             host_out.copy_(torch.cat([spec[:, :1], dx[:, 0, :]], dim=1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
-
-    host_all = torch.empty((world, NW, NX + 1), dtype=torch.float64, pin_memory=True) if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -253,6 +363,19 @@ def run_b200(args, cfg):
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def timed(fn, reps, warm=1):
+        """ms per call, CUDA events on the current stream, max over ranks."""
+        for _ in range(warm):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        barrier()
+        return reduce_max(a.elapsed_time(b) / reps)
 
     # ---- device-resident timing ------------------------------------------------------------------
     staged = hp.stage(ev, True, M)
@@ -268,7 +391,7 @@ def run_b200(args, cfg):
     t_wall0 = time.perf_counter()
     st[0].record()
     for i in range(K):
-        step_resident(staged, kt[i])
+        spec_d, dx_d = step_resident(staged, kt[i])
         st[i + 1].record()
     barrier()
     t_wall1 = time.perf_counter()
@@ -276,6 +399,7 @@ def run_b200(args, cfg):
     launches = hp.launches - launches0
     k_ms = statistics.mean(a.elapsed_time(b) for a, b in kt)
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    got_spec, got_dx = spec_d.cpu().numpy(), dx_d.cpu().numpy()       # what the timed loop computed last
 
     # ---- end to end through the public API with host buffers ---------------------------------------
     for _ in range(max(1, args.warmup)):
@@ -290,6 +414,7 @@ def run_b200(args, cfg):
     e2e_ms = reduce_max(e0.elapsed_time(e1))
     h2d = int(ev.h2d_bytes)
     d2h = int((world if world > 1 else 1) * NW * (NX + 1) * 8)
+    e2e_block = (host_all[0] if world > 1 else host_out).numpy() if rank == 0 else None
 
     if args.stage_times and rank == 0:
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -305,9 +430,56 @@ def run_b200(args, cfg):
         sys.stderr.write("stage ms: gas_opacity %.3f radiance %.3f project %.3f\n" % (
             evs[0].elapsed_time(evs[1]), evs[1].elapsed_time(evs[2]), evs[2].elapsed_time(evs[3])))
 
+    # ---- strong scaling of ONE evaluation under wavenumber sharding (N > 1) ----------------------------
+    strong = None
+    if world > 1 and not args.no_extras:
+        strong = {}
+        reps = max(3, min(K, 10))
+        for name, cc, mode in (("config2", c0, engine.THERMAL), ("config4_64_paths", limb_case(c0, 64), engine.TRANSMISSION)):
+            evx, Mx = make_evaluation(cc, mode=mode), fold_M(cc)
+            npath = cc["LAYINC"].shape[1]
+            s1 = hp.stage(evx, True, Mx)                       # every rank: the whole evaluation on its full replica
+            ms1 = timed(lambda: hp.run(s1), reps)
+            ws = adist.WavenumberShard(engine.HotPath, tab["K"], tab["PRESS"], tab["TEMP"], tab["DELG"], tab["WAVE"],
+                                       rank, world)
+            sN = ws.hotpath.stage(ws.slice_evaluation(evx), True, Mx)
+
+            def step_strong():
+                spec, dx, _ = ws.hotpath.run(sN)
+                blk = torch.cat([spec.unsqueeze(2), dx], dim=2)        # [NWAVE/N, NPATH, 1+NX]
+                return adist.all_gather_rows(blk, NW, dim=0)
+            msN = timed(step_strong, reps)
+            full = step_strong()
+            one = hp.run(s1)
+            same = bool(torch.equal(full[:, :, 0], one[0]) and torch.equal(full[:, :, 1:], one[1]))
+            strong[name] = dict(ms_per_eval=msN, ms_per_eval_1gpu=ms1, speedup_vs_1=ms1 / msN, npath=npath,
+                                sharding="wavenumber rows (dist.WavenumberShard), NCCL all-gather of [NWAVE,NPATH,1+NX]",
+                                equals_single_gpu_result=same)
+            ws.hotpath.close()
+            del ws, sN, s1, full, one
+            torch.cuda.empty_cache()
+
     if rank == 0:
         ms_step = ms_total / K
         value = world * 1e3 / ms_step
+        # ---- parity of what was timed, and the CPU baseline ------------------------------------------
+        nthreads = host_threads()
+        cb = None
+        if world == 1 and not args.no_cpu_baseline and args.parity_rows == 0:
+            t_cpu, s_ref, x_ref = cpu_full_pass(c, nthreads)
+            cb = cpu_baseline_dict(t_cpu, nthreads, NW, 1)
+            rows = np.arange(NW)
+        else:
+            n = args.parity_rows or 64
+            rows = np.unique(np.linspace(0, NW - 1, min(n, NW)).astype(int))
+            s_ref, x_ref = cpu_forward_jacobian(c, rows, nthreads)
+        e_s, e_x = parity_of(got_spec[rows], got_dx[rows], s_ref, x_ref)
+        blk = np.concatenate([got_spec[:, :1], got_dx[:, 0, :]], axis=1)
+        parity = dict(max_rel_spec=e_s, max_col_jac=e_x, rows=int(len(rows)), tolerance=1e-9,
+                      against="CPU oracle (oracle/ansb200_oracle.c) on the same rows of the timed case",
+                      e2e_equals_resident=bool(np.array_equal(e2e_block, blk)))
+        ok = e_s < 1e-9 and e_x < 1e-9 and parity["e2e_equals_resident"]
+
         # roofline of the dominant kernel (fused k-interp + overlap), SURVEY.md 8d B_kio
         U = plan.planes_touched(staged.plan_host, cfg["ntemp"])
         plane = cfg["nwave"] * cfg["ng"] * cfg["ngas"] * 8
@@ -319,7 +491,7 @@ def run_b200(args, cfg):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = b_kio / (k_ms * 1e-3) / 1e9
-        roof = dict(kernel="ans_koverlap_kernel (ansb200_gas_opacity: fused k-interp + random overlap, gradients)",
+        roof = dict(kernel=KERNEL_NAME,
                     bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                     traffic=TRAFFIC if cfg["nwave"] == CFG["nwave"] else None,
                     peak_source="measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
@@ -327,21 +499,123 @@ def run_b200(args, cfg):
                     ncu_utilisation=NCU_UTIL if cfg["nwave"] == CFG["nwave"] else None)
         line = dict(metric=METRIC, value=value, unit="spectra/s", n_gpus=world, steps=K, warmup=args.warmup,
                     ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
-                    data="synthetic",
-                    config=dict(workload=workload_name(cfg), sharding="one geometry per rank, table replicated, "
-                                "NCCL all-gather of [spectrum|Jacobian] rows" if world > 1 else "single GPU",
-                                l2="per-step working set (%.0f MB of table planes + 512 MB of tau/dk) exceeds the "
-                                   "126 MB L2; no explicit flush" % (U * plane / 1e6)),
+                    data="synthetic", config=config_dict(cfg, world),
                     e2e=dict(value=world * 1e3 / (e2e_ms / K), unit="spectra/s", h2d_bytes_per_step=h2d,
                              d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / K),
-                    gpu_launches=launches, roofline=roof, clocks=clocks)
-        if not args.no_cpu_baseline and world == 1:
-            cb, _ = time_cpu_sampled(cfg, args.cpu_sample_waves)
+                    gpu_launches=launches, roofline=roof, clocks=clocks, parity=parity)
+        if cb is not None:
             line["cpu_baseline"] = cb
+        if strong is not None:
+            line["strong"] = strong
+        if world == 1 and not args.no_extras:
+            line["extra"] = run_extras(hp, c, cfg, nthreads)
         print(json.dumps(line))
+        sys.stdout.flush()
+    else:
+        ok = True
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if not ok:
+        sys.stderr.write("bench.py: parity check FAILED (%s)\n" % json.dumps(parity))
+        sys.exit(1)
+
+
+def run_extras(hp, c, cfg, nthreads):
+    """BASELINE configs 3, 4, 5 on one GPU, each with its own small parity check; a failure is recorded, it never
+    takes the headline line down."""
+    import torch
+    from archnemesis_dist_b200 import engine, lbl, synthetic
+    out = {}
+
+    def timeit(fn, reps=3, warm=1):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    NW = cfg["nwave"]
+    # config 4: 64 limb / occultation paths on the same atmosphere and table
+    try:
+        c4 = limb_case(c, 64)
+        M4 = fold_M(c4)
+        rows = np.unique(np.linspace(0, NW - 1, 4).astype(int))
+        r4 = {}
+        for name, mode in (("transmission", engine.TRANSMISSION), ("thermal", engine.THERMAL)):
+            ev4 = make_evaluation(c4, mode=mode)
+            s4 = hp.stage(ev4, True, M4)
+            ms = timeit(lambda: hp.run(s4))
+            go = hp.gas_opacity(s4)
+            ms_fin = timeit(lambda: hp.finish(s4, go))
+            spec, dx, _ = hp.run(s4)
+            s_ref, x_ref = cpu_limb_rows(c4, rows, mode == engine.TRANSMISSION, nthreads)
+            e_s, e_x = parity_of(spec.cpu().numpy()[rows], dx.cpu().numpy()[rows], s_ref, x_ref)
+            r4[name] = dict(ms_per_eval=ms, ms_gas_opacity=ms - ms_fin, ms_radiance_and_projection=ms_fin,
+                            geometry_spectra_per_s=64 * 1e3 / ms, parity=dict(max_rel_spec=e_s, max_col_jac=e_x, rows=len(rows)))
+            del s4, go, spec, dx
+        out["config4"] = dict(workload="64 limb paths, NLAYIN up to %d, NWAVE=%d NX=%d, forward+Jacobian of all paths "
+                                       "in one evaluation" % (int(c4["NLAYIN"].max()), NW, cfg["nx"]), **r4)
+    except Exception as e:                                   # noqa: BLE001
+        out["config4"] = dict(error=repr(e))
+    torch.cuda.empty_cache()
+    # config 5: the widest state vector of the sweep on the same table (NX = 1000)
+    try:
+        small = synthetic.make_fm_case(nwave=8, ng=cfg["ng"], npress=cfg["npress"], ntemp=cfg["ntemp"], ngas=cfg["ngas"],
+                                       nlay=cfg["nlay"], nvmr=cfg["nvmr"], ndust=cfg["ndust"], npro=cfg["npro"], nx=1000,
+                                       seed=1003)
+        c5 = dict(c)
+        c5["xmap"] = small["xmap"]
+        M5 = fold_M(c5)
+        s5 = hp.stage(make_evaluation(c5), True, M5)
+        ms = timeit(lambda: hp.run(s5))
+        spec, dx, _ = hp.run(s5)
+        rows = np.unique(np.linspace(0, NW - 1, 16).astype(int))
+        s_ref, x_ref = cpu_forward_jacobian(c5, rows, nthreads)
+        e_s, e_x = parity_of(spec.cpu().numpy()[rows], dx.cpu().numpy()[rows], s_ref, x_ref)
+        out["config5"] = dict(workload="NX=1000 state vector, NWAVE=%d (rest as config 2)" % NW, ms_per_eval=ms,
+                              jacobian_columns_per_s=1000 * 1e3 / ms,
+                              parity=dict(max_rel_spec=e_s, max_col_jac=e_x, rows=len(rows)))
+        del s5, spec, dx
+    except Exception as e:                                   # noqa: BLE001
+        out["config5"] = dict(error=repr(e))
+    torch.cuda.empty_cache()
+    # config 3: line-by-line Voigt cross-sections, 10^6 lines x 10^5 wavenumbers, one (p,T) point of the 20x15 grid
+    try:
+        nlines, nwave = 1000000, 100000
+        wn = np.linspace(1000.0, 1000.0 + 0.002 * (nwave - 1), nwave)
+        lines = synthetic.make_line_list(nlines, wn[0], wn[-1], seed=0)
+        res = lbl.resident_lines(lines)
+        wn_d = torch.from_numpy(wn).cuda()
+        press = np.exp(np.linspace(-15, 2, 20))
+        temps = np.linspace(70, 300, 15)
+        npt = 6                                               # 6 of the 300 grid points per launch (one wave of CTAs)
+        pts6 = [(float(temps[(3 * i) % 15]), float(press[(7 * i + 5) % 20]), 1.0) for i in range(npt)]
+        pts = [(190.0, 0.1, 1.0)]
+        mix = np.array([0.1, 0.9])
+        ms = timeit(lambda: lbl.lbl_absorption(wn_d, res, pts6, 296.0, 1.0, 1.0, 28.0, mix), reps=2, warm=1) / npt
+        nu = lines["nu"]
+        win = float((np.searchsorted(wn, nu + 75.0) - np.searchsorted(wn, nu - 75.0)).sum())
+        # parity on a cut: the first 2048 grid points against the lines that reach them
+        from oracle import oracle as orc
+        sub = nu < wn[2047] + 75.0
+        cut = {k: (v[..., sub] if k == "broadening" else v[sub]) for k, v in lines.items()}
+        keep = np.sort(np.random.default_rng(0).choice(int(sub.sum()), size=min(3000, int(sub.sum())), replace=False))
+        cut = {k: (v[..., keep] if k == "broadening" else v[keep]) for k, v in cut.items()}
+        got = lbl.lbl_absorption(wn[:2048], cut, pts, 296.0, 1.0, 1.0, 28.0, mix).cpu().numpy()[0]
+        ref = orc.lbl_absorption(wn[:2048], cut, 190.0, 0.1, 296.0, 1.0, 1.0, 1.0, 28.0, mix)
+        out["config3"] = dict(workload="line-by-line Voigt: 1e6 lines x 1e5 wavenumbers, 6 of the 20x15 (p,T) points per launch",
+                              ms_per_pt_point=ms, line_point_pairs_per_s=win / (ms * 1e-3), s_for_300_point_grid=ms * 0.3,
+                              parity=dict(max_rel=float(np.abs(got - ref).max() / np.abs(ref).max()),
+                                          lines=int(len(keep)), points=2048))
+    except Exception as e:                                   # noqa: BLE001
+        out["config3"] = dict(error=repr(e))
+    return out
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at config 2, from the
@@ -349,18 +623,10 @@ def run_b200(args, cfg):
 # once, 467.3 MB written; algorithmic B_kio is 715.5 MB, the remainder of the output was still in L2).
 # The same capture says what the kernel IS bound by (it is not HBM): issue slots 47 % busy with 16 resident
 # warps per SM stalled on fixed-latency dependencies, shared-memory data pipe 48 %, FP64 pipe 9 %.
+KERNEL_NAME = "ans_koverlap_kernel (ansb200_gas_opacity: fused k-interp + random overlap, gradients)"
 TRAFFIC = 674.4e6
 NCU_UTIL = dict(issue_slots_pct=47.3, smem_data_pipe_pct=47.6, fp64_pipe_pct=9.2, warps_active_pct=24.1,
                 source="profiles/r01_ncu_full_config2.txt (ncu --set full, not taken during the timed run)")
-
-
-def time_cpu_sampled(cfg, nsample):
-    c = make_case(cfg, nwave=max(nsample, 8))
-    cb, t = time_cpu(c, nsample, steps=1, warmup=1)
-    value = 1.0 / (t * cfg["nwave"] / c["tab"]["NWAVE"])
-    cb["value"] = value
-    cb["sample"] = cb["sample"].replace("of %d wavenumbers" % c["tab"]["NWAVE"], "of %d wavenumbers" % cfg["nwave"])
-    return cb, t
 
 
 def main():
