@@ -1,5 +1,7 @@
 // koverlap.cu -- C entry points of the random-overlap kernels (implementation: koverlap_impl.cuh).
 #include "koverlap_impl.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 // NGAS == 1: ForwardModel_0.py:5871-5876 / :6056-6058
 template <bool GRAD>
@@ -26,6 +28,31 @@ __global__ void ans_koverlap_single_kernel(OvParams P)
     }
 }
 
+bool ov_fast_supported(const OvParams &P, bool grad);
+int ov_fast_launch(const OvParams &P, bool grad, int *scratch, int *why, cudaStream_t stream);
+
+static int ov_general(const OvParams &P, bool grad, cudaStream_t stream)
+{
+    const int NN = P.NG * P.NG;
+    if (NN <= 128) return ov_dispatch_4(P, grad, stream);
+    if (NN <= 256) return ov_dispatch_8(P, grad, stream);
+    return ov_dispatch_16(P, grad, stream);
+}
+
+// diagnostics: ANSB200_OVERLAP=general forces the general kernel; ANSB200_OVERLAP=stats prints how many cells
+// the fast kernel handed over (synchronises the stream)
+static int ov_mode()
+{
+    static const int mode = [] {
+        const char *e = getenv("ANSB200_OVERLAP");
+        if (!e) return 0;
+        if (!strcmp(e, "general")) return 1;
+        if (!strcmp(e, "stats")) return 2;
+        return 0;
+    }();
+    return mode;
+}
+
 static int ov_run(OvParams &P, bool grad, cudaStream_t stream)
 {
     ANS_REQUIRE(P.NWAVE > 0 && P.NG > 0 && P.NLAY > 0 && P.NGAS > 0, "koverlap: bad shape");
@@ -42,10 +69,34 @@ static int ov_run(OvParams &P, bool grad, cudaStream_t stream)
         return ANSB200_OK;
     }
     ANS_REQUIRE(P.weight && P.g_ord, "koverlap: weight/g_ord tables are required for NGAS > 1");
-    const int NN = P.NG * P.NG;
-    if (NN <= 128) return ov_dispatch_4(P, grad, stream);
-    if (NN <= 256) return ov_dispatch_8(P, grad, stream);
-    return ov_dispatch_16(P, grad, stream);
+    if (ov_mode() != 1 && ov_fast_supported(P, grad)) {
+        // fast kernel for the common case; the cells it declines (tie order, non-monotone k, ...) are listed for
+        // the general kernel, which runs on that list afterwards (usually empty: it exits before its set-up)
+        const long long ncell = (long long)P.NWAVE * P.NLAY;
+        ANS_REQUIRE(ncell < 0x7fffffffLL, "koverlap: NWAVE*NLAY too large");
+        int *scratch = nullptr;
+        const bool stats = ov_mode() == 2;
+        ANS_CUDA_CHECK(cudaMallocAsync((void **)&scratch, (size_t)(ncell + 1 + 8) * sizeof(int), stream));
+        ANS_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(int), stream));
+        if (stats) ANS_CUDA_CHECK(cudaMemsetAsync(scratch + ncell + 1, 0, 8 * sizeof(int), stream));
+        int rc = ov_fast_launch(P, grad, scratch, stats ? scratch + ncell + 1 : nullptr, stream);
+        if (rc == ANSB200_OK) {
+            P.cell_count = scratch;
+            P.cell_list = scratch + 1;
+            rc = ov_general(P, grad, stream);
+        }
+        if (rc == ANSB200_OK && ov_mode() == 2) {
+            int c = 0, why[8];
+            cudaMemcpyAsync(&c, scratch, sizeof(int), cudaMemcpyDeviceToHost, stream);
+            cudaMemcpyAsync(why, scratch + ncell + 1, sizeof(why), cudaMemcpyDeviceToHost, stream);
+            cudaStreamSynchronize(stream);
+            fprintf(stderr, "[ansb200] overlap: %d of %lld cells left to the general kernel (non-monotone %d, open bin %d, "
+                            "group %d, tie %d)\n", c, ncell, why[0], why[1], why[2], why[3]);
+        }
+        cudaFreeAsync(scratch, stream);
+        return rc;
+    }
+    return ov_general(P, grad, stream);
 }
 
 // The host checks (plan.overlap_tables) that no sorted element can straddle two bin edges; if it

@@ -1,0 +1,617 @@
+// koverlap_fast.cu -- random-overlap gas mixing, the common case, as "sort + marginal matrices".
+//
+// Reference: k_overlapg + rankg / k_overlap + rank (archnemesis/ForwardModel_0.py:5842-6026, :6029-6173).
+//
+// What rankg computes for bin m is  sum_e omega_m(e) x_e / sum_e omega_m(e),  where e runs over the NG*NG
+// elements (i,j) of the key matrix  tau_i + k_j*amount,  omega_m(e) is the part of e's weight
+// del_g[i]*del_g[j] that falls between the bin edges g_ord[m], g_ord[m+1] on the cumulative-weight axis of
+// the key-sorted sequence, and x_e is the key or a gradient entry.  Every x_e is a row term plus a column
+// term (key = a_i + b_j; d/d amount of an already folded gas = dk_i; of the gas being folded = k_j;
+// d/dT = dT_i + bT_j), so
+//     bin m = [ sum_i R[i][m] X[i][:] + sum_j C[j][m] Y[j][:] ] / sum_i R[i][m]
+// with the marginals  R[i][m] = sum_j omega_m(i,j),  C[j][m] = sum_i omega_m(i,j).  The bins, as sets, and
+// the element that straddles each edge depend on the ORDER of the keys only where an edge falls, so the
+// sort needs to be exact only there:
+//   1. keys are packed as (23 key bits | 9-bit element number) -- 6 exponent bits below the largest key and the
+//      17 leading mantissa bits, cut straight out of the float64 pattern (truncation is monotone) -- and
+//      sorted by the 32-bit min/max bitonic network of koverlap_impl.cuh, in registers;
+//   2. cumulative weights: lane-local sums + one warp scan (exact: float32-born weights); every element
+//      stores the bin it starts in (one byte), the straddler of every edge its position and the cumulative
+//      weight before it;
+//   3. lane m checks that the straddler of edge m has key bits of its own (then everything before it is
+//      strictly smaller and everything after strictly larger, whatever the order inside groups of equal
+//      key bits and whatever order numba's unstable sort would give equal keys); a pair of elements with
+//      equal key bits around an edge is put right with the exact float64 keys; anything else (larger
+//      groups, exactly equal keys on an edge, non-monotone inputs, ...) sends the CELL to the work list of
+//      the general kernel (ans_koverlap_kernel), which replays numba's tie order;
+//   4. R and C are built by lane-per-row / lane-per-column walks over the bin bytes (run lengths, no
+//      atomics), the straddlers' (1-frac) parts are moved to the next bin, and the two small products
+//      above are lane-per-bin FMA loops with broadcast operand rows.
+// Row-/column-major key orders (one gas far weaker than the other) have data-independent marginals, made
+// once per CTA; they are used when the static straddlers are strictly separated from their neighbours.
+//
+// One warp per (wavenumber, layer) cell, persistent CTAs, no CTA barrier after the set-up.  Agreement with
+// the reference ~1e-15 (another summation order); the literal sequential scan (force_seq) stays with the
+// general kernel.
+#include "koverlap_impl.cuh"
+
+namespace {
+
+constexpr int KF_NONE = 0xffff;
+
+template <int NG>
+struct KfShared {
+    double gord[NG + 2];            // bin edges, gord[NG+1] = +inf
+    double wtabd[NG * NG];          // element weights (float32 products widened)
+    float wtabf[512];               // the same as float32, 0 beyond NG*NG (padding of the sort)
+    double stat[2][2][NG * NG];     // [order][rows | columns][i*NG + m]  marginals of the static orders
+    unsigned short sstr[2][NG + 1][4];   // [order][edge] -> element before / the straddler / element after
+    int ok_f32, ok_static;
+};
+
+// per-warp shared memory, in doubles (every block a multiple of 16 bytes)
+template <int NG, int XS>
+struct KfWarpLayout {
+    static constexpr int NGASMAX = XS > 2 ? XS - 2 : 16;
+    static constexpr int RC = 0;                                  // [NG*NG] marginals; aliased by the sorted words
+    static constexpr int X = RC + NG * NG;                        // [NG][XS] rows {tau_i, dT_i, gas columns}
+    static constexpr int Y = X + NG * XS;                         // [NG][4]  columns {b_j, bT_j, k_j, -}
+    static constexpr int AV = Y + NG * 4;                         // [NG] compact copies for the key loop
+    static constexpr int BV = AV + NG;
+    static constexpr int KBUF = BV + NG;                          // [NG*NGASMAX]
+    static constexpr int DBUF = KBUF + NG * NGASMAX;
+    static constexpr int GBS = DBUF + (XS > 2 ? NG * NGASMAX : 0);   // [NG+2] cumulative weight before the straddler
+    static constexpr int SPOS = GBS + NG + 2;                     // [NG+2] ints: sorted position of the straddler
+    static constexpr int BIN = SPOS + (NG + 2 + 1) / 2 + 1;       // [512] bytes
+    static constexpr int TOTAL = (BIN + 64 + 1) & ~1;
+};
+
+__device__ __forceinline__ int kf_vaddr(int p) { return ((((p & 15) >> 2) * 32 + (p >> 4)) << 2) + (p & 3); }
+
+// Static orders: replay rankg's loop over the row-major (o = 0) / column-major (o = 1) sequence once.
+template <int NG>
+__device__ void kf_static_setup(KfShared<NG> &S)
+{
+    const int o = threadIdx.x;
+    if (o < 2) {
+        double *RA = S.stat[o][0], *RB = S.stat[o][1];
+        double run = 0.0;
+        int ig = 0, prev = KF_NONE, pending = -1;
+        bool ok = true;
+        for (int m = 0; m <= NG; ++m) { S.sstr[o][m][0] = S.sstr[o][m][1] = S.sstr[o][m][2] = KF_NONE; }
+        for (int q = 0; q < NG; ++q) {
+            for (int r = 0; r < NG; ++r) {
+                const int i = o == 0 ? q : r, j = o == 0 ? r : q, e = i * NG + j;
+                if (pending >= 0) { S.sstr[o][pending][2] = (unsigned short)e; pending = -1; }
+                const double w = S.wtabd[e];
+                const double gdn = __dadd_rn(run, w);
+                if (ig < NG) {
+                    if (gdn < S.gord[ig + 1]) {
+                        RA[i * NG + ig] = __dadd_rn(RA[i * NG + ig], w);
+                        RB[j * NG + ig] = __dadd_rn(RB[j * NG + ig], w);
+                    } else {
+                        const double frac = __ddiv_rn(__dsub_rn(S.gord[ig + 1], run), __dsub_rn(gdn, run));
+                        const double f = __dmul_rn(frac, w);
+                        RA[i * NG + ig] = __dadd_rn(RA[i * NG + ig], f);
+                        RB[j * NG + ig] = __dadd_rn(RB[j * NG + ig], f);
+                        ++ig;
+                        S.sstr[o][ig][0] = (unsigned short)prev;
+                        S.sstr[o][ig][1] = (unsigned short)e;
+                        pending = ig;
+                        if (ig < NG) {
+                            const double f2 = __dmul_rn(__dsub_rn(1.0, frac), w);
+                            RA[i * NG + ig] = __dadd_rn(RA[i * NG + ig], f2);
+                            RB[j * NG + ig] = __dadd_rn(RB[j * NG + ig], f2);
+                            if (gdn >= S.gord[ig + 1]) ok = false;      // one element over two edges
+                        }
+                    }
+                }
+                prev = e;
+                run = gdn;
+            }
+        }
+        if (ig < NG - 1) ok = false;     // some bin never closed
+        if (!ok) atomicAnd(&S.ok_static, 0);
+    } else if (o == 32) {
+        // in any order: no element may lie over two edges (the host plan checks the same and asks for the
+        // sequential scan otherwise)
+        double wmax = 0.0, dmin = INFINITY;
+        for (int e = 0; e < NG * NG; ++e) wmax = fmax(wmax, S.wtabd[e]);
+        for (int m = 0; m < NG; ++m) dmin = fmin(dmin, __dsub_rn(S.gord[m + 1], S.gord[m]));
+        if (!(wmax < dmin)) atomicAnd(&S.ok_static, 0);
+    }
+}
+
+// lane-per-bin accumulation  acc += sum_t M[t*NG + m] * rows[t][:]
+template <int NG, int XS, bool GRAD>
+__device__ __forceinline__ void kf_accum_x(const double *__restrict__ M, const double *__restrict__ X, int igas, int m,
+                                           double &sw, double (&acc)[XS])
+{
+    if (m < NG) {
+#pragma unroll 2
+        for (int t = 0; t < NG; ++t) {
+            const double r = M[t * NG + m];
+            sw = __dadd_rn(sw, r);
+            if (GRAD) {
+                const double2 *row = reinterpret_cast<const double2 *>(X + t * XS);
+                const double2 x0 = row[0];
+                acc[0] = __fma_rn(r, x0.x, acc[0]);
+                acc[1] = __fma_rn(r, x0.y, acc[1]);
+#pragma unroll
+                for (int q = 1; q < XS / 2; ++q) {
+                    if (2 * q - 2 <= igas) {
+                        const double2 x = row[q];
+                        acc[2 * q] = __fma_rn(r, x.x, acc[2 * q]);
+                        acc[2 * q + 1] = __fma_rn(r, x.y, acc[2 * q + 1]);
+                    }
+                }
+            } else {
+                acc[0] = __fma_rn(r, X[t * XS], acc[0]);
+            }
+        }
+    }
+}
+
+template <int NG, bool GRAD>
+__device__ __forceinline__ void kf_accum_y(const double *__restrict__ M, const double *__restrict__ Y, int m,
+                                           double &yb, double &yT, double &yk)
+{
+    if (m < NG) {
+#pragma unroll 2
+        for (int t = 0; t < NG; ++t) {
+            const double c = M[t * NG + m];
+            if (GRAD) {
+                const double2 y0 = *reinterpret_cast<const double2 *>(Y + 4 * t);
+                yb = __fma_rn(c, y0.x, yb);
+                yT = __fma_rn(c, y0.y, yT);
+                yk = __fma_rn(c, Y[4 * t + 2], yk);
+            } else {
+                yb = __fma_rn(c, Y[4 * t], yb);
+            }
+        }
+    }
+}
+
+// lane-per-row (sa = NG, sb = 1) or lane-per-column (sa = 1, sb = NG) walk over the bin bytes: run lengths of
+// equal bins are summed in a register and added to M[lane*NG + bin]
+template <int NG>
+__device__ __forceinline__ void kf_walk(const unsigned char *__restrict__ bin, const double *__restrict__ wtabd,
+                                        double *__restrict__ M, int lane, int sa, int sb)
+{
+    if (lane < NG) {
+        const unsigned char *bp = bin + lane * sa;
+        int mc = bp[0];
+        double acc = 0.0;
+#pragma unroll
+        for (int t = 0; t < NG; ++t) {
+            const int mt = bp[t * sb];
+            if (mt != mc) {
+                if (mc < NG) M[lane * NG + mc] = __dadd_rn(M[lane * NG + mc], acc);
+                acc = 0.0;
+                mc = mt;
+            }
+            acc = __dadd_rn(acc, wtabd[t * NG + lane]);     // (the weight table is symmetric)
+        }
+        if (mc < NG) M[lane * NG + mc] = __dadd_rn(M[lane * NG + mc], acc);
+    }
+}
+
+// move the (1-frac) part of every straddler from the bin it starts in to the next one; lane = edge, line = the
+// straddler's row (or column)
+template <int NG>
+__device__ __forceinline__ void kf_correct(double *__restrict__ M, int lane, int line, double cw)
+{
+    const bool act = line >= 0;
+    if (act) M[line * NG + lane - 1] = __dsub_rn(M[line * NG + lane - 1], cw);
+    __syncwarp();
+    if (act && lane < NG) M[line * NG + lane] = __dadd_rn(M[line * NG + lane], cw);
+    __syncwarp();
+}
+
+template <int NG, int XS, bool GRAD, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32, 1)
+ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict__ fb_list, int *__restrict__ fb_why)
+{
+    using L = KfWarpLayout<NG, XS>;
+    constexpr int NN = NG * NG;
+    constexpr int EPL = 16;
+    static_assert(NN <= 400 + 112 && NN > 256, "16 keys per lane");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    KfShared<NG> &S = *reinterpret_cast<KfShared<NG> *>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int NGAS = P.NGAS, NLAY = P.NLAY, NP1 = NGAS + 1;
+    double *wb = reinterpret_cast<double *>(smem_raw + ((sizeof(KfShared<NG>) + 15) & ~(size_t)15)) + (size_t)warp * L::TOTAL;
+    double *RC = wb + L::RC, *X = wb + L::X, *Y = wb + L::Y, *av = wb + L::AV, *bv = wb + L::BV;
+    double *kbuf = wb + L::KBUF, *dbuf = wb + L::DBUF, *gbs = wb + L::GBS;
+    int *spos = reinterpret_cast<int *>(wb + L::SPOS);
+    unsigned char *bin = reinterpret_cast<unsigned char *>(wb + L::BIN);
+    unsigned *vbuf = reinterpret_cast<unsigned *>(RC);
+
+    // ---- CTA set-up ----------------------------------------------------------------------------
+    if (threadIdx.x == 0) { S.ok_f32 = 1; S.ok_static = 1; }
+    for (int i = threadIdx.x; i <= NG; i += blockDim.x) S.gord[i] = P.g_ord[i];
+    if (threadIdx.x == 0) S.gord[NG + 1] = INFINITY;
+    for (int e = threadIdx.x; e < 2 * 2 * NN; e += blockDim.x) (&S.stat[0][0][0])[e] = 0.0;
+    __syncthreads();
+    {
+        bool ok = true;
+        for (int e = threadIdx.x; e < 512; e += blockDim.x) {
+            float wf = 0.0f;
+            if (e < NN) {
+                const int i = e / NG, j = e - i * NG;
+                const double di = P.del_g[i], dj = P.del_g[j];
+                wf = __fmul_rn((float)di, (float)dj);
+                ok = ok && (double)(float)di == di && (double)wf == P.weight[e] && wf > 0.0f;
+                S.wtabd[e] = (double)wf;
+            }
+            S.wtabf[e] = wf;
+        }
+        if (!ok) atomicAnd(&S.ok_f32, 0);
+    }
+    __syncthreads();
+    kf_static_setup<NG>(S);
+    __syncthreads();
+    const long long ncell = (long long)P.NWAVE * NLAY;
+    if (!S.ok_f32 || !S.ok_static) {
+        // weights that are not float32 products, or a quadrature in which one element can lie over two bin
+        // edges: everything goes to the general kernel
+        if (blockIdx.x == 0 && threadIdx.x == 0) *fb_count = -1;
+        return;
+    }
+
+    for (long long cell = (long long)blockIdx.x * NWARPS + warp; cell < ncell; cell += (long long)gridDim.x * NWARPS) {
+        const int iw = (int)(cell / NLAY);
+        const int l = (int)(cell - (long long)iw * NLAY);
+        bool fallback = false;
+        int why = 0;
+
+        // k (and dk/dT) of the cell
+        if (P.fused) {
+            const size_t plane = (size_t)P.NWAVE * NG * NGAS;
+            const size_t toff = ((size_t)__ldg(P.plan.ip_lo + l) * P.NT + __ldg(P.plan.it_lo + l)) * plane +
+                                (size_t)iw * NG * NGAS;
+            const double *w = P.plan.w4 + 4 * l;
+            const double w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+            const double omv = GRAD ? __ldg(P.plan.omv + l) : 0.0, vv = GRAD ? __ldg(P.plan.vv + l) : 0.0,
+                         dudt = GRAD ? __ldg(P.plan.dudt + l) : 0.0;
+            for (int e = lane; e < NG * NGAS; e += 32) {
+                double kv, dv = 0.0;
+                ans_kinterp_elem<GRAD>(P.lnK, P.K, toff + e, P.NT, plane, w0, w1, w2, w3, omv, vv, dudt, kv, dv);
+                kbuf[e] = kv;
+                if (GRAD) dbuf[e] = dv;
+            }
+        } else {
+            for (int e = lane; e < NG * NGAS; e += 32) {
+                const int g = e / NGAS, gas = e - g * NGAS;
+                const size_t o = (((size_t)iw * NG + g) * NLAY + l) * NGAS + gas;
+                kbuf[e] = __ldg(P.k + o);
+                if (GRAD) dbuf[e] = __ldg(P.dkdT + o);
+            }
+        }
+        for (int i = lane; i < NG * XS; i += 32) X[i] = 0.0;
+        for (int i = lane; i < NG; i += 32) av[i] = 0.0;
+        __syncwarp();
+
+#define KB(g, gas) kbuf[(g) * NGAS + (gas)]
+#define DB(g, gas) dbuf[(g) * NGAS + (gas)]
+        for (int igas = 0; igas < NGAS - 1 && !fallback; ++igas) {
+            const int g1 = igas + 1;
+            const double am1 = __ldg(P.amount + (size_t)g1 * NLAY + l);
+            const bool next_neg = __all_sync(FULL, __dmul_rn(KB(NG - 1, g1), am1) <= 0.0);
+            bool do_fold = false;
+            // short cuts of the reference (ForwardModel_0.py:5897-5909, :5929-5938)
+            if (igas == 0) {
+                const double am0 = __ldg(P.amount + l);
+                const bool first_neg = __all_sync(FULL, __dmul_rn(KB(NG - 1, 0), am0) <= 0.0);
+                if (lane < NG) {
+                    const int i = lane;
+                    if (first_neg) {
+                        av[i] = X[i * XS] = __dmul_rn(KB(i, 1), am1);
+                        if (GRAD) { X[i * XS + 3] = KB(i, 1); X[i * XS + 1] = __dmul_rn(DB(i, 1), am1); }
+                    } else {
+                        av[i] = X[i * XS] = __dmul_rn(KB(i, 0), am0);
+                        if (GRAD) { X[i * XS + 2] = KB(i, 0); X[i * XS + 1] = __dmul_rn(DB(i, 0), am0); }
+                    }
+                }
+                do_fold = !first_neg && !next_neg;
+            } else {
+                if (next_neg) {
+                    if (GRAD && lane < NG) X[lane * XS + 2 + g1] = __dmul_rn(X[lane * XS + 1], 0.0);
+                } else if (__all_sync(FULL, av[NG - 1] <= 0.0)) {
+                    __syncwarp();
+                    if (lane < NG) {
+                        const int i = lane;
+                        av[i] = X[i * XS] = __dmul_rn(KB(i, g1), am1);
+                        if (GRAD) { X[i * XS + 2 + g1] = KB(i, g1); X[i * XS + 1] = __dmul_rn(DB(i, g1), am1); }
+                    }
+                } else {
+                    do_fold = true;
+                }
+            }
+            if (do_fold && lane < NG) {
+                const double b = __dmul_rn(KB(lane, g1), am1);
+                bv[lane] = b;
+                Y[4 * lane] = b;
+                if (GRAD) { Y[4 * lane + 1] = __dmul_rn(DB(lane, g1), am1); Y[4 * lane + 2] = KB(lane, g1); }
+            }
+            __syncwarp();
+            if (!do_fold) continue;
+
+            // ---- preconditions and data-independent orders -----------------------------------------
+            const int l0 = lane < NG ? lane : NG - 1, l1 = lane + 1 < NG ? lane + 1 : NG - 1;
+            const double a_l = av[l0], a_n = av[l1], b_l = bv[l0], b_n = bv[l1];
+            const double a_first = av[0], a_last = av[NG - 1], b_first = bv[0], b_last = bv[NG - 1];
+            const double kmax = __dadd_rn(a_last, b_last);
+            const int ek = (__double2hiint(kmax) >> 20) & 0x7ff;
+            // (lanes >= NG-1 compare an element with itself: false only for NaN)
+            const bool mono = (a_l <= a_n) & (b_l <= b_n) & (kmax > 0.0) & (ek > 100) & (ek < 2000);
+            if (!__all_sync(FULL, mono)) { fallback = true; why = 1; break; }
+            const bool inner = lane < NG - 1;
+            const bool rowok = __all_sync(FULL, !inner || __dadd_rn(a_l, b_last) <= __dadd_rn(a_n, b_first));
+            const bool colok = !rowok && __all_sync(FULL, !inner || __dadd_rn(a_last, b_l) < __dadd_rn(a_first, b_n));
+            int ord = rowok ? 0 : (colok ? 1 : -1);
+            if (ord >= 0) {
+                // the static straddlers must be strictly separated from their neighbours in the order
+                bool sep = true;
+                if (lane >= 1 && lane <= NG) {
+                    const int pe = S.sstr[ord][lane][0], se = S.sstr[ord][lane][1], ne = S.sstr[ord][lane][2];
+                    if (se != KF_NONE) {
+                        const double ks = __dadd_rn(av[se / NG], bv[se % NG]);
+                        if (pe != KF_NONE) sep &= __dadd_rn(av[pe / NG], bv[pe % NG]) < ks;
+                        if (ne != KF_NONE) sep &= ks < __dadd_rn(av[ne / NG], bv[ne % NG]);
+                    }
+                }
+                if (!__all_sync(FULL, sep)) ord = -1;
+            }
+
+            double sw = 0.0, yb = 0.0, yT = 0.0, yk = 0.0;
+            double acc[XS];
+#pragma unroll
+            for (int q = 0; q < XS; ++q) acc[q] = 0.0;
+
+            if (ord >= 0) {
+                kf_accum_x<NG, XS, GRAD>(S.stat[ord][0], X, igas, lane, sw, acc);
+                kf_accum_y<NG, GRAD>(S.stat[ord][1], Y, lane, yb, yT, yk);
+            } else {
+                // ---- 1. packed keys, sorted in registers --------------------------------------------
+                unsigned v[EPL];
+                {
+                    const int basehi = (ek - 62) << 20;
+                    const int ebase = lane * EPL;
+                    const int i0 = ebase / NG, j0 = ebase - i0 * NG;
+                    const double a0 = av[i0 < NG ? i0 : NG - 1], a1 = av[i0 + 1 < NG ? i0 + 1 : NG - 1];
+#pragma unroll
+                    for (int r = 0; r < EPL; ++r) {
+                        const bool wrap = j0 + r >= NG;
+                        const int j = wrap ? j0 + r - NG : j0 + r;
+                        const double key = __dadd_rn(wrap ? a1 : a0, bv[j]);
+                        const int t = max(__double2hiint(key) - basehi, 0);
+                        v[r] = ebase + r < NN ? (((unsigned)t << 6) & 0xfffffe00u) | (unsigned)(ebase + r) : 0xffffffffu;
+                    }
+                }
+                ov_bitonic_sort_u32<EPL>(v, lane);
+                // sorted words for the straddler checks (16-byte units, lane-interleaved: conflict-free)
+                {
+                    uint4 *vb4 = reinterpret_cast<uint4 *>(vbuf);
+#pragma unroll
+                    for (int q = 0; q < EPL / 4; ++q) vb4[q * 32 + lane] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                }
+                if (lane <= NG + 1) spos[lane] = KF_NONE;
+                // ---- 2. cumulative weights, bin of every element, straddlers ------------------------
+                float wf[EPL];
+                double local = 0.0;
+#pragma unroll
+                for (int r = 0; r < EPL; ++r) {
+                    wf[r] = S.wtabf[v[r] & 511u];
+                    local = __dadd_rn(local, (double)wf[r]);
+                }
+                double incl = local;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const double up = shfl_up_d(incl, d);
+                    if (lane >= d) incl = __dadd_rn(incl, up);
+                }
+                const double base = __dsub_rn(incl, local);      // exact
+                int m;
+                {   // number of edges g_ord[1..NG] <= base
+                    int lo = 0, hi = NG;
+#pragma unroll
+                    for (int it = 0; it < 5; ++it) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (S.gord[mid] <= base) lo = mid; else hi = mid - 1;
+                    }
+                    m = lo;
+                }
+                __syncwarp();
+                {
+                    double rel = 0.0;
+                    double edge_rel = __dsub_rn(S.gord[m + 1], base);
+#pragma unroll
+                    for (int r = 0; r < EPL; ++r) {
+                        const double relb = rel;
+                        rel = __dadd_rn(rel, (double)wf[r]);
+                        bin[v[r] & 511u] = (unsigned char)m;
+                        if (rel >= edge_rel) {       // straddler of edge m+1 (ForwardModel_0.py:6009-6024)
+                            ++m;
+                            gbs[m] = __dadd_rn(base, relb);
+                            spos[m] = lane * EPL + r;
+                            edge_rel = __dsub_rn(S.gord[m + 1], base);
+                        }
+                    }
+                }
+                __syncwarp();
+                // ---- 3. the straddler of edge `lane` ---------------------------------------------------
+                int se = -1;            // element number of the straddler
+                double cw = 0.0;        // (1-frac) * weight: goes to the next bin
+                bool bad = false;
+                if (lane >= 1 && lane <= NG) {
+                    const int p = spos[lane];
+                    if (p == KF_NONE) {
+                        bad = lane < NG;       // only the last edge may stay open (:6025-6027)
+                        if (bad) why = 2;
+                    } else {
+                        const unsigned vp = vbuf[kf_vaddr(p)];
+                        const unsigned vl = p > 0 ? vbuf[kf_vaddr(p - 1)] : ~vp, vr = vbuf[kf_vaddr(p + 1)];
+                        const bool al = ((vp ^ vl) >> 9) == 0u, ar = ((vp ^ vr) >> 9) == 0u;
+                        se = (int)(vp & 511u);
+                        double gb = gbs[lane];
+                        if (al | ar) {
+                            // Equal key bits next to an edge.  The packed order is (key bits, element number); it is
+                            // the true one around p if every member of p's group before p has a strictly smaller
+                            // exact key and every member after p a strictly larger one (then the elements before p
+                            // are exactly those with a smaller key, in any order of equal keys elsewhere).
+                            const double kp = __dadd_rn(av[se / NG], bv[se % NG]);
+                            bool sep = true, tie = false;
+                            int nl = 0, nr = 0;
+                            for (int x = p - 1; x >= 0; --x) {
+                                const unsigned vx = vbuf[kf_vaddr(x)];
+                                if (((vx ^ vp) >> 9) != 0u) break;
+                                const int ex = (int)(vx & 511u);
+                                const double kx = __dadd_rn(av[ex / NG], bv[ex % NG]);
+                                sep &= kx < kp;
+                                tie |= kx == kp;
+                                ++nl;
+                            }
+                            for (int x = p + 1; x < 512; ++x) {
+                                const unsigned vx = vbuf[kf_vaddr(x)];
+                                if (((vx ^ vp) >> 9) != 0u) break;
+                                const int ex = (int)(vx & 511u);
+                                const double kx = __dadd_rn(av[ex / NG], bv[ex % NG]);
+                                sep &= kx > kp;
+                                tie |= kx == kp;
+                                ++nr;
+                            }
+                            if (!sep) {
+                                const int pm = spos[lane - 1], pn = spos[lane + 1];
+                                const int px = nl ? p - 1 : p, py = px + 1;
+                                if (tie) {
+                                    bad = true;  // a true tie on an edge: numba's order decides (general kernel)
+                                    why = 8;
+                                } else if (nl + nr != 1 || pm == px || pn == py) {
+                                    bad = true;  // a misordered group of three or more, or two edges inside a pair
+                                    why = 4;
+                                } else {
+                                    // a lone pair in the wrong order: x = first, y = second in the packed order, ky < kx
+                                    const unsigned vx = nl ? vl : vp, vy = nl ? vp : vr;
+                                    const int ex = (int)(vx & 511u), ey = (int)(vy & 511u);
+                                    const double wx = S.wtabd[ex], wy = S.wtabd[ey];
+                                    const double q = nl ? __dsub_rn(gb, wx) : gb;     // cumulative weight before the pair
+                                    const double qy = __dadd_rn(q, wy);
+                                    if (qy >= S.gord[lane]) {          // y straddles, x follows it whole
+                                        se = ey; gb = q;
+                                        bin[ey] = (unsigned char)(lane - 1);
+                                        bin[ex] = (unsigned char)lane;
+                                    } else {                           // y lies before the edge, x straddles
+                                        se = ex; gb = qy;
+                                        bin[ey] = (unsigned char)(lane - 1);
+                                        bin[ex] = (unsigned char)(lane - 1);
+                                    }
+                                }
+                            }
+                        }
+                        const double w = S.wtabd[se];
+                        const double frac = __ddiv_rn(__dsub_rn(S.gord[lane], gb), w);
+                        cw = __dmul_rn(__dsub_rn(1.0, frac), w);
+                    }
+                }
+                if (__any_sync(FULL, bad)) { fallback = true; break; }
+                __syncwarp();       // (the sorted words alias the marginals)
+                // ---- 4. marginals and products ----------------------------------------------------------
+                {
+                    double2 *z = reinterpret_cast<double2 *>(RC);
+                    for (int t = lane; t < NN / 2; t += 32) z[t] = make_double2(0.0, 0.0);
+                }
+                __syncwarp();
+                kf_walk<NG>(bin, S.wtabd, RC, lane, NG, 1);
+                __syncwarp();
+                kf_correct<NG>(RC, lane, se >= 0 ? se / NG : -1, cw);
+                kf_accum_x<NG, XS, GRAD>(RC, X, igas, lane, sw, acc);
+                __syncwarp();
+                {
+                    double2 *z = reinterpret_cast<double2 *>(RC);
+                    for (int t = lane; t < NN / 2; t += 32) z[t] = make_double2(0.0, 0.0);
+                }
+                __syncwarp();
+                kf_walk<NG>(bin, S.wtabd, RC, lane, 1, NG);
+                __syncwarp();
+                kf_correct<NG>(RC, lane, se >= 0 ? se % NG : -1, cw);
+                kf_accum_y<NG, GRAD>(RC, Y, lane, yb, yT, yk);
+            }
+            __syncwarp();
+            // ---- bin m: normalise (ForwardModel_0.py:6016-6017, :6026-6027) and store -------------------
+            if (lane < NG) {
+                const double rs = __ddiv_rn(1.0, sw);
+                const double ta = __dmul_rn(__dadd_rn(acc[0], yb), rs);
+                av[lane] = ta;
+                if (GRAD) {
+                    double2 *row = reinterpret_cast<double2 *>(X + lane * XS);
+                    row[0] = make_double2(ta, __dmul_rn(__dadd_rn(acc[1], yT), rs));
+#pragma unroll
+                    for (int q = 1; q < XS / 2; ++q) {
+                        const int p0 = 2 * q - 2, p1 = 2 * q - 1;
+                        const double x0 = p0 <= igas ? __dmul_rn(acc[2 * q], rs) : (p0 == g1 ? __dmul_rn(yk, rs) : 0.0);
+                        const double x1 = p1 <= igas ? __dmul_rn(acc[2 * q + 1], rs) : (p1 == g1 ? __dmul_rn(yk, rs) : 0.0);
+                        if (p0 <= g1) row[q] = make_double2(x0, x1);
+                    }
+                } else {
+                    X[lane * XS] = ta;
+                }
+            }
+            __syncwarp();
+        }
+#undef KB
+#undef DB
+        if (fallback) {
+            if (lane == 0) fb_list[atomicAdd(fb_count, 1)] = (int)cell;
+            if (fb_why) {
+                const unsigned wm = __reduce_or_sync(FULL, (unsigned)why);
+                if (lane == 0) for (int b = 0; b < 8; ++b) if (wm >> b & 1u) atomicAdd(fb_why + b, 1);
+            }
+        } else {
+            for (int g = lane; g < NG; g += 32) {
+                const size_t o = ((size_t)iw * NG + g) * NLAY + l;
+                P.tau[o] = X[g * XS];
+                if (GRAD) {
+                    for (int p = 0; p < NGAS; ++p) P.dk[o * NP1 + p] = X[g * XS + 2 + p];
+                    P.dk[o * NP1 + NGAS] = X[g * XS + 1];
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int NG, int XS, bool GRAD, int NWARPS>
+int kf_launch(const OvParams &P, int *scratch, int *why, cudaStream_t stream)
+{
+    using L = KfWarpLayout<NG, XS>;
+    const size_t smem = ((sizeof(KfShared<NG>) + 15) & ~(size_t)15) + (size_t)NWARPS * L::TOTAL * 8;
+    auto kern = ans_koverlap_fast_kernel<NG, XS, GRAD, NWARPS>;
+    ANS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, nsm = 148;
+    ANS_CUDA_CHECK(cudaGetDevice(&dev));
+    ANS_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    const long long ncell = (long long)P.NWAVE * P.NLAY;
+    long long grid = ans_div_up(ncell, NWARPS);
+    if (grid > nsm) grid = nsm;
+    kern<<<(unsigned)grid, NWARPS * 32, smem, stream>>>(P, scratch, scratch + 1, why);
+    ANS_LAUNCH_CHECK();
+    return ANSB200_OK;
+}
+
+}   // namespace
+
+// Is there a fast kernel for this shape?  (the general kernel covers everything else)
+bool ov_fast_supported(const OvParams &P, bool grad)
+{
+    (void)grad;
+    return P.NG == 20 && P.NGAS >= 2 && P.NGAS <= 14 && !P.seq_rebin && P.del_g != nullptr && P.weight && P.g_ord;
+}
+
+// scratch: [0] = number of cells left for the general kernel (-1: all of them), [1..] = their numbers
+int ov_fast_launch(const OvParams &P, bool grad, int *scratch, int *why, cudaStream_t stream)
+{
+    if (!grad) return kf_launch<20, 2, false, 24>(P, scratch, why, stream);
+    if (P.NGAS <= 6) return kf_launch<20, 8, true, 24>(P, scratch, why, stream);
+    return kf_launch<20, 16, true, 16>(P, scratch, why, stream);
+}

@@ -48,6 +48,9 @@ struct OvParams {
     int NWAVE, NG, NLAY, NGAS;
     double *tau, *dk;
     int fused, seq_rebin;
+    // work list of the fast kernel (koverlap_fast.cu): cell_count[0] cells, numbered in cell_list; NULL or a
+    // negative count = every cell
+    const int *cell_count, *cell_list;
 };
 
 __device__ __forceinline__ double shfl_xor_d(double v, int m)
@@ -1124,6 +1127,13 @@ ans_koverlap_kernel(OvParams P)
     const int NG = P.NG, NGAS = P.NGAS, NLAY = P.NLAY, NN = NG * NG, NP1 = NGAS + 1;
     constexpr int DS = NPMAX + 2, BS = (NPMAX + 3) | 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long ncell = (long long)P.NWAVE * NLAY;
+    const int *cell_list = nullptr;
+    if (P.cell_count) {
+        const int c = *P.cell_count;
+        if (c >= 0) { ncell = c; cell_list = P.cell_list; }
+        if ((long long)blockIdx.x * OV_WARPS >= ncell) return;     // (before the set-up: usually nothing is left)
+    }
 
     double *wtab = reinterpret_cast<double *>(smem_raw);
     double *gord = wtab + NN;
@@ -1176,11 +1186,11 @@ ans_koverlap_kernel(OvParams P)
     const bool static_ok = ov_static_setup(stat, wtab, gord, NG) && !P.seq_rebin;
 
     // persistent CTAs: every warp walks the (wavenumber, layer) cells with the grid's stride
-    const long long ncell = (long long)P.NWAVE * NLAY;
     for (long long cell0 = (long long)blockIdx.x * OV_WARPS; cell0 < ncell; cell0 += (long long)gridDim.x * OV_WARPS) {
     long long cell = cell0 + warp;
     const bool live = cell < ncell;        // idle warps of the last round shadow the last cell (they join the barriers)
     if (!live) cell = ncell - 1;
+    if (cell_list) cell = cell_list[cell];
     const int iw = (int)(cell / NLAY);
     const int l = (int)(cell - (long long)iw * NLAY);
 
