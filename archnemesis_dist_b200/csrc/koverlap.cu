@@ -1,6 +1,8 @@
 // koverlap.cu -- C entry points of the random-overlap kernels (implementation: koverlap_impl.cuh).
 #include "koverlap_impl.cuh"
 #include <stdlib.h>
+#include <mutex>
+#include <vector>
 #include <string.h>
 
 // NGAS == 1: ForwardModel_0.py:5871-5876 / :6056-6058
@@ -39,6 +41,48 @@ static int ov_general(const OvParams &P, bool grad, cudaStream_t stream)
     return ov_dispatch_16(P, grad, stream);
 }
 
+// Work-list scratch of the fast kernel: device buffers are kept for re-use; a buffer handed back carries an
+// event recorded after its last use and the next user makes its stream wait for it, so nothing blocks the host
+// and distinct streams / threads never share a live buffer.
+namespace {
+struct OvScratch { int *p; size_t n; cudaEvent_t ev; int dev; };
+std::mutex ov_scratch_mu;
+std::vector<OvScratch> ov_scratch_free;
+
+int ov_scratch_get(size_t n, cudaStream_t stream, OvScratch &out)
+{
+    int dev = 0;
+    ANS_CUDA_CHECK(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> g(ov_scratch_mu);
+        for (size_t i = 0; i < ov_scratch_free.size(); ++i) {
+            if (ov_scratch_free[i].dev == dev && ov_scratch_free[i].n >= n) {
+                out = ov_scratch_free[i];
+                ov_scratch_free.erase(ov_scratch_free.begin() + i);
+                ANS_CUDA_CHECK(cudaStreamWaitEvent(stream, out.ev, 0));
+                return ANSB200_OK;
+            }
+        }
+    }
+    out.n = n < (1u << 20) ? (1u << 20) : n;
+    out.dev = dev;
+    if (cudaMalloc((void **)&out.p, out.n * sizeof(int)) != cudaSuccess) {
+        cudaGetLastError();
+        ansb200_set_error("koverlap: cannot allocate %zu bytes of work-list scratch", out.n * sizeof(int));
+        return ANSB200_ENOMEM;
+    }
+    ANS_CUDA_CHECK(cudaEventCreateWithFlags(&out.ev, cudaEventDisableTiming));
+    return ANSB200_OK;
+}
+
+void ov_scratch_put(OvScratch &sc, cudaStream_t stream)
+{
+    cudaEventRecord(sc.ev, stream);
+    std::lock_guard<std::mutex> g(ov_scratch_mu);
+    ov_scratch_free.push_back(sc);
+}
+}   // namespace
+
 // diagnostics: ANSB200_OVERLAP=general forces the general kernel; ANSB200_OVERLAP=stats prints how many cells
 // the fast kernel handed over (synchronises the stream)
 static int ov_mode()
@@ -74,9 +118,13 @@ static int ov_run(OvParams &P, bool grad, cudaStream_t stream)
         // the general kernel, which runs on that list afterwards (usually empty: it exits before its set-up)
         const long long ncell = (long long)P.NWAVE * P.NLAY;
         ANS_REQUIRE(ncell < 0x7fffffffLL, "koverlap: NWAVE*NLAY too large");
-        int *scratch = nullptr;
         const bool stats = ov_mode() == 2;
-        ANS_CUDA_CHECK(cudaMallocAsync((void **)&scratch, (size_t)(ncell + 1 + 8) * sizeof(int), stream));
+        OvScratch sc{};
+        {
+            const int rc0 = ov_scratch_get((size_t)ncell + 1 + 8, stream, sc);
+            if (rc0 != ANSB200_OK) return rc0;
+        }
+        int *scratch = sc.p;
         ANS_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(int), stream));
         if (stats) ANS_CUDA_CHECK(cudaMemsetAsync(scratch + ncell + 1, 0, 8 * sizeof(int), stream));
         int rc = ov_fast_launch(P, grad, scratch, stats ? scratch + ncell + 1 : nullptr, stream);
@@ -93,7 +141,7 @@ static int ov_run(OvParams &P, bool grad, cudaStream_t stream)
             fprintf(stderr, "[ansb200] overlap: %d of %lld cells left to the general kernel (non-monotone %d, open bin %d, "
                             "group %d, tie %d)\n", c, ncell, why[0], why[1], why[2], why[3]);
         }
-        cudaFreeAsync(scratch, stream);
+        ov_scratch_put(sc, stream);
         return rc;
     }
     return ov_general(P, grad, stream);

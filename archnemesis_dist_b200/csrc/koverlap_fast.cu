@@ -66,6 +66,50 @@ struct KfWarpLayout {
     static constexpr int TOTAL = (BIN + 64 + 1) & ~1;
 };
 
+// 32-bit min/max bitonic network over 32*16 packed words, blocked layout (element = 16*lane + r), all-ascending form
+// (koverlap_impl.cuh).  Every lane arrives with a BITONIC sequence (the key loop lays the tail of one row of the key
+// matrix ascending and the head of the next one descending), so the in-lane phases reduce to one 4-stage merge.
+// Cross-lane comparators: "take the partner's word if (partner < mine) != keep_high" is one ISETP.LT.XOR + SEL.
+__device__ __forceinline__ void kf_sort(unsigned (&v)[16], int lane)
+{
+#define KF_CE(x, y) do { const unsigned lo__ = min(x, y), hi__ = max(x, y); x = lo__; y = hi__; } while (0)
+#pragma unroll
+    for (int j = 8; j > 0; j >>= 1) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+            if ((r & j) == 0) KF_CE(v[r], v[r | j]);
+    }
+#pragma unroll 1
+    for (int kl = 2; kl <= 32; kl <<= 1) {
+        {
+            const bool keep_high = (lane & (kl >> 1)) != 0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int q = 15 - r;
+                const unsigned pr = __shfl_xor_sync(FULL, v[q], kl - 1), pq = __shfl_xor_sync(FULL, v[r], kl - 1);
+                v[r] = ((pr < v[r]) != keep_high) ? pr : v[r];
+                v[q] = ((pq < v[q]) != keep_high) ? pq : v[q];
+            }
+        }
+#pragma unroll 1
+        for (int lm = kl >> 2; lm > 0; lm >>= 1) {
+            const bool keep_high = (lane & lm) != 0;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const unsigned pv = __shfl_xor_sync(FULL, v[r], lm);
+                v[r] = ((pv < v[r]) != keep_high) ? pv : v[r];
+            }
+        }
+#pragma unroll
+        for (int j = 8; j > 0; j >>= 1) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+                if ((r & j) == 0) KF_CE(v[r], v[r | j]);
+        }
+    }
+#undef KF_CE
+}
+
 __device__ __forceinline__ int kf_vaddr(int p) { return ((((p & 15) >> 2) * 32 + (p >> 4)) << 2) + (p & 3); }
 
 // Static orders: replay rankg's loop over the row-major (o = 0) / column-major (o = 1) sequence once.
@@ -182,7 +226,7 @@ __device__ __forceinline__ void kf_walk(const unsigned char *__restrict__ bin, c
         const unsigned char *bp = bin + lane * sa;
         int mc = bp[0];
         double acc = 0.0;
-#pragma unroll
+#pragma unroll 1
         for (int t = 0; t < NG; ++t) {
             const int mt = bp[t * sb];
             if (mt != mc) {
@@ -215,7 +259,7 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
     using L = KfWarpLayout<NG, XS>;
     constexpr int NN = NG * NG;
     constexpr int EPL = 16;
-    static_assert(NN <= 400 + 112 && NN > 256, "16 keys per lane");
+    static_assert(NN <= 512 && NN > 256 && NN % 16 == 0, "16 keys per lane, whole lanes");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     KfShared<NG> &S = *reinterpret_cast<KfShared<NG> *>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -380,16 +424,20 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                     const int ebase = lane * EPL;
                     const int i0 = ebase / NG, j0 = ebase - i0 * NG;
                     const double a0 = av[i0 < NG ? i0 : NG - 1], a1 = av[i0 + 1 < NG ? i0 + 1 : NG - 1];
+                    // slots 0 .. n0-1: the tail of row i0, ascending in j; slots n0 .. 15: the head of row i0+1,
+                    // DESCENDING in j -- a bitonic sequence (b is ascending)
+                    const int n0 = NG - j0 < EPL ? NG - j0 : EPL;
 #pragma unroll
                     for (int r = 0; r < EPL; ++r) {
-                        const bool wrap = j0 + r >= NG;
-                        const int j = wrap ? j0 + r - NG : j0 + r;
-                        const double key = __dadd_rn(wrap ? a1 : a0, bv[j]);
+                        const bool second = r >= n0;
+                        const int j = second ? EPL - 1 - r : j0 + r;
+                        const int e = second ? ebase + n0 + (EPL - 1 - r) : ebase + r;
+                        const double key = __dadd_rn(second ? a1 : a0, bv[j]);
                         const int t = max(__double2hiint(key) - basehi, 0);
-                        v[r] = ebase + r < NN ? (((unsigned)t << 6) & 0xfffffe00u) | (unsigned)(ebase + r) : 0xffffffffu;
+                        v[r] = ebase < NN ? (((unsigned)t << 6) & 0xfffffe00u) | (unsigned)e : 0xffffffffu;
                     }
                 }
-                ov_bitonic_sort_u32<EPL>(v, lane);
+                kf_sort(v, lane);
                 // sorted words for the straddler checks (16-byte units, lane-interleaved: conflict-free)
                 {
                     uint4 *vb4 = reinterpret_cast<uint4 *>(vbuf);

@@ -29,7 +29,7 @@ def run(nwave, want_grad, out=None):
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     times = []
-    for _ in range(5):
+    for _ in range(10):
         ev0.record()
         res = ops.gas_opacity(T, dp, am, otab, want_grad)
         ev1.record()

@@ -1,33 +1,94 @@
-"""Per-source-line summary of an ncu report: python tools/ncu_lines.py report.ncu-rep [top]
-Uses `ncu --page source --print-source cuda,sass`; prints executed warp instructions and stall
-samples per CUDA source line (needs -lineinfo)."""
-import csv, subprocess, sys
-rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 60
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
-                     capture_output=True, text=True).stdout
-rows = list(csv.reader(out.splitlines()))
-fname = None; agg = {}; hdr = None
-for r in rows:
-    if len(r) == 2 and r[0] == "File Path": fname = r[1].split("/")[-1]; continue
-    if len(r) > 8 and r[0] == "Line No": hdr = r; continue
-    if hdr and len(r) > 8 and r[0] not in ("", "Line No"):
-        try:
-            line = int(r[0]); samples = int(r[6]); inst = int(r[7])
-        except ValueError:
+"""Per-CUDA-line digest of an `ncu --page source --csv --print-source cuda,sass` export.
+
+    ncu -i prof.ncu-rep --page source --csv --print-source cuda,sass > prof_cs.csv
+    python tools/ncu_lines.py prof_cs.csv [top_n]
+
+For every source line: executed warp instructions, stall samples, shared-memory wavefronts (and the excess over
+the ideal count), and the number of SASS instructions generated for it (static size / executed size: what the
+instruction cache has to hold).
+"""
+import csv
+import sys
+from collections import defaultdict
+
+
+def main():
+    path = sys.argv[1]
+    top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+    rows = list(csv.reader(open(path, newline="")))
+    cur_file = "?"
+    hdr = None
+    lines = {}
+    sass_static = defaultdict(int)
+    sass_hot = defaultdict(int)
+    cur_line = None
+    max_exec = 0
+    raw = []
+    for r in rows:
+        if not r:
             continue
-        k = (fname, line)
-        a = agg.setdefault(k, [0, 0, r[1]])
-        a[0] += inst; a[1] += samples
-ti = sum(a[0] for a in agg.values()); ts = sum(a[1] for a in agg.values())
-print("total inst %d samples %d" % (ti, ts))
-for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
-    print("%-20s %5d  inst %5.1f%%  samples %5.1f%%  %s" % (k[0], k[1], 100 * a[0] / ti, 100 * a[1] / ts, a[2].strip()[:90]))
-if len(sys.argv) > 3:
-    # ranges "name:lo-hi,..." over koverlap_impl.cuh
-    for spec in sys.argv[3].split(","):
-        name, rng = spec.split(":"); lo, hi = map(int, rng.split("-"))
-        i = sum(a[0] for k, a in agg.items() if k[0] == "koverlap_impl.cuh" and lo <= k[1] <= hi)
-        s_ = sum(a[1] for k, a in agg.items() if k[0] == "koverlap_impl.cuh" and lo <= k[1] <= hi)
-        print("%-12s inst %5.1f%% samples %5.1f%%" % (name, 100 * i / ti, 100 * s_ / ts))
-    i = sum(a[0] for k, a in agg.items() if k[0] != "koverlap_impl.cuh"); s_ = sum(a[1] for k, a in agg.items() if k[0] != "koverlap_impl.cuh")
-    print("%-12s inst %5.1f%% samples %5.1f%%" % ("other files", 100 * i / ti, 100 * s_ / ts))
+        if r[0] == "File Path":
+            cur_file = r[1].split("/")[-1]
+            continue
+        if r[0] == "Line No":
+            hdr = r
+            idx = {h: i for i, h in enumerate(hdr)}
+            # two "Source" columns: 1 = cuda text, 3 = sass text
+            continue
+        if r[0] == "Function Name" or hdr is None:
+            continue
+        if r[0] != "-" and r[0] != "":
+            # a CUDA line row (aggregated)
+            try:
+                ln = int(r[0])
+            except ValueError:
+                continue
+            cur_line = (cur_file, ln)
+
+            def num(name):
+                try:
+                    return float(r[idx[name]])
+                except (ValueError, KeyError, IndexError):
+                    return 0.0
+            lines[cur_line] = dict(text=r[1].strip(), inst=num("Instructions Executed"), samples=num("# Samples"),
+                                   wf=num("L1 Wavefronts Shared"), wfx=num("L1 Wavefronts Shared Excessive"),
+                                   noinst=num("stall_no_inst"), ssb=num("stall_short_sb"), wait=num("stall_wait"),
+                                   bar=num("stall_barrier"), lsb=num("stall_long_sb"))
+        else:
+            # a SASS row under the current CUDA line
+            try:
+                ex = float(r[idx["Instructions Executed"]])
+            except (ValueError, KeyError, IndexError):
+                ex = 0.0
+            raw.append((cur_line, ex))
+            max_exec = max(max_exec, ex)
+    for ln, ex in raw:
+        sass_static[ln] += 1
+        if ex >= 0.02 * max_exec:
+            sass_hot[ln] += 1
+    tot_i = sum(v["inst"] for v in lines.values()) or 1.0
+    tot_s = sum(v["samples"] for v in lines.values()) or 1.0
+    tot_w = sum(v["wf"] for v in lines.values()) or 1.0
+    print("total executed warp instructions %.0f, samples %.0f, shared wavefronts %.0f (excess %.0f)" %
+          (tot_i, tot_s, tot_w, sum(v["wfx"] for v in lines.values())))
+    print("static SASS %d instr (%.1f KB); executed >= 2%% of max: %d instr (%.1f KB)" %
+          (sum(sass_static.values()), sum(sass_static.values()) * 16 / 1024.0, sum(sass_hot.values()),
+           sum(sass_hot.values()) * 16 / 1024.0))
+    print("%-22s %5s %6s %6s %6s %6s %5s %5s  %s" % ("file", "line", "inst%", "smpl%", "wf%", "wfx%", "sass", "hot", "source"))
+    for key, v in sorted(lines.items(), key=lambda kv: -kv[1]["inst"])[:top]:
+        print("%-22s %5d %6.2f %6.2f %6.2f %6.1f %5d %5d  %s" %
+              (key[0][:22], key[1], 100 * v["inst"] / tot_i, 100 * v["samples"] / tot_s, 100 * v["wf"] / tot_w,
+               100 * v["wfx"] / v["wf"] if v["wf"] else 0.0, sass_static[key], sass_hot[key], v["text"][:90]))
+    print("\nstall samples by reason (sum over lines): no_inst %.0f short_sb %.0f wait %.0f barrier %.0f long_sb %.0f" %
+          tuple(sum(v[k] for v in lines.values()) for k in ("noinst", "ssb", "wait", "bar", "lsb")))
+    # hot code by file region
+    print("\nhot SASS by 25-line block:")
+    blocks = defaultdict(int)
+    for (f, ln), c in sass_hot.items():
+        blocks[(f, ln // 25 * 25)] += c
+    for (f, b), c in sorted(blocks.items(), key=lambda kv: -kv[1])[:20]:
+        print("  %-22s lines %4d-%4d  %5d instr %6.1f KB" % (f, b, b + 24, c, c * 16 / 1024.0))
+
+
+if __name__ == "__main__":
+    main()
