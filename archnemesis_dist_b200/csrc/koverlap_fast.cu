@@ -55,8 +55,9 @@ struct KfWarpLayout {
     static constexpr int NGASMAX = XS > 2 ? XS - 2 : 16;
     static constexpr int RC = 0;                                  // [NG*NG] marginals; aliased by the sorted words
     static constexpr int X = RC + NG * NG;                        // [NG][XS] rows {tau_i, dT_i, gas columns}
-    static constexpr int Y = X + NG * XS;                         // [NG][4]  columns {b_j, bT_j, k_j, -}
-    static constexpr int AV = Y + NG * 4;                         // [NG] compact copies for the key loop
+    static constexpr int YS = XS > 2 ? XS : 2;                    // gradients: Y rows are laid out like X rows
+    static constexpr int Y = X + NG * XS;                         // [NG][YS] columns {b_j, bT_j, 0.., k_j at the new gas, 0..}
+    static constexpr int AV = Y + NG * YS;                        // [NG] compact copies for the key loop
     static constexpr int BV = AV + NG;
     static constexpr int KBUF = BV + NG;                          // [NG*NGASMAX]
     static constexpr int DBUF = KBUF + NG * NGASMAX;
@@ -210,8 +211,36 @@ __device__ __forceinline__ void kf_accum_y(const double *__restrict__ M, const d
                 yT = __fma_rn(c, y0.y, yT);
                 yk = __fma_rn(c, Y[4 * t + 2], yk);
             } else {
-                yb = __fma_rn(c, Y[4 * t], yb);
+                yb = __fma_rn(c, Y[2 * t], yb);
             }
+        }
+    }
+}
+
+// The same product on the FP64 tensor cores (gradient kernels): D[bin][column] += sum_t M[t][bin] * rows[t][column] as
+// mma.m8n8k4 tiles -- 3 tiles of 8 bins (the last one half empty), XS/8 tiles of 8 columns, NG/4 steps of 4 rows.
+// Fragments (PTX ISA, mma.m8n8k4 .f64): a = A[lane>>2][lane&3], b = B[lane&3][lane>>2], d = D[lane>>2][2*(lane&3) + {0,1}].
+// With the marginals stored [t][bin] at stride NG = 20 the sixteen 8-byte words of a half-warp's A load fall in
+// sixteen different bank pairs.  `rsum` gathers the lane's share of sum_t M[t][bin] (the normalisation).
+template <int NG, int XS, bool SUM>
+__device__ __forceinline__ void kf_mma(const double *__restrict__ M, const double *__restrict__ rows, int lane,
+                                       double (&d)[3][XS / 8][2], double (&rsum)[3])
+{
+    static_assert(NG % 4 == 0 && NG <= 24, "three 8-bin tiles, whole k-steps");
+    const int kk = lane & 3, mm = lane >> 2;
+#pragma unroll
+    for (int k0 = 0; k0 < NG; k0 += 4) {
+        double b[XS / 8];
+#pragma unroll
+        for (int n = 0; n < XS / 8; ++n) b[n] = rows[(k0 + kk) * XS + 8 * n + mm];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const double a = M[(k0 + kk) * NG + 8 * t + mm];     // (bins >= NG: whatever follows; those rows are dropped)
+            if (SUM) rsum[t] = __dadd_rn(rsum[t], a);
+#pragma unroll
+            for (int n = 0; n < XS / 8; ++n)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(d[t][n][0]), "+d"(d[t][n][1]) : "d"(a), "d"(b[n]));
         }
     }
 }
@@ -375,8 +404,17 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
             if (do_fold && lane < NG) {
                 const double b = __dmul_rn(KB(lane, g1), am1);
                 bv[lane] = b;
-                Y[4 * lane] = b;
-                if (GRAD) { Y[4 * lane + 1] = __dmul_rn(DB(lane, g1), am1); Y[4 * lane + 2] = KB(lane, g1); }
+                if (GRAD) {
+                    // a row of the second operand of the product: {b_j, bT_j, 0 .., k_j in the column of gas g1, 0 ..}
+                    const double bT = __dmul_rn(DB(lane, g1), am1), kj = KB(lane, g1);
+                    double2 *row = reinterpret_cast<double2 *>(Y + lane * L::YS);
+                    row[0] = make_double2(b, bT);
+#pragma unroll
+                    for (int q = 1; q < XS / 2; ++q)
+                        row[q] = make_double2(2 * q - 2 == g1 ? kj : 0.0, 2 * q - 1 == g1 ? kj : 0.0);
+                } else {
+                    Y[L::YS * lane] = b;
+                }
             }
             __syncwarp();
             if (!do_fold) continue;
@@ -409,13 +447,25 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
             }
 
             double sw = 0.0, yb = 0.0, yT = 0.0, yk = 0.0;
-            double acc[XS];
+            double acc[GRAD ? 1 : XS];
+            acc[0] = 0.0;
+            constexpr int NT8 = GRAD ? XS / 8 : 1;
+            double dfr[3][NT8][2], rsum[3];
 #pragma unroll
-            for (int q = 0; q < XS; ++q) acc[q] = 0.0;
+            for (int t = 0; t < 3; ++t) {
+                rsum[t] = 0.0;
+#pragma unroll
+                for (int n = 0; n < NT8; ++n) dfr[t][n][0] = dfr[t][n][1] = 0.0;
+            }
 
             if (ord >= 0) {
-                kf_accum_x<NG, XS, GRAD>(S.stat[ord][0], X, igas, lane, sw, acc);
-                kf_accum_y<NG, GRAD>(S.stat[ord][1], Y, lane, yb, yT, yk);
+                if constexpr (GRAD) {
+                    kf_mma<NG, XS, true>(S.stat[ord][0], X, lane, dfr, rsum);
+                    kf_mma<NG, XS, false>(S.stat[ord][1], Y, lane, dfr, rsum);
+                } else {
+                    kf_accum_x<NG, XS, GRAD>(S.stat[ord][0], X, igas, lane, sw, acc);
+                    kf_accum_y<NG, GRAD>(S.stat[ord][1], Y, lane, yb, yT, yk);
+                }
             } else {
                 // ---- 1. packed keys, sorted in registers --------------------------------------------
                 unsigned v[EPL];
@@ -573,7 +623,8 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                 kf_walk<NG>(bin, S.wtabd, RC, lane, NG, 1);
                 __syncwarp();
                 kf_correct<NG>(RC, lane, se >= 0 ? se / NG : -1, cw);
-                kf_accum_x<NG, XS, GRAD>(RC, X, igas, lane, sw, acc);
+                if constexpr (GRAD) kf_mma<NG, XS, true>(RC, X, lane, dfr, rsum);
+                else kf_accum_x<NG, XS, GRAD>(RC, X, igas, lane, sw, acc);
                 __syncwarp();
                 {
                     double2 *z = reinterpret_cast<double2 *>(RC);
@@ -583,27 +634,41 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                 kf_walk<NG>(bin, S.wtabd, RC, lane, 1, NG);
                 __syncwarp();
                 kf_correct<NG>(RC, lane, se >= 0 ? se % NG : -1, cw);
-                kf_accum_y<NG, GRAD>(RC, Y, lane, yb, yT, yk);
+                if constexpr (GRAD) kf_mma<NG, XS, false>(RC, Y, lane, dfr, rsum);
+                else kf_accum_y<NG, GRAD>(RC, Y, lane, yb, yT, yk);
             }
             __syncwarp();
             // ---- bin m: normalise (ForwardModel_0.py:6016-6017, :6026-6027) and store -------------------
-            if (lane < NG) {
+            if constexpr (GRAD) {
+                // sum of the marginals of a bin: the four lanes of a fragment row hold a quarter each
+                double *sws = gbs;
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    rsum[t] = __dadd_rn(rsum[t], shfl_xor_d(rsum[t], 1));
+                    rsum[t] = __dadd_rn(rsum[t], shfl_xor_d(rsum[t], 2));
+                    if ((lane & 3) == 0 && 8 * t + (lane >> 2) < NG) sws[8 * t + (lane >> 2)] = rsum[t];
+                }
+                __syncwarp();
+                if (lane < NG) sws[lane] = __ddiv_rn(1.0, sws[lane]);
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const int mrow = 8 * t + (lane >> 2);
+                    if (mrow < NG) {
+                        const double rs = sws[mrow];
+#pragma unroll
+                        for (int n = 0; n < NT8; ++n) {
+                            const double x0 = __dmul_rn(dfr[t][n][0], rs), x1 = __dmul_rn(dfr[t][n][1], rs);
+                            *reinterpret_cast<double2 *>(X + mrow * XS + 8 * n + 2 * (lane & 3)) = make_double2(x0, x1);
+                            if (n == 0 && (lane & 3) == 0) av[mrow] = x0;
+                        }
+                    }
+                }
+            } else if (lane < NG) {
                 const double rs = __ddiv_rn(1.0, sw);
                 const double ta = __dmul_rn(__dadd_rn(acc[0], yb), rs);
                 av[lane] = ta;
-                if (GRAD) {
-                    double2 *row = reinterpret_cast<double2 *>(X + lane * XS);
-                    row[0] = make_double2(ta, __dmul_rn(__dadd_rn(acc[1], yT), rs));
-#pragma unroll
-                    for (int q = 1; q < XS / 2; ++q) {
-                        const int p0 = 2 * q - 2, p1 = 2 * q - 1;
-                        const double x0 = p0 <= igas ? __dmul_rn(acc[2 * q], rs) : (p0 == g1 ? __dmul_rn(yk, rs) : 0.0);
-                        const double x1 = p1 <= igas ? __dmul_rn(acc[2 * q + 1], rs) : (p1 == g1 ? __dmul_rn(yk, rs) : 0.0);
-                        if (p0 <= g1) row[q] = make_double2(x0, x1);
-                    }
-                } else {
-                    X[lane * XS] = ta;
-                }
+                X[lane * XS] = ta;
             }
             __syncwarp();
         }
