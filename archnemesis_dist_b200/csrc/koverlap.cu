@@ -139,7 +139,8 @@ static int ov_run(OvParams &P, bool grad, cudaStream_t stream)
             cudaMemcpyAsync(why, scratch + ncell + 1, sizeof(why), cudaMemcpyDeviceToHost, stream);
             cudaStreamSynchronize(stream);
             fprintf(stderr, "[ansb200] overlap: %d of %lld cells left to the general kernel (non-monotone %d, open bin %d, "
-                            "group %d, tie %d)\n", c, ncell, why[0], why[1], why[2], why[3]);
+                            "group %d, tie %d, walk %d); folds: %d static, %d sorted (%d static orders with an unseparated straddler)\n",
+                    c, ncell, why[0], why[1], why[2], why[3], why[4], why[5], why[6], why[7]);
         }
         ov_scratch_put(sc, stream);
         return rc;

@@ -44,24 +44,24 @@ struct KfShared {
     double gord[NG + 2];            // bin edges, gord[NG+1] = +inf
     double wtabd[NG * NG];          // element weights (float32 products widened)
     float wtabf[512];               // the same as float32, 0 beyond NG*NG (padding of the sort)
-    double stat[2][2][NG * NG];     // [order][rows | columns][i*NG + m]  marginals of the static orders
+    double stat[2][2][NG * NG];     // [order][rows | columns][m*NG + i]  marginals of the static orders
     unsigned short sstr[2][NG + 1][4];   // [order][edge] -> element before / the straddler / element after
     int ok_f32, ok_static;
 };
 
 // per-warp shared memory, in doubles (every block a multiple of 16 bytes)
-template <int NG, int XS>
+template <int NG, int XS, int KG, bool GRAD>
 struct KfWarpLayout {
-    static constexpr int NGASMAX = XS > 2 ? XS - 2 : 16;
+    static constexpr int NGASMAX = KG;
     static constexpr int RC = 0;                                  // [NG*NG] marginals; aliased by the sorted words
     static constexpr int X = RC + NG * NG;                        // [NG][XS] rows {tau_i, dT_i, gas columns}
-    static constexpr int YS = XS > 2 ? XS : 2;                    // gradients: Y rows are laid out like X rows
+    static constexpr int YS = XS;                                 // Y rows are laid out like X rows
     static constexpr int Y = X + NG * XS;                         // [NG][YS] columns {b_j, bT_j, 0.., k_j at the new gas, 0..}
     static constexpr int AV = Y + NG * YS;                        // [NG] compact copies for the key loop
     static constexpr int BV = AV + NG;
     static constexpr int KBUF = BV + NG;                          // [NG*NGASMAX]
     static constexpr int DBUF = KBUF + NG * NGASMAX;
-    static constexpr int GBS = DBUF + (XS > 2 ? NG * NGASMAX : 0);   // [NG+2] cumulative weight before the straddler
+    static constexpr int GBS = DBUF + (GRAD ? NG * NGASMAX : 0);   // [NG+2] cumulative weight before the straddler
     static constexpr int SPOS = GBS + NG + 2;                     // [NG+2] ints: sorted position of the straddler
     static constexpr int BIN = SPOS + (NG + 2 + 1) / 2 + 1;       // [512] bytes
     static constexpr int TOTAL = (BIN + 64 + 1) & ~1;
@@ -132,21 +132,21 @@ __device__ void kf_static_setup(KfShared<NG> &S)
                 const double gdn = __dadd_rn(run, w);
                 if (ig < NG) {
                     if (gdn < S.gord[ig + 1]) {
-                        RA[i * NG + ig] = __dadd_rn(RA[i * NG + ig], w);
-                        RB[j * NG + ig] = __dadd_rn(RB[j * NG + ig], w);
+                        RA[ig * NG + i] = __dadd_rn(RA[ig * NG + i], w);
+                        RB[ig * NG + j] = __dadd_rn(RB[ig * NG + j], w);
                     } else {
                         const double frac = __ddiv_rn(__dsub_rn(S.gord[ig + 1], run), __dsub_rn(gdn, run));
                         const double f = __dmul_rn(frac, w);
-                        RA[i * NG + ig] = __dadd_rn(RA[i * NG + ig], f);
-                        RB[j * NG + ig] = __dadd_rn(RB[j * NG + ig], f);
+                        RA[ig * NG + i] = __dadd_rn(RA[ig * NG + i], f);
+                        RB[ig * NG + j] = __dadd_rn(RB[ig * NG + j], f);
                         ++ig;
                         S.sstr[o][ig][0] = (unsigned short)prev;
                         S.sstr[o][ig][1] = (unsigned short)e;
                         pending = ig;
                         if (ig < NG) {
                             const double f2 = __dmul_rn(__dsub_rn(1.0, frac), w);
-                            RA[i * NG + ig] = __dadd_rn(RA[i * NG + ig], f2);
-                            RB[j * NG + ig] = __dadd_rn(RB[j * NG + ig], f2);
+                            RA[ig * NG + i] = __dadd_rn(RA[ig * NG + i], f2);
+                            RB[ig * NG + j] = __dadd_rn(RB[ig * NG + j], f2);
                             if (gdn >= S.gord[ig + 1]) ok = false;      // one element over two edges
                         }
                     }
@@ -167,61 +167,11 @@ __device__ void kf_static_setup(KfShared<NG> &S)
     }
 }
 
-// lane-per-bin accumulation  acc += sum_t M[t*NG + m] * rows[t][:]
-template <int NG, int XS, bool GRAD>
-__device__ __forceinline__ void kf_accum_x(const double *__restrict__ M, const double *__restrict__ X, int igas, int m,
-                                           double &sw, double (&acc)[XS])
-{
-    if (m < NG) {
-#pragma unroll 2
-        for (int t = 0; t < NG; ++t) {
-            const double r = M[t * NG + m];
-            sw = __dadd_rn(sw, r);
-            if (GRAD) {
-                const double2 *row = reinterpret_cast<const double2 *>(X + t * XS);
-                const double2 x0 = row[0];
-                acc[0] = __fma_rn(r, x0.x, acc[0]);
-                acc[1] = __fma_rn(r, x0.y, acc[1]);
-#pragma unroll
-                for (int q = 1; q < XS / 2; ++q) {
-                    if (2 * q - 2 <= igas) {
-                        const double2 x = row[q];
-                        acc[2 * q] = __fma_rn(r, x.x, acc[2 * q]);
-                        acc[2 * q + 1] = __fma_rn(r, x.y, acc[2 * q + 1]);
-                    }
-                }
-            } else {
-                acc[0] = __fma_rn(r, X[t * XS], acc[0]);
-            }
-        }
-    }
-}
-
-template <int NG, bool GRAD>
-__device__ __forceinline__ void kf_accum_y(const double *__restrict__ M, const double *__restrict__ Y, int m,
-                                           double &yb, double &yT, double &yk)
-{
-    if (m < NG) {
-#pragma unroll 2
-        for (int t = 0; t < NG; ++t) {
-            const double c = M[t * NG + m];
-            if (GRAD) {
-                const double2 y0 = *reinterpret_cast<const double2 *>(Y + 4 * t);
-                yb = __fma_rn(c, y0.x, yb);
-                yT = __fma_rn(c, y0.y, yT);
-                yk = __fma_rn(c, Y[4 * t + 2], yk);
-            } else {
-                yb = __fma_rn(c, Y[2 * t], yb);
-            }
-        }
-    }
-}
-
-// The same product on the FP64 tensor cores (gradient kernels): D[bin][column] += sum_t M[t][bin] * rows[t][column] as
-// mma.m8n8k4 tiles -- 3 tiles of 8 bins (the last one half empty), XS/8 tiles of 8 columns, NG/4 steps of 4 rows.
+// The product on the FP64 tensor cores: D[bin][column] += sum_t M[bin][t] * rows[t][column] as mma.m8n8k4 tiles --
+// 3 tiles of 8 bins (the last one half empty), XS/8 tiles of 8 columns, NG/4 steps of 4 rows.
 // Fragments (PTX ISA, mma.m8n8k4 .f64): a = A[lane>>2][lane&3], b = B[lane&3][lane>>2], d = D[lane>>2][2*(lane&3) + {0,1}].
-// With the marginals stored [t][bin] at stride NG = 20 the sixteen 8-byte words of a half-warp's A load fall in
-// sixteen different bank pairs.  `rsum` gathers the lane's share of sum_t M[t][bin] (the normalisation).
+// With the marginals stored [bin][t] at stride NG = 20 the sixteen 8-byte words of a half-warp's A load fall in
+// sixteen different bank pairs.  `rsum` gathers the lane's share of sum_t M[bin][t] (the normalisation).
 template <int NG, int XS, bool SUM>
 __device__ __forceinline__ void kf_mma(const double *__restrict__ M, const double *__restrict__ rows, int lane,
                                        double (&d)[3][XS / 8][2], double (&rsum)[3])
@@ -235,7 +185,7 @@ __device__ __forceinline__ void kf_mma(const double *__restrict__ M, const doubl
         for (int n = 0; n < XS / 8; ++n) b[n] = rows[(k0 + kk) * XS + 8 * n + mm];
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-            const double a = M[(k0 + kk) * NG + 8 * t + mm];     // (bins >= NG: whatever follows; those rows are dropped)
+            const double a = M[(8 * t + mm) * NG + k0 + kk];     // (bins >= NG: whatever follows; those rows are dropped)
             if (SUM) rsum[t] = __dadd_rn(rsum[t], a);
 #pragma unroll
             for (int n = 0; n < XS / 8; ++n)
@@ -245,28 +195,34 @@ __device__ __forceinline__ void kf_mma(const double *__restrict__ M, const doubl
     }
 }
 
-// lane-per-row (sa = NG, sb = 1) or lane-per-column (sa = 1, sb = NG) walk over the bin bytes: run lengths of
-// equal bins are summed in a register and added to M[lane*NG + bin]
-template <int NG>
-__device__ __forceinline__ void kf_walk(const unsigned char *__restrict__ bin, const double *__restrict__ wtabd,
-                                        double *__restrict__ M, int lane, int sa, int sb)
+// Lane-per-row (SA = NG, SB = 1) or lane-per-column (SA = 1, SB = NG) walk over the bin bytes: the weights of a run of
+// equal bins are summed in a register and stored to M[bin*NG + lane] (zero-filled before).  Along a row or a column
+// of the key matrix the bins cannot decrease; if they do, something upstream is wrong and the cell is handed over.
+template <int NG, int SA, int SB>
+__device__ __forceinline__ bool kf_walk(const unsigned char *__restrict__ bin, const double *__restrict__ wtabd,
+                                        double *__restrict__ M, int lane)
 {
+    bool bad = false;
     if (lane < NG) {
-        const unsigned char *bp = bin + lane * sa;
+        const unsigned char *bp = bin + lane * SA;
+        const double *wp = wtabd + lane;                    // (the weight table is symmetric)
+        double *mp = M + lane;
         int mc = bp[0];
         double acc = 0.0;
-#pragma unroll 1
+#pragma unroll 5
         for (int t = 0; t < NG; ++t) {
-            const int mt = bp[t * sb];
+            const int mt = bp[t * SB];
             if (mt != mc) {
-                if (mc < NG) M[lane * NG + mc] = __dadd_rn(M[lane * NG + mc], acc);
+                bad |= mt < mc;
+                if (mc < NG) mp[mc * NG] = acc;
                 acc = 0.0;
                 mc = mt;
             }
-            acc = __dadd_rn(acc, wtabd[t * NG + lane]);     // (the weight table is symmetric)
+            acc = __dadd_rn(acc, wp[t * NG]);
         }
-        if (mc < NG) M[lane * NG + mc] = __dadd_rn(M[lane * NG + mc], acc);
+        if (mc < NG) mp[mc * NG] = acc;
     }
+    return bad;
 }
 
 // move the (1-frac) part of every straddler from the bin it starts in to the next one; lane = edge, line = the
@@ -275,17 +231,17 @@ template <int NG>
 __device__ __forceinline__ void kf_correct(double *__restrict__ M, int lane, int line, double cw)
 {
     const bool act = line >= 0;
-    if (act) M[line * NG + lane - 1] = __dsub_rn(M[line * NG + lane - 1], cw);
+    if (act) M[(lane - 1) * NG + line] = __dsub_rn(M[(lane - 1) * NG + line], cw);
     __syncwarp();
-    if (act && lane < NG) M[line * NG + lane] = __dadd_rn(M[line * NG + lane], cw);
+    if (act && lane < NG) M[lane * NG + line] = __dadd_rn(M[lane * NG + line], cw);
     __syncwarp();
 }
 
-template <int NG, int XS, bool GRAD, int NWARPS>
+template <int NG, int XS, int KG, bool GRAD, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32, 1)
 ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict__ fb_list, int *__restrict__ fb_why)
 {
-    using L = KfWarpLayout<NG, XS>;
+    using L = KfWarpLayout<NG, XS, KG, GRAD>;
     constexpr int NN = NG * NG;
     constexpr int EPL = 16;
     static_assert(NN <= 512 && NN > 256 && NN % 16 == 0, "16 keys per lane, whole lanes");
@@ -404,17 +360,14 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
             if (do_fold && lane < NG) {
                 const double b = __dmul_rn(KB(lane, g1), am1);
                 bv[lane] = b;
-                if (GRAD) {
-                    // a row of the second operand of the product: {b_j, bT_j, 0 .., k_j in the column of gas g1, 0 ..}
-                    const double bT = __dmul_rn(DB(lane, g1), am1), kj = KB(lane, g1);
-                    double2 *row = reinterpret_cast<double2 *>(Y + lane * L::YS);
-                    row[0] = make_double2(b, bT);
+                // a row of the second operand of the product: {b_j, bT_j, 0 .., k_j in the column of gas g1, 0 ..}
+                // (without gradients only column 0 is used: the rest of X and Y stays zero)
+                const double bT = GRAD ? __dmul_rn(DB(lane, g1), am1) : 0.0, kj = GRAD ? KB(lane, g1) : 0.0;
+                double2 *row = reinterpret_cast<double2 *>(Y + lane * L::YS);
+                row[0] = make_double2(b, bT);
 #pragma unroll
-                    for (int q = 1; q < XS / 2; ++q)
-                        row[q] = make_double2(2 * q - 2 == g1 ? kj : 0.0, 2 * q - 1 == g1 ? kj : 0.0);
-                } else {
-                    Y[L::YS * lane] = b;
-                }
+                for (int q = 1; q < XS / 2; ++q)
+                    row[q] = make_double2(2 * q - 2 == g1 ? kj : 0.0, 2 * q - 1 == g1 ? kj : 0.0);
             }
             __syncwarp();
             if (!do_fold) continue;
@@ -443,13 +396,11 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                         if (ne != KF_NONE) sep &= ks < __dadd_rn(av[ne / NG], bv[ne % NG]);
                     }
                 }
-                if (!__all_sync(FULL, sep)) ord = -1;
+                if (!__all_sync(FULL, sep)) { ord = -1; if (fb_why && lane == 0) atomicAdd(fb_why + 7, 1); }
             }
+            if (fb_why && lane == 0) atomicAdd(fb_why + (ord >= 0 ? 5 : 6), 1);
 
-            double sw = 0.0, yb = 0.0, yT = 0.0, yk = 0.0;
-            double acc[GRAD ? 1 : XS];
-            acc[0] = 0.0;
-            constexpr int NT8 = GRAD ? XS / 8 : 1;
+            constexpr int NT8 = XS / 8;
             double dfr[3][NT8][2], rsum[3];
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
@@ -459,13 +410,8 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
             }
 
             if (ord >= 0) {
-                if constexpr (GRAD) {
-                    kf_mma<NG, XS, true>(S.stat[ord][0], X, lane, dfr, rsum);
-                    kf_mma<NG, XS, false>(S.stat[ord][1], Y, lane, dfr, rsum);
-                } else {
-                    kf_accum_x<NG, XS, GRAD>(S.stat[ord][0], X, igas, lane, sw, acc);
-                    kf_accum_y<NG, GRAD>(S.stat[ord][1], Y, lane, yb, yT, yk);
-                }
+                kf_mma<NG, XS, true>(S.stat[ord][0], X, lane, dfr, rsum);
+                kf_mma<NG, XS, false>(S.stat[ord][1], Y, lane, dfr, rsum);
             } else {
                 // ---- 1. packed keys, sorted in registers --------------------------------------------
                 unsigned v[EPL];
@@ -620,26 +566,25 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                     for (int t = lane; t < NN / 2; t += 32) z[t] = make_double2(0.0, 0.0);
                 }
                 __syncwarp();
-                kf_walk<NG>(bin, S.wtabd, RC, lane, NG, 1);
+                bool wbad = kf_walk<NG, NG, 1>(bin, S.wtabd, RC, lane);
                 __syncwarp();
                 kf_correct<NG>(RC, lane, se >= 0 ? se / NG : -1, cw);
-                if constexpr (GRAD) kf_mma<NG, XS, true>(RC, X, lane, dfr, rsum);
-                else kf_accum_x<NG, XS, GRAD>(RC, X, igas, lane, sw, acc);
+                kf_mma<NG, XS, true>(RC, X, lane, dfr, rsum);
                 __syncwarp();
                 {
                     double2 *z = reinterpret_cast<double2 *>(RC);
                     for (int t = lane; t < NN / 2; t += 32) z[t] = make_double2(0.0, 0.0);
                 }
                 __syncwarp();
-                kf_walk<NG>(bin, S.wtabd, RC, lane, 1, NG);
+                wbad |= kf_walk<NG, 1, NG>(bin, S.wtabd, RC, lane);
                 __syncwarp();
                 kf_correct<NG>(RC, lane, se >= 0 ? se % NG : -1, cw);
-                if constexpr (GRAD) kf_mma<NG, XS, false>(RC, Y, lane, dfr, rsum);
-                else kf_accum_y<NG, GRAD>(RC, Y, lane, yb, yT, yk);
+                kf_mma<NG, XS, false>(RC, Y, lane, dfr, rsum);
+                if (__any_sync(FULL, wbad)) { fallback = true; why = 16; break; }
             }
             __syncwarp();
             // ---- bin m: normalise (ForwardModel_0.py:6016-6017, :6026-6027) and store -------------------
-            if constexpr (GRAD) {
+            {
                 // sum of the marginals of a bin: the four lanes of a fragment row hold a quarter each
                 double *sws = gbs;
 #pragma unroll
@@ -664,11 +609,6 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                         }
                     }
                 }
-            } else if (lane < NG) {
-                const double rs = __ddiv_rn(1.0, sw);
-                const double ta = __dmul_rn(__dadd_rn(acc[0], yb), rs);
-                av[lane] = ta;
-                X[lane * XS] = ta;
             }
             __syncwarp();
         }
@@ -678,7 +618,7 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
             if (lane == 0) fb_list[atomicAdd(fb_count, 1)] = (int)cell;
             if (fb_why) {
                 const unsigned wm = __reduce_or_sync(FULL, (unsigned)why);
-                if (lane == 0) for (int b = 0; b < 8; ++b) if (wm >> b & 1u) atomicAdd(fb_why + b, 1);
+                if (lane == 0) for (int b = 0; b < 5; ++b) if (wm >> b & 1u) atomicAdd(fb_why + b, 1);
             }
         } else {
             for (int g = lane; g < NG; g += 32) {
@@ -694,12 +634,12 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
     }
 }
 
-template <int NG, int XS, bool GRAD, int NWARPS>
+template <int NG, int XS, int KG, bool GRAD, int NWARPS>
 int kf_launch(const OvParams &P, int *scratch, int *why, cudaStream_t stream)
 {
-    using L = KfWarpLayout<NG, XS>;
+    using L = KfWarpLayout<NG, XS, KG, GRAD>;
     const size_t smem = ((sizeof(KfShared<NG>) + 15) & ~(size_t)15) + (size_t)NWARPS * L::TOTAL * 8;
-    auto kern = ans_koverlap_fast_kernel<NG, XS, GRAD, NWARPS>;
+    auto kern = ans_koverlap_fast_kernel<NG, XS, KG, GRAD, NWARPS>;
     ANS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, nsm = 148;
     ANS_CUDA_CHECK(cudaGetDevice(&dev));
@@ -724,7 +664,8 @@ bool ov_fast_supported(const OvParams &P, bool grad)
 // scratch: [0] = number of cells left for the general kernel (-1: all of them), [1..] = their numbers
 int ov_fast_launch(const OvParams &P, bool grad, int *scratch, int *why, cudaStream_t stream)
 {
-    if (!grad) return kf_launch<20, 2, false, 24>(P, scratch, why, stream);
-    if (P.NGAS <= 6) return kf_launch<20, 8, true, 24>(P, scratch, why, stream);
-    return kf_launch<20, 16, true, 16>(P, scratch, why, stream);
+    if (!grad) return P.NGAS <= 6 ? kf_launch<20, 8, 6, false, 24>(P, scratch, why, stream)
+                                  : kf_launch<20, 8, 14, false, 20>(P, scratch, why, stream);
+    if (P.NGAS <= 6) return kf_launch<20, 8, 6, true, 24>(P, scratch, why, stream);
+    return kf_launch<20, 16, 14, true, 16>(P, scratch, why, stream);
 }
