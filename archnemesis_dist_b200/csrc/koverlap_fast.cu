@@ -160,10 +160,16 @@ __device__ void kf_static_setup(KfShared<NG> &S)
     } else if (o == 32) {
         // in any order: no element may lie over two edges (the host plan checks the same and asks for the
         // sequential scan otherwise)
-        double wmax = 0.0, dmin = INFINITY;
-        for (int e = 0; e < NG * NG; ++e) wmax = fmax(wmax, S.wtabd[e]);
+        double wmax = 0.0, wmin = INFINITY, dmin = INFINITY, total = 0.0;
+        for (int e = 0; e < NG * NG; ++e) {
+            wmax = fmax(wmax, S.wtabd[e]);
+            wmin = fmin(wmin, S.wtabd[e]);
+            total = __dadd_rn(total, S.wtabd[e]);
+        }
         for (int m = 0; m < NG; ++m) dmin = fmin(dmin, __dsub_rn(S.gord[m + 1], S.gord[m]));
         if (!(wmax < dmin)) atomicAnd(&S.ok_static, 0);
+        // and no element may START beyond the last edge (bins are numbered 0 .. NG-1 in the marginal matrices)
+        if (!(__dsub_rn(total, wmin) < S.gord[NG])) atomicAnd(&S.ok_static, 0);
     }
 }
 
@@ -196,33 +202,33 @@ __device__ __forceinline__ void kf_mma(const double *__restrict__ M, const doubl
 }
 
 // Lane-per-row (SA = NG, SB = 1) or lane-per-column (SA = 1, SB = NG) walk over the bin bytes: the weights of a run of
-// equal bins are summed in a register and stored to M[bin*NG + lane] (zero-filled before).  Along a row or a column
-// of the key matrix the bins cannot decrease; if they do, something upstream is wrong and the cell is handed over.
+// equal bins are summed in a register and stored to M[bin*NG + lane] (zero-filled before; the set-up has checked that
+// no element can start beyond the last edge, so bin < NG).  The run store is two predicated instructions (PTX: ptxas would branch).  Along a row
+// or a column of the key matrix the bins cannot decrease; if they do, something upstream is wrong and the cell is
+// handed over.
 template <int NG, int SA, int SB>
 __device__ __forceinline__ bool kf_walk(const unsigned char *__restrict__ bin, const double *__restrict__ wtabd,
                                         double *__restrict__ M, int lane)
 {
-    bool bad = false;
+    int dec = 0;
     if (lane < NG) {
         const unsigned char *bp = bin + lane * SA;
         const double *wp = wtabd + lane;                    // (the weight table is symmetric)
-        double *mp = M + lane;
-        int mc = bp[0];
+        const unsigned mbase = (unsigned)__cvta_generic_to_shared(M + lane);
+        unsigned ma = mbase + (unsigned)bp[0] * (NG * 8);   // shared-memory address of the current run's slot
         double acc = 0.0;
 #pragma unroll 5
         for (int t = 0; t < NG; ++t) {
-            const int mt = bp[t * SB];
-            if (mt != mc) {
-                bad |= mt < mc;
-                if (mc < NG) mp[mc * NG] = acc;
-                acc = 0.0;
-                mc = mt;
-            }
+            const unsigned na = mbase + (unsigned)bp[t * SB] * (NG * 8);
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, %2;\n\t@p st.shared.f64 [%2], %0;\n\t"
+                         "@p mov.f64 %0, 0d0000000000000000;\n\t}" : "+d"(acc) : "r"(na), "r"(ma) : "memory");
+            dec |= (int)(na - ma);
+            ma = na;
             acc = __dadd_rn(acc, wp[t * NG]);
         }
-        if (mc < NG) mp[mc * NG] = acc;
+        asm volatile("st.shared.f64 [%0], %1;" :: "r"(ma), "d"(acc) : "memory");
     }
-    return bad;
+    return dec < 0;
 }
 
 // move the (1-frac) part of every straddler from the bin it starts in to the next one; lane = edge, line = the

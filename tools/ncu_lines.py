@@ -60,9 +60,33 @@ def main():
                 ex = float(r[idx["Instructions Executed"]])
             except (ValueError, KeyError, IndexError):
                 ex = 0.0
-            raw.append((cur_line, ex))
+            raw.append((cur_line, ex, r[idx["Address"]] if "Address" in idx else len(raw), r))
             max_exec = max(max_exec, ex)
-    for ln, ex in raw:
+    # An instruction inlined from a header is listed under the header line AND under its call sites: keep one
+    # listing per SASS address, preferring the line in the .cu file (the call site), and rebuild the per-line sums
+    prefer = sys.argv[3] if len(sys.argv) > 3 else ".cu"
+    by_addr = {}
+    for ln, ex, addr, r in raw:
+        if addr not in by_addr or (prefer in ln[0] and prefer not in by_addr[addr][0][0]):
+            by_addr[addr] = (ln, ex, r)
+    for v in lines.values():
+        v["inst"] = v["samples"] = v["wf"] = v["wfx"] = v["noinst"] = v["ssb"] = v["wait"] = v["bar"] = v["lsb"] = 0.0
+    def fnum(r, name):
+        try:
+            return float(r[idx[name]])
+        except (ValueError, KeyError, IndexError):
+            return 0.0
+    raw2 = []
+    for addr, (ln, ex, r) in by_addr.items():
+        raw2.append((ln, ex))
+        v = lines[ln]
+        v["inst"] += ex
+        v["samples"] += fnum(r, "# Samples")
+        v["wf"] += fnum(r, "L1 Wavefronts Shared")
+        v["wfx"] += fnum(r, "L1 Wavefronts Shared Excessive")
+        v["noinst"] += fnum(r, "stall_no_inst"); v["ssb"] += fnum(r, "stall_short_sb"); v["wait"] += fnum(r, "stall_wait")
+        v["bar"] += fnum(r, "stall_barrier"); v["lsb"] += fnum(r, "stall_long_sb")
+    for ln, ex in raw2:
         sass_static[ln] += 1
         if ex >= 0.02 * max_exec:
             sass_hot[ln] += 1
