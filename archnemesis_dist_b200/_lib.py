@@ -19,6 +19,8 @@ _u = ctypes.c_uint
 EXPORTS = {
     "ansb200_last_error": (ctypes.c_char_p, []),
     "ansb200_version": (_i, []),
+    "ansb200_overlap_mode": (_i, [_i]),
+    "ansb200_overlap_stats": (None, [ctypes.POINTER(ctypes.c_int32)]),
     "ansb200_table_create": (_i, [_vp, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_vp), _vp]),
     "ansb200_table_destroy": (_i, [_vp]),
     "ansb200_table_shape": (_i, [_vp] + [ctypes.POINTER(_i)] * 5),

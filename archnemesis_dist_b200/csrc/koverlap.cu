@@ -1,6 +1,7 @@
 // koverlap.cu -- C entry points of the random-overlap kernels (implementation: koverlap_impl.cuh).
 #include "koverlap_impl.cuh"
 #include <stdlib.h>
+#include <atomic>
 #include <mutex>
 #include <vector>
 #include <string.h>
@@ -83,18 +84,33 @@ void ov_scratch_put(OvScratch &sc, cudaStream_t stream)
 }
 }   // namespace
 
-// diagnostics: ANSB200_OVERLAP=general forces the general kernel; ANSB200_OVERLAP=stats prints how many cells
-// the fast kernel handed over (synchronises the stream)
+// Diagnostics.  Mode 0 = fast kernel + work list (default), 1 = general kernel only, 2 = as 0 but every call
+// synchronises its stream and records how many cells were handed over and why (ansb200_overlap_stats).  The mode
+// comes from ansb200_overlap_mode() or, initially, from the environment (ANSB200_OVERLAP=general|stats).
+static std::atomic<int> g_ov_mode{-1};
+static std::atomic<int> g_ov_stats[9];
+
 static int ov_mode()
 {
-    static const int mode = [] {
+    int m = g_ov_mode.load(std::memory_order_relaxed);
+    if (m < 0) {
         const char *e = getenv("ANSB200_OVERLAP");
-        if (!e) return 0;
-        if (!strcmp(e, "general")) return 1;
-        if (!strcmp(e, "stats")) return 2;
-        return 0;
-    }();
-    return mode;
+        m = !e ? 0 : (!strcmp(e, "general") ? 1 : (!strcmp(e, "stats") ? 2 : 0));
+        g_ov_mode.store(m, std::memory_order_relaxed);
+    }
+    return m;
+}
+
+extern "C" int ansb200_overlap_mode(int mode)
+{
+    const int old = ov_mode();
+    if (mode >= 0 && mode <= 2) g_ov_mode.store(mode, std::memory_order_relaxed);
+    return old;
+}
+
+extern "C" void ansb200_overlap_stats(int32_t *out9)
+{
+    for (int i = 0; i < 9; ++i) out9[i] = g_ov_stats[i].load(std::memory_order_relaxed);
 }
 
 static int ov_run(OvParams &P, bool grad, cudaStream_t stream)
@@ -138,9 +154,12 @@ static int ov_run(OvParams &P, bool grad, cudaStream_t stream)
             cudaMemcpyAsync(&c, scratch, sizeof(int), cudaMemcpyDeviceToHost, stream);
             cudaMemcpyAsync(why, scratch + ncell + 1, sizeof(why), cudaMemcpyDeviceToHost, stream);
             cudaStreamSynchronize(stream);
-            fprintf(stderr, "[ansb200] overlap: %d of %lld cells left to the general kernel (non-monotone %d, open bin %d, "
-                            "group %d, tie %d, walk %d); folds: %d static, %d sorted (%d static orders with an unseparated straddler)\n",
-                    c, ncell, why[0], why[1], why[2], why[3], why[4], why[5], why[6], why[7]);
+            g_ov_stats[0].store(c, std::memory_order_relaxed);
+            for (int i = 0; i < 8; ++i) g_ov_stats[1 + i].store(why[i], std::memory_order_relaxed);
+            if (getenv("ANSB200_OVERLAP_VERBOSE"))
+                fprintf(stderr, "[ansb200] overlap: %d of %lld cells left to the general kernel (non-monotone %d, open bin %d, "
+                                "group %d, tie %d, walk %d); folds: %d static, %d sorted (%d static orders with an unseparated "
+                                "straddler)\n", c, ncell, why[0], why[1], why[2], why[3], why[4], why[5], why[6], why[7]);
         }
         ov_scratch_put(sc, stream);
         return rc;

@@ -640,9 +640,21 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
     }
 }
 
-template <int NG, int XS, int KG, bool GRAD, int NWARPS>
+// warps per CTA (one CTA per SM): as many as 227 KB of shared memory hold, at most 24 (80 registers per thread)
+template <int NG, int XS, int KG, bool GRAD>
+constexpr int kf_warps()
+{
+    constexpr size_t cta = (sizeof(KfShared<NG>) + 15) & ~(size_t)15;
+    constexpr size_t per_warp = (size_t)KfWarpLayout<NG, XS, KG, GRAD>::TOTAL * 8;
+    constexpr size_t fit = (232448 - cta) / per_warp;
+    return fit > 24 ? 24 : (int)fit;
+}
+
+template <int NG, int XS, int KG, bool GRAD>
 int kf_launch(const OvParams &P, int *scratch, int *why, cudaStream_t stream)
 {
+    constexpr int NWARPS = kf_warps<NG, XS, KG, GRAD>();
+    static_assert(NWARPS >= 8, "too little shared memory per warp");
     using L = KfWarpLayout<NG, XS, KG, GRAD>;
     const size_t smem = ((sizeof(KfShared<NG>) + 15) & ~(size_t)15) + (size_t)NWARPS * L::TOTAL * 8;
     auto kern = ans_koverlap_fast_kernel<NG, XS, KG, GRAD, NWARPS>;
@@ -670,8 +682,8 @@ bool ov_fast_supported(const OvParams &P, bool grad)
 // scratch: [0] = number of cells left for the general kernel (-1: all of them), [1..] = their numbers
 int ov_fast_launch(const OvParams &P, bool grad, int *scratch, int *why, cudaStream_t stream)
 {
-    if (!grad) return P.NGAS <= 6 ? kf_launch<20, 8, 6, false, 24>(P, scratch, why, stream)
-                                  : kf_launch<20, 8, 14, false, 20>(P, scratch, why, stream);
-    if (P.NGAS <= 6) return kf_launch<20, 8, 6, true, 24>(P, scratch, why, stream);
-    return kf_launch<20, 16, 14, true, 16>(P, scratch, why, stream);
+    if (!grad) return P.NGAS <= 6 ? kf_launch<20, 8, 6, false>(P, scratch, why, stream)
+                                  : kf_launch<20, 8, 14, false>(P, scratch, why, stream);
+    if (P.NGAS <= 6) return kf_launch<20, 8, 6, true>(P, scratch, why, stream);
+    return kf_launch<20, 16, 14, true>(P, scratch, why, stream);
 }

@@ -129,6 +129,22 @@ def koverlap(k, amount, otab, dkdT=None, force_seq=False):
     return (tau, dk) if grad else tau
 
 
+def overlap_mode(mode=-1):
+    """Diagnostics switch of the overlap kernels (include/ansb200.h): 0 = fast kernel + work list for the general one
+    (default), 1 = general kernel only, 2 = as 0 with per-call statistics.  Returns the previous mode."""
+    return int(_lib.load().ansb200_overlap_mode(int(mode)))
+
+
+def overlap_stats():
+    """Counts of the last overlap call made in mode 2: cells handed to the general kernel and why, kinds of folds."""
+    import ctypes
+    buf = (ctypes.c_int32 * 9)()
+    _lib.load().ansb200_overlap_stats(buf)
+    names = ("handed_over", "non_monotone", "open_bin", "key_group", "exact_tie", "bins_not_monotone", "static_folds",
+             "sorted_folds", "static_rejected")
+    return dict(zip(names, [int(v) for v in buf]))
+
+
 def gas_opacity(table, dplan, amount, otab, want_grad=False, force_seq=False):
     """Fused calc_k[g] + k_overlap[g] (K_TABLES branch of calculate_gaseous_line_opacity)."""
     _require_cuda()

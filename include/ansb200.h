@@ -76,8 +76,8 @@ int ansb200_kinterp(const ansb200_table *t, int NLAY, const int32_t *ip_lo, cons
  * up; it is used only when it reproduces `weight` bit for bit (checked on the device).
  * amount[NGAS,NLAY] in cm-2.  Output tau[NWAVE,NG,NLAY]; if want_grad also
  * dk[NWAVE,NG,NLAY,NGAS+1] (d tau/d amount_gas ..., d tau/dT).
- * Ties between sort keys are broken by original index (the reference's numba quicksort leaves
- * their order unspecified). */
+ * Equal sort keys follow the order of numba's (unstable) quicksort, which the reference's np.argsort uses:
+ * the split of their gradient rows across a bin edge depends on it ("Ties"). */
 int ansb200_koverlap(const double *k, const double *dkdT, const double *amount, const double *weight,
                      const double *g_ord, const double *del_g, int NWAVE, int NG, int NLAY, int NGAS, int want_grad,
                      double *tau, double *dk, void *stream);
@@ -88,6 +88,17 @@ int ansb200_gas_opacity(const ansb200_table *t, int NLAY, const int32_t *ip_lo, 
                         const double *w4, const double *omv, const double *vv, const double *dudt,
                         const double *amount, const double *weight, const double *g_ord, const double *del_g,
                         int want_grad, double *tau, double *dk, void *stream);
+
+/* Diagnostics of the two overlap kernels.  The common case (NG = 20, float32-born quadrature weights, k ascending in
+ * g) runs in a fast kernel that hands the cells it declines -- equal sort keys on a bin edge, where the reference's
+ * result depends on numba's unstable argsort, non-monotone k, ... -- to the general kernel through a device-side
+ * work list.  ansb200_overlap_mode: 0 = that (default), 1 = general kernel only, 2 = as 0 but every call
+ * synchronises and records its counts; returns the previous mode (mode < 0 only queries).  ansb200_overlap_stats:
+ * out[0] = cells handed over by the last call in mode 2 (-1: all), out[1..5] = reasons (non-monotone input, bin left
+ * open, group of equal key bits, exact tie on an edge, non-monotone bins), out[6] / out[7] = folds that used a
+ * data-independent / a sorted order, out[8] = static orders rejected for an unseparated straddler. */
+int ansb200_overlap_mode(int mode);
+void ansb200_overlap_stats(int32_t *out9);
 
 /* ---- path radiance + layer-space Jacobian -------------------------------------------------
  * Replaces, for every path at once, the opacity assembly of calculate_layer_opacity
