@@ -55,10 +55,9 @@ struct KfWarpLayout {
     static constexpr int NGASMAX = KG;
     static constexpr int RC = 0;                                  // [NG*NG] marginals; aliased by the sorted words
     static constexpr int X = RC + NG * NG;                        // [NG][XS] rows {tau_i, dT_i, gas columns}
-    static constexpr int YS = XS;                                 // Y rows are laid out like X rows
-    static constexpr int Y = X + NG * XS;                         // [NG][YS] columns {b_j, bT_j, 0.., k_j at the new gas, 0..}
-    static constexpr int AV = Y + NG * YS;                        // [NG] compact copies for the key loop
-    static constexpr int BV = AV + NG;
+    static constexpr int BT = X + NG * XS;                        // [NG] dk/dT * amount of the gas being folded
+    static constexpr int AV = BT + NG;                            // [NG] running tau (copy of X[:,0] for the key loop)
+    static constexpr int BV = AV + NG;                            // [NG] k * amount of the gas being folded
     static constexpr int KBUF = BV + NG;                          // [NG*NGASMAX]
     static constexpr int DBUF = KBUF + NG * NGASMAX;
     static constexpr int GBS = DBUF + (GRAD ? NG * NGASMAX : 0);   // [NG+2] cumulative weight before the straddler
@@ -71,7 +70,7 @@ struct KfWarpLayout {
 // (koverlap_impl.cuh).  Every lane arrives with a BITONIC sequence (the key loop lays the tail of one row of the key
 // matrix ascending and the head of the next one descending), so the in-lane phases reduce to one 4-stage merge.
 // Cross-lane comparators: "take the partner's word if (partner < mine) != keep_high" is one ISETP.LT.XOR + SEL.
-__device__ __forceinline__ void kf_sort(unsigned (&v)[16], int lane)
+__device__ __forceinline__ void kf_sort(unsigned (&v)[16], int lane)   // @phase sort
 {
 #define KF_CE(x, y) do { const unsigned lo__ = min(x, y), hi__ = max(x, y); x = lo__; y = hi__; } while (0)
 #pragma unroll
@@ -111,11 +110,11 @@ __device__ __forceinline__ void kf_sort(unsigned (&v)[16], int lane)
 #undef KF_CE
 }
 
-__device__ __forceinline__ int kf_vaddr(int p) { return ((((p & 15) >> 2) * 32 + (p >> 4)) << 2) + (p & 3); }
+__device__ __forceinline__ int kf_vaddr(int p) { return ((((p & 15) >> 2) * 32 + (p >> 4)) << 2) + (p & 3); }   // @phase resolve
 
 // Static orders: replay rankg's loop over the row-major (o = 0) / column-major (o = 1) sequence once.
 template <int NG>
-__device__ void kf_static_setup(KfShared<NG> &S)
+__device__ void kf_static_setup(KfShared<NG> &S)   // @phase cta_setup
 {
     const int o = threadIdx.x;
     if (o < 2) {
@@ -178,9 +177,12 @@ __device__ void kf_static_setup(KfShared<NG> &S)
 // Fragments (PTX ISA, mma.m8n8k4 .f64): a = A[lane>>2][lane&3], b = B[lane&3][lane>>2], d = D[lane>>2][2*(lane&3) + {0,1}].
 // With the marginals stored [bin][t] at stride NG = 20 the sixteen 8-byte words of a half-warp's A load fall in
 // sixteen different bank pairs.  `rsum` gathers the lane's share of sum_t M[bin][t] (the normalisation).
+// The second operand is read through one pointer and one stride per lane and column tile (NULL = the column is zero):
+// for the row terms that is X[t][column]; the column terms {b_t, bT_t, 0 .., k_t in the column of the gas being
+// folded, 0 ..} are read where they lie (kf_yptr), no matrix of them is built.
 template <int NG, int XS, bool SUM>
-__device__ __forceinline__ void kf_mma(const double *__restrict__ M, const double *__restrict__ rows, int lane,
-                                       double (&d)[3][XS / 8][2], double (&rsum)[3])
+__device__ __forceinline__ void kf_mma(const double *__restrict__ M, const double *const (&bp)[XS / 8],   // @phase mma
+                                       const int (&bs)[XS / 8], int lane, double (&d)[3][XS / 8][2], double (&rsum)[3])
 {
     static_assert(NG % 4 == 0 && NG <= 24, "three 8-bin tiles, whole k-steps");
     const int kk = lane & 3, mm = lane >> 2;
@@ -188,7 +190,7 @@ __device__ __forceinline__ void kf_mma(const double *__restrict__ M, const doubl
     for (int k0 = 0; k0 < NG; k0 += 4) {
         double b[XS / 8];
 #pragma unroll
-        for (int n = 0; n < XS / 8; ++n) b[n] = rows[(k0 + kk) * XS + 8 * n + mm];
+        for (int n = 0; n < XS / 8; ++n) b[n] = bp[n] ? bp[n][(k0 + kk) * bs[n]] : 0.0;
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
             const double a = M[(8 * t + mm) * NG + k0 + kk];     // (bins >= NG: whatever follows; those rows are dropped)
@@ -207,7 +209,7 @@ __device__ __forceinline__ void kf_mma(const double *__restrict__ M, const doubl
 // or a column of the key matrix the bins cannot decrease; if they do, something upstream is wrong and the cell is
 // handed over.
 template <int NG, int SA, int SB>
-__device__ __forceinline__ bool kf_walk(const unsigned char *__restrict__ bin, const double *__restrict__ wtabd,
+__device__ __forceinline__ bool kf_walk(const unsigned char *__restrict__ bin, const double *__restrict__ wtabd,   // @phase walk
                                         double *__restrict__ M, int lane)
 {
     int dec = 0;
@@ -234,7 +236,7 @@ __device__ __forceinline__ bool kf_walk(const unsigned char *__restrict__ bin, c
 // move the (1-frac) part of every straddler from the bin it starts in to the next one; lane = edge, line = the
 // straddler's row (or column)
 template <int NG>
-__device__ __forceinline__ void kf_correct(double *__restrict__ M, int lane, int line, double cw)
+__device__ __forceinline__ void kf_correct(double *__restrict__ M, int lane, int line, double cw)   // @phase correct
 {
     const bool act = line >= 0;
     if (act) M[(lane - 1) * NG + line] = __dsub_rn(M[(lane - 1) * NG + line], cw);
@@ -245,7 +247,7 @@ __device__ __forceinline__ void kf_correct(double *__restrict__ M, int lane, int
 
 template <int NG, int XS, int KG, bool GRAD, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32, 1)
-ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict__ fb_list, int *__restrict__ fb_why)
+ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict__ fb_list, int *__restrict__ fb_why)   // @phase cta_setup
 {
     using L = KfWarpLayout<NG, XS, KG, GRAD>;
     constexpr int NN = NG * NG;
@@ -256,7 +258,7 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int NGAS = P.NGAS, NLAY = P.NLAY, NP1 = NGAS + 1;
     double *wb = reinterpret_cast<double *>(smem_raw + ((sizeof(KfShared<NG>) + 15) & ~(size_t)15)) + (size_t)warp * L::TOTAL;
-    double *RC = wb + L::RC, *X = wb + L::X, *Y = wb + L::Y, *av = wb + L::AV, *bv = wb + L::BV;
+    double *RC = wb + L::RC, *X = wb + L::X, *bT = wb + L::BT, *av = wb + L::AV, *bv = wb + L::BV;
     double *kbuf = wb + L::KBUF, *dbuf = wb + L::DBUF, *gbs = wb + L::GBS;
     int *spos = reinterpret_cast<int *>(wb + L::SPOS);
     unsigned char *bin = reinterpret_cast<unsigned char *>(wb + L::BIN);
@@ -294,7 +296,7 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
         return;
     }
 
-    for (long long cell = (long long)blockIdx.x * NWARPS + warp; cell < ncell; cell += (long long)gridDim.x * NWARPS) {
+    for (long long cell = (long long)blockIdx.x * NWARPS + warp; cell < ncell; cell += (long long)gridDim.x * NWARPS) {   // @phase cell_prologue
         const int iw = (int)(cell / NLAY);
         const int l = (int)(cell - (long long)iw * NLAY);
         bool fallback = false;
@@ -329,7 +331,7 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
 
 #define KB(g, gas) kbuf[(g) * NGAS + (gas)]
 #define DB(g, gas) dbuf[(g) * NGAS + (gas)]
-        for (int igas = 0; igas < NGAS - 1 && !fallback; ++igas) {
+        for (int igas = 0; igas < NGAS - 1 && !fallback; ++igas) {   // @phase fold_setup
             const int g1 = igas + 1;
             const double am1 = __ldg(P.amount + (size_t)g1 * NLAY + l);
             const bool next_neg = __all_sync(FULL, __dmul_rn(KB(NG - 1, g1), am1) <= 0.0);
@@ -366,19 +368,12 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
             if (do_fold && lane < NG) {
                 const double b = __dmul_rn(KB(lane, g1), am1);
                 bv[lane] = b;
-                // a row of the second operand of the product: {b_j, bT_j, 0 .., k_j in the column of gas g1, 0 ..}
-                // (without gradients only column 0 is used: the rest of X and Y stays zero)
-                const double bT = GRAD ? __dmul_rn(DB(lane, g1), am1) : 0.0, kj = GRAD ? KB(lane, g1) : 0.0;
-                double2 *row = reinterpret_cast<double2 *>(Y + lane * L::YS);
-                row[0] = make_double2(b, bT);
-#pragma unroll
-                for (int q = 1; q < XS / 2; ++q)
-                    row[q] = make_double2(2 * q - 2 == g1 ? kj : 0.0, 2 * q - 1 == g1 ? kj : 0.0);
+                if (GRAD) bT[lane] = __dmul_rn(DB(lane, g1), am1);
             }
             __syncwarp();
             if (!do_fold) continue;
 
-            // ---- preconditions and data-independent orders -----------------------------------------
+            // ---- preconditions and data-independent orders -----------------------------------------   // @phase precond
             const int l0 = lane < NG ? lane : NG - 1, l1 = lane + 1 < NG ? lane + 1 : NG - 1;
             const double a_l = av[l0], a_n = av[l1], b_l = bv[l0], b_n = bv[l1];
             const double a_first = av[0], a_last = av[NG - 1], b_first = bv[0], b_last = bv[NG - 1];
@@ -406,7 +401,7 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
             }
             if (fb_why && lane == 0) atomicAdd(fb_why + (ord >= 0 ? 5 : 6), 1);
 
-            constexpr int NT8 = XS / 8;
+            constexpr int NT8 = XS / 8;   // @phase static_mma
             double dfr[3][NT8][2], rsum[3];
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
@@ -415,11 +410,23 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                 for (int n = 0; n < NT8; ++n) dfr[t][n][0] = dfr[t][n][1] = 0.0;
             }
 
+            // second operands of the two products, per lane (fragment row kk = lane & 3, column 8n + (lane >> 2))
+            const double *xp[NT8], *yp[NT8];
+            int xs[NT8], ys[NT8];
+#pragma unroll
+            for (int n = 0; n < NT8; ++n) {
+                const int col = 8 * n + (lane >> 2);
+                xp[n] = X + col;
+                xs[n] = XS;
+                yp[n] = col == 0 ? bv : ((GRAD && col == 1) ? bT : ((GRAD && col == 2 + g1) ? kbuf + g1 : nullptr));
+                ys[n] = (GRAD && col == 2 + g1) ? NGAS : 1;
+            }
+
             if (ord >= 0) {
-                kf_mma<NG, XS, true>(S.stat[ord][0], X, lane, dfr, rsum);
-                kf_mma<NG, XS, false>(S.stat[ord][1], Y, lane, dfr, rsum);
+                kf_mma<NG, XS, true>(S.stat[ord][0], xp, xs, lane, dfr, rsum);
+                kf_mma<NG, XS, false>(S.stat[ord][1], yp, ys, lane, dfr, rsum);
             } else {
-                // ---- 1. packed keys, sorted in registers --------------------------------------------
+                // ---- 1. packed keys, sorted in registers --------------------------------------------   // @phase keys
                 unsigned v[EPL];
                 {
                     const int basehi = (ek - 62) << 20;
@@ -439,7 +446,7 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                         v[r] = ebase < NN ? (((unsigned)t << 6) & 0xfffffe00u) | (unsigned)e : 0xffffffffu;
                     }
                 }
-                kf_sort(v, lane);
+                kf_sort(v, lane);   // @phase sort_call
                 // sorted words for the straddler checks (16-byte units, lane-interleaved: conflict-free)
                 {
                     uint4 *vb4 = reinterpret_cast<uint4 *>(vbuf);
@@ -447,7 +454,7 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                     for (int q = 0; q < EPL / 4; ++q) vb4[q * 32 + lane] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 }
                 if (lane <= NG + 1) spos[lane] = KF_NONE;
-                // ---- 2. cumulative weights, bin of every element, straddlers ------------------------
+                // ---- 2. cumulative weights, bin of every element, straddlers ------------------------   // @phase pass1_scan
                 float wf[EPL];
                 double local = 0.0;
 #pragma unroll
@@ -474,7 +481,7 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                 }
                 __syncwarp();
                 {
-                    double rel = 0.0;
+                    double rel = 0.0;   // @phase pass2
                     double edge_rel = __dsub_rn(S.gord[m + 1], base);
 #pragma unroll
                     for (int r = 0; r < EPL; ++r) {
@@ -490,7 +497,7 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                     }
                 }
                 __syncwarp();
-                // ---- 3. the straddler of edge `lane` ---------------------------------------------------
+                // ---- 3. the straddler of edge `lane` ---------------------------------------------------   // @phase resolve
                 int se = -1;            // element number of the straddler
                 double cw = 0.0;        // (1-frac) * weight: goes to the next bin
                 bool bad = false;
@@ -566,7 +573,7 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                 }
                 if (__any_sync(FULL, bad)) { fallback = true; break; }
                 __syncwarp();       // (the sorted words alias the marginals)
-                // ---- 4. marginals and products ----------------------------------------------------------
+                // ---- 4. marginals and products ----------------------------------------------------------   // @phase marginals
                 {
                     double2 *z = reinterpret_cast<double2 *>(RC);
                     for (int t = lane; t < NN / 2; t += 32) z[t] = make_double2(0.0, 0.0);
@@ -575,7 +582,7 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                 bool wbad = kf_walk<NG, NG, 1>(bin, S.wtabd, RC, lane);
                 __syncwarp();
                 kf_correct<NG>(RC, lane, se >= 0 ? se / NG : -1, cw);
-                kf_mma<NG, XS, true>(RC, X, lane, dfr, rsum);
+                kf_mma<NG, XS, true>(RC, xp, xs, lane, dfr, rsum);
                 __syncwarp();
                 {
                     double2 *z = reinterpret_cast<double2 *>(RC);
@@ -585,11 +592,11 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                 wbad |= kf_walk<NG, 1, NG>(bin, S.wtabd, RC, lane);
                 __syncwarp();
                 kf_correct<NG>(RC, lane, se >= 0 ? se % NG : -1, cw);
-                kf_mma<NG, XS, false>(RC, Y, lane, dfr, rsum);
+                kf_mma<NG, XS, false>(RC, yp, ys, lane, dfr, rsum);
                 if (__any_sync(FULL, wbad)) { fallback = true; why = 16; break; }
             }
             __syncwarp();
-            // ---- bin m: normalise (ForwardModel_0.py:6016-6017, :6026-6027) and store -------------------
+            // ---- bin m: normalise (ForwardModel_0.py:6016-6017, :6026-6027) and store -------------------   // @phase normalise
             {
                 // sum of the marginals of a bin: the four lanes of a fragment row hold a quarter each
                 double *sws = gbs;
@@ -620,7 +627,7 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
         }
 #undef KB
 #undef DB
-        if (fallback) {
+        if (fallback) {   // @phase cell_epilogue
             if (lane == 0) fb_list[atomicAdd(fb_count, 1)] = (int)cell;
             if (fb_why) {
                 const unsigned wm = __reduce_or_sync(FULL, (unsigned)why);
