@@ -43,7 +43,7 @@ template <int NG>
 struct KfShared {
     double gord[NG + 2];            // bin edges, gord[NG+1] = +inf
     double wtabd[NG * NG];          // element weights (float32 products widened)
-    float wtabf[512];               // the same as float32, 0 beyond NG*NG (padding of the sort)
+    float wtabf[NG * NG + 16];      // the same as float32; entry NG*NG = 0 is the padding of the sort
     double stat[2][2][NG * NG];     // [order][rows | columns][m*NG + i]  marginals of the static orders
     unsigned short sstr[2][NG + 1][4];   // [order][edge] -> element before / the straddler / element after
     int ok_f32, ok_static;
@@ -62,8 +62,8 @@ struct KfWarpLayout {
     static constexpr int DBUF = KBUF + NG * NGASMAX;
     static constexpr int GBS = DBUF + (GRAD ? NG * NGASMAX : 0);   // [NG+2] cumulative weight before the straddler
     static constexpr int SPOS = GBS + NG + 2;                     // [NG+2] ints: sorted position of the straddler
-    static constexpr int BIN = SPOS + (NG + 2 + 1) / 2 + 1;       // [512] bytes
-    static constexpr int TOTAL = (BIN + 64 + 1) & ~1;
+    static constexpr int BIN = SPOS + (NG + 2 + 1) / 2 + 1;       // [NG*NG + 16] bytes (entry NG*NG: padding)
+    static constexpr int TOTAL = (BIN + (NG * NG + 16) / 8 + 1) & ~1;
 };
 
 // 32-bit min/max bitonic network over 32*16 packed words, blocked layout (element = 16*lane + r), all-ascending form
@@ -272,7 +272,7 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
     __syncthreads();
     {
         bool ok = true;
-        for (int e = threadIdx.x; e < 512; e += blockDim.x) {
+        for (int e = threadIdx.x; e < NN + 16; e += blockDim.x) {
             float wf = 0.0f;
             if (e < NN) {
                 const int i = e / NG, j = e - i * NG;
@@ -443,7 +443,7 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                         const int e = second ? ebase + n0 + (EPL - 1 - r) : ebase + r;
                         const double key = __dadd_rn(second ? a1 : a0, bv[j]);
                         const int t = max(__double2hiint(key) - basehi, 0);
-                        v[r] = ebase < NN ? (((unsigned)t << 6) & 0xfffffe00u) | (unsigned)e : 0xffffffffu;
+                        v[r] = ebase < NN ? (((unsigned)t << 6) & 0xfffffe00u) | (unsigned)e : (0xfffffe00u | (unsigned)NN);
                     }
                 }
                 kf_sort(v, lane);   // @phase sort_call
@@ -647,14 +647,14 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
     }
 }
 
-// warps per CTA (one CTA per SM): as many as 227 KB of shared memory hold, at most 24 (80 registers per thread)
+// warps per CTA (one CTA per SM): as many as 227 KB of shared memory hold, at most 28 (72 registers per thread)
 template <int NG, int XS, int KG, bool GRAD>
 constexpr int kf_warps()
 {
     constexpr size_t cta = (sizeof(KfShared<NG>) + 15) & ~(size_t)15;
     constexpr size_t per_warp = (size_t)KfWarpLayout<NG, XS, KG, GRAD>::TOTAL * 8;
     constexpr size_t fit = (232448 - cta) / per_warp;
-    return fit > 24 ? 24 : (int)fit;
+    return fit > 28 ? 28 : (int)fit;
 }
 
 template <int NG, int XS, int KG, bool GRAD>
