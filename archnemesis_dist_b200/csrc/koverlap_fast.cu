@@ -422,10 +422,10 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                 ys[n] = (GRAD && col == 2 + g1) ? NGAS : 1;
             }
 
-            if (ord >= 0) {
-                kf_mma<NG, XS, true>(S.stat[ord][0], xp, xs, lane, dfr, rsum);
-                kf_mma<NG, XS, false>(S.stat[ord][1], yp, ys, lane, dfr, rsum);
-            } else {
+            int se = -1;            // element number of the straddler of edge `lane`
+            double cw = 0.0;        // (1-frac) * its weight: goes to the next bin
+            bool wbad = false;
+            if (ord < 0) {
                 // ---- 1. packed keys, sorted in registers --------------------------------------------   // @phase keys
                 unsigned v[EPL];
                 {
@@ -498,8 +498,6 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                 }
                 __syncwarp();
                 // ---- 3. the straddler of edge `lane` ---------------------------------------------------   // @phase resolve
-                int se = -1;            // element number of the straddler
-                double cw = 0.0;        // (1-frac) * weight: goes to the next bin
                 bool bad = false;
                 if (lane >= 1 && lane <= NG) {
                     const int p = spos[lane];
@@ -579,10 +577,13 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                     for (int t = lane; t < NN / 2; t += 32) z[t] = make_double2(0.0, 0.0);
                 }
                 __syncwarp();
-                bool wbad = kf_walk<NG, NG, 1>(bin, S.wtabd, RC, lane);
+                wbad = kf_walk<NG, NG, 1>(bin, S.wtabd, RC, lane);
                 __syncwarp();
                 kf_correct<NG>(RC, lane, se >= 0 ? se / NG : -1, cw);
-                kf_mma<NG, XS, true>(RC, xp, xs, lane, dfr, rsum);
+            }
+            // (one copy of each product for both kinds of fold: the hot code must stay inside the instruction cache)
+            kf_mma<NG, XS, true>(ord >= 0 ? S.stat[ord][0] : RC, xp, xs, lane, dfr, rsum);
+            if (ord < 0) {
                 __syncwarp();
                 {
                     double2 *z = reinterpret_cast<double2 *>(RC);
@@ -592,9 +593,9 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                 wbad |= kf_walk<NG, 1, NG>(bin, S.wtabd, RC, lane);
                 __syncwarp();
                 kf_correct<NG>(RC, lane, se >= 0 ? se % NG : -1, cw);
-                kf_mma<NG, XS, false>(RC, yp, ys, lane, dfr, rsum);
-                if (__any_sync(FULL, wbad)) { fallback = true; why = 16; break; }
             }
+            kf_mma<NG, XS, false>(ord >= 0 ? S.stat[ord][1] : RC, yp, ys, lane, dfr, rsum);
+            if (__any_sync(FULL, wbad)) { fallback = true; why = 16; break; }
             __syncwarp();
             // ---- bin m: normalise (ForwardModel_0.py:6016-6017, :6026-6027) and store -------------------   // @phase normalise
             {
