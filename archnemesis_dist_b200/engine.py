@@ -226,7 +226,10 @@ class HotPath:
             out = self.ops.gas_opacity(self.table, s.dplan, s.amount, self.otab, s.grad)
         if timers is not None:
             timers[1].record()
-        self.launches += 1
+        if self.lbl_table:
+            self.launches += 1
+        else:
+            self.launches += self.ops.overlap_kernel_launches(self.otab.NG, self.table.shape[4], self.otab.seq)
         return out
 
     def run(self, s, timers=None):

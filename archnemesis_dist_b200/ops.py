@@ -135,6 +135,13 @@ def overlap_mode(mode=-1):
     return int(_lib.load().ansb200_overlap_mode(int(mode)))
 
 
+def overlap_kernel_launches(NG, NGAS, seq=False):
+    """Kernels one ansb200_koverlap / ansb200_gas_opacity call launches: the fast kernel plus the general one on its
+    work list where a fast kernel exists (csrc/koverlap_fast.cu: ov_fast_supported), else the general kernel alone."""
+    fast = NG == 20 and 2 <= NGAS <= 14 and not seq and overlap_mode() != 1
+    return 2 if fast else 1
+
+
 def overlap_stats():
     """Counts of the last overlap call made in mode 2: cells handed to the general kernel and why, kinds of folds."""
     import ctypes
