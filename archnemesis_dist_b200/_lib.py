@@ -10,6 +10,8 @@ LIB_PATH = os.path.join(_HERE, "libansb200.so")
 OK, EINVAL, ECUDA, ENOMEM = 0, -1, -2, -3
 RAD_GRAD, RAD_NAN_TO_NUM = 1, 2
 MAX_NG, MAX_NGAS = 22, 15
+MAX_LBL_NGAS = 128      # csrc/klbl.cu: gas sum of the line-by-line-table kernel
+MAX_NCONV = 65535       # csrc/convolve.cu: grid.y
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int

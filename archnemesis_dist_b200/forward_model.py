@@ -30,6 +30,7 @@ import types
 
 import numpy as np
 
+from . import _lib
 from . import engine as _engine
 from . import plan as _plan
 
@@ -220,7 +221,13 @@ def _table_on_device(sp):
     if sp.NGAS < 1 or sp.K is None:
         return False
     ilbl = int(sp.ILBL)
-    return (ilbl == _K_TABLES and np.ndim(sp.K) == 5) or (ilbl == _LBL_TABLES and np.ndim(sp.K) == 4)
+    # shapes beyond the native limits (include/ansb200.h: NG*NG sort keys per warp, gradient columns, gas sum of the
+    # LBL kernel) stay with the reference instead of raising from inside CIRSrad
+    if ilbl == _K_TABLES and np.ndim(sp.K) == 5:
+        return int(sp.NG) <= _lib.MAX_NG and int(sp.NGAS) <= _lib.MAX_NGAS
+    if ilbl == _LBL_TABLES and np.ndim(sp.K) == 4:
+        return int(sp.NGAS) <= _lib.MAX_LBL_NGAS
+    return False
 
 
 class B200HotPathMixin:
@@ -413,6 +420,8 @@ class B200HotPathMixin:
         M = self.Measurement
         if not (self._b200_mode() is not None and int(M.NAV[IGEOM]) == 1 and self.Telluric is None and
                 self.PathX.NPATH == 1):
+            return False
+        if int(M.NCONV[IGEOM]) > _lib.MAX_NCONV:       # grid limit of ans_convolve_kernel: convolve on the host
             return False
         if int(M.IFORM) == _IFORM_INTEGRATED_RADIANCE:
             return float(M.FWHM) < 0.0            # integrate_filterg raises for FWHM >= 0 (Measurement_0.py:2772)

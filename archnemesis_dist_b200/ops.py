@@ -228,7 +228,16 @@ def radiance(mode, tau, dk, gas_slot, taucia, taudust, tauray, dtaucon, layinc, 
 def jacobian_project(dspec, M):
     """dspec[NWAVE,NPATH,NPAR,NLAYMAX] x M[NPATH,NPAR*NLAYMAX,NX] -> [NWAVE,NPATH,NX] (map2pro+map2xvec)."""
     _require_cuda()
+    if dspec.dim() != 4 or M.dim() != 3:
+        raise ValueError("jacobian_project: dspec must be [NWAVE,NPATH,NPAR,NLAYMAX] and M [NPATH,NPAR*NLAYMAX,NX]")
     NWAVE, NPATH, NPAR, NLM = dspec.shape
+    if M.shape[0] != NPATH or M.shape[1] != NPAR * NLM:
+        # (the reference raises a tensordot shape error when xmap and the gradient array disagree, ForwardModel_0.py:5420)
+        raise ValueError("jacobian_project: M is %s, expected (%d, %d, NX) for dspec %s"
+                         % (tuple(M.shape), NPATH, NPAR * NLM, tuple(dspec.shape)))
+    for name, t in (("dspec", dspec), ("M", M)):
+        if t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous():
+            raise ValueError("jacobian_project: %s must be a contiguous float64 CUDA tensor" % name)
     NX = M.shape[2]
     out = torch.empty((NWAVE, NPATH, NX), dtype=torch.float64, device="cuda")
     _lib.check(_lib.load().ansb200_jacobian_project(_ptr(dspec), _ptr(M), NWAVE, NPAR, NLM, NPATH, NX, _ptr(out),
