@@ -630,6 +630,10 @@ def install(archnemesis=None):
     if spec_mod is not None and "read_tables" not in _INSTALLED:
         _INSTALLED["read_tables"] = spec_mod.Spectroscopy_0.read_tables
         spec_mod.Spectroscopy_0.read_tables = make_cached_read_tables(_INSTALLED["read_tables"])
+    # run-time line-by-line cross sections (ILBL = 1: calc_klbl[g]_online, calc_lbltable): the pair loop of
+    # add_line_set_monochromatic_absorption on the device, line lists resident (linedata.py)
+    from . import linedata as _linedata
+    _linedata.install_lbl()
     return cls
 
 
@@ -646,6 +650,8 @@ def uninstall(archnemesis=None):
         sys.modules["archnemesis.ForwardModel_0"].map2xvec = _INSTALLED.pop("map2xvec")
     if "read_tables" in _INSTALLED:
         sys.modules["archnemesis.Spectroscopy_0"].Spectroscopy_0.read_tables = _INSTALLED.pop("read_tables")
+    from . import linedata as _linedata
+    _linedata.uninstall_lbl()
     sys.modules["archnemesis.ForwardModel_0"].ForwardModel_0 = ref_cls
     archnemesis.ForwardModel_0 = ref_cls
     oe = sys.modules.get("archnemesis.OptimalEstimation_0")
