@@ -64,6 +64,79 @@ class Evaluation:
     h2d_bytes: int = field(default=0, init=False)
 
 
+def batch_key(ev: Evaluation):
+    """Evaluations with equal keys can be merged by combine_evaluations (everything that is per evaluation, not per
+    layer or per path, in the C ABI: path type, surface temperature, parameter layout, per-wavenumber surface terms)."""
+    def h(a):
+        return None if a is None else hash(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    return (int(ev.mode), int(ev.ISPACE), float(ev.TSURF), int(ev.NVMR), int(ev.NPAR), tuple(int(g) for g in ev.gas_slot),
+            h(ev.EMISSIVITY), h(ev.xfac), h(ev.SOLFLUX), h(ev.REFLECTANCE), ev.EMTEMP is None, ev.SOL_ANG is None)
+
+
+def combine_evaluations(evs):
+    """Several atmosphere states as ONE evaluation (no gradients): the states' layers are laid side by side on the layer
+    axis (the k-interp plan, the amounts and the continuum terms are per layer; every (wavenumber, layer) cell of the gas
+    opacity is independent) and their paths side by side on the path axis, each path's layer list pointing into its own
+    state's block.  This is how the numerical-Jacobian columns of jacobian_nemesis (ForwardModel_0.py:2184-2361: one
+    forward model per perturbed state-vector element, joblib workers in the reference) become an extra grid dimension
+    of one launch.  Returns (combined Evaluation, [(first path, number of paths)] per state)."""
+    if len({batch_key(e) for e in evs}) != 1:
+        raise ValueError("combine_evaluations: evaluations differ in a per-evaluation quantity (see batch_key)")
+    e0 = evs[0]
+    nlay = [len(e.press_atm) for e in evs]
+    off = np.concatenate([[0], np.cumsum(nlay)]).astype(np.int64)
+    nlm = max(e.LAYINC.shape[0] for e in evs)
+    npath = [e.LAYINC.shape[1] for e in evs]
+    nw = None
+    for e in evs:
+        for a in (e.taucia, e.taudust, e.tauray):
+            if a is not None:
+                nw = a.shape[0]
+
+    def per_layer(name, axis):
+        parts = [getattr(e, name) for e in evs]
+        if all(p is None for p in parts):
+            return None
+        full = []
+        for e, p in zip(evs, parts):
+            if p is None:
+                p = np.zeros((nw, len(e.press_atm)))
+            full.append(np.asarray(p, dtype=np.float64))
+        return np.ascontiguousarray(np.concatenate(full, axis=axis))
+
+    def per_path(name, dtype, shift=False, fill=0):
+        parts = [getattr(e, name) for e in evs]
+        if all(p is None for p in parts):
+            return None
+        out = np.full((nlm, sum(npath)), fill, dtype=dtype)
+        c = 0
+        for i, (e, p) in enumerate(zip(evs, parts)):
+            p = np.asarray(p)
+            blk = p.astype(dtype) + (off[i] if shift else 0)
+            out[:p.shape[0], c:c + p.shape[1]] = blk
+            c += p.shape[1]
+        return out
+
+    def cat1(name, dtype):
+        parts = [getattr(e, name) for e in evs]
+        if all(p is None for p in parts):
+            return None
+        return np.concatenate([np.atleast_1d(np.asarray(p, dtype=dtype)) for p in parts])
+
+    ev = Evaluation(press_atm=np.concatenate([np.asarray(e.press_atm, dtype=np.float64) for e in evs]),
+                    temp=np.concatenate([np.asarray(e.temp, dtype=np.float64) for e in evs]),
+                    amount=np.ascontiguousarray(np.concatenate([np.asarray(e.amount, dtype=np.float64) for e in evs], axis=1)),
+                    gas_slot=e0.gas_slot, NVMR=e0.NVMR, NPAR=e0.NPAR,
+                    LAYINC=per_path("LAYINC", np.int32, shift=True), SCALE=per_path("SCALE", np.float64),
+                    NLAYIN=cat1("NLAYIN", np.int32), EMTEMP=per_path("EMTEMP", np.float64),
+                    LAYPRESS=cat1("LAYPRESS", np.float64), taucia=per_layer("taucia", 1), taudust=per_layer("taudust", 1),
+                    tauray=per_layer("tauray", 1), dtaucon=None, mode=e0.mode, ISPACE=e0.ISPACE, TSURF=e0.TSURF,
+                    EMISSIVITY=e0.EMISSIVITY, xfac=e0.xfac, SOLFLUX=e0.SOLFLUX, REFLECTANCE=e0.REFLECTANCE,
+                    SOL_ANG=cat1("SOL_ANG", np.float64), EMISS_ANG=cat1("EMISS_ANG", np.float64))
+    first = np.concatenate([[0], np.cumsum(npath)])
+    return ev, [(int(first[i]), int(npath[i])) for i in range(len(evs))]
+
+
 class _Stager:
     """Pinned host staging + async H2D on the current stream; counts the bytes it moves."""
     CHUNK_BYTES = 16 << 20

@@ -57,21 +57,31 @@ class _TableCache:
     host array -- and with it the device copy -- is reused when the files, wavemin and wavemax repeat."""
 
     def __init__(self, capacity=4):
+        import threading
         self.capacity = capacity
-        self.items = []   # (key, host K ref, HotPath)
+        self.items = []   # (key, host K ref, HotPath), least recently used first
+        self.lock = threading.Lock()       # (the forward models of a numerical Jacobian run in threads)
 
     def get(self, spec, factory):
         K = spec.K
         key = (id(K), K.shape, str(np.asarray(spec.PRESS).dtype), str(np.asarray(spec.DELG).dtype))
-        for k, ref, hp in self.items:
-            if k == key and ref is K:
-                return hp
-        hp = factory()
-        self.items.append((key, K, hp))
-        while len(self.items) > self.capacity:
-            _, _, old = self.items.pop(0)
-            old.close()
-        return hp
+        with self.lock:
+            for n, (k, ref, hp) in enumerate(self.items):
+                if k == key and ref is K:
+                    self.items.append(self.items.pop(n))      # a hit refreshes the entry
+                    return hp
+            try:
+                hp = factory()
+            except MemoryError:
+                # device memory: drop the other resident tables and try once more
+                while self.items:
+                    self.items.pop(0)[2].close()
+                hp = factory()
+            self.items.append((key, K, hp))
+            while len(self.items) > self.capacity:
+                _, _, old = self.items.pop(0)
+                old.close()
+            return hp
 
 
 _TABLES = _TableCache()
@@ -89,7 +99,9 @@ def make_cached_read_tables(ref_read_tables, capacity=4):
     an edited table is read again.  Run-time line-by-line, on-line HDF5 tables and objects without LOCATION go
     straight to the reference method."""
     import os
-    cache = []      # [(key, WAVE, K)]
+    import threading
+    cache = []      # [(key, WAVE, K)], least recently used first
+    lock = threading.Lock()
 
     def stamp(path):
         for cand in (path, path + ".kta", path + ".lta", path + ".h5"):
@@ -110,18 +122,24 @@ def make_cached_read_tables(ref_read_tables, capacity=4):
         key = (ilbl, tuple(stamp(str(f)) for f in self.LOCATION), float(wavemin), float(wavemax),
                len(W), float(W[0]) if len(W) else 0.0, float(W[-1]) if len(W) else 0.0,
                int(self.NG), int(self.NP), int(self.NT), int(self.NGAS))
-        for k, wave, K in cache:
-            if k == key:
-                self.WAVE, self.NWAVE, self.K = wave, len(wave), K
-                read_tables.hits += 1
-                return None
-        out = ref_read_tables(self, wavemin=wavemin, wavemax=wavemax, wavedelta=wavedelta)
-        if isinstance(self.K, np.ndarray) and isinstance(self.WAVE, np.ndarray):
-            self.K.setflags(write=False)          # shared between evaluations from now on
-            self.WAVE.setflags(write=False)
-            cache.append((key, self.WAVE, self.K))
-            del cache[:-capacity]
-        return out
+        if any(st[1] is None for st in key[1]):
+            # a table file that cannot be stat'ed (resolved some other way by the reader): nothing to tell a stale
+            # entry by, so do not memoise
+            return ref_read_tables(self, wavemin=wavemin, wavemax=wavemax, wavedelta=wavedelta)
+        with lock:      # (one reader at a time: concurrent forward models of a numerical Jacobian share the result)
+            for n, (k, wave, K) in enumerate(cache):
+                if k == key:
+                    cache.append(cache.pop(n))
+                    self.WAVE, self.NWAVE, self.K = wave, len(wave), K
+                    read_tables.hits += 1
+                    return None
+            out = ref_read_tables(self, wavemin=wavemin, wavemax=wavemax, wavedelta=wavedelta)
+            if isinstance(self.K, np.ndarray) and isinstance(self.WAVE, np.ndarray):
+                self.K.setflags(write=False)          # shared between evaluations from now on
+                self.WAVE.setflags(write=False)
+                cache.append((key, self.WAVE, self.K))
+                del cache[:-capacity]
+            return out
 
     read_tables.hits = 0
     read_tables.cache = cache
@@ -228,6 +246,73 @@ def _table_on_device(sp):
     if ilbl == _LBL_TABLES and np.ndim(sp.K) == 4:
         return int(sp.NGAS) <= _lib.MAX_LBL_NGAS
     return False
+
+
+class StateBatch:
+    """Rendezvous of the forward models of a numerical Jacobian (jacobian_nemesis, ForwardModel_0.py:2184-2361).
+
+    The reference runs one forward model per perturbed state-vector element in joblib worker processes.  Here every
+    forward model runs the reference's own driver (nemesisfm / nemesisSOfm / ...) in a THREAD of this process; its
+    CIRSrad call hands the host-side inputs of the radiative transfer to this object and waits.  When every live
+    thread waits, all pending evaluations are merged -- the states become one more dimension of the launch
+    (engine.combine_evaluations) -- and run in one gas-opacity + one radiance launch per group of compatible
+    evaluations; the threads then carry on with their own results.  Forward models with several CIRSrad calls
+    (geometries, averaging points) simply meet again."""
+
+    def __init__(self, nthreads):
+        import threading
+        self.cv = threading.Condition()
+        self.active = nthreads
+        self.pending = []
+        self.results = {}
+        self.error = None
+        self.rounds = 0
+        self.launch_groups = 0
+        self.evaluations = 0
+
+    def submit(self, hp, ev):
+        """Called from CIRSrad(return_grad=False) of a worker thread: returns SPECOUT[NWAVE,NPATH] (numpy)."""
+        with self.cv:
+            ticket = object()
+            self.pending.append((ticket, hp, ev))
+            if len(self.pending) >= self.active:
+                self._run_locked()
+            else:
+                while ticket not in self.results and self.error is None:
+                    self.cv.wait()
+            if ticket not in self.results:
+                raise RuntimeError("batched forward models: a companion evaluation failed") from self.error
+            return self.results.pop(ticket)
+
+    def done(self):
+        """A worker thread has finished (or died): it will not submit again."""
+        with self.cv:
+            self.active -= 1
+            if self.pending and len(self.pending) >= self.active:
+                self._run_locked()
+
+    def _run_locked(self):
+        pending, self.pending = self.pending, []
+        try:
+            groups = {}
+            for ticket, hp, ev in pending:
+                groups.setdefault((id(hp), _engine.batch_key(ev)), []).append((ticket, hp, ev))
+            for items in groups.values():
+                hp = items[0][1]
+                if len(items) == 1:
+                    out = hp.to_host(hp.cirsrad(items[0][2], False))
+                    self.results[items[0][0]] = np.array(out)
+                else:
+                    ev, cols = _engine.combine_evaluations([it[2] for it in items])
+                    out = hp.to_host(hp.cirsrad(ev, False))
+                    for (ticket, _, _), (c0, n) in zip(items, cols):
+                        self.results[ticket] = np.array(out[:, c0:c0 + n])
+                self.launch_groups += 1
+                self.evaluations += len(items)
+            self.rounds += 1
+        except BaseException as e:       # noqa: BLE001  (handed to every waiting thread)
+            self.error = e
+        self.cv.notify_all()
 
 
 class B200HotPathMixin:
@@ -376,6 +461,9 @@ class B200HotPathMixin:
             return super().CIRSrad(return_grad)
         hp = self._b200_hotpath()
         ev = self._b200_evaluation(mode, return_grad)
+        batch = getattr(self, "_b200_batch", None)
+        if batch is not None and not return_grad:
+            return batch.submit(hp, ev)           # numerical Jacobian: evaluated together with the other states
         out = hp.cirsrad(ev, return_grad)
         if not return_grad:
             return hp.to_host(out)
@@ -598,6 +686,110 @@ def make_forward_model_class(reference_cls):
                 SPECONV[0:n, IGEOM] = S1[0:n]
                 dSPECONV[0:n, IGEOM, :] = dS1[0:n, :]
             return self.subspecret(SPECONV, dSPECONV)
+
+        b200_max_states = 64          # forward models per rendezvous (threads alive at once)
+
+        def _b200_batchable(self):
+            """Do the forward models of this retrieval reach the device (k-tables or line-by-line tables, no
+            scattering)?  Otherwise the reference's joblib workers are the better tool."""
+            try:
+                return int(self.Spectroscopy.ILBL) in (_K_TABLES, _LBL_TABLES) and int(self.Scatter.ISCAT) == 0 and \
+                    self.Spectroscopy.NGAS >= 1
+            except Exception:      # noqa: BLE001
+                return False
+
+        def jacobian_nemesis(self, NCores=1, nemesisSO=False, nemesisL=False, nemesisC=False, nemesisdisc=False,
+                             nemesisPT=False, analytical_gradient=True):
+            """ForwardModel_0.jacobian_nemesis (archnemesis/ForwardModel_0.py:2184-2361) with the forward models of
+            the numerical columns evaluated together on the device instead of in `NCores` joblib processes (NCores is
+            ignored on that route).  Same outputs: YN[NY], KK[NY,NX].  (Every forward model works on its own copy of the
+            state vector, like the reference's worker processes; with NCores = 1 the reference's joblib runs in-process
+            and leaves Variables.XN at the last perturbed state, which rescales its last numerical column -- not
+            reproduced.)"""
+            if not self._b200_batchable():
+                return super().jacobian_nemesis(NCores=NCores, nemesisSO=nemesisSO, nemesisL=nemesisL, nemesisC=nemesisC,
+                                                nemesisdisc=nemesisdisc, nemesisPT=nemesisPT,
+                                                analytical_gradient=analytical_gradient)
+            import copy
+            import threading
+            V, Mm = self.Variables, self.Measurement
+            V.calc_DSTEP()
+            xnx = np.zeros([V.NX, V.NX + 1], dtype=float)
+            xnx[:, 0] = V.XN
+            xnx[:, 1:] = np.repeat(V.XN[:, None], V.NX, axis=1) + np.diag(V.DSTEP)
+            zeros_mask = xnx[:, 1:] == 0
+            xnx[:, 1:][zeros_mask] = 0.05
+            if analytical_gradient is False:
+                V.NUM[:] = 1
+            ian1 = np.where(V.NUM == 0)[0]
+            iYN = 0
+            KK = np.zeros([Mm.NY, V.NX])
+            if len(ian1) > 0:
+                method = self.select_nemesis_fm(nemesisSO=nemesisSO, nemesisL=nemesisL, nemesisC=nemesisC,
+                                                nemesisdisc=nemesisdisc, nemesisPT=nemesisPT, analytical_gradient=True)
+                SPECMOD, dSPECMOD = method()
+                YN = np.zeros(Mm.NY)
+                ik = 0
+                for igeom in range(Mm.NGEOM):
+                    n = Mm.NCONV[igeom]
+                    YN[ik:ik + n] = SPECMOD[0:n, igeom]
+                    KK[ik:ik + n, :] = dSPECMOD[0:n, igeom, :]
+                    ik += n
+                iYN = 1
+            inum = np.where((V.NUM == 1) & (V.FIX == 0))[0]
+            if iYN == 0:
+                nfm = len(inum) + 1
+                ixrun = np.zeros(nfm, dtype='int32')
+                ixrun[1:nfm] = inum[:] + 1
+            else:
+                nfm = len(inum)
+                ixrun = np.zeros(nfm, dtype='int32')
+                ixrun[0:nfm] = inum[:] + 1
+            YNtot = np.zeros((Mm.NY, nfm))
+            self.b200_batch_stats = dict(forward_models=nfm, rounds=0, launch_groups=0, evaluations=0)
+            for lo in range(0, nfm, self.b200_max_states):
+                hi = min(nfm, lo + self.b200_max_states)
+                batch = StateBatch(hi - lo)
+                cols, errors = {}, []
+
+                def worker(ifm):
+                    try:
+                        # (what a joblib worker gets by pickling: its own forward model; the base objects are only
+                        # read -- nemesisfm copies them into the *X attributes before changing anything)
+                        fm = copy.copy(self)
+                        fm.Variables = copy.deepcopy(self.Variables)
+                        fm.Measurement = copy.deepcopy(self.Measurement)
+                        fm._b200_batch = batch
+                        out = fm.execute_fm((ifm, nfm, xnx, ixrun, nemesisSO, nemesisL, nemesisC, nemesisdisc, nemesisPT,
+                                             np.zeros((Mm.NY, nfm)), 1))
+                        cols[ifm] = out[:, ifm]
+                    except BaseException as e:      # noqa: BLE001
+                        errors.append(e)
+                    finally:
+                        batch.done()
+
+                threads = [threading.Thread(target=worker, args=(ifm,), name="ansb200-fm-%d" % ifm) for ifm in range(lo, hi)]
+                for t in threads:
+                    t.start()
+                for t in threads:
+                    t.join()
+                if errors:
+                    raise errors[0]
+                for ifm in range(lo, hi):
+                    YNtot[:, ifm] = cols[ifm]
+                for k in ("rounds", "launch_groups", "evaluations"):
+                    self.b200_batch_stats[k] += getattr(batch, k)
+            if iYN == 0 and nfm > 0:
+                YN = np.zeros(Mm.NY)
+                YN[:] = YNtot[0:Mm.NY, 0]
+            for i in range(len(inum)):
+                ifm = i + 1 if iYN == 0 else i
+                xn1 = V.XN[inum[i]] * 1.05
+                if xn1 == 0.0:
+                    xn1 = 0.05
+                if V.FIX[inum[i]] == 0:
+                    KK[:, inum[i]] = (YNtot[:, ifm] - YN) / (xn1 - V.XN[inum[i]])
+            return YN, KK
 
     ForwardModel_B200.__name__ = "ForwardModel_B200"
     return ForwardModel_B200

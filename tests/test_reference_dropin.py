@@ -125,3 +125,72 @@ def test_line_by_line_table_deck_matches_reference():
     for ix in range(dS_ref.shape[2]):
         assert colerr(dS[:, :, ix], dS_ref[:, :, ix]) < 1e-12, ix
         assert colerr(dS_lazy[:, :, ix], dS_ref[:, :, ix]) < 1e-12, ix
+
+
+def test_numerical_jacobian_columns_are_batched(jupiter):
+    """jacobian_nemesis(analytical_gradient=False) (ForwardModel_0.py:2184-2361): the reference runs one forward model
+    per free state-vector element (joblib workers); the drop-in runs the same drivers in threads whose CIRSrad calls
+    meet in ONE device evaluation (states laid side by side on the layer / path axes).  Same YN and KK."""
+    ans, deck, mg = jupiter
+    from archnemesis_dist_b200 import forward_model as fmod
+    from tests import cpu_engine
+    ref_cls = sys.modules["archnemesis.ForwardModel_0"].ForwardModel_0
+    cwd = os.getcwd()
+    os.chdir(deck)
+    try:
+        def variables(objs):
+            V = objs["Variables"]
+            V.FIX[:] = 1
+            V.FIX[[3, 40, 77]] = 0          # three free elements -> 1 + 3 forward models
+            return objs
+        ref = mg.make_forward_model(ans, ref_cls, variables(mg.load_jupiter(ans, deck)), deck)
+        XN0 = np.array(ref.Variables.XN)
+        YN_ref, KK_ref = ref.jacobian_nemesis(NCores=1, analytical_gradient=False)
+        # With NCores = 1 joblib runs the forward models in THIS process and execute_fm (:2154) leaves
+        # ref.Variables.XN at the last perturbed state, so the reference divides the last column's difference by
+        # 0.05 * (perturbed value); its worker processes (NCores > 1) and the drop-in keep XN.  Undo that for the
+        # comparison (loky workers cannot import the reference here: h5py is stubbed in this process only).
+        assert ref.Variables.XN[77] != XN0[77] and np.array_equal(np.delete(ref.Variables.XN, 77), np.delete(XN0, 77))
+        KK_ref[:, 77] *= ref.Variables.XN[77] / XN0[77]
+        cls = fmod.install(ans)
+        try:
+            cls.b200_engine = cpu_engine
+            calls = []
+            orig = cpu_engine.HotPath.cirsrad
+
+            def counting(self, ev, return_grad=False):
+                calls.append((len(ev.press_atm), ev.LAYINC.shape[1]))
+                return orig(self, ev, return_grad)
+            cpu_engine.HotPath.cirsrad = counting
+            try:
+                fm = mg.make_forward_model(ans, ans.ForwardModel_0, variables(mg.load_jupiter(ans, deck)), deck)
+                YN, KK = fm.jacobian_nemesis(NCores=4, analytical_gradient=False)
+            finally:
+                cpu_engine.HotPath.cirsrad = orig
+            st = fm.b200_batch_stats
+            # mixed analytic / numerical: NUM = 0 elements come from nemesisfmg, the rest from the batch
+            fm2 = mg.make_forward_model(ans, ans.ForwardModel_0, variables(mg.load_jupiter(ans, deck)), deck)
+            fm2.Variables.NUM[:] = 0
+            fm2.Variables.NUM[40] = 1
+            YN2, KK2 = fm2.jacobian_nemesis()
+        finally:
+            fmod.uninstall(ans)
+        ref2 = mg.make_forward_model(ans, ref_cls, variables(mg.load_jupiter(ans, deck)), deck)
+        ref2.Variables.NUM[:] = 0
+        ref2.Variables.NUM[40] = 1
+        YN2_ref, KK2_ref = ref2.jacobian_nemesis()
+        KK2_ref[:, 40] *= ref2.Variables.XN[40] / XN0[40]       # (the same in-process quirk)
+    finally:
+        os.chdir(cwd)
+    assert st == dict(forward_models=4, rounds=1, launch_groups=1, evaluations=4)
+    nlay = calls[0][0] // 4
+    assert calls == [(4 * nlay, 4)]                 # ONE engine call: four states' layers and paths side by side
+    assert relerr(YN, YN_ref) < 1e-12
+    assert np.array_equal(KK[:, [0, 1, 2, 50]], np.zeros((KK.shape[0], 4)))        # fixed elements stay zero
+    for ix in (3, 40, 77):
+        assert np.abs(KK_ref[:, ix]).max() > 0.0
+        # a forward difference of two spectra that agree to ~1e-13: compare on the scale of the difference quotient
+        assert colerr(KK[:, ix], KK_ref[:, ix]) < 1e-8, ix
+    assert relerr(YN2, YN2_ref) < 1e-12
+    for ix in range(KK2_ref.shape[1]):
+        assert colerr(KK2[:, ix], KK2_ref[:, ix]) < (1e-8 if ix == 40 else 1e-11), ix
