@@ -811,6 +811,17 @@ def install(archnemesis=None):
     oe = sys.modules.get("archnemesis.OptimalEstimation_0")
     if oe is not None and hasattr(oe, "ForwardModel_0"):
         oe.ForwardModel_0 = cls
+    # the optimal-estimation algebra under coreretOE: coreretOE builds its solver object with
+    # `from archnemesis import OptimalEstimation_0` (OptimalEstimation_0.py:1254, :1263), i.e. through the package
+    # attribute, which -- like ForwardModel_0 -- is the class
+    if oe is not None and hasattr(oe, "OptimalEstimation_0"):
+        from . import oe as _oe_mod
+        if "oe_reference" not in _INSTALLED:
+            _INSTALLED["oe_reference"] = oe.OptimalEstimation_0
+        oe_cls = _oe_mod.make_oe_class(_INSTALLED["oe_reference"])
+        _INSTALLED["oe_cls"] = oe_cls
+        oe.OptimalEstimation_0 = oe_cls
+        archnemesis.OptimalEstimation_0 = oe_cls
     # the two module functions every driver calls by bare name after CIRSrad: with them
     # rebound, nemesisSOfmg / nemesisLfmg / process_IAV get the fused device projection unchanged
     if "map2pro" not in _INSTALLED:
@@ -844,6 +855,11 @@ def uninstall(archnemesis=None):
         sys.modules["archnemesis.Spectroscopy_0"].Spectroscopy_0.read_tables = _INSTALLED.pop("read_tables")
     from . import linedata as _linedata
     _linedata.uninstall_lbl()
+    if "oe_reference" in _INSTALLED:
+        oe_ref = _INSTALLED.pop("oe_reference")
+        _INSTALLED.pop("oe_cls", None)
+        sys.modules["archnemesis.OptimalEstimation_0"].OptimalEstimation_0 = oe_ref
+        archnemesis.OptimalEstimation_0 = oe_ref
     sys.modules["archnemesis.ForwardModel_0"].ForwardModel_0 = ref_cls
     archnemesis.ForwardModel_0 = ref_cls
     oe = sys.modules.get("archnemesis.OptimalEstimation_0")

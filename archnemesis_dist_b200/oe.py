@@ -68,21 +68,43 @@ def calc_serr(DD, AA, SA, SE, simple=False):
     return SM, SN, SN + SM
 
 
+def _np(a):
+    return a.cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+
+
 class OptimalEstimationDeviceMixin:
     """The four methods over an OptimalEstimation_0-like object; results land on the attributes the reference
-    sets, as numpy arrays.  ``class OE_B200(OptimalEstimationDeviceMixin, archnemesis.OptimalEstimation_0)``."""
+    sets, as numpy arrays.  ``class OE_B200(OptimalEstimationDeviceMixin, archnemesis.OptimalEstimation_0)`` is what
+    ``forward_model.install()`` puts under ``coreretOE`` (OptimalEstimation_0.py:1263).  `b200_oe` is the module
+    whose functions do the algebra (this one; tests substitute an oracle-backed namespace on CPU-only machines)."""
+
+    b200_oe = None
+
+    def _oe(self):
+        import sys
+        return self.b200_oe if self.b200_oe is not None else sys.modules[__name__]
 
     def calc_gain_matrix(self):
-        DD, AA = calc_gain_matrix(self.KK, self.SA, self.SE)
-        self.DD, self.AA = DD.cpu().numpy(), AA.cpu().numpy()
+        DD, AA = self._oe().calc_gain_matrix(self.KK, self.SA, self.SE)
+        self.DD, self.AA = _np(DD), _np(AA)
 
     def calc_phiret(self):
-        self.CHISQ, self.PHI = calc_phiret(self.Y[:self.NY], self.YN[:self.NY], self.XN[:self.NX], self.XA[:self.NX],
-                                           self.SE, self.SA)
+        self.CHISQ, self.PHI = self._oe().calc_phiret(self.Y[:self.NY], self.YN[:self.NY], self.XN[:self.NX],
+                                                      self.XA[:self.NX], self.SE, self.SA)
+        assert not np.isnan(self.PHI), "PHI cannot be NAN"
+        assert not np.isnan(self.CHISQ), "CHISQ cannot be NAN"
 
     def calc_next_xn(self):
-        return calc_next_xn(self.XA, self.XN, self.Y, self.YN, self.DD, self.AA).cpu().numpy()
+        return _np(self._oe().calc_next_xn(self.XA, self.XN, self.Y, self.YN, self.DD, self.AA))
 
     def calc_serr(self, simple=False):
-        SM, SN, ST = calc_serr(self.DD, self.AA, self.SA, self.SE, simple)
-        self.SM, self.SN, self.ST = SM.cpu().numpy(), SN.cpu().numpy(), ST.cpu().numpy()
+        SM, SN, ST = self._oe().calc_serr(self.DD, self.AA, self.SA, self.SE, simple)
+        self.SM, self.SN, self.ST = _np(SM), _np(SN), _np(ST)
+
+
+def make_oe_class(reference_cls):
+    """OE_B200: the reference's OptimalEstimation_0 with the four algebra methods on the device."""
+    cls = type("OE_B200", (OptimalEstimationDeviceMixin, reference_cls),
+               {"__doc__": (reference_cls.__doc__ or "") + "\n\n(B200: gain matrix, cost function, state update and error "
+                                                              "covariances on the device -- archnemesis_dist_b200.oe)"})
+    return cls

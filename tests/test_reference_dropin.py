@@ -194,3 +194,54 @@ def test_numerical_jacobian_columns_are_batched(jupiter):
     assert relerr(YN2, YN2_ref) < 1e-12
     for ix in range(KK2_ref.shape[1]):
         assert colerr(KK2[:, ix], KK2_ref[:, ix]) < (1e-8 if ix == 40 else 1e-11), ix
+
+
+def test_coreretOE_runs_on_the_dropin_classes(jupiter):
+    """One optimal-estimation retrieval (OptimalEstimation_0.coreretOE, :1173-1585; two iterations) with install():
+    the forward model AND the solver object coreretOE builds are the drop-in classes (ForwardModel_B200, OE_B200 --
+    gain matrix, cost function, state update, error covariances on the engine), against the unmodified reference."""
+    ans, deck, mg = jupiter
+    from archnemesis_dist_b200 import forward_model as fmod
+    from tests import cpu_engine
+    from oracle import oracle as orc
+    import types
+    oe_mod = sys.modules["archnemesis.OptimalEstimation_0"]
+    oracle_oe = types.SimpleNamespace(calc_gain_matrix=orc.oe_gain_matrix, calc_phiret=orc.oe_phiret,
+                                      calc_next_xn=orc.oe_next_xn, calc_serr=orc.oe_serr)
+    cwd = os.getcwd()
+    os.chdir(deck)
+
+    def retrieve():
+        o = mg.load_jupiter(ans, deck)
+        return oe_mod.coreretOE(os.path.join(deck, "cirstest"), o["Variables"], o["Measurement"], o["Atmosphere"],
+                                o["Spectroscopy"], o["Scatter"], o["Stellar"], o["Surface"], o["CIA"], o["Layer"], None,
+                                NITER=2, PHILIMIT=0.0, NCores=1)
+    try:
+        ref = retrieve()
+        ref_cls = type(ref)
+        cls = fmod.install(ans)
+        try:
+            cls.b200_engine = cpu_engine
+            oe_cls = fmod._INSTALLED["oe_cls"]
+            assert ans.OptimalEstimation_0 is oe_cls and oe_mod.OptimalEstimation_0 is oe_cls
+            assert issubclass(oe_cls, ref_cls) and oe_cls.__name__ == "OE_B200"
+            oe_cls.b200_oe = oracle_oe
+            calls = []
+            for name in ("calc_gain_matrix", "calc_phiret", "calc_next_xn", "calc_serr"):
+                def wrap(f, name=name):
+                    def g(*a, **k):
+                        calls.append(name)
+                        return f(*a, **k)
+                    return g
+                setattr(oracle_oe, name, wrap(getattr(oracle_oe, name)))
+            got = retrieve()
+        finally:
+            fmod.uninstall(ans)
+        assert ans.OptimalEstimation_0 is ref_cls and oe_mod.OptimalEstimation_0 is ref_cls
+    finally:
+        os.chdir(cwd)
+    assert type(got).__name__ == "OE_B200" and {"calc_gain_matrix", "calc_phiret", "calc_next_xn", "calc_serr"} <= set(calls)
+    assert relerr(got.YN, ref.YN) < 1e-10 and relerr(got.XN, ref.XN) < 1e-9
+    assert abs(got.PHI - ref.PHI) <= 1e-8 * abs(ref.PHI) and abs(got.CHISQ - ref.CHISQ) <= 1e-8 * abs(ref.CHISQ)
+    for name in ("KK", "DD", "AA", "SM", "SN", "ST"):
+        assert colerr(getattr(got, name), getattr(ref, name)) < 1e-8, name
