@@ -61,6 +61,9 @@ class Evaluation:
     REFLECTANCE: Optional[np.ndarray] = None
     SOL_ANG: Optional[np.ndarray] = None
     EMISS_ANG: Optional[np.ndarray] = None
+    # (continuum.ContinuumTables, plan dict): taucia / taudust / tauray / dtaucon are then made on the device from it
+    # (ansb200_continuum) and the four dense arrays above stay None
+    continuum: Optional[tuple] = None
     h2d_bytes: int = field(default=0, init=False)
 
 

@@ -379,6 +379,94 @@ class B200HotPathMixin:
             TAUCIA = None                 # calculate_vertical_cia_opacity returned zeros (:3894-3896)
         return TAUCIA, TAUDUST, TAURAY, (dTAUCON if touched else None)
 
+    # -- continuum terms as a device plan (continuum.py) ------------------------------------------------
+    b200_device_continuum = True       # False: always hand the dense host arrays of _b200_continuum to the engine
+
+    def _b200_rayleigh_factors(self):
+        """(ur[NR,NWAVE], vr[NR,NLAY], vrd[NR,NLAY]) with TAURAY = sum ur*vr, dTAURAY = sum ur*vrd, or None when this
+        Rayleigh mode is not a product of a spectrum and a layer quantity (JOVIAN_AIR: per-layer composition)."""
+        fm = sys.modules["archnemesis.ForwardModel_0"]
+        iray = int(self.ScatterX.IRAY)
+        WAVEC = self.SpectroscopyX.WAVE
+        TOTAM = np.asarray(self.LayerX.TOTAM, dtype=np.float64)
+        if iray == 0:
+            return np.zeros((0, len(WAVEC))), np.zeros((0, len(TOTAM))), np.zeros((0, len(TOTAM)))
+        ispace = fm.WaveUnitEnum(self.MeasurementX.ISPACE)
+        one = np.ones(1)
+        if iray == int(fm.RayleighScatteringModeEnum.GAS_GIANT_ATM):
+            t, d = fm.calc_tau_rayleighj(ispace, WAVEC, one)       # cross section * 1.0: the spectrum itself (:5586-5594)
+        elif iray == int(fm.RayleighScatteringModeEnum.C02_DOMINATED_ATM):
+            t, d = fm.calc_tau_rayleighv2(ispace, WAVEC, one)
+        else:
+            return None
+        if not np.array_equal(t[:, 0], d[:, 0]):
+            return None
+        return t[:, 0][None, :].copy(), TOTAM[None, :].copy(), np.ones((1, len(TOTAM)))
+
+    def _b200_dust_spectra(self):
+        """ud[NDUST,NWAVE] = kext * 1e-4 exactly as calc_tau_dust interpolates it (:4832-4863): the reference routine
+        itself on a one-layer column of unit density.  Applies the same renormalisation of LayerX.CONT (:4834-4835)."""
+        nd = int(self.ScatterX.NDUST)
+        NW = self.SpectroscopyX.NWAVE
+        if nd == 0:
+            return np.zeros((0, NW))
+        lay = self.LayerX
+        for i in range(nd):
+            if i in self.AtmosphereX.DUST_RENORMALISATION.keys():
+                lay.CONT[:, i] = lay.CONT[:, i] / lay.CONT[:, i].sum() * 1e4 * self.AtmosphereX.DUST_RENORMALISATION[i]
+        unit = types.SimpleNamespace(NLAY=1, CONT=np.ones((1, nd)))
+        saved = self.AtmosphereX.DUST_RENORMALISATION
+        self.AtmosphereX.DUST_RENORMALISATION = {}
+        try:
+            _, TAUCLSCAT, dT, dS = self.calc_tau_dust(Layer=unit)
+        finally:
+            self.AtmosphereX.DUST_RENORMALISATION = saved
+        # (side products the reference keeps on LayerX: scattering opacities, as _b200_continuum sets them)
+        ksca = np.ascontiguousarray(dS[:, 0, :].T)
+        self.LayerX.TAUCLSCAT = ksca.T[:, None, :] * np.asarray(lay.CONT)[None, :, :nd]
+        self.LayerX.TAUSCAT = np.sum(self.LayerX.TAUCLSCAT, 2)
+        return np.ascontiguousarray(dT[:, 0, :].T)
+
+    def _b200_continuum_plan(self, hp):
+        """(tables, plan) for ansb200_continuum, or None when some term is outside what the plan expresses (then the
+        dense arrays of _b200_continuum are sent instead)."""
+        from . import continuum as _cont
+        if not self.b200_device_continuum or not hasattr(hp, "continuum_tables"):
+            return None
+        atm, lay = self.AtmosphereX, self.LayerX
+        if atm.NVMR + 2 > _cont.MAX_SLOTS:
+            return None
+        ray = self._b200_rayleigh_factors()
+        if ray is None:
+            return None
+        cia = getattr(self, "CIAX", None)
+        fm = sys.modules["archnemesis.ForwardModel_0"]
+        WAVEC = self.SpectroscopyX.WAVE
+
+        def make_tables():
+            cia_mod = sys.modules.get("archnemesis.CIA_0")
+            if cia_mod is None:
+                import importlib
+                cia_mod = importlib.import_module("archnemesis.CIA_0")
+            gas_enum = sys.modules["archnemesis"].enum.GasEnum
+            return _cont.build_tables(int(self.MeasurementX.ISPACE), WAVEC, cia, atm,
+                                      (cia_mod.co2cia, cia_mod.n2n2cia, cia_mod.n2h2cia), gas_enum)
+        if cia is None:
+            key = ("nocia", len(WAVEC))
+        else:
+            kc = np.ascontiguousarray(cia.K_CIA)
+            key = (hash(kc.tobytes()), kc.shape, hash(np.ascontiguousarray(cia.WAVEN).tobytes()),
+                   hash(np.ascontiguousarray(WAVEC).tobytes()), tuple(int(x) for x in atm.ID), tuple(int(x) for x in atm.ISO),
+                   int(cia.INORMAL), tuple(int(x) for x in cia.INORMALT), tuple(int(x) for x in cia.IPAIRG1),
+                   tuple(int(x) for x in cia.IPAIRG2), int(self.MeasurementX.ISPACE))
+        tables = hp.continuum_tables(key, make_tables)
+        ud = self._b200_dust_spectra()
+        plan = _cont.build_plan(tables, cia, atm, lay, int(self.ScatterX.NDUST), ray, ud, _SQ_CM_TO_SQ_METER)
+        if plan is None:
+            return None
+        del fm
+        return tables, plan
+
     def _b200_surface_terms(self, mode):
         """xfac, EMISSIVITY, SOLFLUX, REFLECTANCE as calculate_thermal_emission_spectrum
         (ForwardModel_0.py:4157-4213) / calculate_transmission_spectrum (:4113-4119) prepare them."""
@@ -416,7 +504,11 @@ class B200HotPathMixin:
         amount = np.zeros((sp.NGAS, lay.NLAY))
         for i in range(sp.NGAS):
             amount[i, :] = lay.AMOUNT[:, gas_slot[i]] * _SQ_CM_TO_SQ_METER      # :3861
-        TAUCIA, TAUDUST, TAURAY, dTAUCON = self._b200_continuum(return_grad)
+        cplan = self._b200_continuum_plan(self._b200_hotpath())
+        if cplan is None:
+            TAUCIA, TAUDUST, TAURAY, dTAUCON = self._b200_continuum(return_grad)
+        else:
+            TAUCIA = TAUDUST = TAURAY = dTAUCON = None       # made on the device from the plan
         xfac, EMISSIVITY, SOLFLUX, REFLECTANCE = self._b200_surface_terms(mode)
         NPAR = atm.NVMR + 2 + self.ScatterX.NDUST
         return _engine.Evaluation(
@@ -426,7 +518,7 @@ class B200HotPathMixin:
             ISPACE=int(self.MeasurementX.ISPACE), TSURF=float(self.SurfaceX.TSURF), EMISSIVITY=EMISSIVITY, xfac=xfac,
             SOLFLUX=SOLFLUX, REFLECTANCE=REFLECTANCE,
             SOL_ANG=None if return_grad else np.asarray(path.SOL_ANG, dtype=np.float64),
-            EMISS_ANG=None if return_grad else np.asarray(path.EMISS_ANG, dtype=np.float64))
+            EMISS_ANG=None if return_grad else np.asarray(path.EMISS_ANG, dtype=np.float64), continuum=cplan)
 
     # -- overridden reference methods ------------------------------------------------------------
     def calculate_gaseous_line_opacity(self, return_grad=False):

@@ -495,3 +495,66 @@ def oe_serr(DD, AA, SA, SE, simple=False):
     b[np.diag_indices_from(b)] -= 1.0
     SN = (b @ SA) @ b.T
     return SM, SN, SN + SM
+
+
+# ----------------------------------------------------------------------------------------------
+# continuum plan (archnemesis_dist_b200.continuum): numpy evaluation in the reference's order of operations
+# (calc_tau_cia :4688-4776, calculate_layer_opacity :3938-3981, calc_tau_dust :4858-4863, calc_tau_rayleigh*)
+# ----------------------------------------------------------------------------------------------
+def continuum_eval(tables, plan, want_grad=True):
+    """TAUCIA, TAUDUST, TAURAY [NWAVE,NLAY] (None where the reference has none) and dTAUCON[NWAVE,NPAR,NLAY] from a
+    continuum plan."""
+    kw, npl = tables.kw, tables.nplanes
+    NW = tables.meta["NWAVE"]
+    NLAY, NVMR, NDUST, NPAR = plan["NLAY"], plan["NVMR"], plan["NDUST"], plan["NPAR"]
+    NS = NVMR + 2
+    taucia = np.zeros((NW, NLAY)) if plan["has_cia"] else None
+    dcia = np.zeros((NW, NLAY, NS))
+    for l in range(NLAY):
+        fhh_t, fhl_t, fhh_f, fhl_f, dfhldT = plan["wt"][l]
+        sum1 = np.zeros(NW)
+        for t in range(plan["NTERM"]):
+            if npl[t] > 1:          # a cross-section table: four (para, T) planes of this layer
+                a, b, c, d = (kw[t, p] for p in plan["pl"][l])
+                ktlo = a * fhh_t + b * fhl_t
+                kthi = c * fhh_t + d * fhl_t
+                k = ktlo * fhh_f + kthi * fhl_f
+                dk = (kthi - ktlo) * dfhldT
+            else:                   # a fixed spectrum (co2cia, n2n2cia, n2h2cia)
+                k, dk = kw[t, 0], None
+            q1, q2 = plan["q1"][t, l], plan["q2"][t, l]
+            sum1 = sum1 + k * q1 * q2
+            sa, sb, st = plan["slots"][t]
+            if sa >= 0:
+                dcia[:, l, sa] = dcia[:, l, sa] + plan["ca"][t, l] * k
+            if sb >= 0:
+                dcia[:, l, sb] = dcia[:, l, sb] + plan["cb"][t, l] * k
+            if st >= 0 and dk is not None:
+                dcia[:, l, st] = dcia[:, l, st] + dk * q1 * q2
+        if taucia is not None:
+            taucia[:, l] = sum1 * plan["xfac"][l]
+        dcia[:, l, :] = dcia[:, l, :] * plan["xfac"][l]
+    NR = plan["ur"].shape[0]
+    tauray = np.zeros((NW, NLAY))
+    dray = np.zeros((NW, NLAY))
+    for r in range(NR):
+        tauray = tauray + plan["ur"][r][:, None] * plan["vr"][r][None, :]
+        dray = dray + plan["ur"][r][:, None] * plan["vrd"][r][None, :]
+    taud1 = np.zeros((NW, NLAY, NDUST))
+    for i in range(NDUST):
+        taud1[:, :, i] = plan["ud"][i][:, None] * plan["vd"][i][None, :]
+    taud1 = np.clip(np.nan_to_num(taud1), 0, 1e20)
+    taudust = np.sum(taud1, 2)
+    if not want_grad:
+        return taucia, taudust, tauray, None
+    dtaucon = np.zeros((NW, NPAR, NLAY))
+    if plan["has_cia"]:
+        dtaucon[:, 0:NVMR, :] = dtaucon[:, 0:NVMR, :] + np.transpose(
+            np.transpose(dcia[:, :, 0:NVMR], axes=(2, 0, 1)) / plan["totam"], axes=(1, 0, 2))
+        dtaucon[:, NVMR, :] = dtaucon[:, NVMR, :] + dcia[:, :, NVMR]
+    if NR > 0:
+        for i in range(NVMR):
+            dtaucon[:, i, :] = dtaucon[:, i, :] + dray
+    for i in range(NDUST):
+        dtaucon[:, NVMR + 1 + i, :] = dtaucon[:, NVMR + 1 + i, :] + plan["ud"][i][:, None]
+    return taucia, taudust, tauray, dtaucon

@@ -25,7 +25,24 @@ class HotPath:
     def stage(self, ev, return_grad, M=None):
         s = Staged()
         s.ev, s.grad, s.M = ev, return_grad, M
+        if getattr(ev, "continuum", None) is not None:
+            # the device makes the dense continuum arrays from the plan (ansb200_continuum); here the oracle does
+            import copy
+            tables, cplan = ev.continuum
+            ev = copy.copy(ev)
+            ev.taucia, ev.taudust, ev.tauray, ev.dtaucon = orc.continuum_eval(tables, cplan, return_grad)
+            s.ev = ev
+            HotPath.continuum_plans += 1
         return s
+
+    continuum_plans = 0
+
+    def continuum_tables(self, key, factory):
+        cache = self.__dict__.setdefault("_cont_tables", {})
+        if key not in cache:
+            cache.clear()
+            cache[key] = factory()
+        return cache[key]
 
     def gas_opacity(self, s, timers=None):
         ev = s.ev
