@@ -30,6 +30,8 @@ EXPORTS = {
     "ansb200_table_lnk": (_vp, [_vp]),
     "ansb200_kinterp": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "ansb200_koverlap": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "ansb200_continuum": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i,
+                                _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "ansb200_gas_opacity": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "ansb200_radiance": (_i, [_i, _u] + [_vp] * 20 + [_i, _d] + [_i] * 8 + [_vp] * 4),
     "ansb200_jacobian_project": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),

@@ -19,6 +19,7 @@ from . import ops as _ops
 from . import plan as _plan
 
 THERMAL, TRANSMISSION = 0, 1
+_CONT_LOCK = __import__("threading").Lock()
 _PINNED_OUT = {}                  # (shape, dtype) -> pinned host buffer of HotPath.to_host
 _PINNED_OUT_MAX = 64 << 20
 
@@ -72,8 +73,12 @@ def batch_key(ev: Evaluation):
     layer or per path, in the C ABI: path type, surface temperature, parameter layout, per-wavenumber surface terms)."""
     def h(a):
         return None if a is None else hash(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    cont = None
+    if ev.continuum is not None:
+        tables, plan = ev.continuum
+        cont = (id(tables), h(plan["ur"]), h(plan["ud"]), plan["slots"].tobytes(), int(plan["NDUST"]), bool(plan["has_cia"]))
     return (int(ev.mode), int(ev.ISPACE), float(ev.TSURF), int(ev.NVMR), int(ev.NPAR), tuple(int(g) for g in ev.gas_slot),
-            h(ev.EMISSIVITY), h(ev.xfac), h(ev.SOLFLUX), h(ev.REFLECTANCE), ev.EMTEMP is None, ev.SOL_ANG is None)
+            h(ev.EMISSIVITY), h(ev.xfac), h(ev.SOLFLUX), h(ev.REFLECTANCE), ev.EMTEMP is None, ev.SOL_ANG is None, cont)
 
 
 def combine_evaluations(evs):
@@ -126,6 +131,21 @@ def combine_evaluations(evs):
             return None
         return np.concatenate([np.atleast_1d(np.asarray(p, dtype=dtype)) for p in parts])
 
+    cont = None
+    if e0.continuum is not None:
+        # continuum plans: everything per layer goes side by side like the layers themselves; the spectra and the
+        # resident tables are shared (batch_key)
+        tables, p0 = e0.continuum
+        plans = [e.continuum[1] for e in evs]
+        merged = dict(p0)
+        merged["NLAY"] = int(sum(nlay))
+        for k in ("pl", "wt"):
+            merged[k] = np.ascontiguousarray(np.concatenate([p[k] for p in plans], axis=0))
+        for k in ("q1", "q2", "ca", "cb", "vr", "vrd", "vd"):
+            merged[k] = np.ascontiguousarray(np.concatenate([p[k] for p in plans], axis=1))
+        for k in ("xfac", "totam"):
+            merged[k] = np.concatenate([p[k] for p in plans])
+        cont = (tables, merged)
     ev = Evaluation(press_atm=np.concatenate([np.asarray(e.press_atm, dtype=np.float64) for e in evs]),
                     temp=np.concatenate([np.asarray(e.temp, dtype=np.float64) for e in evs]),
                     amount=np.ascontiguousarray(np.concatenate([np.asarray(e.amount, dtype=np.float64) for e in evs], axis=1)),
@@ -135,7 +155,7 @@ def combine_evaluations(evs):
                     LAYPRESS=cat1("LAYPRESS", np.float64), taucia=per_layer("taucia", 1), taudust=per_layer("taudust", 1),
                     tauray=per_layer("tauray", 1), dtaucon=None, mode=e0.mode, ISPACE=e0.ISPACE, TSURF=e0.TSURF,
                     EMISSIVITY=e0.EMISSIVITY, xfac=e0.xfac, SOLFLUX=e0.SOLFLUX, REFLECTANCE=e0.REFLECTANCE,
-                    SOL_ANG=cat1("SOL_ANG", np.float64), EMISS_ANG=cat1("EMISS_ANG", np.float64))
+                    SOL_ANG=cat1("SOL_ANG", np.float64), EMISS_ANG=cat1("EMISS_ANG", np.float64), continuum=cont)
     first = np.concatenate([[0], np.cumsum(npath)])
     return ev, [(int(first[i]), int(npath[i])) for i in range(len(evs))]
 
@@ -274,8 +294,11 @@ class HotPath:
         st = self._stage
         i32 = torch.int32
         s.gas_slot = st("gas_slot", ev.gas_slot, i32)
-        s.taucia, s.taudust, s.tauray = st("taucia", ev.taucia), st("taudust", ev.taudust), st("tauray", ev.tauray)
-        s.dtaucon = st("dtaucon", ev.dtaucon) if s.grad else None
+        if ev.continuum is not None:
+            s.taucia, s.taudust, s.tauray, s.dtaucon = self._continuum_from_plan(ev.continuum, s.grad)
+        else:
+            s.taucia, s.taudust, s.tauray = st("taucia", ev.taucia), st("taudust", ev.taudust), st("tauray", ev.tauray)
+            s.dtaucon = st("dtaucon", ev.dtaucon) if s.grad else None
         s.layinc, s.scale, s.nlayin = st("layinc", ev.LAYINC, i32), st("scale", ev.SCALE), st("nlayin", ev.NLAYIN, i32)
         s.emtemp, s.laypress = st("emtemp", ev.EMTEMP), st("laypress", ev.LAYPRESS)
         s.emissivity, s.xfac = st("emissivity", ev.EMISSIVITY), st("xfac", ev.xfac)
@@ -285,6 +308,52 @@ class HotPath:
         s.mode, s.ISPACE, s.TSURF, s.NVMR, s.NPAR = ev.mode, ev.ISPACE, ev.TSURF, ev.NVMR, ev.NPAR
         ev.h2d_bytes = st.bytes
         return s
+
+    # -- continuum terms from a plan (continuum.py) ------------------------------------------------------
+    def continuum_tables(self, key, factory):
+        """The resident CIA cross sections for `key` (built by `factory` on a miss; two entries are kept)."""
+        with _CONT_LOCK:          # (the forward models of a numerical Jacobian run in threads)
+            cache = self.__dict__.setdefault("_cont_tables", [])
+            for n, (k, t) in enumerate(cache):
+                if k == key:
+                    cache.append(cache.pop(n))
+                    return t
+            t = factory()
+            t.device = (self.ops.to_dev(t.kw) if t.kw.size else None,
+                        self.ops.to_dev(t.nplanes, torch.int32) if t.nplanes.size else None)
+            cache.append((key, t))
+            del cache[:-2]
+            return t
+
+    def _continuum_from_plan(self, cont, want_grad):
+        """Upload the per-layer coefficients and the few spectra of a continuum plan (one pinned buffer, one copy) and
+        make taucia / taudust / tauray / dtaucon on the device (ansb200_continuum)."""
+        tables, plan = cont
+        if tables.device is None:
+            tables.device = (self.ops.to_dev(tables.kw) if tables.kw.size else None,
+                             self.ops.to_dev(tables.nplanes, torch.int32) if tables.nplanes.size else None)
+        fkeys = ("wt", "q1", "q2", "ca", "cb", "xfac", "totam", "ur", "vr", "vrd", "ud", "vd")
+        ikeys = ("pl", "slots")
+        ints = np.concatenate([np.ascontiguousarray(plan[k], dtype=np.int32).reshape(-1) for k in ikeys])
+        if ints.size & 1:
+            ints = np.concatenate([ints, np.zeros(1, np.int32)])
+        packed = self._stage("continuum_plan", np.concatenate(
+            [np.ascontiguousarray(plan[k], dtype=np.float64).reshape(-1) for k in fkeys] + [ints.view(np.float64)]))
+        dev = {k: plan[k] for k in ("NLAY", "NVMR", "NDUST", "NTERM", "has_cia")}
+        off = 0
+        for k in fkeys:
+            a = plan[k]
+            dev[k] = packed[off:off + a.size].view(a.shape) if a.size else torch.empty(a.shape, dtype=torch.float64, device="cuda")
+            off += a.size
+        iv = packed[off:].view(torch.int32)
+        o2 = 0
+        for k in ikeys:
+            a = plan[k]
+            dev[k] = iv[o2:o2 + a.size].view(a.shape) if a.size else torch.empty(a.shape, dtype=torch.int32, device="cuda")
+            o2 += a.size
+        out = self.ops.continuum(tables.device[0], tables.device[1], dev, self.NWAVE, want_grad)
+        self.launches += 1
+        return out
 
     def stage(self, ev: Evaluation, return_grad, M=None):
         """Copy one evaluation's inputs (pinned staging, async on the current stream) and build the

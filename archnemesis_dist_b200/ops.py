@@ -167,6 +167,27 @@ def gas_opacity(table, dplan, amount, otab, want_grad=False, force_seq=False):
     return (tau, dk) if want_grad else tau
 
 
+def continuum(kw, nplanes, plan, NWAVE, want_grad):
+    """ansb200_continuum: dense continuum arrays on the device from a plan (continuum.build_plan uploaded: a dict of
+    device tensors with the plan's keys).  Returns taucia (None without a CIA object), taudust, tauray [NWAVE,NLAY] and
+    dtaucon[NWAVE,NPAR,NLAY] (None unless want_grad)."""
+    _require_cuda()
+    NLAY, NVMR, NDUST, NTERM = int(plan["NLAY"]), int(plan["NVMR"]), int(plan["NDUST"]), int(plan["NTERM"])
+    NR = int(plan["ur"].shape[0])
+    NPL = int(kw.shape[1]) if kw is not None and kw.dim() == 3 else 1
+    has_cia = bool(plan["has_cia"])
+    taucia = torch.empty((NWAVE, NLAY), dtype=torch.float64, device="cuda") if has_cia else None
+    taudust = torch.empty((NWAVE, NLAY), dtype=torch.float64, device="cuda")
+    tauray = torch.empty((NWAVE, NLAY), dtype=torch.float64, device="cuda")
+    dtaucon = torch.empty((NWAVE, NVMR + 2 + NDUST, NLAY), dtype=torch.float64, device="cuda") if want_grad else None
+    _lib.check(_lib.load().ansb200_continuum(
+        _ptr(kw), _ptr(nplanes), NTERM, NPL, _ptr(plan["pl"]), _ptr(plan["wt"]), _ptr(plan["q1"]), _ptr(plan["q2"]),
+        _ptr(plan["ca"]), _ptr(plan["cb"]), _ptr(plan["slots"]), _ptr(plan["xfac"]), _ptr(plan["totam"]),
+        _ptr(plan["ur"]), _ptr(plan["vr"]), _ptr(plan["vrd"]), NR, _ptr(plan["ud"]), _ptr(plan["vd"]), NDUST, NWAVE, NLAY,
+        NVMR, int(has_cia), int(bool(want_grad)), _ptr(taucia), _ptr(taudust), _ptr(tauray), _ptr(dtaucon), _stream()))
+    return taucia, taudust, tauray, dtaucon
+
+
 class LblDevicePlan:
     """plan.klbl_plan uploaded to the device."""
 

@@ -112,3 +112,55 @@ def make_line_list(nlines, wn_lo, wn_hi, seed=0, n_amb=1, pad=75.0):
         br[3 * (a + 1) + 1] = rng.uniform(0.5, 0.8, nlines)
         br[3 * (a + 1) + 2] = rng.uniform(-0.01, 0.0, nlines)
     return dict(nu=nu, sw=sw, e_lower=e_lower, stim_ref=stim_ref, broadening=br)
+
+
+def make_continuum(nwave, nlay, nvmr, ndust=0, seed=0, npairs=5, ntemp=12, temp=None):
+    """A synthetic continuum plan of the reference's structure (continuum.py): `npairs` collision-induced pairs with
+    cross-section tables on `ntemp` temperatures (one para-H2 plane, as in the reference's isotest.tab), one fixed
+    spectrum, gas-giant Rayleigh scattering and `ndust` aerosols.  Returns (ContinuumTables, plan) with magnitudes like
+    the config-2 synthetic `taucon` (1e-6 .. 1e-2) so that benchmark cases can swap one for the other."""
+    from . import continuum as _cont
+    rng = np.random.default_rng(seed + 11)
+    nterm = npairs + 1
+    wgrid = np.linspace(0.0, 1.0, nwave)
+    kw = np.zeros((nterm, ntemp, nwave))
+    for t in range(npairs):
+        shape = np.exp(-0.5 * ((wgrid - rng.uniform(0.1, 0.9)) / rng.uniform(0.05, 0.4)) ** 2) + 0.05
+        tdep = (1.0 + 0.3 * rng.uniform(-1, 1)) ** np.linspace(-1.0, 1.0, ntemp)
+        kw[t] = 10.0 ** rng.uniform(-46.0, -44.0) * tdep[:, None] * shape[None, :]
+    kw[npairs, 0] = 10.0 ** rng.uniform(-47.0, -46.0) * (1.0 + wgrid)
+    nplanes = np.array([ntemp] * npairs + [1], dtype=np.int32)
+    pairs = [(int(rng.integers(0, nvmr)), int(rng.integers(0, nvmr))) for _ in range(npairs)]
+    ext = int(rng.integers(0, nvmr))
+    terms = [("pair", a, b) for a, b in pairs] + [("co2", ext, ext)]
+    tables = _cont.ContinuumTables(kw, nplanes, dict(terms=terms, NWAVE=nwave, npl=ntemp, has_cia=True))
+    # per layer: temperatures on the table grid, mixing ratios, column densities
+    tgrid = np.linspace(60.0, 320.0, ntemp)
+    temp = np.asarray(temp if temp is not None else 110.0 + 60.0 * np.abs(np.linspace(-1.0, 1.0, nlay)), dtype=np.float64)
+    itl = np.clip(np.searchsorted(tgrid, temp) - 1, 0, ntemp - 2)
+    fhl = (temp - tgrid[itl]) / (tgrid[itl + 1] - tgrid[itl])
+    pl = np.stack([itl, itl + 1, itl, itl + 1], axis=1).astype(np.int32)
+    wt = np.stack([1.0 - fhl, fhl, np.full(nlay, 0.5), np.full(nlay, 0.5), 1.0 / (tgrid[itl + 1] - tgrid[itl])], axis=1)
+    q = rng.dirichlet(np.ones(nvmr), size=nlay)                         # (NLAY, NVMR)
+    totam = 10.0 ** rng.uniform(26.0, 29.0, nlay)                       # m-2
+    xfac = (totam * 1.0e-4) ** 2 / (10.0 ** rng.uniform(5.5, 6.5, nlay))
+    q1 = np.zeros((nterm, nlay))
+    q2 = np.zeros((nterm, nlay))
+    ca = np.zeros((nterm, nlay))
+    cb = np.zeros((nterm, nlay))
+    slots = np.full((nterm, 3), -1, dtype=np.int32)
+    for t, (kind, a, b) in enumerate(terms):
+        q1[t], q2[t] = q[:, a], q[:, b]
+        if kind == "pair":
+            slots[t] = (a, b, nvmr - 2)
+            ca[t], cb[t] = q[:, b], q[:, a]
+        else:
+            slots[t] = (a, -1, -1)
+            ca[t] = 2.0 * q[:, a]
+    ur = (10.0 ** rng.uniform(-33.0, -32.0) * (1.0 + 3.0 * wgrid) ** 4)[None, :]
+    ud = 10.0 ** rng.uniform(-13.0, -12.0, size=(ndust, 1)) * (1.0 + wgrid)[None, :]
+    vd = 10.0 ** rng.uniform(6.0, 9.0, size=(ndust, nlay))
+    plan = dict(NLAY=nlay, NVMR=nvmr, NDUST=ndust, NPAR=nvmr + 2 + ndust, NTERM=nterm, pl=pl, wt=wt, q1=q1, q2=q2,
+                slots=slots, ca=ca, cb=cb, xfac=xfac, totam=totam, ur=ur, ud=ud, vr=totam[None, :].copy(),
+                vrd=np.ones((1, nlay)), vd=vd, has_cia=True)
+    return tables, plan

@@ -50,6 +50,8 @@ def parse():
                     help="rows compared with the CPU oracle after the timed loop (0: every row at N=1, 64 at N>1)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the full CPU pass (parity on 64 rows only)")
     ap.add_argument("--no-extras", action="store_true", help="skip the config 3/4/5 and strong-scaling extras")
+    ap.add_argument("--dense-continuum", action="store_true",
+                    help="continuum terms as dense host arrays [NWAVE,NPAR,NLAY] (36 MB per step over PCIe) instead of the device plan")
     ap.add_argument("--stage-times", action="store_true", help="also print per-kernel times to stderr")
     return ap.parse_args()
 
@@ -63,9 +65,35 @@ def workload_name(cfg):
 def make_case(cfg, nwave=None):
     """The synthetic config-2 case (SURVEY.md 8d recipe, seeded): table + rank 0's atmosphere."""
     from archnemesis_dist_b200 import synthetic
-    return synthetic.make_fm_case(nwave=nwave or cfg["nwave"], ng=cfg["ng"], npress=cfg["npress"], ntemp=cfg["ntemp"],
-                                  ngas=cfg["ngas"], nlay=cfg["nlay"], nvmr=cfg["nvmr"], ndust=cfg["ndust"],
-                                  npro=cfg["npro"], nx=cfg["nx"], seed=cfg["seed"])
+    c = synthetic.make_fm_case(nwave=nwave or cfg["nwave"], ng=cfg["ng"], npress=cfg["npress"], ntemp=cfg["ntemp"],
+                               ngas=cfg["ngas"], nlay=cfg["nlay"], nvmr=cfg["nvmr"], ndust=cfg["ndust"],
+                               npro=cfg["npro"], nx=cfg["nx"], seed=cfg["seed"])
+    return with_continuum_plan(c, cfg)
+
+
+def with_continuum_plan(c, cfg):
+    """Continuum terms of the case as the reference structures them (collision-induced pairs on a temperature grid, a
+    fixed spectrum, Rayleigh): a plan the device turns into TAUCIA / TAURAY / dTAUCON (ansb200_continuum) instead of
+    dense host arrays.  The CPU legs evaluate the same plan with the oracle (dense_continuum)."""
+    if cfg.get("dense_continuum"):
+        return c
+    from archnemesis_dist_b200 import synthetic
+    c = dict(c)
+    c["continuum"] = synthetic.make_continuum(c["tab"]["NWAVE"], len(c["press"]), c["NVMR"], c["NDUST"], seed=cfg["seed"],
+                                              temp=c["temp"])
+    c.pop("_dense", None)
+    return c
+
+
+def dense_continuum(c):
+    """taucon[NWAVE,NLAY], dtaucon[NWAVE,NPAR,NLAY] of case c for the CPU legs (oracle evaluation of the plan)."""
+    if "continuum" not in c:
+        return c["taucon"], c["dtaucon"]
+    if "_dense" not in c:
+        from oracle import oracle as orc
+        cia, dust, ray, dcon = orc.continuum_eval(c["continuum"][0], c["continuum"][1], True)
+        c["_dense"] = (cia + dust + ray, dcon)
+    return c["_dense"]
 
 
 def perturb_case(c0, rank_seed):
@@ -78,6 +106,13 @@ def perturb_case(c0, rank_seed):
     c["amount"] = c0["amount"] * 10.0 ** rng.uniform(-0.2, 0.2, size=c0["amount"].shape)
     c["SCALE"] = np.full_like(c0["SCALE"], 1.0 / np.cos(np.deg2rad(5.0 + 5.0 * rank_seed)))
     c["EMTEMP"] = c["temp"][c0["LAYINC"][:, 0]].reshape(-1, 1).copy()
+    if "continuum" in c0:
+        from archnemesis_dist_b200 import synthetic
+        tables, plan0 = c0["continuum"]
+        _, plan = synthetic.make_continuum(c0["tab"]["NWAVE"], len(c["press"]), c["NVMR"], c["NDUST"],
+                                           seed=CFG["seed"], temp=c["temp"])
+        c["continuum"] = (tables, plan)        # the same resident tables, this state's layer weights
+        c.pop("_dense", None)
     return c
 
 
@@ -114,8 +149,9 @@ def cpu_forward_jacobian(c, rows, nthreads):
     k, dkdT = orc.calc_k(sl(tab["K"]), tab["PRESS"], tab["TEMP"], c["press"], c["temp"], want_grad=True, nthreads=nthreads)
     tau, dk = orc.k_overlap(tab["DELG"], k, c["amount"], dkdT=dkdT, nthreads=nthreads)
     del k, dkdT
-    tl, tp, dtl = orc.assemble_opacity(tau, dk, c["gas_slot"], c["NVMR"], c["NPAR"], sl(c["taucon"]),
-                                       sl(c["dtaucon"]), c["LAYINC"], c["SCALE"])
+    taucon, dtaucon = dense_continuum(c)
+    tl, tp, dtl = orc.assemble_opacity(tau, dk, c["gas_slot"], c["NVMR"], c["NPAR"], sl(taucon),
+                                       sl(dtaucon), c["LAYINC"], c["SCALE"])
     del tau, dk
     S, dS, dT = orc.thermal_paths(c["ISPACE"], sl(tab["WAVE"]), tl, dtl, c["NVMR"], c["NLAYIN"], c["EMTEMP"],
                                   c["LAYPRESS"], c["LAYINC"], c["TSURF"], sl(c["EMISSIVITY"]), sl(c["xfac"]),
@@ -243,8 +279,12 @@ def make_evaluation(c, **kw):
     from archnemesis_dist_b200 import engine
     a = dict(press_atm=c["press"], temp=c["temp"], amount=c["amount"], gas_slot=c["gas_slot"], NVMR=c["NVMR"],
              NPAR=c["NPAR"], LAYINC=c["LAYINC"], SCALE=c["SCALE"], NLAYIN=c["NLAYIN"], EMTEMP=c["EMTEMP"],
-             LAYPRESS=c["LAYPRESS"], taucia=c["taucon"], dtaucon=c["dtaucon"], mode=engine.THERMAL,
+             LAYPRESS=c["LAYPRESS"], mode=engine.THERMAL,
              ISPACE=c["ISPACE"], TSURF=c["TSURF"], EMISSIVITY=c["EMISSIVITY"], xfac=c["xfac"])
+    if "continuum" in c:
+        a["continuum"] = c["continuum"]         # CIA / Rayleigh / aerosol terms made on the device from the plan
+    else:
+        a.update(taucia=c["taucon"], dtaucon=c["dtaucon"])
     a.update(kw)
     return engine.Evaluation(**a)
 
@@ -283,8 +323,9 @@ def cpu_limb_rows(c4, rows, transmission, nthreads):
     K = np.ascontiguousarray(tab["K"][rows])
     k, dkdT = orc.calc_k(K, tab["PRESS"], tab["TEMP"], c4["press"], c4["temp"], want_grad=True, nthreads=nthreads)
     tau, dk = orc.k_overlap(tab["DELG"], k, c4["amount"], dkdT=dkdT, nthreads=nthreads)
-    tl, tp, dtl = orc.assemble_opacity(tau, dk, c4["gas_slot"], c4["NVMR"], c4["NPAR"], c4["taucon"][rows],
-                                       c4["dtaucon"][rows], c4["LAYINC"], c4["SCALE"])
+    taucon, dtaucon = dense_continuum(c4)
+    tl, tp, dtl = orc.assemble_opacity(tau, dk, c4["gas_slot"], c4["NVMR"], c4["NPAR"], taucon[rows],
+                                       dtaucon[rows], c4["LAYINC"], c4["SCALE"])
     if transmission:
         S, dS = orc.transmission(tp, dtl, c4["xfac"][rows])
         dT = None
@@ -636,6 +677,7 @@ def main():
     cfg = dict(CFG)
     cfg["nwave"] = args.nwave
     cfg["nx"] = args.nx
+    cfg["dense_continuum"] = bool(args.dense_continuum)
     if args.impl == "reference":
         run_reference_arm(args, cfg)
     else:

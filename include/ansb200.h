@@ -127,6 +127,26 @@ int ansb200_radiance(int mode, unsigned flags, const double *tau, const double *
                      int NVMR, int NPAR, int NLAYMAX, int NPATH, double *spec, double *dspec, double *dtsurf,
                      void *stream);
 
+/* ---- continuum opacities ------------------------------------------------------------------------
+ * Replaces the dense host arrays of calc_tau_cia (archnemesis/ForwardModel_0.py:4516-4788), calc_tau_rayleighj / v2
+ * (:5524-5710), calc_tau_dust (:4790-4867) and their fold into dTAUCON in calculate_layer_opacity (:3938-3981).  The
+ * host (continuum.py) evaluates the reference's per-layer logic and hands over a plan; this makes the arrays
+ * ansb200_radiance reads, on the device:
+ *   kw[NTERM,NPL,NWAVE]   CIA cross sections on the calculation wavenumbers (resident); nplanes[NTERM] = NPL for a
+ *                         table term, 1 for a fixed spectrum (CO2-CO2, N2-N2, N2-H2)
+ *   pl[NLAY,4] int32, wt[NLAY,5]   the layer's four (para, T) planes and (fhh_t, fhl_t, fhh_f, fhl_f, dfhl/dT)
+ *   q1,q2,ca,cb[NTERM,NLAY], slots[NTERM,3] int32   mixing ratios of the pair, coefficients and gradient slots of
+ *                         d/dq1, d/dq2, d/dT (-1: none); xfac[NLAY] = TOTAM^2/XLEN, totam[NLAY]
+ *   ur[NR,NWAVE], vr/vrd[NR,NLAY]   Rayleigh: TAURAY = sum ur*vr, dTAURAY = sum ur*vrd
+ *   ud[NDUST,NWAVE], vd[NDUST,NLAY] aerosols: kext*1e-4 and column densities
+ * Outputs taucia / taudust / tauray [NWAVE,NLAY] (any may be NULL) and, if want_grad, dtaucon[NWAVE,NVMR+2+NDUST,NLAY].
+ * NVMR + 2 <= 24. */
+int ansb200_continuum(const double *kw, const int32_t *nplanes, int NTERM, int NPL, const int32_t *pl, const double *wt,
+                      const double *q1, const double *q2, const double *ca, const double *cb, const int32_t *slots,
+                      const double *xfac, const double *totam, const double *ur, const double *vr, const double *vrd,
+                      int NR, const double *ud, const double *vd, int NDUST, int NWAVE, int NLAY, int NVMR, int has_cia,
+                      int want_grad, double *taucia, double *taudust, double *tauray, double *dtaucon, void *stream);
+
 /* ---- gas opacity from line-by-line tables ------------------------------------------------------
  * Replaces Spectroscopy_0.calc_klbl / calc_klblg (archnemesis/Spectroscopy_0.py:1768-1919, :1601-1765)
  * and the LBL-table branch of calculate_gaseous_line_opacity (ForwardModel_0.py:3795-3815).  The table

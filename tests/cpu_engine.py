@@ -37,12 +37,15 @@ class HotPath:
 
     continuum_plans = 0
 
+    _cont_lock = __import__("threading").Lock()
+
     def continuum_tables(self, key, factory):
-        cache = self.__dict__.setdefault("_cont_tables", {})
-        if key not in cache:
-            cache.clear()
-            cache[key] = factory()
-        return cache[key]
+        with HotPath._cont_lock:
+            cache = self.__dict__.setdefault("_cont_tables", {})
+            if key not in cache:
+                cache.clear()
+                cache[key] = factory()
+            return cache[key]
 
     def gas_opacity(self, s, timers=None):
         ev = s.ev
