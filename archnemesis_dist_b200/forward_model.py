@@ -652,6 +652,8 @@ class B200HotPathMixin:
 
 
 class ArrayForwardModel(B200HotPathMixin):
+    b200_device_continuum = False      # the continuum terms arrive as arrays, there is no reference object to plan from
+
     """The mix-in over plain namespaces: for hosts without the reference package.  `objects` maps
     the names SpectroscopyX, LayerX, PathX, AtmosphereX, SurfaceX, MeasurementX, ScatterX,
     StellarX, Variables to objects carrying the attributes listed in SURVEY.md 8b; the continuum
