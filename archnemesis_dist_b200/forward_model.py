@@ -931,6 +931,10 @@ def install(archnemesis=None):
     # add_line_set_monochromatic_absorption on the device, line lists resident (linedata.py)
     from . import linedata as _linedata
     _linedata.install_lbl()
+    # vectorised .kta / .lta readers under read_tables (the first touch of a table set costs ~16 s of per-record
+    # Python in the reference at the config-2 size, table_io.py)
+    from . import table_io as _table_io
+    _table_io.install_readers()
     return cls
 
 
@@ -949,6 +953,8 @@ def uninstall(archnemesis=None):
         sys.modules["archnemesis.Spectroscopy_0"].Spectroscopy_0.read_tables = _INSTALLED.pop("read_tables")
     from . import linedata as _linedata
     _linedata.uninstall_lbl()
+    from . import table_io as _table_io
+    _table_io.uninstall_readers()
     if "oe_reference" in _INSTALLED:
         oe_ref = _INSTALLED.pop("oe_reference")
         _INSTALLED.pop("oe_cls", None)
