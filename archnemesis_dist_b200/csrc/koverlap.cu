@@ -32,7 +32,7 @@ __global__ void ans_koverlap_single_kernel(OvParams P)
 }
 
 bool ov_fast_supported(const OvParams &P, bool grad);
-int ov_fast_launch(const OvParams &P, bool grad, int *scratch, int *why, cudaStream_t stream);
+int ov_fast_launch(const OvParams &P, bool grad, int *scratch, int *why, int *work, cudaStream_t stream);
 
 static int ov_general(const OvParams &P, bool grad, cudaStream_t stream)
 {
@@ -137,13 +137,13 @@ static int ov_run(OvParams &P, bool grad, cudaStream_t stream)
         const bool stats = ov_mode() == 2;
         OvScratch sc{};
         {
-            const int rc0 = ov_scratch_get((size_t)ncell + 1 + 8, stream, sc);
+            const int rc0 = ov_scratch_get((size_t)ncell + 1 + 8 + 1, stream, sc);
             if (rc0 != ANSB200_OK) return rc0;
         }
         int *scratch = sc.p;
         ANS_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(int), stream));
-        if (stats) ANS_CUDA_CHECK(cudaMemsetAsync(scratch + ncell + 1, 0, 8 * sizeof(int), stream));
-        int rc = ov_fast_launch(P, grad, scratch, stats ? scratch + ncell + 1 : nullptr, stream);
+        ANS_CUDA_CHECK(cudaMemsetAsync(scratch + ncell + 1, 0, 9 * sizeof(int), stream));      // statistics + work counter
+        int rc = ov_fast_launch(P, grad, scratch, stats ? scratch + ncell + 1 : nullptr, scratch + ncell + 9, stream);
         if (rc == ANSB200_OK) {
             P.cell_count = scratch;
             P.cell_list = scratch + 1;

@@ -247,7 +247,8 @@ __device__ __forceinline__ void kf_correct(double *__restrict__ M, int lane, int
 
 template <int NG, int XS, int KG, bool GRAD, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32, 1)
-ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict__ fb_list, int *__restrict__ fb_why)   // @phase cta_setup
+ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict__ fb_list, int *__restrict__ fb_why,
+                         int *__restrict__ work)   // @phase cta_setup
 {
     using L = KfWarpLayout<NG, XS, KG, GRAD>;
     constexpr int NN = NG * NG;
@@ -296,7 +297,12 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
         return;
     }
 
-    for (long long cell = (long long)blockIdx.x * NWARPS + warp; cell < ncell; cell += (long long)gridDim.x * NWARPS) {   // @phase cell_prologue
+    // Cells cost between one and five sorted folds: the first round is dealt out statically, after that a warp takes
+    // the next cell from a counter when it is done (the ticket is drawn while the current cell is being worked on).
+    long long cell = (long long)blockIdx.x * NWARPS + warp;
+    while (cell < ncell) {   // @phase cell_prologue
+        int ticket = 0;
+        if (lane == 0) ticket = atomicAdd(work, 1);
         const int iw = (int)(cell / NLAY);
         const int l = (int)(cell - (long long)iw * NLAY);
         bool fallback = false;
@@ -645,6 +651,7 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
             }
         }
         __syncwarp();
+        cell = (long long)gridDim.x * NWARPS + __shfl_sync(FULL, ticket, 0);
     }
 }
 
@@ -659,7 +666,7 @@ constexpr int kf_warps()
 }
 
 template <int NG, int XS, int KG, bool GRAD>
-int kf_launch(const OvParams &P, int *scratch, int *why, cudaStream_t stream)
+int kf_launch(const OvParams &P, int *scratch, int *why, int *work, cudaStream_t stream)
 {
     constexpr int NWARPS = kf_warps<NG, XS, KG, GRAD>();
     static_assert(NWARPS >= 8, "too little shared memory per warp");
@@ -673,7 +680,7 @@ int kf_launch(const OvParams &P, int *scratch, int *why, cudaStream_t stream)
     const long long ncell = (long long)P.NWAVE * P.NLAY;
     long long grid = ans_div_up(ncell, NWARPS);
     if (grid > nsm) grid = nsm;
-    kern<<<(unsigned)grid, NWARPS * 32, smem, stream>>>(P, scratch, scratch + 1, why);
+    kern<<<(unsigned)grid, NWARPS * 32, smem, stream>>>(P, scratch, scratch + 1, why, work);
     ANS_LAUNCH_CHECK();
     return ANSB200_OK;
 }
@@ -687,11 +694,12 @@ bool ov_fast_supported(const OvParams &P, bool grad)
     return P.NG == 20 && P.NGAS >= 2 && P.NGAS <= 14 && !P.seq_rebin && P.del_g != nullptr && P.weight && P.g_ord;
 }
 
-// scratch: [0] = number of cells left for the general kernel (-1: all of them), [1..] = their numbers
-int ov_fast_launch(const OvParams &P, bool grad, int *scratch, int *why, cudaStream_t stream)
+// scratch: [0] = number of cells left for the general kernel (-1: all of them), [1..] = their numbers; work: a zeroed
+// counter (dynamic cell assignment)
+int ov_fast_launch(const OvParams &P, bool grad, int *scratch, int *why, int *work, cudaStream_t stream)
 {
-    if (!grad) return P.NGAS <= 6 ? kf_launch<20, 8, 6, false>(P, scratch, why, stream)
-                                  : kf_launch<20, 8, 14, false>(P, scratch, why, stream);
-    if (P.NGAS <= 6) return kf_launch<20, 8, 6, true>(P, scratch, why, stream);
-    return kf_launch<20, 16, 14, true>(P, scratch, why, stream);
+    if (!grad) return P.NGAS <= 6 ? kf_launch<20, 8, 6, false>(P, scratch, why, work, stream)
+                                  : kf_launch<20, 8, 14, false>(P, scratch, why, work, stream);
+    if (P.NGAS <= 6) return kf_launch<20, 8, 6, true>(P, scratch, why, work, stream);
+    return kf_launch<20, 16, 14, true>(P, scratch, why, work, stream);
 }
