@@ -112,6 +112,22 @@ class WavenumberShard:
             a = getattr(ev, name)
             if a is not None:
                 setattr(e, name, np.ascontiguousarray(np.asarray(a)[self.lo:self.hi]))
+        if getattr(ev, "continuum", None) is not None:
+            # a continuum plan: the rank's rows of the resident CIA cross sections (cut once per table object) and of
+            # the Rayleigh / aerosol spectra; the per-layer coefficients are shared
+            from . import continuum as _cont
+            tables, plan = ev.continuum
+            cache = self.__dict__.setdefault("_cont_slices", {})
+            mine = cache.get(id(tables))
+            if mine is None or mine[0] is not tables:
+                meta = dict(tables.meta, NWAVE=self.hi - self.lo)
+                mine = (tables, _cont.ContinuumTables(tables.kw[:, :, self.lo:self.hi], tables.nplanes, meta))
+                cache.clear()
+                cache[id(tables)] = mine
+            p = dict(plan)
+            p["ur"] = np.ascontiguousarray(plan["ur"][:, self.lo:self.hi])
+            p["ud"] = np.ascontiguousarray(plan["ud"][:, self.lo:self.hi])
+            e.continuum = (mine[1], p)
         return e
 
     def forward_jacobian(self, ev, M, to_tensor=None):

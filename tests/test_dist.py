@@ -82,6 +82,17 @@ def _worker(rank, world, port, out_dir):
         assert wsl.hotpath.lbl_table and wsl.hotpath.K.shape[0] == (3 if rank == 0 else 2)
         for a, b in zip(wsl.forward_jacobian(evl, Ml, to_tensor=t), full_l):
             assert a.shape == b.shape and np.abs(a.numpy() - b).max() <= 1e-13 * np.abs(b).max()
+        # (4b) the same evaluation with its continuum terms as a device plan: every rank cuts its rows of the CIA tables
+        #      and of the Rayleigh / aerosol spectra
+        import dataclasses
+        tables, cplan = syn.make_continuum(5, 8, 3, ndust=0, seed=2, temp=cl["temp"])
+        evp = dataclasses.replace(evl, taucia=None, dtaucon=None, continuum=(tables, cplan))
+        full_p = cpu_engine.HotPath(K4, tl["PRESS"], tl["TEMP"], one, tl["WAVE"]).forward_jacobian(evp, Ml)
+        assert np.abs(full_p[0] - full_l[0]).max() > 0.0            # (other continuum numbers than case 4)
+        for a, b in zip(wsl.forward_jacobian(evp, Ml, to_tensor=t), full_p):
+            assert a.shape == b.shape and np.abs(a.numpy() - b).max() <= 1e-13 * np.abs(b).max()
+        sl = wsl.slice_evaluation(evp).continuum
+        assert sl[0].kw.shape[2] == wsl.hi - wsl.lo and sl[1]["ur"].shape[1] == wsl.hi - wsl.lo
         # (5) (p,T)-grid sharding of the line-by-line generation: 5 state points over 2 ranks (3 + 2)
         from oracle import oracle as orc
         wn = np.linspace(1000.0, 1001.0, 41)
