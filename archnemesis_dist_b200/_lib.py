@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libansb200.so")
 OK, EINVAL, ECUDA, ENOMEM = 0, -1, -2, -3
 RAD_GRAD, RAD_NAN_TO_NUM = 1, 2
 MAX_NG, MAX_NGAS = 22, 15
+TABLE_F64, TABLE_K32, TABLE_F32 = 0, 1, 2
 MAX_LBL_NGAS = 128      # csrc/klbl.cu: gas sum of the line-by-line-table kernel
 MAX_NCONV = 65535       # csrc/convolve.cu: grid.y
 
@@ -24,6 +25,7 @@ EXPORTS = {
     "ansb200_overlap_mode": (_i, [_i]),
     "ansb200_overlap_stats": (None, [ctypes.POINTER(ctypes.c_int32)]),
     "ansb200_table_create": (_i, [_vp, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_vp), _vp]),
+    "ansb200_table_create_ex": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_vp), _vp]),
     "ansb200_table_destroy": (_i, [_vp]),
     "ansb200_table_shape": (_i, [_vp] + [ctypes.POINTER(_i)] * 5),
     "ansb200_table_k": (_vp, [_vp]),

@@ -15,7 +15,7 @@ constexpr int KI_UNROLL = 4;
 
 template <bool GRAD>
 __global__ void __launch_bounds__(KI_THREADS, 3)
-ans_kinterp_kernel(const double *__restrict__ lnK, const double *__restrict__ K, AnsLayerPlan plan, int npairs,
+ans_kinterp_kernel(AnsTab T, AnsLayerPlan plan, int npairs,
                    int NP, int NT, int NGAS, int NLAY, double *__restrict__ kout, double *__restrict__ dkout)
 {
     const size_t plane = (size_t)npairs * NGAS;          // elements per (p,T) plane
@@ -48,7 +48,7 @@ ans_kinterp_kernel(const double *__restrict__ lnK, const double *__restrict__ K,
                 for (int q = 0; q < KI_EPT; ++q) {
                     if (!live[q]) continue;
                     double kv, dv = 0.0;
-                    ans_kinterp_elem<GRAD>(lnK, K, tbase + off[q], NT, plane, w0[q], w1[q], w2[q], w3[q], omv[q], vv[q],
+                    ans_kinterp_elem<GRAD>(T, tbase + off[q], NT, plane, w0[q], w1[q], w2[q], w3[q], omv[q], vv[q],
                                            dudt[q], kv, dv);
                     kout[obase + q * KI_THREADS] = kv;
                     if (GRAD) dkout[obase + q * KI_THREADS] = dv;
@@ -71,10 +71,10 @@ extern "C" int ansb200_kinterp(const ansb200_table *t, int NLAY, const int32_t *
     int grid = ans_div_up(npairs, KI_UNROLL);
     if (grid > 148 * 12) grid = 148 * 12;      // persistent-style: a multiple of the SM count, pairs strided over CTAs
     if (want_grad)
-        ans_kinterp_kernel<true><<<grid, KI_THREADS, 0, stream>>>(t->lnK, t->K, plan, npairs, t->NP, t->NT, t->NGAS,
+        ans_kinterp_kernel<true><<<grid, KI_THREADS, 0, stream>>>(ans_tab(t), plan, npairs, t->NP, t->NT, t->NGAS,
                                                                   NLAY, k, dkdT);
     else
-        ans_kinterp_kernel<false><<<grid, KI_THREADS, 0, stream>>>(t->lnK, t->K, plan, npairs, t->NP, t->NT, t->NGAS,
+        ans_kinterp_kernel<false><<<grid, KI_THREADS, 0, stream>>>(ans_tab(t), plan, npairs, t->NP, t->NT, t->NGAS,
                                                                    NLAY, k, nullptr);
     ANS_LAUNCH_CHECK();
     return ANSB200_OK;

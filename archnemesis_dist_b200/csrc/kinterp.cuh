@@ -15,17 +15,26 @@ struct AnsLayerPlan {
 // NWAVE*NG*NGAS run, so the NG*NGAS values a wavenumber needs from a plane are 960 contiguous bytes
 // (at 20 x 6) instead of twenty 48-byte pieces 14 KB apart in the reference's layout.
 // off00 addresses the (ip_lo, it_lo) corner; `plane` = NWAVE*NG*NGAS elements between consecutive T planes.
+__device__ __forceinline__ double ans_tab_lnk(const AnsTab &T, size_t o)
+{
+    return T.lnK ? __ldg(T.lnK + o) : (double)__ldg(T.lnKf + o);
+}
+__device__ __forceinline__ double ans_tab_k(const AnsTab &T, size_t o)
+{
+    return T.K ? __ldg(T.K + o) : (double)__ldg(T.Kf + o);
+}
+
 template <bool GRAD>
-__device__ __forceinline__ void ans_kinterp_elem(const double *__restrict__ lnK, const double *__restrict__ K,
+__device__ __forceinline__ void ans_kinterp_elem(const AnsTab &T,
                                                  size_t off00, int NT, size_t plane, double w0, double w1, double w2,
                                                  double w3, double omv, double v, double dudt, double &kout,
                                                  double &dkout)
 {
     const size_t off01 = off00 + plane, off10 = off00 + (size_t)NT * plane, off11 = off10 + plane;
-    double l00 = __ldg(lnK + off00), l01 = __ldg(lnK + off01), l10 = __ldg(lnK + off10), l11 = __ldg(lnK + off11);
+    double l00 = ans_tab_lnk(T, off00), l01 = ans_tab_lnk(T, off01), l10 = ans_tab_lnk(T, off10), l11 = ans_tab_lnk(T, off11);
     bool fast = isfinite(l00) && isfinite(l01) && isfinite(l10) && isfinite(l11);
     if (!fast) {
-        double k00 = __ldg(K + off00), k01 = __ldg(K + off01), k10 = __ldg(K + off10), k11 = __ldg(K + off11);
+        double k00 = ans_tab_k(T, off00), k01 = ans_tab_k(T, off01), k10 = ans_tab_k(T, off10), k11 = ans_tab_k(T, off11);
         if (k00 > 0.0 && k01 > 0.0 && k10 > 0.0 && k11 > 0.0) {
             l00 = log(k00); l01 = log(k01); l10 = log(k10); l11 = log(k11);   // only +inf entries land here
             fast = true;

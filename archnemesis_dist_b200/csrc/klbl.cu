@@ -149,6 +149,7 @@ extern "C" int ansb200_lbl_table_opacity(const ansb200_table *t, int NLAY, const
     cudaStream_t stream = (cudaStream_t)stream_;
     ANS_REQUIRE(t && corner && w4 && amount && tau, "lbl_table_opacity: null pointer");
     ANS_REQUIRE(t->NG == 1, "lbl_table_opacity: the table must have NG = 1 (got %d)", t->NG);
+    ANS_REQUIRE(t->storage == ANSB200_TABLE_F64, "lbl_table_opacity: float32 table storage is for k-tables only");
     ANS_REQUIRE(NLAY > 0, "lbl_table_opacity: NLAY must be positive");
     ANS_REQUIRE(t->NGAS <= 128, "lbl_table_opacity: NGAS=%d exceeds 128", t->NGAS);
     ANS_REQUIRE(!want_grad || (omv && vv && du1dt && du2dt && dk), "lbl_table_opacity: gradient requested without omv/vv/du1dt/du2dt/dk");

@@ -18,7 +18,7 @@ __global__ void ans_koverlap_single_kernel(OvParams P)
             const size_t pair = o / P.NLAY;
             const size_t plane = (size_t)P.NWAVE * P.NG;          // NGAS == 1
             const double *w = P.plan.w4 + 4 * l;
-            ans_kinterp_elem<GRAD>(P.lnK, P.K, ((size_t)P.plan.ip_lo[l] * P.NT + P.plan.it_lo[l]) * plane + pair, P.NT,
+            ans_kinterp_elem<GRAD>(P.tab, ((size_t)P.plan.ip_lo[l] * P.NT + P.plan.it_lo[l]) * plane + pair, P.NT,
                                    plane, w[0], w[1], w[2], w[3], GRAD ? P.plan.omv[l] : 0.0, GRAD ? P.plan.vv[l] : 0.0,
                                    GRAD ? P.plan.dudt[l] : 0.0, kv, dv);
         } else {
@@ -191,7 +191,7 @@ extern "C" int ansb200_gas_opacity(const ansb200_table *t, int NLAY, const int32
     ANS_REQUIRE(t && ip_lo && it_lo && w4, "gas_opacity: null pointer");
     ANS_REQUIRE(!grad || (omv && vv && dudt), "gas_opacity: gradient requested without omv/vv/dudt");
     OvParams P{};
-    P.lnK = t->lnK; P.K = t->K; P.plan = AnsLayerPlan{ip_lo, it_lo, w4, omv, vv, dudt};
+    P.tab = ans_tab(t); P.plan = AnsLayerPlan{ip_lo, it_lo, w4, omv, vv, dudt};
     P.NP = t->NP; P.NT = t->NT;
     P.amount = amount; P.weight = weight; P.g_ord = g_ord; P.del_g = del_g;
     P.NWAVE = t->NWAVE; P.NG = t->NG; P.NLAY = NLAY; P.NGAS = t->NGAS; P.tau = tau; P.dk = dk;

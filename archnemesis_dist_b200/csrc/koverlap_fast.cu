@@ -319,7 +319,7 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                          dudt = GRAD ? __ldg(P.plan.dudt + l) : 0.0;
             for (int e = lane; e < NG * NGAS; e += 32) {
                 double kv, dv = 0.0;
-                ans_kinterp_elem<GRAD>(P.lnK, P.K, toff + e, P.NT, plane, w0, w1, w2, w3, omv, vv, dudt, kv, dv);
+                ans_kinterp_elem<GRAD>(P.tab, toff + e, P.NT, plane, w0, w1, w2, w3, omv, vv, dudt, kv, dv);
                 kbuf[e] = kv;
                 if (GRAD) dbuf[e] = dv;
             }

@@ -40,7 +40,7 @@ constexpr unsigned OV_KEY_BASE = (227u - 62u) << 23;   // float32 pattern of 2^(
 
 struct OvParams {
     const double *k, *dkdT;                 // unfused source [NWAVE,NG,NLAY,NGAS]
-    const double *lnK, *K;                  // fused source (table)
+    AnsTab tab;                             // fused source (table)
     AnsLayerPlan plan;
     int NP, NT;
     const double *amount, *weight, *g_ord;
@@ -1206,7 +1206,7 @@ ans_koverlap_kernel(OvParams P)
                      dudt = GRAD ? __ldg(P.plan.dudt + l) : 0.0;
         for (int e = lane; e < NG * NGAS; e += 32) {
             double kv, dv = 0.0;
-            ans_kinterp_elem<GRAD>(P.lnK, P.K, toff + e, P.NT, plane, w0, w1, w2, w3, omv, v, dudt, kv, dv);
+            ans_kinterp_elem<GRAD>(P.tab, toff + e, P.NT, plane, w0, w1, w2, w3, omv, v, dudt, kv, dv);
             s.kbuf[e] = kv;
             if (GRAD) s.dbuf[e] = dv;
         }

@@ -210,14 +210,14 @@ class HotPath:
            everything downstream is shared.
     """
 
-    def __init__(self, K, PRESS, TEMP, DELG, WAVE, ops=_ops):
+    def __init__(self, K, PRESS, TEMP, DELG, WAVE, ops=_ops, table_storage="f64"):
         self.ops = ops
         self.lbl_table = len(K.shape) == 4
         if self.lbl_table:
             K = K.reshape(K.shape[0], 1, K.shape[1], K.shape[2], K.shape[3])
             if len(np.asarray(DELG)) != 1:
                 raise ValueError("a line-by-line table has one g-ordinate (DELG = [1.0])")
-        self.table = ops.Table(K)
+        self.table = ops.Table(K, table_storage) if table_storage != "f64" else ops.Table(K)
         self.NWAVE, self.NG, self.NP, self.NT, self.NGAS = (int(x) for x in K.shape)
         self.PRESS = np.asarray(PRESS)
         self.TEMP = np.asarray(TEMP)

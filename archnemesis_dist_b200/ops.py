@@ -42,9 +42,13 @@ def to_dev(a, dtype=torch.float64):
 class Table:
     """Device-resident k-table (K and ln K), replacing the per-call read_tables of
     archnemesis/Spectroscopy_0.py:1448-1528.  `K` is [NWAVE,NG,NP,NT,NGAS] float64 (host array
-    or device tensor)."""
+    or device tensor).  `storage`: "f64" (default), "k32" (K as float32 -- lossless for .kta data, bit-identical
+    results, 12 instead of 16 bytes per entry) or "f32" (K and ln K as float32: the FP32 k-interp variant, ~4e-6
+    relative in k); see ansb200_table_create_ex."""
 
-    def __init__(self, K):
+    STORAGE = {"f64": _lib.TABLE_F64, "k32": _lib.TABLE_K32, "f32": _lib.TABLE_F32}
+
+    def __init__(self, K, storage="f64"):
         _require_cuda()
         lib = _lib.load()
         self.shape = tuple(int(x) for x in K.shape)
@@ -56,10 +60,11 @@ class Table:
         else:
             Kh = np.ascontiguousarray(K, dtype=np.float64)
             src, is_dev = ctypes.c_void_p(Kh.ctypes.data), 0
-        _lib.check(lib.ansb200_table_create(src, is_dev, *self.shape, ctypes.byref(h), _stream()))
+        self.storage = storage
+        _lib.check(lib.ansb200_table_create_ex(src, is_dev, *self.shape, self.STORAGE[storage], ctypes.byref(h), _stream()))
         torch.cuda.current_stream().synchronize()   # the source buffer may be released now
         self._h = h
-        self.nbytes = 2 * 8 * int(np.prod(self.shape))
+        self.nbytes = {"f64": 16, "k32": 12, "f32": 8}[storage] * int(np.prod(self.shape))
 
     @property
     def handle(self):

@@ -605,6 +605,34 @@ def run_extras(hp, c, cfg, nthreads):
     except Exception as e:                                   # noqa: BLE001
         out["config4"] = dict(error=repr(e))
     torch.cuda.empty_cache()
+    # float32 storage variants of the resident table (BASELINE.json: "any FP32 k-interp variant is
+    # reported separately with its stated tolerance"): K as float32 is lossless for .kta data, K + ln K as float32 is not
+    try:
+        tab = c["tab"]
+        ev = make_evaluation(c)
+        s0 = hp.stage_opacity(ev, True)
+        ref_tau, ref_dk = hp.gas_opacity(s0)
+        ts = {}
+        for st in ("k32", "f32"):
+            h2 = engine.HotPath(tab["K"], tab["PRESS"], tab["TEMP"], tab["DELG"], tab["WAVE"], table_storage=st)
+            s2 = h2.stage_opacity(ev, True)
+            ms = timeit(lambda: h2.gas_opacity(s2))
+            tau2, dk2 = h2.gas_opacity(s2)
+            d = (tau2 - ref_tau).abs()
+            m = torch.maximum(tau2.abs(), ref_tau.abs())
+            rel = float((d / torch.where(m > 0, m, torch.ones_like(m))).max())
+            ts[st] = dict(ms_gas_opacity=ms, table_bytes=int(h2.table.nbytes), max_rel_tau_vs_f64=rel,
+                          bit_identical=bool(torch.equal(tau2, ref_tau) and torch.equal(dk2, ref_dk)))
+            h2.close()
+            del h2, s2, tau2, dk2
+            torch.cuda.empty_cache()
+        ts["f64"] = dict(table_bytes=int(hp.table.nbytes))
+        ts["tolerance_f32"] = 2e-5
+        out["table_storage"] = ts
+        del ref_tau, ref_dk
+    except Exception as e:                                   # noqa: BLE001
+        out["table_storage"] = dict(error=repr(e))
+    torch.cuda.empty_cache()
     # config 5: the widest state vector of the sweep on the same table (NX = 1000)
     try:
         small = synthetic.make_fm_case(nwave=8, ng=cfg["ng"], npress=cfg["npress"], ntemp=cfg["ntemp"], ngas=cfg["ngas"],

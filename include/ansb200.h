@@ -51,6 +51,18 @@ int ansb200_version(void);
  * `K` may be a host or a device pointer (is_device selects). */
 int ansb200_table_create(const double *K, int is_device, int NWAVE, int NG, int NP, int NT, int NGAS,
                          ansb200_table **out, void *stream);
+/* Storage variants of the resident copy (k-tables only; ansb200_table_create = F64):
+ *   ANSB200_TABLE_F64  K and ln K as float64 (16 bytes per entry)
+ *   ANSB200_TABLE_K32  K as float32, ln K as float64 (12 bytes): LOSSLESS for .kta / .lta data, whose values are
+ *                      float32 (Spectroscopy_0.py:2849) -- results are bit-identical to F64; refused (EINVAL) if some
+ *                      value is not a float32 number
+ *   ANSB200_TABLE_F32  K and ln K as float32 (8 bytes): the FP32 k-interp variant BASELINE.json allows, reported
+ *                      separately; ln K rounded to float32 costs ~4e-6 relative in k (tolerance 2e-5 in the tests) */
+#define ANSB200_TABLE_F64 0
+#define ANSB200_TABLE_K32 1
+#define ANSB200_TABLE_F32 2
+int ansb200_table_create_ex(const double *K, int is_device, int NWAVE, int NG, int NP, int NT, int NGAS, int storage,
+                            ansb200_table **out, void *stream);
 int ansb200_table_destroy(ansb200_table *t);
 int ansb200_table_shape(const ansb200_table *t, int *NWAVE, int *NG, int *NP, int *NT, int *NGAS);
 /* device pointers to the resident copies (for tests / diagnostics) */

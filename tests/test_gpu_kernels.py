@@ -540,3 +540,35 @@ def test_thermal_many_limb_paths_staged_kernel(mods, want_grad):
         assert relerr(cpu(dts), t_ref) < 1e-12
     else:
         assert relerr(cpu(out), orc.g_integrate(S, None, None, dg)) < 1e-12
+
+
+def test_float32_table_storage_variants():
+    """ansb200_table_create_ex: K as float32 is lossless for .kta data (bit-identical k-interp and fused gas opacity);
+    K and ln K as float32 -- the FP32 k-interp variant -- stays within 2e-5 of the float64 table; a table that is not
+    float32-representable is refused for the lossless variant."""
+    import torch
+    from archnemesis_dist_b200 import ops, plan, synthetic
+    c = synthetic.make_fm_case(nwave=24, ng=20, ngas=6, nlay=60, npro=60, nx=8, nvmr=8, seed=4, zero_fraction=0.1)
+    tab = c["tab"]
+    hp = plan.kinterp_plan(tab["PRESS"], tab["TEMP"], c["press"], c["temp"], True)
+    dp = ops.DevicePlan(hp, True)
+    otab = ops.OverlapTables(tab["DELG"])
+    am = ops.to_dev(c["amount"])
+    out = {}
+    for st in ("f64", "k32", "f32"):
+        T = ops.Table(tab["K"], st)
+        assert T.nbytes == {"f64": 16, "k32": 12, "f32": 8}[st] * tab["K"].size
+        k, d = ops.kinterp(T, dp, True)
+        tau, dk = ops.gas_opacity(T, dp, am, otab, True)
+        out[st] = [cpu(x) for x in (k, d, tau, dk)]
+        T.close()
+    for a, b in zip(out["k32"], out["f64"]):
+        assert np.array_equal(a, b)
+    for name, a, b in zip(("k", "dkdT", "tau", "dk"), out["f32"], out["f64"]):
+        err = relerr(a, b) if name in ("k", "tau") else colerr(a, b)
+        assert 0.0 < err < 2e-5, (name, err)
+    K2 = tab["K"].copy()
+    K2[3, 2, 1, 1, 0] *= 1.0 + 1e-12                     # not a float32 number any more
+    with pytest.raises(ValueError):
+        ops.Table(K2, "k32")
+    ops.Table(K2, "f32").close()
