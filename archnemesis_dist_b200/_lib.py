@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libansb200.so")
 
 OK, EINVAL, ECUDA, ENOMEM = 0, -1, -2, -3
-RAD_GRAD, RAD_NAN_TO_NUM = 1, 2
+RAD_GRAD, RAD_NAN_TO_NUM, RAD_LAYER_SPACE = 1, 2, 4
 MAX_NG, MAX_NGAS = 22, 15
 TABLE_F64, TABLE_K32, TABLE_F32 = 0, 1, 2
 MAX_LBL_NGAS = 128      # csrc/klbl.cu: gas sum of the line-by-line-table kernel
@@ -25,6 +25,8 @@ EXPORTS = {
     "ansb200_overlap_mode": (_i, [_i]),
     "ansb200_overlap_stats": (None, [ctypes.POINTER(ctypes.c_int32)]),
     "ansb200_table_create": (_i, [_vp, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_vp), _vp]),
+    "ansb200_radiance_layer_space": (_i, [_i, _u, _i, _i, _i, _i, _i, _i, _i]),
+    "ansb200_jacobian_project_shared": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "ansb200_table_create_ex": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_vp), _vp]),
     "ansb200_table_destroy": (_i, [_vp]),
     "ansb200_table_shape": (_i, [_vp] + [ctypes.POINTER(_i)] * 5),

@@ -21,14 +21,14 @@ constexpr int PJ_BM = 128, PJ_BN = 64, PJ_BK = 16, PJ_THREADS = 256;
 
 __global__ void __launch_bounds__(PJ_THREADS, 2)
 ans_project_kernel(const double *__restrict__ dspec, const double *__restrict__ M, int NWAVE, int E, int NPATH, int NX,
-                   double *__restrict__ out)
+                   double *__restrict__ out, size_t mstride)
 {
     __shared__ __align__(16) double sA[2][PJ_BK][PJ_BM];      // [k][row]
     __shared__ __align__(16) double sB[2][PJ_BK][PJ_BN];      // [k][col]
     const int ipath = blockIdx.z;
     const int w0 = blockIdx.x * PJ_BM, x0 = blockIdx.y * PJ_BN;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double *Mp = M + (size_t)ipath * E * NX;
+    const double *Mp = M + (size_t)ipath * mstride;       // (0: one layer-space matrix for every path)
     double acc[4][8];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
@@ -112,7 +112,23 @@ extern "C" int ansb200_jacobian_project(const double *dspec, const double *M, in
     ANS_REQUIRE(NWAVE > 0 && NPAR > 0 && NLAYMAX > 0 && NPATH > 0 && NX > 0, "jacobian_project: bad shape");
     ANS_REQUIRE(NPATH <= 65535, "jacobian_project: NPATH too large");
     dim3 grid(ans_div_up(NWAVE, PJ_BM), ans_div_up(NX, PJ_BN), NPATH);
-    ans_project_kernel<<<grid, PJ_THREADS, 0, stream>>>(dspec, M, NWAVE, NPAR * NLAYMAX, NPATH, NX, out);
+    ans_project_kernel<<<grid, PJ_THREADS, 0, stream>>>(dspec, M, NWAVE, NPAR * NLAYMAX, NPATH, NX, out,
+                                                        (size_t)NPAR * NLAYMAX * NX);
+    ANS_LAUNCH_CHECK();
+    return ANSB200_OK;
+}
+
+// The same product with ONE matrix M[NPAR*NLAY, NX] for all paths: layer-space gradients (ANSB200_RAD_LAYER_SPACE), where
+// the layer -> profile -> state map does not depend on the path.
+extern "C" int ansb200_jacobian_project_shared(const double *dspec, const double *M, int NWAVE, int NPAR, int NLAY,
+                                               int NPATH, int NX, double *out, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ANS_REQUIRE(dspec && M && out, "jacobian_project: null pointer");
+    ANS_REQUIRE(NWAVE > 0 && NPAR > 0 && NLAY > 0 && NPATH > 0 && NX > 0, "jacobian_project: bad shape");
+    ANS_REQUIRE(NPATH <= 65535, "jacobian_project: NPATH too large");
+    dim3 grid(ans_div_up(NWAVE, PJ_BM), ans_div_up(NX, PJ_BN), NPATH);
+    ans_project_kernel<<<grid, PJ_THREADS, 0, stream>>>(dspec, M, NWAVE, NPAR * NLAY, NPATH, NX, out, (size_t)0);
     ANS_LAUNCH_CHECK();
     return ANSB200_OK;
 }

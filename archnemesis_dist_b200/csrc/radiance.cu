@@ -421,7 +421,9 @@ ans_transmission_paths_kernel(RadParams P)
     double *scon = stau + (size_t)NG * NLAY;                       // [NLAY] continuum (cia + dust + rayleigh)
     double *sdelg = scon + NLAY;                                   // [NG]
     double *sc = sdelg + NG;                                       // [RADT_WARPS][NG] c_g of the warp's current path
-    double *sdcon = sc + (size_t)RADT_WARPS * NG;                  // [NPAR*NLAY] dtaucon of the wavenumber (grad)
+    const bool layer_space = grad && (P.flags & ANSB200_RAD_LAYER_SPACE) != 0;
+    double *sS = sc + (size_t)RADT_WARPS * NG;                     // [RADT_WARPS][NLAY] sum of SCALE over a layer's visits
+    double *sdcon = sS + (layer_space ? (size_t)RADT_WARPS * NLAY : 0);   // [NPAR*NLAY] dtaucon of the wavenumber (grad)
     double *sdk = sdcon + ((grad && P.dtaucon) ? (size_t)NPAR * NLAY : 0);   // [NG*NLAY*NP1] dk of the wavenumber (grad)
     int *scol = reinterpret_cast<int *>(sdk + ((grad && P.dk) ? (size_t)NG * NLAY * NP1 : 0));   // [NPAR]
     const int nthr = blockDim.x;
@@ -482,7 +484,45 @@ ans_transmission_paths_kernel(RadParams P)
         }
         if (lane == 0) P.spec[(size_t)iw * NPATH + ipath] = spec;
         __syncwarp();
-        if (grad) {
+        if (layer_space) {
+            // Layer-space gradients: a limb path meets a layer twice, and the projection that follows is linear, so the
+            // two visits are added here -- dspec[NWAVE,NPATH,NPAR,NLAY] (half the size for limb geometry) and ONE
+            // projection matrix for all paths.  d spec / d q[k,l] = -(sum of SCALE over the visits of l) * (...).
+            double *myS = sS + (size_t)warp * NLAY;
+            for (int l = lane; l < NLAY; l += 32) myS[l] = 0.0;
+            __syncwarp();
+            for (int j = lane; j < n; j += 32)
+                atomicAdd(&myS[P.layinc[(size_t)j * NPATH + ipath]], P.scale[(size_t)j * NPATH + ipath]);
+            __syncwarp();
+            double *out = P.dspec + ((size_t)iw * NPATH + ipath) * NPAR * NLAY;
+            for (int l0 = 0; l0 < NLAY; l0 += 32) {
+                const int l = l0 + lane;
+                const bool live = l < NLAY;
+                const double scl = live ? myS[l] : 0.0;
+                for (int k = 0; k < NPAR; ++k) {
+                    double v = 0.0;
+                    if (live && scl != 0.0) {
+                        const int col = scol[k];
+                        double a = 0.0;
+                        if (col >= 0) {
+                            const double *dkp = sdk + (size_t)l * NP1 + col;
+                            double a0 = 0.0, a1 = 0.0;
+                            int g = 0;
+                            for (; g + 1 < NG; g += 2) {
+                                a0 = fma(myc[g], dkp[(size_t)g * NLAY * NP1], a0);
+                                a1 = fma(myc[g + 1], dkp[(size_t)(g + 1) * NLAY * NP1], a1);
+                            }
+                            if (g < NG) a0 = fma(myc[g], dkp[(size_t)g * NLAY * NP1], a0);
+                            a = (a0 + a1) * (col < P.NGAS ? 1.0e-4 : 1.0);
+                        }
+                        if (P.dtaucon) a = fma(sdcon[(size_t)k * NLAY + l], csum, a);
+                        v = -(a * scl);
+                        if (P.flags & ANSB200_RAD_NAN_TO_NUM) v = ans_nan_to_num(v);
+                    }
+                    if (live) out[(size_t)k * NLAY + l] = v;
+                }
+            }
+        } else if (grad) {
             double *out = P.dspec + ((size_t)iw * NPATH + ipath) * NPAR * NLM;
             for (int j0 = 0; j0 < NLM; j0 += 32) {
                 const int j = j0 + lane;
@@ -709,6 +749,16 @@ ans_thermal_paths_kernel(RadParams P)
     }
 }
 
+// Can ansb200_radiance produce layer-space gradients (ANSB200_RAD_LAYER_SPACE) for this shape?
+extern "C" int ansb200_radiance_layer_space(int mode, unsigned flags, int NG, int NLAY, int NGAS, int NPAR, int NPATH,
+                                            int has_dk, int has_dtaucon)
+{
+    if (mode != 1 || NPATH < 4 || !(flags & ANSB200_RAD_GRAD)) return 0;
+    const size_t nd_t = (size_t)NG * NLAY + NLAY + NG + (size_t)32 * NG + (has_dtaucon ? (size_t)NPAR * NLAY : 0) +
+                        (size_t)32 * NLAY + (has_dk ? (size_t)NG * NLAY * (NGAS + 1) : 0);
+    return nd_t * 8 + (size_t)NPAR * 4 + 16 <= 227 * 1024 ? 1 : 0;
+}
+
 extern "C" int ansb200_radiance(int mode, unsigned flags, const double *tau, const double *dk, const int32_t *gas_slot,
                                 const double *taucia, const double *taudust, const double *tauray,
                                 const double *dtaucon, const int32_t *layinc, const double *scale,
@@ -752,9 +802,13 @@ extern "C" int ansb200_radiance(int mode, unsigned flags, const double *tau, con
     // Several paths: one CTA per (wavenumber, path group) with the wavenumber's slabs staged once, as many
     // groups as keep every SM busy (>= 4 paths per CTA so that the staging pays).  One path, or slabs that do
     // not fit: one CTA per (wavenumber, path), slabs read through L2 (consecutive CTAs share the wavenumber).
+    const bool layer_space = (flags & ANSB200_RAD_LAYER_SPACE) != 0;
+    ANS_REQUIRE(!layer_space || ansb200_radiance_layer_space(mode, flags, NG, NLAY, NGAS, NPAR, NPATH, dk != nullptr, dtaucon != nullptr),
+                "radiance: layer-space gradients are available for transmission over >= 4 paths whose slabs fit in shared memory");
     if (!thermal && NPATH >= 4) {
         // transmission with several paths: warp-per-path kernel if the wavenumber's slabs fit in shared memory
         const size_t nd_t = (size_t)NG * NLAY + NLAY + NG + (size_t)RADT_WARPS * NG + ((grad && dtaucon) ? (size_t)NPAR * NLAY : 0) +
+                            ((grad && layer_space) ? (size_t)RADT_WARPS * NLAY : 0) +
                             ((grad && dk) ? (size_t)NG * NLAY * (NGAS + 1) : 0);
         const size_t smem_t = nd_t * 8 + (size_t)NPAR * 4 + 16;
         if (smem_t <= 227 * 1024) {

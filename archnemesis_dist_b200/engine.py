@@ -289,8 +289,10 @@ class HotPath:
         s.grad, s.plan_host, s.dplan, s.M = return_grad, hp, d, None
         return s
 
-    def stage_radiance(self, s, ev: Evaluation, M=None):
-        """Inputs of the radiance / projection kernels (continuum terms, path, surface, M)."""
+    def stage_radiance(self, s, ev: Evaluation, M=None, Mlay=None):
+        """Inputs of the radiance / projection kernels (continuum terms, path, surface, M).  Mlay: the layer-space
+        projection matrix (plan.fold_projection_layers); when given and the shape allows (transmission over several
+        paths) the gradients are produced per layer and projected with that one matrix instead of the per-path M."""
         st = self._stage
         i32 = torch.int32
         s.gas_slot = st("gas_slot", ev.gas_slot, i32)
@@ -304,8 +306,15 @@ class HotPath:
         s.emissivity, s.xfac = st("emissivity", ev.EMISSIVITY), st("xfac", ev.xfac)
         s.solflux, s.reflectance = st("solflux", ev.SOLFLUX), st("reflectance", ev.REFLECTANCE)
         s.sol_ang, s.emiss_ang = st("sol_ang", ev.SOL_ANG), st("emiss_ang", ev.EMISS_ANG)
-        s.M = st("M", M) if M is not None else None
         s.mode, s.ISPACE, s.TSURF, s.NVMR, s.NPAR = ev.mode, ev.ISPACE, ev.TSURF, ev.NVMR, ev.NPAR
+        s.layer_space = bool(
+            Mlay is not None and s.grad and hasattr(self.ops, "radiance_layer_space_ok") and
+            self.ops.radiance_layer_space_ok(ev.mode, self.NG, len(ev.press_atm), self.NGAS, ev.NPAR,
+                                             ev.LAYINC.shape[1], True, s.dtaucon is not None))
+        if s.layer_space:
+            s.M = st("Mlay", Mlay)
+        else:
+            s.M = st("M", M) if M is not None else None
         ev.h2d_bytes = st.bytes
         return s
 
@@ -355,10 +364,10 @@ class HotPath:
         self.launches += 1
         return out
 
-    def stage(self, ev: Evaluation, return_grad, M=None):
+    def stage(self, ev: Evaluation, return_grad, M=None, Mlay=None):
         """Copy one evaluation's inputs (pinned staging, async on the current stream) and build the
         k-interp plan.  Returns a Staged object; ev.h2d_bytes records the bytes moved."""
-        return self.stage_radiance(self.stage_opacity(ev, return_grad), ev, M)
+        return self.stage_radiance(self.stage_opacity(ev, return_grad), ev, M, Mlay)
 
     # -- device stages ---------------------------------------------------------------------------
     def gas_opacity(self, s, timers=None):
@@ -388,14 +397,14 @@ class HotPath:
         out = self.ops.radiance(s.mode, tau, dk, s.gas_slot, s.taucia, s.taudust, s.tauray, s.dtaucon, s.layinc, s.scale,
                                 s.nlayin, s.emtemp, s.laypress, self.wave_d, self.delg_d, s.emissivity, s.xfac,
                                 s.solflux, s.reflectance, s.sol_ang, s.emiss_ang, s.ISPACE, s.TSURF, s.NVMR, s.NPAR,
-                                s.grad)
+                                s.grad, **({"layer_space": True} if getattr(s, "layer_space", False) else {}))
         self.launches += 1
         if not s.grad:
             return out
         spec, dspec, dtsurf = out
         if s.M is None:
             return spec, dspec, dtsurf
-        dx = self.ops.jacobian_project(dspec, s.M)
+        dx = self.ops.jacobian_project(dspec, s.M, **({"shared": True} if getattr(s, "layer_space", False) else {}))
         self.launches += 1
         return spec, dx, dtsurf
 

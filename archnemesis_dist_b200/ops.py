@@ -226,9 +226,11 @@ THERMAL, TRANSMISSION = 0, 1
 
 def radiance(mode, tau, dk, gas_slot, taucia, taudust, tauray, dtaucon, layinc, scale, nlayin, emtemp, laypress,
              wave, delg, emissivity, xfac, solflux, reflectance, sol_ang, emiss_ang, ispace, tsurf, NVMR, NPAR,
-             want_grad, nan_to_num=True):
+             want_grad, nan_to_num=True, layer_space=False):
     """Path radiance (+ layer-space Jacobian) for all paths; see include/ansb200.h.
-    Returns spec[NWAVE,NPATH] and, with gradients, dspec[NWAVE,NPATH,NPAR,NLAYMAX], dtsurf[NWAVE,NPATH]."""
+    Returns spec[NWAVE,NPATH] and, with gradients, dspec[NWAVE,NPATH,NPAR,NLAYMAX], dtsurf[NWAVE,NPATH].
+    layer_space: gradients per layer instead of per path position, dspec[NWAVE,NPATH,NPAR,NLAY] (the visits of a layer
+    added; see radiance_layer_space_ok)."""
     _require_cuda()
     NWAVE, NG, NLAY = tau.shape
     NLAYMAX, NPATH = layinc.shape
@@ -240,7 +242,9 @@ def radiance(mode, tau, dk, gas_slot, taucia, taudust, tauray, dtaucon, layinc, 
         flags |= _lib.RAD_GRAD
         if nan_to_num:
             flags |= _lib.RAD_NAN_TO_NUM
-        dspec = torch.empty((NWAVE, NPATH, NPAR, NLAYMAX), dtype=torch.float64, device="cuda")
+        if layer_space:
+            flags |= _lib.RAD_LAYER_SPACE
+        dspec = torch.empty((NWAVE, NPATH, NPAR, NLAY if layer_space else NLAYMAX), dtype=torch.float64, device="cuda")
         dtsurf = torch.zeros((NWAVE, NPATH), dtype=torch.float64, device="cuda")
     _lib.check(_lib.load().ansb200_radiance(
         int(mode), flags, _ptr(tau), _ptr(dk), _ptr(gas_slot), _ptr(taucia), _ptr(taudust), _ptr(tauray),
@@ -251,13 +255,20 @@ def radiance(mode, tau, dk, gas_slot, taucia, taudust, tauray, dtaucon, layinc, 
     return (spec, dspec, dtsurf) if want_grad else spec
 
 
-def jacobian_project(dspec, M):
-    """dspec[NWAVE,NPATH,NPAR,NLAYMAX] x M[NPATH,NPAR*NLAYMAX,NX] -> [NWAVE,NPATH,NX] (map2pro+map2xvec)."""
+def radiance_layer_space_ok(mode, NG, NLAY, NGAS, NPAR, NPATH, has_dk=True, has_dtaucon=True):
+    """Can ansb200_radiance hand back layer-space gradients for this shape (transmission over >= 4 paths)?"""
+    return bool(_lib.load().ansb200_radiance_layer_space(int(mode), _lib.RAD_GRAD, int(NG), int(NLAY), int(NGAS), int(NPAR),
+                                                         int(NPATH), int(has_dk), int(has_dtaucon)))
+
+
+def jacobian_project(dspec, M, shared=False):
+    """dspec[NWAVE,NPATH,NPAR,NLAYMAX] x M[NPATH,NPAR*NLAYMAX,NX] -> [NWAVE,NPATH,NX] (map2pro+map2xvec).
+    shared: M[1,NPAR*NLAY,NX] is one layer-space matrix for every path (dspec from radiance(layer_space=True))."""
     _require_cuda()
     if dspec.dim() != 4 or M.dim() != 3:
         raise ValueError("jacobian_project: dspec must be [NWAVE,NPATH,NPAR,NLAYMAX] and M [NPATH,NPAR*NLAYMAX,NX]")
     NWAVE, NPATH, NPAR, NLM = dspec.shape
-    if M.shape[0] != NPATH or M.shape[1] != NPAR * NLM:
+    if M.shape[0] != (1 if shared else NPATH) or M.shape[1] != NPAR * NLM:
         # (the reference raises a tensordot shape error when xmap and the gradient array disagree, ForwardModel_0.py:5420)
         raise ValueError("jacobian_project: M is %s, expected (%d, %d, NX) for dspec %s"
                          % (tuple(M.shape), NPATH, NPAR * NLM, tuple(dspec.shape)))
@@ -266,8 +277,8 @@ def jacobian_project(dspec, M):
             raise ValueError("jacobian_project: %s must be a contiguous float64 CUDA tensor" % name)
     NX = M.shape[2]
     out = torch.empty((NWAVE, NPATH, NX), dtype=torch.float64, device="cuda")
-    _lib.check(_lib.load().ansb200_jacobian_project(_ptr(dspec), _ptr(M), NWAVE, NPAR, NLM, NPATH, NX, _ptr(out),
-                                                    _stream()))
+    fn = _lib.load().ansb200_jacobian_project_shared if shared else _lib.load().ansb200_jacobian_project
+    _lib.check(fn(_ptr(dspec), _ptr(M), NWAVE, NPAR, NLM, NPATH, NX, _ptr(out), _stream()))
     return out
 
 

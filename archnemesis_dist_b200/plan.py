@@ -246,6 +246,14 @@ def fold_projection(xmap, LAYINC, NLAYIN, DTE, DAM, DCO, NVMR, NDUST):
     return np.ascontiguousarray(M.reshape(NPATH, NPAR * NLM, NX))
 
 
+def fold_projection_layers(xmap, NLAY, DTE, DAM, DCO, NVMR, NDUST):
+    """The layer-space form of fold_projection: M[1, NPAR*NLAY, NX] with M[0, k*NLAY+l, x] = sum_pro D_k[l,pro]
+    xmap[x,k,pro] -- what every path's M is before its rows are gathered by LAYINC.  Used with gradients per layer
+    (ansb200_radiance with ANSB200_RAD_LAYER_SPACE): sum_j dspec[k,j] M_path[(k,j)] = sum_l (sum of the visits of l) M[(k,l)]."""
+    ident = np.arange(NLAY, dtype=np.int32).reshape(NLAY, 1)
+    return fold_projection(xmap, ident, np.array([NLAY], dtype=np.int32), DTE, DAM, DCO, NVMR, NDUST)
+
+
 # ------------------------------------------------------------------------------------------------
 # Instrument line shape as a sparse operator on the wavenumber axis (Measurement_0.conv / convg,
 # archnemesis/Measurement_0.py:2288-2465 / :2467-2692), for the two modes convg supports with k-tables.

@@ -294,6 +294,11 @@ def fold_M(c):
     return plan.fold_projection(c["xmap"], c["LAYINC"], c["NLAYIN"], c["DTE"], c["DAM"], c["DCO"], c["NVMR"], c["NDUST"])
 
 
+def fold_Mlay(c):
+    from archnemesis_dist_b200 import plan
+    return plan.fold_projection_layers(c["xmap"], len(c["press"]), c["DTE"], c["DAM"], c["DCO"], c["NVMR"], c["NDUST"])
+
+
 def limb_case(c, npath):
     """BASELINE config 4 on the atmosphere of case c: `npath` limb / occultation paths, path g sees the layers
     above its tangent layer twice (NLAYIN up to 2 NLAY), padded like Path_0 pads them."""
@@ -585,12 +590,12 @@ def run_extras(hp, c, cfg, nthreads):
     # config 4: 64 limb / occultation paths on the same atmosphere and table
     try:
         c4 = limb_case(c, 64)
-        M4 = fold_M(c4)
+        M4, Ml4 = fold_M(c4), fold_Mlay(c4)
         rows = np.unique(np.linspace(0, NW - 1, 4).astype(int))
         r4 = {}
         for name, mode in (("transmission", engine.TRANSMISSION), ("thermal", engine.THERMAL)):
             ev4 = make_evaluation(c4, mode=mode)
-            s4 = hp.stage(ev4, True, M4)
+            s4 = hp.stage(ev4, True, M4, Mlay=Ml4)       # (layer-space gradients + one projection matrix where supported)
             ms = timeit(lambda: hp.run(s4))
             go = hp.gas_opacity(s4)
             ms_fin = timeit(lambda: hp.finish(s4, go))
@@ -598,6 +603,7 @@ def run_extras(hp, c, cfg, nthreads):
             s_ref, x_ref = cpu_limb_rows(c4, rows, mode == engine.TRANSMISSION, nthreads)
             e_s, e_x = parity_of(spec.cpu().numpy()[rows], dx.cpu().numpy()[rows], s_ref, x_ref)
             r4[name] = dict(ms_per_eval=ms, ms_gas_opacity=ms - ms_fin, ms_radiance_and_projection=ms_fin,
+                            layer_space_gradients=bool(getattr(s4, "layer_space", False)),
                             geometry_spectra_per_s=64 * 1e3 / ms, parity=dict(max_rel_spec=e_s, max_col_jac=e_x, rows=len(rows)))
             del s4, go, spec, dx
         out["config4"] = dict(workload="64 limb paths, NLAYIN up to %d, NWAVE=%d NX=%d, forward+Jacobian of all paths "

@@ -38,6 +38,9 @@ extern "C" {
 /* ansb200_radiance flags */
 #define ANSB200_RAD_GRAD 1u          /* produce layer-space gradients */
 #define ANSB200_RAD_NAN_TO_NUM 2u    /* np.nan_to_num on g-integrated gradients (ForwardModel_0.py:4507) */
+#define ANSB200_RAD_LAYER_SPACE 4u   /* gradients per LAYER, dspec[NWAVE,NPATH,NPAR,NLAY]: the visits of a layer by a limb /
+                                        occultation path are added (the projection is linear); where
+                                        ansb200_radiance_layer_space() says so */
 
 typedef struct ansb200_table ansb200_table;
 
@@ -159,6 +162,10 @@ int ansb200_continuum(const double *kw, const int32_t *nplanes, int NTERM, int N
                       int NR, const double *ud, const double *vd, int NDUST, int NWAVE, int NLAY, int NVMR, int has_cia,
                       int want_grad, double *taucia, double *taudust, double *tauray, double *dtaucon, void *stream);
 
+/* 1 if ansb200_radiance can produce layer-space gradients for this shape (transmission over >= 4 paths). */
+int ansb200_radiance_layer_space(int mode, unsigned flags, int NG, int NLAY, int NGAS, int NPAR, int NPATH, int has_dk,
+                                 int has_dtaucon);
+
 /* ---- gas opacity from line-by-line tables ------------------------------------------------------
  * Replaces Spectroscopy_0.calc_klbl / calc_klblg (archnemesis/Spectroscopy_0.py:1768-1919, :1601-1765)
  * and the LBL-table branch of calculate_gaseous_line_opacity (ForwardModel_0.py:3795-3815).  The table
@@ -177,6 +184,10 @@ int ansb200_lbl_table_opacity(const ansb200_table *t, int NLAY, const int32_t *c
  * this computes out[NWAVE,NPATH,NX] = sum_{k,j} dspec[NWAVE,path,k,j] * M[path,(k,j),x]. */
 int ansb200_jacobian_project(const double *dspec, const double *M, int NWAVE, int NPAR, int NLAYMAX,
                              int NPATH, int NX, double *out, void *stream);
+/* The same with layer-space gradients dspec[NWAVE,NPATH,NPAR,NLAY] and ONE matrix M[NPAR*NLAY, NX] for all paths
+ * (M[k*NLAY + l, x] = sum_pro D_k[l,pro] xmap[x,k,pro]: D does not depend on the path). */
+int ansb200_jacobian_project_shared(const double *dspec, const double *M, int NWAVE, int NPAR, int NLAY, int NPATH,
+                                    int NX, double *out, void *stream);
 
 /* ---- instrument line shape -------------------------------------------------------------------
  * Replaces Measurement_0.conv / convg for k-tables (archnemesis/Measurement_0.py:2288-2465,

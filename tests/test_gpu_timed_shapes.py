@@ -279,3 +279,45 @@ def test_lbl_ten_thousand_lines_many_tiles(mods):
     for i, (t, p, q) in enumerate(pts):
         ref = orc.lbl_absorption(wn, lines, t, p, 296.0, 1.0, q, 0.99, 28.0, mix)
         assert relerr(cpu(out[i]), ref) < 1e-10, i
+
+
+def test_layer_space_gradients_of_limb_transmission(mods):
+    """ANSB200_RAD_LAYER_SPACE: for limb / occultation paths (every layer above the tangent is crossed twice) the
+    transmission kernel adds the two visits and the projection uses ONE layer-space matrix for all paths.  Same
+    spectrum and state-vector Jacobian as the path-space route (dspec[NWAVE,NPATH,NPAR,NLAYIN] x per-path M)."""
+    import bench
+    ops, plan, engine = mods["ops"], mods["plan"], mods["engine"]
+    c = mods["syn"].make_fm_case(nwave=24, ng=20, ngas=6, nlay=100, npro=100, nx=60, nvmr=8, seed=7)
+    c4 = bench.limb_case(c, 16)
+    tab = c["tab"]
+    hp = engine.HotPath(tab["K"], tab["PRESS"], tab["TEMP"], tab["DELG"], tab["WAVE"])
+    M = plan.fold_projection(c4["xmap"], c4["LAYINC"], c4["NLAYIN"], c4["DTE"], c4["DAM"], c4["DCO"], c4["NVMR"], c4["NDUST"])
+    Mlay = plan.fold_projection_layers(c4["xmap"], 100, c4["DTE"], c4["DAM"], c4["DCO"], c4["NVMR"], c4["NDUST"])
+    assert Mlay.shape == (1, c4["NPAR"] * 100, 60) and M.shape[1] == c4["NPAR"] * int(c4["LAYINC"].shape[0])
+    ev = _evaluation(mods, c4, mode=engine.TRANSMISSION)
+    s_path = hp.stage(ev, True, M)
+    s_lay = hp.stage(ev, True, M, Mlay=Mlay)
+    assert s_lay.layer_space and not getattr(s_path, "layer_space", False)
+    a_spec, a_dx, _ = hp.run(s_path)
+    b_spec, b_dx, _ = hp.run(s_lay)
+    assert mods["torch"].equal(a_spec, b_spec)
+    got, ref = cpu(b_dx), cpu(a_dx)
+    for ix in range(ref.shape[-1]):
+        assert colerr(got[..., ix], ref[..., ix]) < 1e-13, ix
+    # the layer-space array itself: the two visits of a layer added
+    tau, dk = hp.gas_opacity(s_path)
+    args = (s_path.mode, tau, dk, s_path.gas_slot, s_path.taucia, s_path.taudust, s_path.tauray, s_path.dtaucon,
+            s_path.layinc, s_path.scale, s_path.nlayin, s_path.emtemp, s_path.laypress, hp.wave_d, hp.delg_d,
+            s_path.emissivity, s_path.xfac, None, None, None, None, s_path.ISPACE, s_path.TSURF, s_path.NVMR, s_path.NPAR, True)
+    _, d_path, _ = ops.radiance(*args)
+    _, d_lay, _ = ops.radiance(*args, layer_space=True)
+    d_path, d_lay = cpu(d_path), cpu(d_lay)
+    assert d_lay.shape == (24, 16, c4["NPAR"], 100)
+    summed = np.zeros_like(d_lay)
+    for p in range(16):
+        n = int(c4["NLAYIN"][p])
+        np.add.at(summed[:, p].transpose(2, 0, 1), c4["LAYINC"][:n, p], d_path[:, p, :, :n].transpose(2, 0, 1))
+    assert colerr(d_lay, summed) < 1e-13
+    # thermal emission keeps path-space gradients
+    assert not hp.stage(_evaluation(mods, c4), True, M, Mlay=Mlay).layer_space
+    hp.close()
