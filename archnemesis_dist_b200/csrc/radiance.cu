@@ -408,6 +408,7 @@ ans_radiance_kernel(RadParams P)
 // sweep the (parameter, layer) outputs with consecutive lanes on consecutive layers (contiguous stores).
 // 5e3 warp instructions per (wavenumber, path) instead of 2.7e4 in the general kernel.
 constexpr int RADT_WARPS = 32;
+constexpr int RADT_GROUP = 64;      // paths per pass of the layer-space gradient phase (8 tiles of 8 paths)
 
 __global__ void __launch_bounds__(RADT_WARPS * 32)
 ans_transmission_paths_kernel(RadParams P)
@@ -422,8 +423,10 @@ ans_transmission_paths_kernel(RadParams P)
     double *sdelg = scon + NLAY;                                   // [NG]
     double *sc = sdelg + NG;                                       // [RADT_WARPS][NG] c_g of the warp's current path
     const bool layer_space = grad && (P.flags & ANSB200_RAD_LAYER_SPACE) != 0;
-    double *sS = sc + (size_t)RADT_WARPS * NG;                     // [RADT_WARPS][NLAY] sum of SCALE over a layer's visits
-    double *sdcon = sS + (layer_space ? (size_t)RADT_WARPS * NLAY : 0);   // [NPAR*NLAY] dtaucon of the wavenumber (grad)
+    double *sS = sc + (size_t)RADT_WARPS * NG;                     // [RADT_GROUP][NLAY] sum of SCALE over a layer's visits
+    double *sC = sS + (layer_space ? (size_t)RADT_GROUP * NLAY : 0);      // [RADT_GROUP][NG] c_g of the group's paths
+    double *sCs = sC + (layer_space ? (size_t)RADT_GROUP * NG : 0);       // [RADT_GROUP] sum_g c_g
+    double *sdcon = sCs + (layer_space ? (size_t)RADT_GROUP : 0);         // [NPAR*NLAY] dtaucon of the wavenumber (grad)
     double *sdk = sdcon + ((grad && P.dtaucon) ? (size_t)NPAR * NLAY : 0);   // [NG*NLAY*NP1] dk of the wavenumber (grad)
     int *scol = reinterpret_cast<int *>(sdk + ((grad && P.dk) ? (size_t)NG * NLAY * NP1 : 0));   // [NPAR]
     const int nthr = blockDim.x;
@@ -451,7 +454,17 @@ ans_transmission_paths_kernel(RadParams P)
     __syncthreads();
     const double xf = P.xfac ? P.xfac[iw] : 1.0;
     double *myc = sc + (size_t)warp * NG;
-    for (int ipath = warp; ipath < NPATH; ipath += (nthr >> 5)) {
+    // (layer-space gradients: the paths are taken in groups of RADT_GROUP -- phase 1 of every path of the group, then
+    // the group's gradients as tensor-core products by the whole CTA; otherwise one pass over all paths)
+    for (int gp0 = 0; gp0 < NPATH; gp0 += (layer_space ? RADT_GROUP : NPATH)) {
+    const int gp1 = layer_space ? min(NPATH, gp0 + RADT_GROUP) : NPATH;
+    if (layer_space) {
+        for (int t = threadIdx.x; t < RADT_GROUP * NLAY; t += nthr) sS[t] = 0.0;
+        for (int t = threadIdx.x; t < RADT_GROUP * NG; t += nthr) sC[t] = 0.0;
+        for (int t = threadIdx.x; t < RADT_GROUP; t += nthr) sCs[t] = 0.0;
+        __syncthreads();
+    }
+    for (int ipath = gp0 + warp; ipath < gp1; ipath += (nthr >> 5)) {
         const int n = P.nlayin[ipath];
         // phase 1: spec_g and c_g.  The lane's path layers (up to 8: NLAYMAX <= 256) stay in registers for all g.
         constexpr int RQ = 8;
@@ -485,43 +498,13 @@ ans_transmission_paths_kernel(RadParams P)
         if (lane == 0) P.spec[(size_t)iw * NPATH + ipath] = spec;
         __syncwarp();
         if (layer_space) {
-            // Layer-space gradients: a limb path meets a layer twice, and the projection that follows is linear, so the
-            // two visits are added here -- dspec[NWAVE,NPATH,NPAR,NLAY] (half the size for limb geometry) and ONE
-            // projection matrix for all paths.  d spec / d q[k,l] = -(sum of SCALE over the visits of l) * (...).
-            double *myS = sS + (size_t)warp * NLAY;
-            for (int l = lane; l < NLAY; l += 32) myS[l] = 0.0;
-            __syncwarp();
+            // the path's NG numbers c_g, their sum, and the sum of SCALE over the visits of every layer (a limb path
+            // meets a layer twice; the projection that follows is linear, so the visits are added)
+            const int r = ipath - gp0;
+            for (int g = lane; g < NG; g += 32) sC[(size_t)r * NG + g] = myc[g];
+            if (lane == 0) sCs[r] = csum;
             for (int j = lane; j < n; j += 32)
-                atomicAdd(&myS[P.layinc[(size_t)j * NPATH + ipath]], P.scale[(size_t)j * NPATH + ipath]);
-            __syncwarp();
-            double *out = P.dspec + ((size_t)iw * NPATH + ipath) * NPAR * NLAY;
-            for (int l0 = 0; l0 < NLAY; l0 += 32) {
-                const int l = l0 + lane;
-                const bool live = l < NLAY;
-                const double scl = live ? myS[l] : 0.0;
-                for (int k = 0; k < NPAR; ++k) {
-                    double v = 0.0;
-                    if (live && scl != 0.0) {
-                        const int col = scol[k];
-                        double a = 0.0;
-                        if (col >= 0) {
-                            const double *dkp = sdk + (size_t)l * NP1 + col;
-                            double a0 = 0.0, a1 = 0.0;
-                            int g = 0;
-                            for (; g + 1 < NG; g += 2) {
-                                a0 = fma(myc[g], dkp[(size_t)g * NLAY * NP1], a0);
-                                a1 = fma(myc[g + 1], dkp[(size_t)(g + 1) * NLAY * NP1], a1);
-                            }
-                            if (g < NG) a0 = fma(myc[g], dkp[(size_t)g * NLAY * NP1], a0);
-                            a = (a0 + a1) * (col < P.NGAS ? 1.0e-4 : 1.0);
-                        }
-                        if (P.dtaucon) a = fma(sdcon[(size_t)k * NLAY + l], csum, a);
-                        v = -(a * scl);
-                        if (P.flags & ANSB200_RAD_NAN_TO_NUM) v = ans_nan_to_num(v);
-                    }
-                    if (live) out[(size_t)k * NLAY + l] = v;
-                }
-            }
+                atomicAdd(&sS[(size_t)r * NLAY + P.layinc[(size_t)j * NPATH + ipath]], P.scale[(size_t)j * NPATH + ipath]);
         } else if (grad) {
             double *out = P.dspec + ((size_t)iw * NPATH + ipath) * NPAR * NLM;
             for (int j0 = 0; j0 < NLM; j0 += 32) {
@@ -555,6 +538,53 @@ ans_transmission_paths_kernel(RadParams P)
         }
         __syncwarp();
     }
+    if (layer_space) {
+        // Gradients of the group in layer space, dspec[NWAVE,NPATH,NPAR,NLAY]:
+        //     d spec / d q[k,l] = -S[path][l] ( unit_k T_k[path][l] + csum[path] dtaucon[k,l] ),
+        //     T_k = C[path][g] x dk[g][l][col_k]   -- a [paths x NG] x [NG x NLAY] product per dk column:
+        // mma.m8n8k4 tiles of 8 paths x 8 layers (a = C[path][g], b = dk[g][l][col]); a warp takes (tile, parameter) units.
+        __syncthreads();
+        const int npt = (gp1 - gp0 + 7) >> 3, nlt = (NLAY + 7) >> 3;
+        const int kk = lane & 3, mm = lane >> 2;
+        for (int unit = warp; unit < npt * nlt * NPAR; unit += (nthr >> 5)) {
+            const int k = unit / (npt * nlt), rem = unit - k * (npt * nlt);
+            const int pt = rem / nlt, lt = rem - pt * nlt;
+            const int col = scol[k];
+            double d0 = 0.0, d1 = 0.0;
+            if (col >= 0) {
+                const int lb = lt * 8 + mm;                 // the layer of this lane's B element
+                for (int g0 = 0; g0 < NG; g0 += 4) {
+                    const int g = g0 + kk;
+                    const double a = g < NG ? sC[(size_t)(pt * 8 + mm) * NG + g] : 0.0;
+                    const double b = (g < NG && lb < NLAY) ? sdk[((size_t)g * NLAY + lb) * NP1 + col] : 0.0;
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+                }
+                const double unit_k = col < P.NGAS ? 1.0e-4 : 1.0;
+                d0 *= unit_k;
+                d1 *= unit_k;
+            }
+            const int r = pt * 8 + mm, path = gp0 + r;
+            if (path < gp1) {
+                const double cs = sCs[r];
+                double *out = P.dspec + (((size_t)iw * NPATH + path) * NPAR + k) * NLAY;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int l = lt * 8 + 2 * kk + h;
+                    if (l < NLAY) {
+                        const double scl = sS[(size_t)r * NLAY + l];
+                        double a = h ? d1 : d0;
+                        if (P.dtaucon) a = fma(sdcon[(size_t)k * NLAY + l], cs, a);
+                        double v = scl != 0.0 ? -(a * scl) : 0.0;
+                        if (P.flags & ANSB200_RAD_NAN_TO_NUM) v = ans_nan_to_num(v);
+                        out[l] = v;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    }   // path groups
 }
 
 // ---- thermal emission with gradients, many paths: one warp per path ------------------------------------------
@@ -755,7 +785,7 @@ extern "C" int ansb200_radiance_layer_space(int mode, unsigned flags, int NG, in
 {
     if (mode != 1 || NPATH < 4 || !(flags & ANSB200_RAD_GRAD)) return 0;
     const size_t nd_t = (size_t)NG * NLAY + NLAY + NG + (size_t)32 * NG + (has_dtaucon ? (size_t)NPAR * NLAY : 0) +
-                        (size_t)32 * NLAY + (has_dk ? (size_t)NG * NLAY * (NGAS + 1) : 0);
+                        (size_t)64 * (NLAY + NG + 1) + (has_dk ? (size_t)NG * NLAY * (NGAS + 1) : 0);
     return nd_t * 8 + (size_t)NPAR * 4 + 16 <= 227 * 1024 ? 1 : 0;
 }
 
@@ -808,7 +838,7 @@ extern "C" int ansb200_radiance(int mode, unsigned flags, const double *tau, con
     if (!thermal && NPATH >= 4) {
         // transmission with several paths: warp-per-path kernel if the wavenumber's slabs fit in shared memory
         const size_t nd_t = (size_t)NG * NLAY + NLAY + NG + (size_t)RADT_WARPS * NG + ((grad && dtaucon) ? (size_t)NPAR * NLAY : 0) +
-                            ((grad && layer_space) ? (size_t)RADT_WARPS * NLAY : 0) +
+                            ((grad && layer_space) ? (size_t)RADT_GROUP * (NLAY + NG + 1) : 0) +
                             ((grad && dk) ? (size_t)NG * NLAY * (NGAS + 1) : 0);
         const size_t smem_t = nd_t * 8 + (size_t)NPAR * 4 + 16;
         if (smem_t <= 227 * 1024) {
