@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--parity-rows", type=int, default=0,
                     help="rows compared with the CPU oracle after the timed loop (0: every row at N=1, 64 at N>1)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the full CPU pass (parity on 64 rows only)")
+    ap.add_argument("--no-reference-baseline", action="store_true",
+                    help="skip timing the unmodified reference's numba overlap on a slice (oracle/_ref)")
     ap.add_argument("--no-extras", action="store_true", help="skip the config 3/4/5 and strong-scaling extras")
     ap.add_argument("--dense-continuum", action="store_true",
                     help="continuum terms as dense host arrays [NWAVE,NPAR,NLAY] (36 MB per step over PCIe) instead of the device plan")
@@ -187,6 +189,52 @@ def cpu_baseline_dict(seconds, nthreads, nw, passes):
                 sample="all %d wavenumbers of the timed case (every layer, g-ordinate, gas and state element), oracle C "
                        "port of the reference path with OpenMP over wavenumbers; %.2f s per pass, %d pass(es) timed, "
                        "nothing extrapolated" % (nw, seconds, passes))
+
+
+REF_ROWS = 64          # wavenumber rows of the timed case the unmodified reference's numba functions are timed on
+
+
+def reference_overlap_baseline(c, nrows=REF_ROWS):
+    """The UNMODIFIED reference (oracle/_ref mirror staged by oracle/make_ref.py, or /root/reference in the build
+    container) on a slice of the timed case: its own numba k_overlapg (ForwardModel_0.py:5842-5957, rankg
+    :5959-6026) over `nrows` strided wavenumber rows x every layer, one core (the function is serial; the reference
+    parallelises over state-vector columns, not inside an evaluation).  k-interpolation and radiance are left to the
+    oracle port here, so this OVER-states the reference's speed.  Returns a cpu_baseline-style dict, or a dict
+    saying why it is unavailable."""
+    try:
+        from oracle.ref_import import import_reference, reference_available, REFERENCE_ROOT
+        if not reference_available():
+            return dict(kind="reference", unavailable="no reference tree (oracle/_ref not staged)")
+        import_reference()
+        k_overlapg = sys.modules["archnemesis.ForwardModel_0"].k_overlapg
+    except Exception as e:      # noqa: BLE001  (numba or a dependency missing on this box)
+        return dict(kind="reference", unavailable="%s: %s" % (type(e).__name__, e))
+    from oracle import oracle as orc
+    tab = c["tab"]
+    NW = tab["NWAVE"]
+    rows = np.unique(np.linspace(0, NW - 1, min(nrows, NW)).astype(int))
+    k, dkdT = orc.calc_k(np.ascontiguousarray(tab["K"][rows]), tab["PRESS"], tab["TEMP"], c["press"], c["temp"],
+                         want_grad=True, nthreads=host_threads())
+    amount = np.ascontiguousarray(c["amount"], dtype=np.float64)        # [NGAS, NLAY], the reference's layout
+    delg = np.asarray(tab["DELG"], dtype=np.float64)
+    k_overlapg(delg, k[:1], dkdT[:1], amount)               # numba compile, untimed
+    t0 = time.perf_counter()
+    tau, dk = k_overlapg(delg, k, dkdT, amount)
+    dt = time.perf_counter() - t0
+    t_port0 = time.perf_counter()
+    tau_p, dk_p = orc.k_overlap(delg, k, c["amount"], dkdT=dkdT, nthreads=1)
+    dt_port = time.perf_counter() - t_port0
+    per_eval = dt / len(rows) * NW
+    return dict(value=1.0 / per_eval, unit="spectra/s", cores=1, kind="reference",
+                sample="the unmodified reference's numba k_overlapg (%s) on %d strided wavenumber rows x %d layers of "
+                       "the timed case: %.2f s, scaled by %d/%d; gas overlap only (interpolation, radiance and "
+                       "projection not included), compile excluded" % (
+                           "oracle/_ref mirror" if REFERENCE_ROOT.endswith("_ref") else "/root/reference", len(rows),
+                           k.shape[2], dt, NW, len(rows)),
+                seconds_per_evaluation=per_eval,
+                port_same_rows_one_core_s=dt_port,
+                port_equals_reference=dict(tau=bool(np.array_equal(tau, tau_p)), dk=bool(np.array_equal(dk, dk_p)),
+                                           max_rel_tau=float(np.abs(tau - tau_p).max() / np.abs(tau).max())))
 
 
 def run_reference_arm(args, cfg):
@@ -551,6 +599,8 @@ def run_b200(args, cfg):
                     gpu_launches=launches, roofline=roof, clocks=clocks, parity=parity)
         if cb is not None:
             line["cpu_baseline"] = cb
+            if not args.no_reference_baseline:
+                line["cpu_baseline_reference"] = reference_overlap_baseline(c)
         if strong is not None:
             line["strong"] = strong
         if world == 1 and not args.no_extras:

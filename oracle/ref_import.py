@@ -7,7 +7,8 @@ and never touched on the legacy-text + ``.kta`` path.  We install a ``sys.meta_p
 hands out permissive stub modules for those roots so ``import archnemesis`` succeeds.
 
 Only ``tests/`` (container-side validation) and ``oracle/make_golden.py`` may import this module.
-It is never imported by the product package and cannot work on the GPU box (no /root/reference).
+It is never imported by the product package.  On the GPU box (no /root/reference) it resolves to the mirror that
+``oracle/make_ref.py`` stages under ``oracle/_ref`` (git-ignored, travels with the snapshot).
 """
 import importlib.abc
 import importlib.machinery
@@ -16,7 +17,17 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("ANSB200_REFERENCE_ROOT", "/root/reference")
+def _reference_root():
+    """/root/reference in the build container; on the GPU box the byte-for-byte mirror oracle/make_ref.py staged."""
+    env = os.environ.get("ANSB200_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/archnemesis"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REFERENCE_ROOT = _reference_root()
 _STUB_ROOTS = {"h5py", "matplotlib", "mpl_toolkits", "corner", "pymultinest", "cdsapi", "hapi",
                "bs4", "mpi4py", "pygrib"}
 
