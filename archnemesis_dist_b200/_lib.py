@@ -25,7 +25,7 @@ EXPORTS = {
     "ansb200_overlap_mode": (_i, [_i]),
     "ansb200_overlap_stats": (None, [ctypes.POINTER(ctypes.c_int32)]),
     "ansb200_table_create": (_i, [_vp, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_vp), _vp]),
-    "ansb200_radiance_layer_space": (_i, [_i, _u, _i, _i, _i, _i, _i, _i, _i]),
+    "ansb200_radiance_layer_space": (_i, [_i, _u, _i, _i, _i, _i, _i, _i, _i, _i]),
     "ansb200_jacobian_project_shared": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "ansb200_table_create_ex": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_vp), _vp]),
     "ansb200_table_destroy": (_i, [_vp]),

@@ -779,11 +779,390 @@ ans_thermal_paths_kernel(RadParams P)
     }
 }
 
-// Can ansb200_radiance produce layer-space gradients (ANSB200_RAD_LAYER_SPACE) for this shape?
-extern "C" int ansb200_radiance_layer_space(int mode, unsigned flags, int NG, int NLAY, int NGAS, int NPAR, int NPATH,
-                                            int has_dk, int has_dtaucon)
+// ---- thermal emission with layer-space gradients, many paths: tiles of 8 paths, g-sums on the tensor cores -------
+// The gradient of a path with respect to the opacity parameters of LAYER l is sum_g sum_{visits j of l} W_j(g) dk[g,l,:]
+// (+ the Planck-derivative term for the temperature), so per layer it is a small matrix product
+//     G_l[path, c] = sum_g  Wl[path, g] * DK_l[g, c],     Wl[path, g] = sum over the path's visits of l of W_j(g)
+// -- 8 paths x (NGAS + 2) columns x NG: one mma.m8n8k4 per 4 g-ordinates.  A CTA owns (wavenumber, 8 paths); warp p
+// scans path p like ans_thermal_paths_kernel (lanes own contiguous chunks of visits, whose layer / scale / Planck
+// value now live in REGISTERS), but instead of the NGAS+1 fused multiply-adds per visit and g it stores the one
+// number W_j(g) into the CTA's W tile [path][g mod 4][layer]; after every 4 g-ordinates all warps fold the tile into
+// G (shared memory) with FP64 tensor-core products whose B operand (dk, plus a column of ones that yields sum_g W for
+// the continuum term) is read from global memory (prefetched into L1 while the scan runs).  Visits of the same layer
+// by the same path (limb: two) are ranked once per path ("legs", last visit first) and stored in as many passes, the
+// later ones read-modify-write, so no shared-memory floating-point atomics are needed.  The chunk length per lane is
+// forced odd: lanes then hit distinct banks in the tau row and in the W tile.  The scan is branch-free: unused slots
+// of a lane point at a zero opacity (exp(-0) = 1, Planck value 0) and exp(-x) is an inlined 13th-degree polynomial
+// after the usual 2^k reduction (relative error < 3e-16; the library routine with its range branches costs 2.5 x
+// as many instructions).  Output: dspec[NWAVE, NPATH, NPAR, NLAY].
+constexpr int TL_PATHS = 8;      // paths per CTA = warps = rows of the product
+constexpr int TL_RQ = 7;         // visits per lane: NLAYIN <= 224
+
+__constant__ double TL_EXPC[12] = {      // 1/13!, 1/12!, ..., 1/2!
+    1.6059043836821613e-10, 2.0876756987868098e-09, 2.5052108385441720e-08, 2.7557319223985893e-07,
+    2.7557319223985888e-06, 2.4801587301587302e-05, 1.9841269841269841e-04, 1.3888888888888889e-03,
+    8.3333333333333332e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 5.0000000000000000e-01};
+
+// exp(-x) for x >= 0 (larger than 708: 2^-1021 instead of a subnormal or 0; NaN propagates)
+__device__ __forceinline__ double tl_expneg(double x)
 {
-    if (mode != 1 || NPATH < 4 || !(flags & ANSB200_RAD_GRAD)) return 0;
+    const double xc = fmin(x, 708.0);
+    const double t = fma(xc, -1.4426950408889634, 6755399441055744.0);      // round(-x log2 e) in the low word
+    const int k = __double2loint(t);
+    const double kf = t - 6755399441055744.0;
+    double r = fma(kf, -6.93147180369123816490e-01, -xc);
+    r = fma(kf, -1.90821492927058770002e-10, r);
+    double pl = TL_EXPC[0];
+#pragma unroll
+    for (int i = 1; i < 12; ++i) pl = fma(pl, r, TL_EXPC[i]);
+    pl = fma(pl, r, 1.0);
+    pl = fma(pl, r, 1.0);
+    const double v = __hiloint2double(__double2hiint(pl) + (k << 20), __double2loint(pl));
+    return x != x ? x : v;
+}
+
+__device__ __forceinline__ double tl_nan_to_num(double v)
+{
+    if ((__double2hiint(v) & 0x7ff00000) == 0x7ff00000) v = ans_nan_to_num(v);     // (rare: one integer test otherwise)
+    return v;
+}
+
+// One g-ordinate of one path, RQ visit slots per lane (RQ = the path's odd chunk length: no slot tests, the seven
+// exponentials of a lane are independent instruction streams).  Adds the g-ordinate's share to spec / dts / esq and
+// leaves W_j(g) in the path's row of the W tile.
+template <int RQ>
+__device__ __forceinline__ void tl_scan_g(const char *tg, char *wp, const int (&lay8)[TL_RQ], const double (&sc)[TL_RQ],
+                                          const double (&Bq)[TL_RQ], double (&esq)[TL_RQ], unsigned m0, unsigned m1,
+                                          unsigned long long legs, int maxleg, bool ground, double radground,
+                                          double dradground, double dg, double xf, int lane, double &spec, double &dts)
+{
+    double Tq[RQ], Wq[RQ];
+    double loc = 1.0;
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) Tq[q] = tl_expneg(*reinterpret_cast<const double *>(tg + lay8[q]) * sc[q]);
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) {
+        loc *= Tq[q];
+        Tq[q] = loc;
+    }
+    double incl = loc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double up = rshfl_up(incl, d);
+        if (lane >= d) incl *= up;
+    }
+    double base = rshfl_up(incl, 1);
+    if (lane == 0) base = 1.0;
+    const double Tn = rshfl_idx(incl, 31);
+    double esum = 0.0;
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) {
+        Tq[q] *= base;
+        const double Tm = q == 0 ? base : Tq[q > 0 ? q - 1 : 0];
+        esum = fma(Tm - Tq[q], Bq[q], esum);
+    }
+    // suffix sums of the emission terms; lane 0's inclusive value is the path's sum
+    double rincl = esum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double dn = rshfl_down(rincl, d);
+        if (lane + d < 32) rincl += dn;
+    }
+    double specg = rshfl_idx(rincl, 0);
+    if (ground) specg += Tn * radground;
+    const double dgx = dg * xf;
+    spec += specg * xf * dg;
+    if (ground) dts += Tn * dradground * xf * dg;
+    double after = rshfl_down(rincl, 1);
+    if (lane == 31) after = 0.0;
+    double suffix = after + (ground ? Tn * radground : 0.0);
+#pragma unroll
+    for (int qq = 0; qq < RQ; ++qq) {
+        const int q = RQ - 1 - qq;
+        const double Tj = Tq[q], Tm = q == 0 ? base : Tq[q > 0 ? q - 1 : 0];
+        Wq[q] = (Tj * Bq[q] - suffix) * sc[q] * dgx;
+        esq[q] = fma(Tm - Tj, dgx, esq[q]);
+        suffix = fma(Tm - Tj, Bq[q], suffix);
+    }
+    // W_j(g) into the tile: one pass per leg, the later ones add to what the earlier ones stored
+#pragma unroll
+    for (int q = 0; q < RQ; ++q)
+        if ((m0 >> q) & 1u) *reinterpret_cast<double *>(wp + lay8[q]) = Wq[q];
+    __syncwarp();
+    if (maxleg >= 1) {
+#pragma unroll
+        for (int q = 0; q < RQ; ++q)
+            if ((m1 >> q) & 1u) *reinterpret_cast<double *>(wp + lay8[q]) += Wq[q];
+        __syncwarp();
+        for (int r = 2; r <= maxleg; ++r) {
+#pragma unroll
+            for (int q = 0; q < RQ; ++q)
+                if ((int)((legs >> (8 * q)) & 0xffull) == r) *reinterpret_cast<double *>(wp + lay8[q]) += Wq[q];
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TL_PATHS * 32, 2)
+ans_thermal_layers_kernel(RadParams P)
+{
+    extern __shared__ __align__(16) unsigned char rad_smem[];
+    const int iw = blockIdx.x, tile = blockIdx.y;
+    const int NG = P.NG, NLAY = P.NLAY, NPATH = P.NPATH, NPAR = P.NPAR, NP1 = P.NGAS + 1;
+    const int NT = (NP1 + 1 + 7) / 8, GS = NT * 64 + 2;
+    const int TS = NLAY + 1;              // tau row: [NLAY] + one zero for the unused slots of a lane
+    const int LS = NLAY | 1;              // W row (odd: the tensor-core A fragment reads 32 rows at one layer)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *sG = reinterpret_cast<double *>(rad_smem);            // [NLAY][GS]: G_l[path][column] (+ 2 pad)
+    double *stau = sG + (size_t)NLAY * GS;                        // [NG][TS]: gas + continuum opacity
+    double *sW = stau + (size_t)NG * TS;                          // [8 paths * 4 g][LS]
+    double *sdelg = sW + (size_t)32 * LS;                         // [NG]
+    int *sfirst = reinterpret_cast<int *>(sdelg + NG);            // per warp [NLAY]: scratch of the visit ranking
+    int *scol = sfirst + TL_PATHS * NLAY;                         // [NPAR]
+    for (int l0 = 0; l0 < NLAY; l0 += 32) {
+        const int l = l0 + lane;
+        double c = 0.0;
+        if (l < NLAY) {
+            if (P.taucia) c += P.taucia[(size_t)iw * NLAY + l];
+            if (P.taudust) c += P.taudust[(size_t)iw * NLAY + l];
+            if (P.tauray) c += P.tauray[(size_t)iw * NLAY + l];
+            for (int g = warp; g < NG; g += TL_PATHS) stau[g * TS + l] = P.tau[((size_t)iw * NG + g) * NLAY + l] + c;
+        }
+    }
+    for (int g = threadIdx.x; g < NG; g += blockDim.x) {
+        stau[g * TS + NLAY] = 0.0;
+        sdelg[g] = P.delg[g];
+    }
+    for (int t = threadIdx.x; t < NLAY * GS; t += blockDim.x) sG[t] = 0.0;
+    for (int t = threadIdx.x; t < 32 * LS; t += blockDim.x) sW[t] = 0.0;
+    for (int t = threadIdx.x; t < TL_PATHS * NLAY; t += blockDim.x) sfirst[t] = -1;
+    for (int k = threadIdx.x; k < NPAR; k += blockDim.x) {
+        int col = -1;
+        if (k == P.NVMR) col = P.NGAS;
+        else for (int i = 0; i < P.NGAS; ++i) if (P.gas_slot[i] == k) col = i;
+        scol[k] = col;
+    }
+    __syncthreads();
+    // ---- the warp's path: visits into registers, ranking of repeated layers ---------------------------------------
+    const int ipath = tile * TL_PATHS + warp;
+    const int n = ipath < NPATH ? P.nlayin[ipath] : 0;
+    const int CH = ((n + 31) / 32) | 1;
+    const int j0 = lane * CH, cnt = max(0, min(n, j0 + CH) - j0);
+    const double wv = P.wave[iw];
+    const double xf = P.xfac ? P.xfac[iw] : 1.0;
+    int lay8[TL_RQ];                     // byte offset of the visit's layer in a tau / W row
+    double sc[TL_RQ], Bq[TL_RQ], esq[TL_RQ];
+#pragma unroll
+    for (int q = 0; q < TL_RQ; ++q) {
+        lay8[q] = NLAY * 8; sc[q] = 0.0; Bq[q] = 0.0; esq[q] = 0.0;
+        if (q < cnt) {
+            const size_t at = (size_t)(j0 + q) * NPATH + ipath;
+            lay8[q] = P.layinc[at] * 8;
+            sc[q] = P.scale[at];
+            double db;
+            ans_planckg(P.ispace, wv, P.emtemp[at], Bq[q], db);
+        }
+    }
+    unsigned long long legs = 0;         // rank of each visit among the path's visits of its layer, 8 bits per slot
+    unsigned m0 = 0u, m1 = 0u;           // slots of rank 0 / rank 1
+    int maxleg = -1;
+    {
+        int *first = sfirst + warp * NLAY;
+        unsigned pend = (1u << cnt) - 1u;
+        while (__any_sync(RFULL, pend != 0u)) {
+            ++maxleg;
+#pragma unroll
+            for (int q = 0; q < TL_RQ; ++q) if ((pend >> q) & 1u) atomicMax(&first[lay8[q] >> 3], j0 + q);
+            __syncwarp();
+            unsigned done = 0u;
+#pragma unroll
+            for (int q = 0; q < TL_RQ; ++q)
+                if (((pend >> q) & 1u) && first[lay8[q] >> 3] == j0 + q) {
+                    legs |= (unsigned long long)maxleg << (8 * q);
+                    done |= 1u << q;
+                }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < TL_RQ; ++q) if ((done >> q) & 1u) first[lay8[q] >> 3] = -1;
+            __syncwarp();
+            if (maxleg == 0) m0 = done;
+            if (maxleg == 1) m1 = done;
+            pend &= ~done;
+        }
+        legs |= 0xff00000000000000ull;                      // (unused slots never match a rank)
+#pragma unroll
+        for (int q = 0; q < TL_RQ; ++q) if (q >= cnt) legs |= 0xffull << (8 * q);
+    }
+    // limb / nadir test and ground term (:6353-6365, :6479-6494)
+    double radground = 0.0, dradground = 0.0;
+    bool ground = false;
+    if (n > 0) {
+        const int jh = n / 2 - 1;
+        const double p1 = P.laypress[P.layinc[(size_t)(jh >= 0 ? jh : n - 1) * NPATH + ipath]];
+        const double p2 = P.laypress[P.layinc[(size_t)(n - 1) * NPATH + ipath]];
+        ground = p2 > p1;
+        if (ground) {
+            if (P.tsurf <= 0.0) {
+                ans_planckg(P.ispace, wv, P.emtemp[(size_t)(n - 1) * NPATH + ipath], radground, dradground);
+            } else {
+                ans_planckg(P.ispace, wv, P.tsurf, radground, dradground);
+                const double em = P.emissivity[iw];
+                radground *= em;
+                dradground *= em;
+            }
+        }
+    }
+    double spec = 0.0, dts = 0.0;
+    const int NCH = (NG + 3) / 4;
+    // tensor-core operands of this lane: row (lane & 3) of the chunk's 4 g, column (lane >> 2) of a column tile
+    const int NTL = (NLAY - warp + TL_PATHS - 1) / TL_PATHS;          // layers warp, warp + 8, ...
+    const double *wl = sW + lane * LS;
+#pragma unroll 1
+    for (int gc = 0; gc < NCH; ++gc) {
+        {   // the chunk's dk rows towards L1 / L2 while the scan runs
+            const char *base = reinterpret_cast<const char *>(P.dk + ((size_t)iw * NG + gc * 4) * NLAY * NP1);
+            const size_t bytes = (size_t)min(4, NG - gc * 4) * NLAY * NP1 * 8;
+            for (size_t o = (size_t)threadIdx.x * 128; o < bytes; o += (size_t)blockDim.x * 128)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(base + o));
+        }
+#pragma unroll 1
+        for (int gi = 0; gi < 4; ++gi) {
+            const int g = gc * 4 + gi;
+            char *wp = reinterpret_cast<char *>(sW + (warp * 4 + gi) * LS);
+            if (g < NG && n > 0) {
+                const char *tg = reinterpret_cast<const char *>(stau + g * TS);
+                const double dg = sdelg[g];
+#define TL_SCAN(RQ) tl_scan_g<RQ>(tg, wp, lay8, sc, Bq, esq, m0, m1, legs, maxleg, ground, radground, dradground, dg, xf, \
+                                  lane, spec, dts)
+                if (CH == 7) TL_SCAN(7);
+                else if (CH == 5) TL_SCAN(5);
+                else if (CH == 3) TL_SCAN(3);
+                else TL_SCAN(1);
+#undef TL_SCAN
+            } else if (n > 0) {
+                // past the last g-ordinate (NG not a multiple of 4): the tile's column must not keep stale numbers
+#pragma unroll
+                for (int q = 0; q < TL_RQ; ++q) if (q < cnt) *reinterpret_cast<double *>(wp + lay8[q]) = 0.0;
+            }
+        }
+        __syncthreads();
+        // G_l += Wl (8 paths x 4 g) * DK_l (4 g x 8 columns) for the warp's layers, four layers' operands in flight
+        {
+            const int g = gc * 4 + (lane & 3);
+            const bool gok = g < NG;
+            for (int nt = 0; nt < NT; ++nt) {
+                const int c = nt * 8 + (lane >> 2);
+                const bool ld = gok && c < NP1;
+                const double bconst = (gok && c == NP1) ? 1.0 : 0.0;
+                const double *dkg = P.dk + ((size_t)iw * NG + (gok ? g : 0)) * NLAY * NP1 + (ld ? c : 0);
+                double *gl = sG + nt * 64 + (lane >> 2) * 8 + 2 * (lane & 3);
+                for (int i0 = 0; i0 < NTL; i0 += 4) {
+                    double a[4], b[4];
+                    unsigned on = 0u;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int l = warp + TL_PATHS * (i0 + u);
+                        a[u] = (i0 + u < NTL) ? wl[l] : 0.0;
+                        if (__ballot_sync(RFULL, a[u] != 0.0) != 0u) on |= 1u << u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int l = warp + TL_PATHS * (i0 + u);
+                        b[u] = bconst;
+                        if (ld && ((on >> u) & 1u)) b[u] = dkg[l * NP1];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if ((on >> u) & 1u) {
+                            const int l = warp + TL_PATHS * (i0 + u);
+                            double2 *dp = reinterpret_cast<double2 *>(gl + l * GS);
+                            double2 d = *dp;
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                         : "+d"(d.x), "+d"(d.y) : "d"(a[u]), "d"(b[u]));
+                            *dp = d;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (lane == 0 && ipath < NPATH) {
+        P.spec[(size_t)iw * NPATH + ipath] = spec;
+        if (P.dtsurf) P.dtsurf[(size_t)iw * NPATH + ipath] = dts;
+    }
+    // (T_{j-1} - T_j) dB_j/dT, summed over g, belongs to the temperature parameter (dk column NGAS) of the visit's layer.
+    // dB/dT from the Planck value already held: B = a / (e - 1)  =>  e - 1 = a / B,  dB/dT = e ap / (e - 1)^2
+    {
+        const int tcol = P.NGAS;
+        double *gp = sG + (tcol >> 3) * 64 + warp * 8 + (tcol & 7);
+        for (int r = 0; r <= maxleg; ++r) {
+#pragma unroll
+            for (int q = 0; q < TL_RQ; ++q) {
+                if ((int)((legs >> (8 * q)) & 0xffull) == r) {
+                    double bb, db;
+                    ans_planckg(P.ispace, wv, P.emtemp[(size_t)(j0 + q) * NPATH + ipath], bb, db);
+                    gp[(lay8[q] >> 3) * GS] += esq[q] * db;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // d spec / d q[k, l] = unit_k G_l[path, col_k] + dtaucon[k, l] G_l[path, ones]: warp p writes path p, a lane
+    // keeps its (up to 4) layers' sum_g W and walks the parameters
+    if (ipath < NPATH) {
+        const double *gone = sG + (NP1 >> 3) * 64 + warp * 8 + (NP1 & 7);
+        double *out = P.dspec + ((size_t)iw * NPATH + ipath) * NPAR * NLAY;
+        const bool ntn = (P.flags & ANSB200_RAD_NAN_TO_NUM) != 0;
+        for (int l0 = 0; l0 < NLAY; l0 += 128) {
+            double ws[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int l = l0 + 32 * u + lane;
+                ws[u] = l < NLAY ? gone[l * GS] : 0.0;
+            }
+#pragma unroll 2
+            for (int k = 0; k < NPAR; ++k) {
+                const int col = scol[k];
+                const double unit = (col >= 0 && col < P.NGAS) ? 1.0e-4 : 0.0 + (col >= 0 ? 1.0 : 0.0);
+                const double *gcol = sG + ((col >= 0 ? col : 0) >> 3) * 64 + warp * 8 + ((col >= 0 ? col : 0) & 7);
+                const double *dc = P.dtaucon ? P.dtaucon + ((size_t)iw * NPAR + k) * NLAY : nullptr;
+                double dv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int l = l0 + 32 * u + lane;
+                    dv[u] = (dc && l < NLAY) ? dc[l] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int l = l0 + 32 * u + lane;
+                    if (l < NLAY) {
+                        double v = col >= 0 ? gcol[l * GS] * unit : 0.0;
+                        if (dc) v = fma(dv[u], ws[u], v);
+                        if (ntn) v = tl_nan_to_num(v);
+                        out[(size_t)k * NLAY + l] = v;
+                    }
+                }
+            }
+        }
+    }
+}
+
+static size_t thermal_layers_smem(int NG, int NLAY, int NGAS, int NPAR)
+{
+    const int NT = (NGAS + 2 + 7) / 8, GS = NT * 64 + 2;
+    return ((size_t)NLAY * GS + (size_t)NG * (NLAY + 1) + (size_t)32 * (NLAY | 1) + NG) * 8 +
+           ((size_t)TL_PATHS * NLAY + NPAR) * 4 + 16;
+}
+
+extern "C" int ansb200_radiance_layer_space(int mode, unsigned flags, int NG, int NLAY, int NGAS, int NPAR, int NPATH,
+                                            int NLAYMAX, int has_dk, int has_dtaucon)
+{
+    if (NPATH < 4 || !(flags & ANSB200_RAD_GRAD)) return 0;
+    if (mode == 0)      // thermal emission: ans_thermal_layers_kernel
+        return has_dk && NLAYMAX <= 32 * TL_RQ && thermal_layers_smem(NG, NLAY, NGAS, NPAR) <= 227 * 1024 ? 1 : 0;
+    if (mode != 1) return 0;
     const size_t nd_t = (size_t)NG * NLAY + NLAY + NG + (size_t)32 * NG + (has_dtaucon ? (size_t)NPAR * NLAY : 0) +
                         (size_t)64 * (NLAY + NG + 1) + (has_dk ? (size_t)NG * NLAY * (NGAS + 1) : 0);
     return nd_t * 8 + (size_t)NPAR * 4 + 16 <= 227 * 1024 ? 1 : 0;
@@ -833,8 +1212,19 @@ extern "C" int ansb200_radiance(int mode, unsigned flags, const double *tau, con
     // groups as keep every SM busy (>= 4 paths per CTA so that the staging pays).  One path, or slabs that do
     // not fit: one CTA per (wavenumber, path), slabs read through L2 (consecutive CTAs share the wavenumber).
     const bool layer_space = (flags & ANSB200_RAD_LAYER_SPACE) != 0;
-    ANS_REQUIRE(!layer_space || ansb200_radiance_layer_space(mode, flags, NG, NLAY, NGAS, NPAR, NPATH, dk != nullptr, dtaucon != nullptr),
-                "radiance: layer-space gradients are available for transmission over >= 4 paths whose slabs fit in shared memory");
+    ANS_REQUIRE(!layer_space || ansb200_radiance_layer_space(mode, flags, NG, NLAY, NGAS, NPAR, NPATH, NLAYMAX, dk != nullptr,
+                                                             dtaucon != nullptr),
+                "radiance: layer-space gradients need >= 4 paths, slabs that fit in shared memory and, for thermal emission, "
+                "NLAYIN <= %d", 32 * TL_RQ);
+    if (thermal && layer_space) {
+        const size_t smem_l = thermal_layers_smem(NG, NLAY, NGAS, NPAR);
+        ANS_CUDA_CHECK(cudaFuncSetAttribute(ans_thermal_layers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(smem_l > 48 * 1024 ? smem_l : 48 * 1024)));
+        const dim3 grid((unsigned)NWAVE, (unsigned)((NPATH + TL_PATHS - 1) / TL_PATHS));
+        ans_thermal_layers_kernel<<<grid, TL_PATHS * 32, smem_l, stream>>>(P);
+        ANS_LAUNCH_CHECK();
+        return ANSB200_OK;
+    }
     if (!thermal && NPATH >= 4) {
         // transmission with several paths: warp-per-path kernel if the wavenumber's slabs fit in shared memory
         const size_t nd_t = (size_t)NG * NLAY + NLAY + NG + (size_t)RADT_WARPS * NG + ((grad && dtaucon) ? (size_t)NPAR * NLAY : 0) +

@@ -310,7 +310,7 @@ class HotPath:
         s.layer_space = bool(
             Mlay is not None and s.grad and hasattr(self.ops, "radiance_layer_space_ok") and
             self.ops.radiance_layer_space_ok(ev.mode, self.NG, len(ev.press_atm), self.NGAS, ev.NPAR,
-                                             ev.LAYINC.shape[1], True, s.dtaucon is not None))
+                                             ev.LAYINC.shape[1], ev.LAYINC.shape[0], True, s.dtaucon is not None))
         if s.layer_space:
             s.M = st("Mlay", Mlay)
         else:

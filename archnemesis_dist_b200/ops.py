@@ -255,10 +255,11 @@ def radiance(mode, tau, dk, gas_slot, taucia, taudust, tauray, dtaucon, layinc, 
     return (spec, dspec, dtsurf) if want_grad else spec
 
 
-def radiance_layer_space_ok(mode, NG, NLAY, NGAS, NPAR, NPATH, has_dk=True, has_dtaucon=True):
-    """Can ansb200_radiance hand back layer-space gradients for this shape (transmission over >= 4 paths)?"""
+def radiance_layer_space_ok(mode, NG, NLAY, NGAS, NPAR, NPATH, NLAYMAX, has_dk=True, has_dtaucon=True):
+    """Can ansb200_radiance hand back layer-space gradients for this shape (>= 4 paths; transmission, or thermal emission
+    with at most 224 positions per path)?"""
     return bool(_lib.load().ansb200_radiance_layer_space(int(mode), _lib.RAD_GRAD, int(NG), int(NLAY), int(NGAS), int(NPAR),
-                                                         int(NPATH), int(has_dk), int(has_dtaucon)))
+                                                         int(NPATH), int(NLAYMAX), int(has_dk), int(has_dtaucon)))
 
 
 def jacobian_project(dspec, M, shared=False):

@@ -162,9 +162,10 @@ int ansb200_continuum(const double *kw, const int32_t *nplanes, int NTERM, int N
                       int NR, const double *ud, const double *vd, int NDUST, int NWAVE, int NLAY, int NVMR, int has_cia,
                       int want_grad, double *taucia, double *taudust, double *tauray, double *dtaucon, void *stream);
 
-/* 1 if ansb200_radiance can produce layer-space gradients for this shape (transmission over >= 4 paths). */
-int ansb200_radiance_layer_space(int mode, unsigned flags, int NG, int NLAY, int NGAS, int NPAR, int NPATH, int has_dk,
-                                 int has_dtaucon);
+/* 1 if ansb200_radiance can produce layer-space gradients for this shape: >= 4 paths whose working set fits in shared
+ * memory; transmission (mode 1), or thermal emission (mode 0) with dk given and NLAYMAX <= 224 path positions. */
+int ansb200_radiance_layer_space(int mode, unsigned flags, int NG, int NLAY, int NGAS, int NPAR, int NPATH, int NLAYMAX,
+                                 int has_dk, int has_dtaucon);
 
 /* ---- gas opacity from line-by-line tables ------------------------------------------------------
  * Replaces Spectroscopy_0.calc_klbl / calc_klblg (archnemesis/Spectroscopy_0.py:1768-1919, :1601-1765)

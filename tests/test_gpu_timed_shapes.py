@@ -281,30 +281,31 @@ def test_lbl_ten_thousand_lines_many_tiles(mods):
         assert relerr(cpu(out[i]), ref) < 1e-10, i
 
 
-def test_layer_space_gradients_of_limb_transmission(mods):
-    """ANSB200_RAD_LAYER_SPACE: for limb / occultation paths (every layer above the tangent is crossed twice) the
-    transmission kernel adds the two visits and the projection uses ONE layer-space matrix for all paths.  Same
-    spectrum and state-vector Jacobian as the path-space route (dspec[NWAVE,NPATH,NPAR,NLAYIN] x per-path M)."""
-    import bench
+def _layer_space_against_path_space(mods, c4, mode, tol=1e-13):
+    """The layer-space route (visits of a layer added in the radiance kernel, ONE projection matrix for all paths)
+    against the path-space route (dspec[NWAVE,NPATH,NPAR,NLAYIN] x per-path M) on the same staged inputs."""
     ops, plan, engine = mods["ops"], mods["plan"], mods["engine"]
-    c = mods["syn"].make_fm_case(nwave=24, ng=20, ngas=6, nlay=100, npro=100, nx=60, nvmr=8, seed=7)
-    c4 = bench.limb_case(c, 16)
-    tab = c["tab"]
+    tab = c4["tab"]
+    nlay, npath, nwave = len(c4["press"]), int(c4["LAYINC"].shape[1]), tab["NWAVE"]
+    nx = c4["xmap"].shape[0]
     hp = engine.HotPath(tab["K"], tab["PRESS"], tab["TEMP"], tab["DELG"], tab["WAVE"])
     M = plan.fold_projection(c4["xmap"], c4["LAYINC"], c4["NLAYIN"], c4["DTE"], c4["DAM"], c4["DCO"], c4["NVMR"], c4["NDUST"])
-    Mlay = plan.fold_projection_layers(c4["xmap"], 100, c4["DTE"], c4["DAM"], c4["DCO"], c4["NVMR"], c4["NDUST"])
-    assert Mlay.shape == (1, c4["NPAR"] * 100, 60) and M.shape[1] == c4["NPAR"] * int(c4["LAYINC"].shape[0])
-    ev = _evaluation(mods, c4, mode=engine.TRANSMISSION)
+    Mlay = plan.fold_projection_layers(c4["xmap"], nlay, c4["DTE"], c4["DAM"], c4["DCO"], c4["NVMR"], c4["NDUST"])
+    assert Mlay.shape == (1, c4["NPAR"] * nlay, nx) and M.shape[1] == c4["NPAR"] * int(c4["LAYINC"].shape[0])
+    ev = _evaluation(mods, c4, mode=mode)
     s_path = hp.stage(ev, True, M)
     s_lay = hp.stage(ev, True, M, Mlay=Mlay)
     assert s_lay.layer_space and not getattr(s_path, "layer_space", False)
-    a_spec, a_dx, _ = hp.run(s_path)
-    b_spec, b_dx, _ = hp.run(s_lay)
-    assert mods["torch"].equal(a_spec, b_spec)
+    a_spec, a_dx, a_dt = hp.run(s_path)
+    b_spec, b_dx, b_dt = hp.run(s_lay)
+    if mode == engine.TRANSMISSION:
+        assert mods["torch"].equal(a_spec, b_spec)
+    else:
+        assert relerr(cpu(b_spec), cpu(a_spec)) < 1e-14 and relerr(cpu(b_dt), cpu(a_dt)) < 1e-14
     got, ref = cpu(b_dx), cpu(a_dx)
     for ix in range(ref.shape[-1]):
-        assert colerr(got[..., ix], ref[..., ix]) < 1e-13, ix
-    # the layer-space array itself: the two visits of a layer added
+        assert colerr(got[..., ix], ref[..., ix]) < tol, ix
+    # the layer-space array itself: the visits of a layer added
     tau, dk = hp.gas_opacity(s_path)
     args = (s_path.mode, tau, dk, s_path.gas_slot, s_path.taucia, s_path.taudust, s_path.tauray, s_path.dtaucon,
             s_path.layinc, s_path.scale, s_path.nlayin, s_path.emtemp, s_path.laypress, hp.wave_d, hp.delg_d,
@@ -312,12 +313,59 @@ def test_layer_space_gradients_of_limb_transmission(mods):
     _, d_path, _ = ops.radiance(*args)
     _, d_lay, _ = ops.radiance(*args, layer_space=True)
     d_path, d_lay = cpu(d_path), cpu(d_lay)
-    assert d_lay.shape == (24, 16, c4["NPAR"], 100)
+    assert d_lay.shape == (nwave, npath, c4["NPAR"], nlay)
     summed = np.zeros_like(d_lay)
-    for p in range(16):
+    for p in range(npath):
         n = int(c4["NLAYIN"][p])
         np.add.at(summed[:, p].transpose(2, 0, 1), c4["LAYINC"][:n, p], d_path[:, p, :, :n].transpose(2, 0, 1))
-    assert colerr(d_lay, summed) < 1e-13
-    # thermal emission keeps path-space gradients
-    assert not hp.stage(_evaluation(mods, c4), True, M, Mlay=Mlay).layer_space
+    for k in range(c4["NPAR"]):
+        assert colerr(d_lay[:, :, k], summed[:, :, k]) < tol, k
     hp.close()
+    return got
+
+
+@pytest.mark.parametrize("mode_name", ["transmission", "thermal"])
+def test_layer_space_gradients_of_limb_paths(mods, mode_name):
+    """ANSB200_RAD_LAYER_SPACE on limb / occultation paths (every layer above the tangent is crossed twice), 16 paths x
+    up to 200 positions: ans_transmission_paths_kernel and ans_thermal_layers_kernel (8-path tiles, tensor-core g-sums)."""
+    import bench
+    engine = mods["engine"]
+    c = mods["syn"].make_fm_case(nwave=24, ng=20, ngas=6, nlay=100, npro=100, nx=60, nvmr=8, seed=7)
+    c4 = bench.limb_case(c, 16)
+    _layer_space_against_path_space(mods, c4, engine.TRANSMISSION if mode_name == "transmission" else engine.THERMAL)
+
+
+@pytest.mark.parametrize("ng,ngas,nlay,npath", [(18, 7, 37, 13), (16, 3, 64, 5), (20, 6, 100, 9)])
+def test_layer_space_thermal_irregular_paths(mods, ng, ngas, nlay, npath):
+    """ans_thermal_layers_kernel away from the timed shape: NG not a multiple of 4, NGAS + 2 > 8 columns (two column
+    tiles), a number of paths that leaves the last tile ragged, and paths of every kind side by side -- limb paths,
+    nadir paths that end on the ground (surface term), a path that crosses some layers three times, one of a single
+    layer -- against the path-space kernel."""
+    engine = mods["engine"]
+    rng = np.random.default_rng(ng * 100 + npath)
+    c = mods["syn"].make_fm_case(nwave=12, ng=ng, ngas=ngas, nlay=nlay, npro=nlay, nx=30, nvmr=ngas + 2, seed=11)
+    nlm = 2 * nlay + 9
+    layinc = np.zeros((nlm, npath), np.int32)
+    scale = np.zeros((nlm, npath))
+    emtemp = np.zeros((nlm, npath))
+    nlayin = np.zeros(npath, np.int32)
+    for p in range(npath):
+        kind = p % 4
+        if kind == 0:      # limb, tangent somewhere in the atmosphere
+            t = int(rng.integers(0, nlay - 1))
+            seq = list(range(nlay - 1, t - 1, -1)) + list(range(t, nlay))
+        elif kind == 1:    # nadir: top to bottom, ends on the ground
+            seq = list(range(nlay - 1, -1, -1))
+        elif kind == 2:    # crosses the upper layers three times (down, up, down again)
+            t = nlay // 2
+            seq = list(range(nlay - 1, t - 1, -1)) + list(range(t, nlay)) + list(range(nlay - 1, nlay - 5, -1))
+        else:              # a single layer
+            seq = [int(rng.integers(0, nlay))]
+        seq = np.array(seq[:nlm])
+        n = len(seq)
+        nlayin[p] = n
+        layinc[:n, p] = seq
+        scale[:n, p] = 1.0 + rng.uniform(0.0, 3.0, n)
+        emtemp[:n, p] = c["temp"][seq]
+    c4 = dict(c, LAYINC=layinc, SCALE=scale, NLAYIN=nlayin, EMTEMP=emtemp)
+    _layer_space_against_path_space(mods, c4, engine.THERMAL)
