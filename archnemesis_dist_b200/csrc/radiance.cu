@@ -803,22 +803,43 @@ __constant__ double TL_EXPC[12] = {      // 1/13!, 1/12!, ..., 1/2!
     2.7557319223985888e-06, 2.4801587301587302e-05, 1.9841269841269841e-04, 1.3888888888888889e-03,
     8.3333333333333332e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 5.0000000000000000e-01};
 
-// exp(-x) for x >= 0 (larger than 708: 2^-1021 instead of a subnormal or 0; NaN propagates)
-__device__ __forceinline__ double tl_expneg(double x)
+// exp(y) for |y| <= 708 (the callers clamp): 2^k reduction, 13th-degree polynomial; NaN propagates
+__device__ __forceinline__ double tl_exp_core(double y)
 {
-    const double xc = fmin(x, 708.0);
-    const double t = fma(xc, -1.4426950408889634, 6755399441055744.0);      // round(-x log2 e) in the low word
+    const double t = fma(y, 1.4426950408889634, 6755399441055744.0);        // round(y log2 e) in the low word
     const int k = __double2loint(t);
     const double kf = t - 6755399441055744.0;
-    double r = fma(kf, -6.93147180369123816490e-01, -xc);
+    double r = fma(kf, -6.93147180369123816490e-01, y);
     r = fma(kf, -1.90821492927058770002e-10, r);
     double pl = TL_EXPC[0];
 #pragma unroll
     for (int i = 1; i < 12; ++i) pl = fma(pl, r, TL_EXPC[i]);
     pl = fma(pl, r, 1.0);
     pl = fma(pl, r, 1.0);
-    const double v = __hiloint2double(__double2hiint(pl) + (k << 20), __double2loint(pl));
-    return x != x ? x : v;
+    return __hiloint2double(__double2hiint(pl) + (k << 20), __double2loint(pl));
+}
+// exp(-x) for x >= 0 (beyond 708: 2^-1021 instead of a subnormal or 0)
+__device__ __forceinline__ double tl_expneg(double x)
+{
+    return tl_exp_core(x > 708.0 ? -708.0 : -x);
+}
+// Planck function with the constants of ans_planckg: a = c1 y^3 (or c1 y^5 / 1e4), c2y = c2 y
+__device__ __forceinline__ double tl_planck(double a, double c2y, double temp)
+{
+    const double x = c2y / temp;
+    return a / (tl_exp_core(x > 708.0 ? 708.0 : x) - 1.0);
+}
+__device__ __forceinline__ void tl_planck_consts(int ispace, double wave, double &a, double &c2y)
+{
+    const double c1 = 1.1911e-12, c2 = 1.439;
+    if (ispace == 0) {
+        a = c1 * (wave * wave * wave);
+        c2y = c2 * wave;
+    } else {
+        const double y = 1.0e4 / wave, y2 = y * y;
+        a = c1 * (y2 * y2 * y) / 1.0e4;
+        c2y = c2 * y;
+    }
 }
 
 __device__ __forceinline__ double tl_nan_to_num(double v)
@@ -849,7 +870,7 @@ __device__ __forceinline__ void tl_scan_g(const char *tg, char *wp, const int (&
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const double up = rshfl_up(incl, d);
-        if (lane >= d) incl *= up;
+        asm("{ .reg .pred p; setp.ge.s32 p, %2, %3; @p mul.f64 %0, %0, %1; }" : "+d"(incl) : "d"(up), "r"(lane), "r"(d));
     }
     double base = rshfl_up(incl, 1);
     if (lane == 0) base = 1.0;
@@ -866,7 +887,7 @@ __device__ __forceinline__ void tl_scan_g(const char *tg, char *wp, const int (&
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const double dn = rshfl_down(rincl, d);
-        if (lane + d < 32) rincl += dn;
+        asm("{ .reg .pred p; setp.lt.s32 p, %2, %3; @p add.f64 %0, %0, %1; }" : "+d"(rincl) : "d"(dn), "r"(lane), "r"(32 - d));
     }
     double specg = rshfl_idx(rincl, 0);
     if (ground) specg += Tn * radground;
@@ -918,7 +939,8 @@ ans_thermal_layers_kernel(RadParams P)
     double *sW = stau + (size_t)NG * TS;                          // [8 paths * 4 g][LS]
     double *sdelg = sW + (size_t)32 * LS;                         // [NG]
     int *sfirst = reinterpret_cast<int *>(sdelg + NG);            // per warp [NLAY]: scratch of the visit ranking
-    int *scol = sfirst + TL_PATHS * NLAY;                         // [NPAR]
+    int *scol = sfirst + TL_PATHS * NLAY;                         // [NPAR]: offset of the parameter's column in a G row (-1: none)
+    int *svis = scol + NPAR;                                      // [NLAY]: layer crossed by any of the tile's paths
     for (int l0 = 0; l0 < NLAY; l0 += 32) {
         const int l = l0 + lane;
         double c = 0.0;
@@ -933,14 +955,15 @@ ans_thermal_layers_kernel(RadParams P)
         stau[g * TS + NLAY] = 0.0;
         sdelg[g] = P.delg[g];
     }
-    for (int t = threadIdx.x; t < NLAY * GS; t += blockDim.x) sG[t] = 0.0;
+    // (G is not cleared: the first chunk's products overwrite the rows of the layers in play, the others are never read)
     for (int t = threadIdx.x; t < 32 * LS; t += blockDim.x) sW[t] = 0.0;
     for (int t = threadIdx.x; t < TL_PATHS * NLAY; t += blockDim.x) sfirst[t] = -1;
+    for (int t = threadIdx.x; t < NLAY; t += blockDim.x) svis[t] = 0;
     for (int k = threadIdx.x; k < NPAR; k += blockDim.x) {
         int col = -1;
         if (k == P.NVMR) col = P.NGAS;
         else for (int i = 0; i < P.NGAS; ++i) if (P.gas_slot[i] == k) col = i;
-        scol[k] = col;
+        scol[k] = col < 0 ? -1 : ((col >> 3) * 64 + (col & 7)) | (col < P.NGAS ? 0x40000000 : 0);   // bit 30: unit 1e-4
     }
     __syncthreads();
     // ---- the warp's path: visits into registers, ranking of repeated layers ---------------------------------------
@@ -950,6 +973,8 @@ ans_thermal_layers_kernel(RadParams P)
     const int j0 = lane * CH, cnt = max(0, min(n, j0 + CH) - j0);
     const double wv = P.wave[iw];
     const double xf = P.xfac ? P.xfac[iw] : 1.0;
+    double pl_a, pl_c2y;
+    tl_planck_consts(P.ispace, wv, pl_a, pl_c2y);
     int lay8[TL_RQ];                     // byte offset of the visit's layer in a tau / W row
     double sc[TL_RQ], Bq[TL_RQ], esq[TL_RQ];
 #pragma unroll
@@ -957,10 +982,11 @@ ans_thermal_layers_kernel(RadParams P)
         lay8[q] = NLAY * 8; sc[q] = 0.0; Bq[q] = 0.0; esq[q] = 0.0;
         if (q < cnt) {
             const size_t at = (size_t)(j0 + q) * NPATH + ipath;
-            lay8[q] = P.layinc[at] * 8;
+            const int l = P.layinc[at];
+            lay8[q] = l * 8;
             sc[q] = P.scale[at];
-            double db;
-            ans_planckg(P.ispace, wv, P.emtemp[at], Bq[q], db);
+            Bq[q] = tl_planck(pl_a, pl_c2y, P.emtemp[at]);
+            svis[l] = 1;
         }
     }
     unsigned long long legs = 0;         // rank of each visit among the path's visits of its layer, 8 bits per slot
@@ -1014,9 +1040,12 @@ ans_thermal_layers_kernel(RadParams P)
     }
     double spec = 0.0, dts = 0.0;
     const int NCH = (NG + 3) / 4;
-    // tensor-core operands of this lane: row (lane & 3) of the chunk's 4 g, column (lane >> 2) of a column tile
-    const int NTL = (NLAY - warp + TL_PATHS - 1) / TL_PATHS;          // layers warp, warp + 8, ...
-    const double *wl = sW + lane * LS;
+    // tensor-core products: the warp folds layers warp, warp + 8, ... -- those that any path of the tile crosses
+    __syncthreads();
+    unsigned vis = 0u;
+    for (int i = 0; warp + TL_PATHS * i < NLAY; ++i) if (svis[warp + TL_PATHS * i]) vis |= 1u << i;
+    const int t_lo = vis ? __ffs(vis) - 1 : 0, t_hi = vis ? 32 - __clz(vis) : 0;     // the warp's layers warp + 8 [t_lo, t_hi)
+    const double *wl = sW + lane * LS + warp + TL_PATHS * t_lo;
 #pragma unroll 1
     for (int gc = 0; gc < NCH; ++gc) {
         {   // the chunk's dk rows towards L1 / L2 while the scan runs
@@ -1046,7 +1075,8 @@ ans_thermal_layers_kernel(RadParams P)
             }
         }
         __syncthreads();
-        // G_l += Wl (8 paths x 4 g) * DK_l (4 g x 8 columns) for the warp's layers, four layers' operands in flight
+        // G_l (+)= Wl (8 paths x 4 g) * DK_l (4 g x 8 columns) for the warp's layers in play, four layers' operands in
+        // flight (a layer inside the range that no path crosses has a zero W row)
         {
             const int g = gc * 4 + (lane & 3);
             const bool gok = g < NG;
@@ -1054,34 +1084,33 @@ ans_thermal_layers_kernel(RadParams P)
                 const int c = nt * 8 + (lane >> 2);
                 const bool ld = gok && c < NP1;
                 const double bconst = (gok && c == NP1) ? 1.0 : 0.0;
-                const double *dkg = P.dk + ((size_t)iw * NG + (gok ? g : 0)) * NLAY * NP1 + (ld ? c : 0);
-                double *gl = sG + nt * 64 + (lane >> 2) * 8 + 2 * (lane & 3);
-                for (int i0 = 0; i0 < NTL; i0 += 4) {
+                const double *db = P.dk + (((size_t)iw * NG + (gok ? g : 0)) * NLAY + warp + TL_PATHS * t_lo) * NP1 + (ld ? c : 0);
+                double *gp = sG + (warp + TL_PATHS * t_lo) * GS + nt * 64 + (lane >> 2) * 8 + 2 * (lane & 3);
+                const double *wa = wl;
+                const int dstep = TL_PATHS * NP1, gstep = TL_PATHS * GS;
+                int i = t_lo;
+                for (; i + 4 <= t_hi; i += 4, wa += 4 * TL_PATHS, db += 4 * dstep, gp += 4 * gstep) {
                     double a[4], b[4];
-                    unsigned on = 0u;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) a[u] = wa[u * TL_PATHS];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) b[u] = ld ? db[u * dstep] : bconst;
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const int l = warp + TL_PATHS * (i0 + u);
-                        a[u] = (i0 + u < NTL) ? wl[l] : 0.0;
-                        if (__ballot_sync(RFULL, a[u] != 0.0) != 0u) on |= 1u << u;
+                        double2 *dp = reinterpret_cast<double2 *>(gp + u * gstep);
+                        double2 d = gc ? *dp : make_double2(0.0, 0.0);
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                     : "+d"(d.x), "+d"(d.y) : "d"(a[u]), "d"(b[u]));
+                        *dp = d;
                     }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int l = warp + TL_PATHS * (i0 + u);
-                        b[u] = bconst;
-                        if (ld && ((on >> u) & 1u)) b[u] = dkg[l * NP1];
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if ((on >> u) & 1u) {
-                            const int l = warp + TL_PATHS * (i0 + u);
-                            double2 *dp = reinterpret_cast<double2 *>(gl + l * GS);
-                            double2 d = *dp;
-                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                                         : "+d"(d.x), "+d"(d.y) : "d"(a[u]), "d"(b[u]));
-                            *dp = d;
-                        }
-                    }
+                }
+                for (; i < t_hi; ++i, wa += TL_PATHS, db += dstep, gp += gstep) {
+                    const double a = wa[0], b = ld ? db[0] : bconst;
+                    double2 *dp = reinterpret_cast<double2 *>(gp);
+                    double2 d = gc ? *dp : make_double2(0.0, 0.0);
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(d.x), "+d"(d.y) : "d"(a), "d"(b));
+                    *dp = d;
                 }
             }
         }
@@ -1092,16 +1121,17 @@ ans_thermal_layers_kernel(RadParams P)
         if (P.dtsurf) P.dtsurf[(size_t)iw * NPATH + ipath] = dts;
     }
     // (T_{j-1} - T_j) dB_j/dT, summed over g, belongs to the temperature parameter (dk column NGAS) of the visit's layer.
-    // dB/dT from the Planck value already held: B = a / (e - 1)  =>  e - 1 = a / B,  dB/dT = e ap / (e - 1)^2
+    // dB/dT from the Planck value already held: B = a / (e - 1)  =>  dB/dT = e ap / (e - 1)^2 = B (1 + B / a) c2 y / T^2
     {
         const int tcol = P.NGAS;
+        const double inv_a = 1.0 / pl_a;
         double *gp = sG + (tcol >> 3) * 64 + warp * 8 + (tcol & 7);
         for (int r = 0; r <= maxleg; ++r) {
 #pragma unroll
             for (int q = 0; q < TL_RQ; ++q) {
                 if ((int)((legs >> (8 * q)) & 0xffull) == r) {
-                    double bb, db;
-                    ans_planckg(P.ispace, wv, P.emtemp[(size_t)(j0 + q) * NPATH + ipath], bb, db);
+                    const double temp = P.emtemp[(size_t)(j0 + q) * NPATH + ipath];
+                    const double db = Bq[q] * fma(Bq[q], inv_a, 1.0) * (pl_c2y / (temp * temp));
                     gp[(lay8[q] >> 3) * GS] += esq[q] * db;
                 }
             }
@@ -1110,38 +1140,39 @@ ans_thermal_layers_kernel(RadParams P)
     }
     __syncthreads();
     // d spec / d q[k, l] = unit_k G_l[path, col_k] + dtaucon[k, l] G_l[path, ones]: warp p writes path p, a lane
-    // keeps its (up to 4) layers' sum_g W and walks the parameters
+    // keeps its (up to 4) layers' sum_g W and walks the parameters; layers the tile never crosses are zero
     if (ipath < NPATH) {
-        const double *gone = sG + (NP1 >> 3) * 64 + warp * 8 + (NP1 & 7);
-        double *out = P.dspec + ((size_t)iw * NPATH + ipath) * NPAR * NLAY;
+        const int one_off = (NP1 >> 3) * 64 + (NP1 & 7);
         const bool ntn = (P.flags & ANSB200_RAD_NAN_TO_NUM) != 0;
         for (int l0 = 0; l0 < NLAY; l0 += 128) {
             double ws[4];
+            const double *grow[4];
+            bool in[4], on[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int l = l0 + 32 * u + lane;
-                ws[u] = l < NLAY ? gone[l * GS] : 0.0;
+                in[u] = l < NLAY;
+                on[u] = in[u] && svis[l] != 0;
+                grow[u] = sG + (in[u] ? l : 0) * GS + warp * 8;
+                ws[u] = on[u] ? grow[u][one_off] : 0.0;
             }
-#pragma unroll 2
-            for (int k = 0; k < NPAR; ++k) {
-                const int col = scol[k];
-                const double unit = (col >= 0 && col < P.NGAS) ? 1.0e-4 : 0.0 + (col >= 0 ? 1.0 : 0.0);
-                const double *gcol = sG + ((col >= 0 ? col : 0) >> 3) * 64 + warp * 8 + ((col >= 0 ? col : 0) & 7);
-                const double *dc = P.dtaucon ? P.dtaucon + ((size_t)iw * NPAR + k) * NLAY : nullptr;
+            double *out = P.dspec + ((size_t)iw * NPATH + ipath) * NPAR * NLAY + l0 + lane;
+            const double *dc = P.dtaucon ? P.dtaucon + (size_t)iw * NPAR * NLAY + l0 + lane : nullptr;
+#pragma unroll 1
+            for (int k = 0; k < NPAR; ++k, out += NLAY) {
+                const int cw = scol[k];
+                const int off = cw < 0 ? 0 : (cw & 0xffff);
+                const double unit = cw < 0 ? 0.0 : ((cw & 0x40000000) ? 1.0e-4 : 1.0);
                 double dv[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int l = l0 + 32 * u + lane;
-                    dv[u] = (dc && l < NLAY) ? dc[l] : 0.0;
-                }
+                for (int u = 0; u < 4; ++u) dv[u] = (dc && in[u]) ? dc[k * NLAY + 32 * u] : 0.0;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int l = l0 + 32 * u + lane;
-                    if (l < NLAY) {
-                        double v = col >= 0 ? gcol[l * GS] * unit : 0.0;
-                        if (dc) v = fma(dv[u], ws[u], v);
+                    if (in[u]) {
+                        double v = 0.0;
+                        if (on[u]) v = cw < 0 ? dv[u] * ws[u] : fma(grow[u][off], unit, dv[u] * ws[u]);
                         if (ntn) v = tl_nan_to_num(v);
-                        out[(size_t)k * NLAY + l] = v;
+                        out[32 * u] = v;
                     }
                 }
             }
@@ -1153,7 +1184,7 @@ static size_t thermal_layers_smem(int NG, int NLAY, int NGAS, int NPAR)
 {
     const int NT = (NGAS + 2 + 7) / 8, GS = NT * 64 + 2;
     return ((size_t)NLAY * GS + (size_t)NG * (NLAY + 1) + (size_t)32 * (NLAY | 1) + NG) * 8 +
-           ((size_t)TL_PATHS * NLAY + NPAR) * 4 + 16;
+           ((size_t)TL_PATHS * NLAY + NPAR + NLAY) * 4 + 16;
 }
 
 extern "C" int ansb200_radiance_layer_space(int mode, unsigned flags, int NG, int NLAY, int NGAS, int NPAR, int NPATH,
