@@ -132,3 +132,41 @@ extern "C" int ansb200_jacobian_project_shared(const double *dspec, const double
     ANS_LAUNCH_CHECK();
     return ANSB200_OK;
 }
+
+// ---- tangent-height interpolation of the path spectra (nemesisSOfmg / nemesisLfmg) ---------------------------------
+// Reference: ForwardModel_0.py:1206-1228 / :1464-1486.  The limb / occultation drivers compute one spectrum per path
+// (tangent layer) and interpolate the pair of paths that brackets each measured tangent height:
+//     SPECMOD[:, i] = SPECOUT[:, lo_i] * wlo_i + SPECOUT[:, hi_i] * whi_i        (hi_i < 0: SPECOUT[:, lo_i] alone)
+// and the same for the Jacobian.  out[NWAVE, NGEOM, 1 + NX] = [SPECMOD | dSPECMOD]: the block the line-shape operator
+// takes next (ansb200_convolve treats NGEOM * (1 + NX) as columns).  Products and sum are rounded separately, like numpy.
+__global__ void __launch_bounds__(256)
+ans_path_mix_kernel(const double *__restrict__ spec, const double *__restrict__ dx, const int32_t *__restrict__ lo,
+                    const int32_t *__restrict__ hi, const double *__restrict__ wlo, const double *__restrict__ whi,
+                    int NPATH, int NX, int NGEOM, double *__restrict__ out)
+{
+    const int iw = blockIdx.x, ig = blockIdx.y;
+    const int pl = lo[ig], ph = hi[ig];
+    const double a = wlo[ig], b = whi[ig];
+    const double *sl = dx + ((size_t)iw * NPATH + pl) * NX, *sh = dx + ((size_t)iw * NPATH + (ph >= 0 ? ph : pl)) * NX;
+    double *o = out + ((size_t)iw * NGEOM + ig) * (NX + 1);
+    if (threadIdx.x == 0) {
+        const double y = spec[(size_t)iw * NPATH + pl];
+        o[0] = ph >= 0 ? __dadd_rn(__dmul_rn(y, a), __dmul_rn(spec[(size_t)iw * NPATH + ph], b)) : y;
+    }
+    for (int x = threadIdx.x; x < NX; x += blockDim.x)
+        o[1 + x] = ph >= 0 ? __dadd_rn(__dmul_rn(sl[x], a), __dmul_rn(sh[x], b)) : sl[x];
+}
+
+extern "C" int ansb200_path_mix(const double *spec, const double *dx, const int32_t *lo, const int32_t *hi,
+                                const double *wlo, const double *whi, int NWAVE, int NPATH, int NX, int NGEOM,
+                                double *out, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ANS_REQUIRE(spec && dx && lo && hi && wlo && whi && out, "path_mix: null pointer");
+    ANS_REQUIRE(NWAVE > 0 && NPATH > 0 && NX > 0 && NGEOM > 0 && NGEOM <= 65535, "path_mix: bad shape");
+    int threads = NX >= 256 ? 256 : ((NX + 31) / 32) * 32;
+    ans_path_mix_kernel<<<dim3((unsigned)NWAVE, (unsigned)NGEOM), threads, 0, stream>>>(spec, dx, lo, hi, wlo, whi, NPATH, NX,
+                                                                                         NGEOM, out);
+    ANS_LAUNCH_CHECK();
+    return ANSB200_OK;
+}

@@ -210,6 +210,8 @@ class HotPath:
            everything downstream is shared.
     """
 
+    layer_space = True      # forward_jacobian accepts Mlay (gradients per layer for decks with many paths)
+
     def __init__(self, K, PRESS, TEMP, DELG, WAVE, ops=_ops, table_storage="f64"):
         self.ops = ops
         self.lbl_table = len(K.shape) == 4
@@ -409,7 +411,7 @@ class HotPath:
         return spec, dx, dtsurf
 
     # -- host-facing calls -------------------------------------------------------------------------
-    def _evaluate(self, ev: Evaluation, return_grad, M=None):
+    def _evaluate(self, ev: Evaluation, return_grad, M=None, Mlay=None):
         """stage -> kernels with the bulk of the host->device traffic (continuum terms, 36 MB at config 2)
         hidden behind the gas-opacity kernel: that kernel needs only the plan and the amounts, so it is
         launched first and the remaining inputs are staged on a side stream while it runs."""
@@ -419,7 +421,7 @@ class HotPath:
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream()
         with torch.cuda.stream(self._copy_stream):
-            self.stage_radiance(s, ev, M)
+            self.stage_radiance(s, ev, M, Mlay)
             done = torch.cuda.Event()
             done.record()
         for t in vars(s).values():
@@ -432,12 +434,13 @@ class HotPath:
         """spec[NWAVE,NPATH] (, dspec[NWAVE,NPATH,NPAR,NLAYMAX], dtsurf[NWAVE,NPATH]) as device tensors."""
         return self._evaluate(ev, return_grad)
 
-    def forward_jacobian(self, ev: Evaluation, M):
+    def forward_jacobian(self, ev: Evaluation, M, Mlay=None):
         """Spectrum and state-vector Jacobian; layer-space gradients never leave the device:
         CIRSrad(return_grad=True) -> map2pro -> map2xvec of nemesisfmg (ForwardModel_0.py:694-714).
-        M = plan.fold_projection(...) [NPATH, NPAR*NLAYMAX, NX].  Returns device tensors
-        spec[NWAVE,NPATH], dspec_x[NWAVE,NPATH,NX], dtsurf[NWAVE,NPATH]."""
-        return self._evaluate(ev, True, M)
+        M = plan.fold_projection(...) [NPATH, NPAR*NLAYMAX, NX]; Mlay = plan.fold_projection_layers(...)
+        [1, NPAR*NLAY, NX] lets decks with many paths take the per-layer route (see stage_radiance).  Returns
+        device tensors spec[NWAVE,NPATH], dspec_x[NWAVE,NPATH,NX], dtsurf[NWAVE,NPATH]."""
+        return self._evaluate(ev, True, M, Mlay)
 
     def forward_jacobian_conv(self, ev: Evaluation, M, conv_op, jsurf=-1, wgeom=1.0):
         """forward_jacobian followed on the device by what nemesisfmg does with its result for one geometry
@@ -456,6 +459,19 @@ class HotPath:
             block *= float(wgeom)
         self.launches += 1
         return self.ops.convolve(conv_op, block)
+
+    def forward_jacobian_mix_conv(self, ev: Evaluation, M, mix, conv_op, Mlay=None):
+        """The limb / occultation drivers' tail on the device (nemesisSOfmg / nemesisLfmg, ForwardModel_0.py:1186-1243,
+        :1444-1513): forward_jacobian over all paths, the tangent-height interpolation of the path spectra
+        (mix = plan.tangent_mix) and the line shape / filter integral applied to every geometry at once (IGEOM='All':
+        one operator, geometry 0's grid).  Returns device tensors specmod[NWAVE,NGEOM] (subspeconv wants it) and
+        [NCONV, NGEOM, 1+NX] = [SPECONV | dSPECONV]."""
+        spec, dx, _ = self._evaluate(ev, True, M, Mlay)
+        block = self.ops.path_mix(spec, dx, mix)
+        nw, ngeom, nc = block.shape
+        self.launches += 2
+        out = self.ops.convolve(conv_op, block.view(nw, ngeom * nc), col0_is_spectrum=False)
+        return block[:, :, 0], out.view(out.shape[0], ngeom, nc)
 
     def project(self, dspec, M):
         """Layer-space gradients still on the device x host-folded projection matrix -> dspec_x[NWAVE,NPATH,NX]

@@ -586,7 +586,13 @@ class B200HotPathMixin:
             hp = self._b200_hotpath()
             ev = self._b200_evaluation(mode, True)
             M = _plan.fold_projection(xmap, path.LAYINC, path.NLAYIN, lay.DTE, lay.DAM, lay.DCO, atm.NVMR, atm.NDUST)
-            spec, dx, dtsurf = hp.forward_jacobian(ev, M)
+            if int(path.NPATH) >= 4 and getattr(hp, "layer_space", False):
+                # many paths (limb / occultation geometries evaluated together): gradients per layer on the device,
+                # one projection matrix for all paths
+                Mlay = _plan.fold_projection_layers(xmap, lay.NLAY, lay.DTE, lay.DAM, lay.DCO, atm.NVMR, atm.NDUST)
+                spec, dx, dtsurf = hp.forward_jacobian(ev, M, Mlay=Mlay)
+            else:
+                spec, dx, dtsurf = hp.forward_jacobian(ev, M)
             SPEC1, dSPEC1, dTSURF = hp.to_host(spec), hp.to_host(dx), hp.to_host(dtsurf)
         if self.Variables.JSURF >= 0:
             dSPEC1[:, 0, self.Variables.JSURF] = dTSURF[:, 0]      # :717-718
@@ -620,12 +626,13 @@ class B200HotPathMixin:
         out = hp.to_host(hp.forward_jacobian_conv(ev, Mx, cop, int(self.Variables.JSURF), float(wgeom)))
         return out[:, 0], out[:, 1:]
 
-    def _b200_conv_operator(self, hp, IGEOM):
+    def _b200_conv_operator(self, hp, IGEOM, integrated=None):
         """The line-shape operator of geometry IGEOM on the device, rebuilt only when the calculation grid or the
-        measurement's line-shape description changes (the analytic shapes cost NCONV x window-length libm calls)."""
+        measurement's line-shape description changes (the analytic shapes cost NCONV x window-length libm calls).
+        integrated: filter integral instead of a line shape (default: IFORM says so; the occultation driver never does)."""
         M, WAVE = self.Measurement, np.asarray(self.SpectroscopyX.WAVE, dtype=np.float64)
         n = int(M.NCONV[IGEOM])
-        integ = int(M.IFORM) == _IFORM_INTEGRATED_RADIANCE
+        integ = int(M.IFORM) == _IFORM_INTEGRATED_RADIANCE if integrated is None else bool(integrated)
         lbl = int(self.Spectroscopy.ILBL) == _LBL_TABLES
         vconv = np.asarray(M.VCONV[0:n, IGEOM], dtype=np.float64)
         key = [IGEOM, integ, lbl, float(M.FWHM), int(getattr(M, "ISHAPE", 0) or 0), float(getattr(M, "V_DOPPLER", 0.0) or 0.0),
@@ -649,6 +656,79 @@ class B200HotPathMixin:
         cop = hp.conv_operator(op)
         cache[IGEOM] = (key, hp, cop)
         return cop
+
+
+    # ---- limb / occultation drivers: every tangent height in one evaluation ---------------------------------------
+    def b200_tangent_conv_ok(self, integrated):
+        """Can the tail of nemesisSOfmg / nemesisLfmg (tangent-height interpolation + line shape with IGEOM='All') run on
+        the device?  The combinations the reference itself supports for IGEOM='All': k-tables with FWHM == 0
+        (Measurement_0.convg :2506-2528 raises otherwise), line-by-line tables with an analytic shape (FWHM > 0, not
+        Hamming: lblconvg_ngeom's Hamming window is empty, :3752-3754) or filter functions (FWHM < 0), and the filter
+        integral of nemesisLfmg; every geometry on geometry 0's grid."""
+        M = self.MeasurementX
+        if self._b200_mode() is None or M.NORDERS_AOTF is not None:
+            return False
+        n0 = int(M.NCONV[0])
+        if n0 > _lib.MAX_NCONV or not np.all(np.asarray(M.NCONV) == n0) or int(np.asarray(M.VCONV).shape[0]) < n0:
+            return False
+        fwhm = float(M.FWHM)
+        if integrated:
+            return fwhm < 0.0
+        if int(self.SpectroscopyX.ILBL) == _LBL_TABLES:
+            return fwhm < 0.0 or (fwhm > 0.0 and int(getattr(M, "ISHAPE", 0) or 0) != _plan.ILS_HAMMING)
+        return fwhm == 0.0
+
+    def b200_tangent_fmg(self, calc_path, filter_integral_allowed):
+        """Body shared by the nemesisSOfmg / nemesisLfmg overrides (ForwardModel_0.py:1160-1243, :1409-1518; the AOTF
+        branch of the occultation driver stays with the reference).  The set-up calls are the reference's; CIRSrad ->
+        map2pro -> map2xvec -> tangent-height interpolation -> line shape run on the device and only
+        SPECMOD[NWAVE,NGEOM] and [NCONV,NGEOM,1+NX] come back (the reference moves dSPECOUT[NWAVE,NPATH,NX]).
+        Returns None when the case is not one the device tail covers (the caller then runs the reference's body)."""
+        from copy import deepcopy
+        self.Variables1 = deepcopy(self.Variables)
+        self.MeasurementX = deepcopy(self.Measurement)
+        self.AtmosphereX = deepcopy(self.Atmosphere)
+        self.ScatterX = deepcopy(self.Scatter)
+        self.StellarX = deepcopy(self.Stellar)
+        self.SurfaceX = deepcopy(self.Surface)
+        self.LayerX = deepcopy(self.Layer)
+        self.SpectroscopyX = deepcopy(self.Spectroscopy)
+        self.CIAX = deepcopy(self.CIA)
+        self.check_gas_spec_atm()
+        self.check_wave_range_consistency()
+        if self.MeasurementX.NORDERS_AOTF is not None:
+            return None
+        self.Measurement.build_ils(IGEOM=0)
+        wmin, wmax = self.Measurement.calc_wave_range(apply_doppler=True, IGEOM=None)
+        if self.SpectroscopyX.NGAS > 0:
+            self.SpectroscopyX.read_tables(wavemin=wmin, wavemax=wmax)
+        self.adjust_hydrostat = False
+        xmap = self.subprofretg()
+        calc_path()
+        MX, path, lay, atm = self.MeasurementX, self.PathX, self.LayerX, self.AtmosphereX
+        integrated = bool(filter_integral_allowed and int(MX.IFORM) == _IFORM_INTEGRATED_RADIANCE)
+        if not self.b200_tangent_conv_ok(integrated):
+            return None
+        BASEH_TANHE = np.zeros(path.NPATH)
+        for i in range(path.NPATH):
+            BASEH_TANHE[i] = lay.BASEH[path.LAYINC[int(path.NLAYIN[i] / 2), i]] / 1.0e3
+        try:
+            mix = _plan.tangent_mix(BASEH_TANHE, MX.TANHE[:, 0] if np.ndim(MX.TANHE) == 2 else MX.TANHE)
+        except ValueError:
+            return None
+        hp = self._b200_hotpath()
+        ev = self._b200_evaluation(self._b200_mode(), True)
+        M = _plan.fold_projection(xmap, path.LAYINC, path.NLAYIN, lay.DTE, lay.DAM, lay.DCO, atm.NVMR, atm.NDUST)
+        Mlay = None
+        if int(path.NPATH) >= 4 and getattr(hp, "layer_space", False):
+            Mlay = _plan.fold_projection_layers(xmap, lay.NLAY, lay.DTE, lay.DAM, lay.DCO, atm.NVMR, atm.NDUST)
+        cop = self._b200_conv_operator(hp, 0, integrated=integrated)
+        specmod, out = hp.forward_jacobian_mix_conv(ev, M, mix, cop, Mlay=Mlay)
+        SPECMOD, out = hp.to_host(specmod), hp.to_host(out)
+        SPECONV, dSPECONV = np.ascontiguousarray(out[:, :, 0]), np.ascontiguousarray(out[:, :, 1:])
+        if not integrated:
+            dSPECONV = self.subspeconv(self.SpectroscopyX.WAVE, SPECMOD, dSPECONV)
+        return self.subspecret(SPECONV, dSPECONV)
 
 
 class ArrayForwardModel(B200HotPathMixin):
@@ -780,6 +860,14 @@ def make_forward_model_class(reference_cls):
                 SPECONV[0:n, IGEOM] = S1[0:n]
                 dSPECONV[0:n, IGEOM, :] = dS1[0:n, :]
             return self.subspecret(SPECONV, dSPECONV)
+
+        def nemesisSOfmg(self):
+            out = self.b200_tangent_fmg(self.calc_pathg_SO, filter_integral_allowed=False)
+            return out if out is not None else super().nemesisSOfmg()
+
+        def nemesisLfmg(self):
+            out = self.b200_tangent_fmg(self.calc_pathg_L, filter_integral_allowed=True)
+            return out if out is not None else super().nemesisLfmg()
 
         b200_max_states = 64          # forward models per rendezvous (threads alive at once)
 

@@ -283,6 +283,25 @@ def jacobian_project(dspec, M, shared=False):
     return out
 
 
+def path_mix(spec, dx, mix):
+    """Tangent-height interpolation of the path spectra (nemesisSOfmg / nemesisLfmg, ForwardModel_0.py:1206-1228):
+    spec[NWAVE,NPATH], dx[NWAVE,NPATH,NX] on the device, mix = plan.tangent_mix(...) -> [NWAVE,NGEOM,1+NX]."""
+    _require_cuda()
+    NWAVE, NPATH, NX = dx.shape
+    if tuple(spec.shape) != (NWAVE, NPATH):
+        raise ValueError("path_mix: spec must be [NWAVE,NPATH] like dx[NWAVE,NPATH,NX]")
+    lo, hi = np.asarray(mix["lo"], np.int32), np.asarray(mix["hi"], np.int32)
+    if lo.min() < 0 or max(lo.max(), hi.max()) >= NPATH:
+        raise ValueError("path_mix: path index out of range")
+    NGEOM = len(lo)
+    out = torch.empty((NWAVE, NGEOM, NX + 1), dtype=torch.float64, device="cuda")
+    lo_d, hi_d = to_dev(lo, torch.int32), to_dev(hi, torch.int32)
+    wl_d, wh_d = to_dev(np.asarray(mix["wlo"], np.float64)), to_dev(np.asarray(mix["whi"], np.float64))
+    _lib.check(_lib.load().ansb200_path_mix(_ptr(spec.contiguous()), _ptr(dx.contiguous()), _ptr(lo_d), _ptr(hi_d),
+                                            _ptr(wl_d), _ptr(wh_d), NWAVE, NPATH, NX, NGEOM, _ptr(out), _stream()))
+    return out
+
+
 class ConvOperator:
     """Device copy of a plan.conv_operator (Measurement_0.conv / convg for k-tables)."""
 

@@ -254,6 +254,33 @@ def fold_projection_layers(xmap, NLAY, DTE, DAM, DCO, NVMR, NDUST):
     return fold_projection(xmap, ident, np.array([NLAY], dtype=np.int32), DTE, DAM, DCO, NVMR, NDUST)
 
 
+def tangent_mix(BASEH_TANHE, TANHE):
+    """The pair of paths and the weights with which nemesisSOfmg / nemesisLfmg interpolate the path spectra to each
+    measured tangent height (ForwardModel_0.py:1206-1228, :1464-1486), as arrays lo, hi (-1: path lo alone), wlo, whi:
+    SPECMOD[:, i] = SPECOUT[:, lo] * wlo + SPECOUT[:, hi] * whi.  Same expressions as the reference, evaluated once on
+    the host; the reference's indices can leave the path range (a tangent height below the lowest path), in which case
+    it raises IndexError or wraps around -- here that is a ValueError."""
+    base = np.asarray(BASEH_TANHE, dtype=np.float64)
+    tan = np.asarray(TANHE, dtype=np.float64).reshape(-1)
+    n, npath = len(tan), len(base)
+    lo, hi = np.zeros(n, np.int32), np.full(n, -1, np.int32)
+    wlo, whi = np.ones(n), np.zeros(n)
+    for i in range(n):
+        ibase = int(np.argmin(np.abs(base - tan[i])))
+        if base[ibase] <= tan[i]:
+            il, ih = ibase, ibase + 1
+        else:
+            il, ih = ibase - 1, ibase
+        if il < 0:
+            raise ValueError("tangent height %g km below the lowest path (%g km)" % (tan[i], base.min()))
+        lo[i] = il
+        if ih <= npath - 1:
+            fhl = (tan[i] - base[il]) / (base[ih] - base[il])
+            fhh = (base[ih] - tan[i]) / (base[ih] - base[il])
+            hi[i], wlo[i], whi[i] = ih, 1. - fhl, 1. - fhh
+    return dict(lo=lo, hi=hi, wlo=wlo, whi=whi)
+
+
 # ------------------------------------------------------------------------------------------------
 # Instrument line shape as a sparse operator on the wavenumber axis (Measurement_0.conv / convg,
 # archnemesis/Measurement_0.py:2288-2465 / :2467-2692), for the two modes convg supports with k-tables.

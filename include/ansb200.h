@@ -190,6 +190,13 @@ int ansb200_jacobian_project(const double *dspec, const double *M, int NWAVE, in
 int ansb200_jacobian_project_shared(const double *dspec, const double *M, int NWAVE, int NPAR, int NLAY, int NPATH,
                                     int NX, double *out, void *stream);
 
+/* ---- tangent-height interpolation of the path spectra ------------------------------------------
+ * Replaces the SPECMOD / dSPECMOD loop of nemesisSOfmg / nemesisLfmg (ForwardModel_0.py:1206-1228, :1464-1486):
+ * out[NWAVE,NGEOM,1+NX] = [spec | dx][:, lo[i]] * wlo[i] + [spec | dx][:, hi[i]] * whi[i]  (hi[i] < 0: path lo[i] alone).
+ * spec[NWAVE,NPATH], dx[NWAVE,NPATH,NX] as ansb200_jacobian_project leaves them; lo/hi/wlo/whi[NGEOM] on the device. */
+int ansb200_path_mix(const double *spec, const double *dx, const int32_t *lo, const int32_t *hi, const double *wlo,
+                     const double *whi, int NWAVE, int NPATH, int NX, int NGEOM, double *out, void *stream);
+
 /* ---- instrument line shape -------------------------------------------------------------------
  * Replaces Measurement_0.conv / convg for k-tables (archnemesis/Measurement_0.py:2288-2465,
  * :2467-2692): mode 0 = FWHM == 0, scipy interp1d onto the convolution points (rows of two entries

@@ -105,6 +105,16 @@ class HotPath:
             block = block * float(wgeom)
         return np.concatenate([orc.apply_conv(conv_op, block[:, 0])[:, None], orc.apply_conv(conv_op, block[:, 1:])], axis=1)
 
+    def forward_jacobian_mix_conv(self, ev, M, mix, conv_op, Mlay=None):
+        spec, dx, _ = self.forward_jacobian(ev, M)
+        full = np.concatenate([spec[:, :, None], dx], axis=2)                  # [NWAVE, NPATH, 1+NX]
+        block = np.zeros((full.shape[0], len(mix["lo"]), full.shape[2]))
+        for i, (lo, hi, a, b) in enumerate(zip(mix["lo"], mix["hi"], mix["wlo"], mix["whi"])):
+            block[:, i] = full[:, lo] if hi < 0 else full[:, lo] * a + full[:, hi] * b
+        nw, ngeom, nc = block.shape
+        out = orc.apply_conv(conv_op, block.reshape(nw, ngeom * nc))
+        return block[:, :, 0], out.reshape(out.shape[0], ngeom, nc)
+
     def project(self, dspec, M):
         nwv, npath, npar, nlm = dspec.shape
         return np.einsum("wpe,pex->wpx", np.asarray(dspec).reshape(nwv, npath, npar * nlm), M)

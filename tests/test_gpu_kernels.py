@@ -572,3 +572,24 @@ def test_float32_table_storage_variants():
     with pytest.raises(ValueError):
         ops.Table(K2, "k32")
     ops.Table(K2, "f32").close()
+
+
+def test_path_mix_matches_numpy_bit_for_bit():
+    """ansb200_path_mix: the tangent-height interpolation of nemesisSOfmg / nemesisLfmg (ForwardModel_0.py:1206-1228)."""
+    import torch
+    from archnemesis_dist_b200 import ops, plan
+    rng = np.random.default_rng(5)
+    nw, npath, nx = 37, 9, 70
+    spec, dx = rng.standard_normal((nw, npath)), rng.standard_normal((nw, npath, nx))
+    base = np.sort(rng.uniform(10.0, 200.0, npath))
+    tan = np.array([base[0], base[0] + 1.0, 0.5 * (base[3] + base[4]), base[5], base[-1] - 1e-3, base[-1], base[-1] + 30.0])
+    mix = plan.tangent_mix(base, tan)
+    assert (mix["hi"] < 0).sum() == 2              # at and above the highest path: that path alone
+    out = ops.path_mix(ops.to_dev(spec), ops.to_dev(dx), mix).cpu().numpy()
+    full = np.concatenate([spec[:, :, None], dx], axis=2)
+    for i, (lo, hi, a, b) in enumerate(zip(mix["lo"], mix["hi"], mix["wlo"], mix["whi"])):
+        want = full[:, lo] if hi < 0 else full[:, lo] * a + full[:, hi] * b
+        assert np.array_equal(out[:, i], want), i
+    with pytest.raises(ValueError):
+        plan.tangent_mix(base, [base[0] - 5.0])
+    assert torch.cuda.is_available()

@@ -245,3 +245,72 @@ def test_coreretOE_runs_on_the_dropin_classes(jupiter):
     assert abs(got.PHI - ref.PHI) <= 1e-8 * abs(ref.PHI) and abs(got.CHISQ - ref.CHISQ) <= 1e-8 * abs(ref.CHISQ)
     for name in ("KK", "DD", "AA", "SM", "SN", "ST"):
         assert colerr(getattr(got, name), getattr(ref, name)) < 1e-8, name
+
+
+def _tangent_geometries(objs, ngeom=4, lo=20.0, hi=160.0):
+    """Turn the nadir measurement of the Jupiter deck into `ngeom` limb / occultation geometries on one spectral grid
+    (what nemesisSOfmg / nemesisLfmg expect: TANHE per geometry, the same VCONV everywhere)."""
+    M = objs["Measurement"]
+    nc = int(M.NCONV[0])
+    M.NGEOM = ngeom
+    M.NAV = np.ones(ngeom, dtype="int32")
+    M.NCONV = np.full(ngeom, nc, dtype="int32")
+    M.VCONV = np.repeat(M.VCONV[:, :1], ngeom, axis=1)
+    M.MEAS = np.full((M.VCONV.shape[0], ngeom), 0.5)
+    M.ERRMEAS = np.repeat(M.ERRMEAS[:, :1], ngeom, axis=1)
+    M.FLAT, M.FLON = np.zeros((ngeom, 1)), np.zeros((ngeom, 1))
+    M.SOL_ANG, M.EMISS_ANG, M.AZI_ANG = np.full((ngeom, 1), 90.0), np.full((ngeom, 1), 90.0), np.zeros((ngeom, 1))
+    M.WGEOM = np.ones((ngeom, 1))
+    M.TANHE = np.linspace(lo, hi, ngeom).reshape(ngeom, 1)
+    M.NY = nc * ngeom
+    return objs
+
+
+@pytest.mark.parametrize("driver,kind", [("nemesisSOfmg", "lbl"), ("nemesisLfmg", "lbl"), ("nemesisSOfmg", "k"),
+                                         ("nemesisLfmg", "k")])
+def test_limb_and_occultation_drivers_keep_their_tail_on_the_engine(driver, kind):
+    """nemesisSOfmg / nemesisLfmg (ForwardModel_0.py:983-1243, :1372-1518) through install(): all tangent paths in one
+    evaluation, then the tangent-height interpolation and the line shape for every geometry at once (IGEOM='All':
+    lblconvg_ngeom for the line-by-line tables with a Gaussian of FWHM 1.5 cm-1, scipy interpolation for k-tables with
+    FWHM = 0) on the engine -- only SPECMOD and [NCONV, NGEOM, 1+NX] come back -- against the unmodified reference."""
+    from oracle.ref_import import import_reference
+    from oracle import make_golden as mg
+    from archnemesis_dist_b200 import forward_model as fmod
+    from tests import cpu_engine
+    ans = import_reference()
+    root = os.path.join(tempfile.mkdtemp(prefix="ansb200_so_"), "deck")
+    deck = mg.build_jupiter_lbl_deck(root, fwhm=1.5) if kind == "lbl" else mg.build_jupiter_deck(root)
+    ref_cls = sys.modules["archnemesis.ForwardModel_0"].ForwardModel_0
+    cwd = os.getcwd()
+    os.chdir(deck)
+    try:
+        objs = _tangent_geometries(mg.load_jupiter(ans, deck))
+        if kind == "k":
+            assert float(objs["Measurement"].FWHM) == 0.0
+        ref = mg.make_forward_model(ans, ref_cls, objs, deck)
+        S_ref, dS_ref = getattr(ref, driver)()
+        cls = fmod.install(ans)
+        try:
+            cls.b200_engine = cpu_engine
+            calls = []
+            orig = cpu_engine.HotPath.forward_jacobian_mix_conv
+
+            def counting(self, ev, M, mix, conv_op, Mlay=None):
+                calls.append((ev.LAYINC.shape[1], len(mix["lo"]), int(np.sum(np.asarray(mix["hi"]) >= 0))))
+                return orig(self, ev, M, mix, conv_op, Mlay)
+            cpu_engine.HotPath.forward_jacobian_mix_conv = counting
+            try:
+                fm = mg.make_forward_model(ans, ans.ForwardModel_0, _tangent_geometries(mg.load_jupiter(ans, deck)), deck)
+                S, dS = getattr(fm, driver)()
+            finally:
+                cpu_engine.HotPath.forward_jacobian_mix_conv = orig
+        finally:
+            fmod.uninstall(ans)
+    finally:
+        os.chdir(cwd)
+    assert len(calls) == 1 and calls[0][0] >= 4 and calls[0][1] == 4 and calls[0][2] >= 3     # one evaluation, all paths
+    assert S.shape == S_ref.shape and dS.shape == dS_ref.shape
+    assert relerr(S, S_ref) < 1e-12
+    assert np.abs(dS_ref).max() > 0.0
+    for ix in range(dS_ref.shape[2]):
+        assert colerr(dS[:, :, ix], dS_ref[:, :, ix]) < 1e-11, ix
