@@ -407,6 +407,12 @@ ans_radiance_kernel(RadParams P)
 // each warp then walks its own paths with no CTA barrier: lanes sum the path's opacity per g (phase 1), then
 // sweep the (parameter, layer) outputs with consecutive lanes on consecutive layers (contiguous stores).
 // 5e3 warp instructions per (wavenumber, path) instead of 2.7e4 in the general kernel.
+__device__ __forceinline__ double tl_nan_to_num_fwd(double v)
+{
+    if ((__double2hiint(v) & 0x7ff00000) == 0x7ff00000) v = ans_nan_to_num(v);     // (rare: one integer test otherwise)
+    return v;
+}
+
 constexpr int RADT_WARPS = 32;
 constexpr int RADT_GROUP = 64;      // paths per pass of the layer-space gradient phase (8 tiles of 8 paths)
 
@@ -430,13 +436,24 @@ ans_transmission_paths_kernel(RadParams P)
     double *sdk = sdcon + ((grad && P.dtaucon) ? (size_t)NPAR * NLAY : 0);   // [NG*NLAY*NP1] dk of the wavenumber (grad)
     int *scol = reinterpret_cast<int *>(sdk + ((grad && P.dk) ? (size_t)NG * NLAY * NP1 : 0));   // [NPAR]
     const int nthr = blockDim.x;
-    for (int t = threadIdx.x; t < NG * NLAY; t += nthr) stau[t] = P.tau[(size_t)iw * NG * NLAY + t];
+    // NG >= 8: the lanes of a warp are the g-ordinates of its path (phase 1 below); the opacity is then kept
+    // layer-major, stau[l][g] = tau + continuum, so that a warp reads one layer's row
+    const bool lanes_g = NG >= 8;
     for (int l = threadIdx.x; l < NLAY; l += nthr) {
         double c = 0.0;                                            // TAUCIA + TAUDUST + TAURAY in the reference's order (:3989)
         if (P.taucia) c += P.taucia[(size_t)iw * NLAY + l];
         if (P.taudust) c += P.taudust[(size_t)iw * NLAY + l];
         if (P.tauray) c += P.tauray[(size_t)iw * NLAY + l];
         scon[l] = c;
+    }
+    if (lanes_g) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < NG * NLAY; t += nthr) {
+            const int g = t / NLAY, l = t - g * NLAY;
+            stau[l * NG + g] = P.tau[(size_t)iw * NG * NLAY + t] + scon[l];
+        }
+    } else {
+        for (int t = threadIdx.x; t < NG * NLAY; t += nthr) stau[t] = P.tau[(size_t)iw * NG * NLAY + t];
     }
     for (int g = threadIdx.x; g < NG; g += nthr) sdelg[g] = P.delg[g];
     if (grad) {
@@ -479,6 +496,33 @@ ans_transmission_paths_kernel(RadParams P)
             cq[q] = scon[lq[q]];
         }
         double spec = 0.0, csum = 0.0;
+        if (lanes_g) {
+            // every lane walks the path for its own g-ordinate; the (layer, scale) pairs the lanes hold are handed
+            // round by shuffles, the NG exponentials are one instruction stream
+            for (int g0 = 0; g0 < NG; g0 += 32) {
+                const int g = g0 + lane;
+                const double *tl = stau + (g < NG ? g : 0);
+                double t = 0.0;
+#pragma unroll
+                for (int q = 0; q < RQ; ++q) {
+                    const int cntq = min(32, n - 32 * q);            // (warp-uniform)
+#pragma unroll 4
+                    for (int jj = 0; jj < cntq; ++jj) {
+                        const int l = __shfl_sync(RFULL, lq[q], jj);
+                        const double sv = rshfl_idx(sq[q], jj);
+                        t = fma(tl[l * NG], sv, t);
+                    }
+                }
+                for (int j = 32 * RQ; j < n; ++j) {                  // (paths longer than 256 layers)
+                    const int l = P.layinc[(size_t)j * NPATH + ipath];
+                    t = fma(tl[l * NG], P.scale[(size_t)j * NPATH + ipath], t);
+                }
+                const double cg = g < NG ? exp(-t) * xf * sdelg[g] : 0.0;
+                if (g < NG) myc[g] = cg;
+                spec += warp_sum(cg);
+            }
+            csum = spec;
+        } else
         for (int g = 0; g < NG; ++g) {
             const double *tg = stau + (size_t)g * NLAY;
             double t = 0.0;
@@ -546,40 +590,66 @@ ans_transmission_paths_kernel(RadParams P)
         __syncthreads();
         const int npt = (gp1 - gp0 + 7) >> 3, nlt = (NLAY + 7) >> 3;
         const int kk = lane & 3, mm = lane >> 2;
-        for (int unit = warp; unit < npt * nlt * NPAR; unit += (nthr >> 5)) {
-            const int k = unit / (npt * nlt), rem = unit - k * (npt * nlt);
-            const int pt = rem / nlt, lt = rem - pt * nlt;
-            const int col = scol[k];
-            double d0 = 0.0, d1 = 0.0;
-            if (col >= 0) {
-                const int lb = lt * 8 + mm;                 // the layer of this lane's B element
-                for (int g0 = 0; g0 < NG; g0 += 4) {
-                    const int g = g0 + kk;
-                    const double a = g < NG ? sC[(size_t)(pt * 8 + mm) * NG + g] : 0.0;
-                    const double b = (g < NG && lb < NLAY) ? sdk[((size_t)g * NLAY + lb) * NP1 + col] : 0.0;
-                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-                }
-                const double unit_k = col < P.NGAS ? 1.0e-4 : 1.0;
-                d0 *= unit_k;
-                d1 *= unit_k;
-            }
+        // a warp keeps one tile of 8 paths (its C fragments stay in registers) and shares the tile's (parameter, layer
+        // tile) units with the other warps on that tile
+        const int nwarps = nthr >> 5;
+        const bool many = nwarps >= npt;
+        constexpr int KS = 5;                                      // k-steps held in registers (NG <= 20); beyond that the operands are re-read
+        for (int pt = many ? warp % npt : warp; pt < npt; pt += many ? npt : nwarps) {
+            const int wsub = many ? warp / npt : 0, wpt = many ? (nwarps - pt + npt - 1) / npt : 1;
             const int r = pt * 8 + mm, path = gp0 + r;
-            if (path < gp1) {
-                const double cs = sCs[r];
-                double *out = P.dspec + (((size_t)iw * NPATH + path) * NPAR + k) * NLAY;
+            double af[KS];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int l = lt * 8 + 2 * kk + h;
-                    if (l < NLAY) {
-                        const double scl = sS[(size_t)r * NLAY + l];
-                        double a = h ? d1 : d0;
-                        if (P.dtaucon) a = fma(sdcon[(size_t)k * NLAY + l], cs, a);
-                        double v = scl != 0.0 ? -(a * scl) : 0.0;
-                        if (P.flags & ANSB200_RAD_NAN_TO_NUM) v = ans_nan_to_num(v);
-                        out[l] = v;
+            for (int i = 0; i < KS; ++i) {
+                const int g = 4 * i + kk;
+                af[i] = g < NG ? sC[(size_t)r * NG + g] : 0.0;
+            }
+            const double cs = sCs[r];
+            const double *srow = sS + (size_t)r * NLAY;
+            int k = wsub / nlt, lt = wsub - k * nlt;
+            while (k < NPAR) {
+                const int col = scol[k];
+                double d0 = 0.0, d1 = 0.0;
+                if (col >= 0) {
+                    const int lb = lt * 8 + mm;                 // the layer of this lane's B element
+                    const double *bp = sdk + ((size_t)kk * NLAY + (lb < NLAY ? lb : 0)) * NP1 + col;
+                    const size_t bstep = (size_t)4 * NLAY * NP1;
+#pragma unroll
+                    for (int i = 0; i < KS; ++i) {
+                        if (4 * i < NG) {
+                            const double bv = (4 * i + kk < NG && lb < NLAY) ? bp[i * bstep] : 0.0;
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                         : "+d"(d0), "+d"(d1) : "d"(af[i]), "d"(bv));
+                        }
+                    }
+                    for (int g0 = 4 * KS; g0 < NG; g0 += 4) {
+                        const int g = g0 + kk;
+                        const double av = g < NG ? sC[(size_t)r * NG + g] : 0.0;
+                        const double bv = (g < NG && lb < NLAY) ? sdk[((size_t)g * NLAY + lb) * NP1 + col] : 0.0;
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                     : "+d"(d0), "+d"(d1) : "d"(av), "d"(bv));
+                    }
+                    const double unit_k = col < P.NGAS ? 1.0e-4 : 1.0;
+                    d0 *= unit_k;
+                    d1 *= unit_k;
+                }
+                if (path < gp1) {
+                    double *out = P.dspec + (((size_t)iw * NPATH + path) * NPAR + k) * NLAY;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int l = lt * 8 + 2 * kk + h;
+                        if (l < NLAY) {
+                            const double scl = srow[l];
+                            double a = h ? d1 : d0;
+                            if (P.dtaucon) a = fma(sdcon[(size_t)k * NLAY + l], cs, a);
+                            double v = scl != 0.0 ? -(a * scl) : 0.0;
+                            if (P.flags & ANSB200_RAD_NAN_TO_NUM) v = tl_nan_to_num_fwd(v);
+                            out[l] = v;
+                        }
                     }
                 }
+                lt += wpt;
+                while (lt >= nlt) { lt -= nlt; ++k; }
             }
         }
         __syncthreads();
