@@ -1023,6 +1023,9 @@ def install(archnemesis=None):
     # Python in the reference at the config-2 size, table_io.py)
     from . import table_io as _table_io
     _table_io.install_readers()
+    # k-table generation (calc_ktable): the per-bin sort / quantile tail of calc_ktable_chunk on the device (ktable.py)
+    from . import ktable as _ktable
+    _ktable.install_ktable()
     return cls
 
 
@@ -1043,6 +1046,8 @@ def uninstall(archnemesis=None):
     _linedata.uninstall_lbl()
     from . import table_io as _table_io
     _table_io.uninstall_readers()
+    from . import ktable as _ktable
+    _ktable.uninstall_ktable()
     if "oe_reference" in _INSTALLED:
         oe_ref = _INSTALLED.pop("oe_reference")
         _INSTALLED.pop("oe_cls", None)

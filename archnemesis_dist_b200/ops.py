@@ -32,7 +32,7 @@ def to_dev(a, dtype=torch.float64):
         return None
     if isinstance(a, torch.Tensor):
         return a.to(device="cuda", dtype=dtype).contiguous()
-    npdt = {torch.float64: np.float64, torch.int32: np.int32}[dtype]
+    npdt = {torch.float64: np.float64, torch.int32: np.int32, torch.int64: np.int64}[dtype]
     h = np.ascontiguousarray(a, dtype=npdt)
     if not h.flags.writeable:           # e.g. the memoised, shared WAVE grid: torch refuses read-only views
         h = h.copy()
@@ -299,6 +299,31 @@ def path_mix(spec, dx, mix):
     wl_d, wh_d = to_dev(np.asarray(mix["wlo"], np.float64)), to_dev(np.asarray(mix["whi"], np.float64))
     _lib.check(_lib.load().ansb200_path_mix(_ptr(spec.contiguous()), _ptr(dx.contiguous()), _ptr(lo_d), _ptr(hi_d),
                                             _ptr(wl_d), _ptr(wh_d), NWAVE, NPATH, NX, NGEOM, _ptr(out), _stream()))
+    return out
+
+
+def kdist_capacity(weighted):
+    return int(_lib.load().ansb200_kdist_capacity(int(bool(weighted))))
+
+
+def kdist(kabs, lo, hi, g_ord, w=None, woff=None):
+    """k-distributions of spectral bins (tail of calc_ktable_chunk, Spectroscopy_0.py:3619-3660): kabs[ncalc] on the
+    device, bins [lo[b], hi[b]) of the grid, optional weights w (bin b at w[woff[b]:...]) -> out[NBIN, NG] (device)."""
+    _require_cuda()
+    lo, hi = np.asarray(lo, np.int32), np.asarray(hi, np.int32)
+    n = hi - lo
+    if len(lo) == 0 or n.min() < 1:
+        raise ValueError("kdist: every bin needs at least one grid point")
+    g = to_dev(np.asarray(g_ord, np.float64))
+    out = torch.empty((len(lo), g.numel()), dtype=torch.float64, device="cuda")
+    lo_d, hi_d = to_dev(lo, torch.int32), to_dev(hi, torch.int32)
+    w_d = woff_d = None
+    if w is not None:
+        w_d = w if isinstance(w, torch.Tensor) else to_dev(np.asarray(w, np.float64))
+        woff_d = to_dev(np.asarray(woff, np.int64), torch.int64)
+    _lib.check(_lib.load().ansb200_kdist(_ptr(kabs), _ptr(w_d) if w_d is not None else None, _ptr(lo_d), _ptr(hi_d),
+                                         _ptr(woff_d) if woff_d is not None else None, len(lo), int(n.max()), _ptr(g),
+                                         int(g.numel()), _ptr(out), _stream()))
     return out
 
 

@@ -197,6 +197,17 @@ int ansb200_jacobian_project_shared(const double *dspec, const double *M, int NW
 int ansb200_path_mix(const double *spec, const double *dx, const int32_t *lo, const int32_t *hi, const double *wlo,
                      const double *whi, int NWAVE, int NPATH, int NX, int NGEOM, double *out, void *stream);
 
+/* ---- k-distributions from a monochromatic spectrum (k-table generation) ------------------------
+ * Replaces the per-bin tail of calc_ktable_chunk (archnemesis/Spectroscopy_0.py:3619-3660): for bin b the absorption
+ * coefficients kabs[lo[b]:hi[b]] of the line-by-line grid are sorted, g_i = cumsum(w_i) / sum(w) in sorted order
+ * (w = the instrument function at the point times the grid step; NULL: equal weights, g_i = (i+1)/n) and
+ * out[b, :] = np.interp(g_ord, g_sorted, k_sorted).  w holds the weights of bin b at w[woff[b] : woff[b] + n_b]
+ * (bins may overlap when an instrument function widens them).  max_n = the longest bin; it must not exceed
+ * ansb200_kdist_capacity(weighted) (16384 / 8192 points: the sort runs in shared memory). */
+int ansb200_kdist_capacity(int weighted);
+int ansb200_kdist(const double *kabs, const double *w, const int32_t *lo, const int32_t *hi, const int64_t *woff,
+                  int NBIN, int max_n, const double *g_ord, int NG, double *out, void *stream);
+
 /* ---- instrument line shape -------------------------------------------------------------------
  * Replaces Measurement_0.conv / convg for k-tables (archnemesis/Measurement_0.py:2288-2465,
  * :2467-2692): mode 0 = FWHM == 0, scipy interp1d onto the convolution points (rows of two entries

@@ -558,3 +558,23 @@ def continuum_eval(tables, plan, want_grad=True):
     for i in range(NDUST):
         dtaucon[:, NVMR + 1 + i, :] = dtaucon[:, NVMR + 1 + i, :] + plan["ud"][i][:, None]
     return taucia, taudust, tauray, dtaucon
+
+
+# ----------------------------------------------------------------------------------------------
+# k-distribution of one spectral bin: the tail of calc_ktable_chunk (Spectroscopy_0.py:3619-3660), numpy as written there
+# ----------------------------------------------------------------------------------------------
+def k_distribution(kabs, wavecalc, vbinmin, vbinmax, g_ord, ils=None):
+    """kabs, wavecalc [ncalc]: the line-by-line spectrum of one (p, T) point; vbinmin / vbinmax [NBIN]; ils(ibin,
+    wavesel) -> the instrument function at those grid points (None: ones).  Returns k[NBIN, NG]."""
+    kabs, wavecalc = np.asarray(kabs, dtype=np.float64), np.asarray(wavecalc, dtype=np.float64)
+    out = np.zeros((len(vbinmin), len(g_ord)))
+    for ib in range(len(vbinmin)):
+        mask = (wavecalc >= vbinmin[ib]) & (wavecalc <= vbinmax[ib])
+        idx = np.argsort(kabs[mask])
+        wavesel = wavecalc[mask]
+        k_sorted = kabs[mask][idx]
+        ils_sorted = np.ones_like(wavesel) if ils is None else np.asarray(ils(ib, wavesel[idx]), dtype=np.float64)
+        delvarray = np.zeros_like(k_sorted) + (wavecalc[1] - wavecalc[0])
+        g_sorted = np.cumsum(ils_sorted * delvarray) / np.sum(ils_sorted * delvarray)
+        out[ib] = np.interp(g_ord, g_sorted, k_sorted)
+    return out

@@ -593,3 +593,41 @@ def test_path_mix_matches_numpy_bit_for_bit():
     with pytest.raises(ValueError):
         plan.tangent_mix(base, [base[0] - 5.0])
     assert torch.cuda.is_available()
+
+
+def test_kdist_kernel_against_golden_and_oracle():
+    """ansb200_kdist: k-distributions of spectral bins (tail of calc_ktable_chunk, Spectroscopy_0.py:3619-3660) against
+    the reference's own output (tests/golden/kdist.npz, made by tests/test_ktable_dropin.py from the live reference),
+    with and without an instrument function, and against the oracle on bins of every size class: one point, a
+    non-power-of-two, the capacity of the shared-memory sort, and one beyond it (library sort on the device)."""
+    import os
+    from archnemesis_dist_b200 import ktable, ops
+    from oracle import oracle
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kdist.npz"))
+    got = ktable.k_distribution(z["plain_kabs"], z["plain_wavecalc"], z["plain_vbinmin"], z["plain_vbinmax"], z["g_ord"])
+    assert relerr(got, z["plain_k"]) < 1e-11        # (g_i = (i+1)/n here, n accumulated steps in the reference)
+    ils = lambda ib, wv: np.interp(wv - z["centres"][ib], z["vfil_rel"], z["afil"])      # noqa: E731
+    got = ktable.k_distribution(z["ils_kabs"], z["ils_wavecalc"], z["ils_vbinmin"], z["ils_vbinmax"], z["g_ord"], ils)
+    assert relerr(got, z["ils_k"]) < 1e-11
+    rng = np.random.default_rng(12)
+    cap = ops.kdist_capacity(False)
+    assert cap == 16384 and ops.kdist_capacity(True) == 8192
+    sizes = [1, 2, 33, 1000, 4097, cap, cap + 5]
+    wave = np.arange(sum(sizes), dtype=np.float64) * 0.25 + 100.0
+    kabs = 10.0 ** rng.uniform(-28.0, -20.0, len(wave))
+    kabs[5:9] = kabs[5]                                # ties
+    edges = np.concatenate([[0], np.cumsum(sizes)])
+    vmin, vmax = wave[edges[:-1]], wave[edges[1:] - 1]
+    g = np.array([0.0, 1e-6, 0.013, 0.25, 0.5, 0.77, 0.987, 1.0 - 1e-9, 1.0])
+    want = oracle.k_distribution(kabs, wave, vmin, vmax, g)
+    got = ktable.k_distribution(kabs, wave, vmin, vmax, g)
+    for ib in range(len(sizes)):
+        assert relerr(got[ib], want[ib]) < 1e-10, sizes[ib]
+    wfun = lambda ib, wv: 0.2 + np.abs(np.sin(wv))                                        # noqa: E731
+    ok = [i for i, n in enumerate(sizes) if n <= cap]
+    want = oracle.k_distribution(kabs, wave, vmin, vmax, g, wfun)
+    got = ktable.k_distribution(kabs, wave, vmin, vmax, g, wfun)       # (the two largest bins: library sort)
+    for ib in ok + [len(sizes) - 1]:
+        assert relerr(got[ib], want[ib]) < 1e-10, sizes[ib]
+    with pytest.raises(ValueError):
+        ktable.k_distribution(kabs, wave, [wave[3] + 0.01], [wave[3] + 0.02], g)          # a bin without grid points

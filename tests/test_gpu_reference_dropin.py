@@ -203,3 +203,29 @@ def test_limb_and_occultation_drivers_on_the_cuda_engine(driver, kind):
     assert calls == [(calls[0][0], True)] and calls[0][0] >= 4
     assert relerr(S, S_ref) < TOL
     _columns_close(dS, dS_ref, TOL, floor=1e-15)
+
+
+@pytest.mark.parametrize("with_ils", [False, True])
+def test_calc_ktable_chunk_on_the_device(with_ils):
+    """k-table generation: Spectroscopy_0.calc_ktable_chunk under install_lbl() + install_ktable() -- the line-by-line
+    spectrum of every (p, T) point from ansb200_lbl_absorption, the per-bin sort and quantiles from ansb200_kdist --
+    against the unmodified reference on synthetic line data."""
+    from archnemesis_dist_b200 import ktable, linedata
+    from tests.test_lbl_dropin import _reference_objects
+    from tests.test_ktable_dropin import _case
+    ans, ld, LineSetData = _reference_objects()
+    sp_mod = sys.modules["archnemesis.Spectroscopy_0"]
+    iwaves = np.arange(3, 12)
+    S, S_LBL, M = _case(ans, ld, LineSetData, with_ils)
+    ref = sp_mod.calc_ktable_chunk(iwaves, S, S_LBL, 0.3, M)
+    linedata.install_lbl()
+    ktable.install_ktable()
+    try:
+        assert isinstance(ktable._BACKEND, ktable.DeviceBackend)
+        S2, S_LBL2, M2 = _case(ans, ld, LineSetData, with_ils)
+        got = sp_mod.calc_ktable_chunk(iwaves, S2, S_LBL2, 0.3, M2)
+    finally:
+        ktable.uninstall_ktable()
+        linedata.uninstall_lbl()
+    assert got.shape == ref.shape and ref.max() > 0.0
+    assert relerr(got, ref) < TOL
