@@ -1,29 +1,44 @@
 """Python face of the drop-in: the hot methods of archNEMESIS' ``ForwardModel_0`` re-routed to the
 device through ``engine.HotPath``.
 
-``B200HotPathMixin`` overrides exactly the methods on the hot path and keeps their
-signatures and return shapes:
+``B200HotPathMixin`` overrides the methods on the hot path and keeps their signatures and return
+shapes:
 
     CIRSrad(return_grad=False)                       archnemesis/ForwardModel_0.py:4376-4511
-    calculate_gaseous_line_opacity(return_grad)      :3781-3891   (K_TABLES branch)
-    calculate_layer_opacity(return_grad)             :3905-4016
-    nemesisfmg() inner triple CIRSrad -> map2pro -> map2xvec       :694-718   (fused, see b200_forward_jacobian)
+    calculate_gaseous_line_opacity(return_grad)      :3781-3891   (k-tables and in-memory line-by-line tables)
+    nemesisfmg()                                     :593-779     (CIRSrad -> map2pro -> map2xvec fused, JSURF column,
+                                                     WGEOM and the instrument line shape on the device when the
+                                                     geometry allows: b200_forward_jacobian[_conv])
+    nemesisSOfmg() / nemesisLfmg()                   :983-1243 / :1372-1518  (all tangent paths in one evaluation,
+                                                     tangent-height interpolation and the IGEOM='All' line shape on the
+                                                     device: b200_tangent_fmg; the AOTF branch stays the reference's)
+    jacobian_nemesis()                               :2184-2361   (numerical columns batched: StateBatch)
     map2pro / map2xvec (module functions)            :5319-5424   (rebound by install(): CIRSrad's gradient stays on
                                                      the device as a DeviceGradient and the projection is fused for
-                                                     every driver -- nemesisSOfmg :1188-1206, nemesisLfmg :1452-1470,
-                                                     process_IAV :2039-2059 -- without overriding them)
+                                                     every other driver body -- process_IAV :2039-2059, the AOTF
+                                                     branch, user code -- without overriding them)
 
-It reads only the attributes the reference methods read (``SpectroscopyX``, ``LayerX``, ``PathX``,
-``AtmosphereX``, ``SurfaceX``, ``MeasurementX``, ``ScatterX``, ``StellarX``, ``Variables``) and
-calls the reference's own host-side continuum routines (``calculate_vertical_cia_opacity``,
-``calc_tau_rayleigh``, ``calc_tau_dust``), which stay Python.  Path types that are out of scope
-(scattering, absorption, emissions, LBL tables) are delegated to the reference implementation
-further up the MRO, unchanged; the supported path has no CPU fallback.
+``calculate_layer_opacity`` (:3905-4016), ``calculate_thermal_emission_spectrum`` and ``calculate_transmission_spectrum``
+are NOT overridden: their work happens inside ``ansb200_radiance`` and is never materialised, so the device ``CIRSrad``
+does not set the diagnostics the reference leaves behind on the way (``LayerX.TAUGAS`` :3925, ``LayerX.TAUTOT`` :3997,
+``LayerX.TAUCIA`` :3901 stay as they were); ``calculate_gaseous_line_opacity`` still returns TAUGAS / dTAUGAS for
+callers that want them.
 
-``install()`` builds ``ForwardModel_B200(B200HotPathMixin, archnemesis.ForwardModel_0)`` and rebinds
-the three names callers resolve at call time, so ``coreretOE``, ``coreretNS`` and
-``retrieval_nemesis`` pick it up without edits.  ``ArrayForwardModel`` is the same mix-in over plain
-namespaces for hosts where the reference package is not installed (the GPU test box).
+The mix-in reads only the attributes the reference methods read (``SpectroscopyX``, ``LayerX``, ``PathX``,
+``AtmosphereX``, ``SurfaceX``, ``MeasurementX``, ``ScatterX``, ``StellarX``, ``CIAX``, ``Variables``).  The continuum
+terms (CIA, Rayleigh, aerosols) are planned on the host from those objects (continuum.py follows
+``calc_tau_cia`` / ``calc_tau_rayleigh*`` / ``calc_tau_dust``) and evaluated on the device; ``ArrayForwardModel``, which
+has no reference objects to plan from, takes them as dense arrays.  Path types that are out of scope (scattering,
+absorption, emissions, run-time line-by-line inside CIRSrad, tables read on line from HDF5, shapes beyond the native
+limits of include/ansb200.h) are delegated to the reference implementation further up the MRO, unchanged; the supported
+path has no CPU fallback.
+
+``install()`` builds ``ForwardModel_B200(B200HotPathMixin, archnemesis.ForwardModel_0)`` and rebinds the three names
+callers resolve at call time, so ``coreretOE``, ``coreretNS`` and ``retrieval_nemesis`` pick it up
+without edits; it also installs ``OE_B200`` (oe.py), the memoised ``read_tables`` with the vectorised table readers
+(table_io.py), the run-time line-by-line functions (linedata.py) and ``calc_ktable_chunk`` (ktable.py).
+``ArrayForwardModel`` is the same mix-in over plain namespaces for hosts where the reference package is not
+installed.
 """
 import sys
 import types
