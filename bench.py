@@ -740,6 +740,34 @@ def run_extras(hp, c, cfg, nthreads):
                                           lines=int(len(keep)), points=2048))
     except Exception as e:                                   # noqa: BLE001
         out["config3"] = dict(error=repr(e))
+    # k-table generation: the per-bin tail of calc_ktable_chunk on one (p, T) point's spectrum
+    try:
+        import time as _time
+        from archnemesis_dist_b200 import ktable, ops
+        from oracle import oracle as orc
+        rng = np.random.default_rng(21)
+        nbin, per = 4000, 2500                                  # 1e7 grid points, 2500 per bin
+        wave = 2000.0 + np.arange(nbin * per) * 1e-4
+        kabs = 10.0 ** rng.uniform(-27.0, -20.0, len(wave))
+        vmin, vmax = wave[::per].copy(), wave[per - 1::per].copy()
+        xg, _ = np.polynomial.legendre.leggauss(20)
+        g = 0.5 * (xg + 1.0)
+        kd = ops.to_dev(kabs)
+        lo, hi = ktable.bin_ranges(wave, vmin, vmax)
+        ms = timeit(lambda: ops.kdist(kd, lo, hi, g))
+        got = ops.kdist(kd, lo, hi, g).cpu().numpy()
+        nb_cpu = 40                                             # the reference's numpy per bin masks the whole grid
+        t0 = _time.perf_counter()
+        ref = orc.k_distribution(kabs, wave, vmin[:nb_cpu], vmax[:nb_cpu], g)
+        t_cpu = (_time.perf_counter() - t0) / nb_cpu * nbin
+        out["ktable_quantiles"] = dict(
+            workload="calc_ktable_chunk tail: %d bins x %d line-by-line points of one (p,T) point -> k[NBIN,20]" % (nbin, per),
+            ms_device=ms, grid_points_per_s=len(wave) / (ms * 1e-3),
+            s_numpy_as_in_reference=t_cpu, numpy_sample="%d bins timed (oracle restatement, one core), scaled to %d" % (nb_cpu, nbin),
+            parity=dict(max_rel=float(np.abs(got[:nb_cpu] - ref).max() / np.abs(ref).max()), bins=nb_cpu))
+        del kd
+    except Exception as e:                                   # noqa: BLE001
+        out["ktable_quantiles"] = dict(error=repr(e))
     return out
 
 
