@@ -271,53 +271,84 @@ def parity_of(spec, dx, s_ref, x_ref):
 # clocks sampler
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU, sampled every few ms by a thread through NVML (nvidia_ml_py), which is
+    initialised when the object is made -- well before the timed region: starting an `nvidia-smi` process next to the
+    timed loop costs that loop tens of ms of driver contention (seen at N = 2).  Falls back to a looping `nvidia-smi`
+    started equally early if NVML cannot be imported."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.rows = []
-        self.proc = None
+    def __init__(self, index, period=0.004):
+        self.rows, self.proc, self.nvml, self.alive, self.period = [], None, None, True, period
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.rows.append((time.perf_counter(), ln.strip()))
+    def _poll(self):
+        n = self.nvml
+        bits = [("hw_slowdown", getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                ("hw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                ("sw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                ("sw_power_cap", getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4))]
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while self.alive:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                r = int(get_reasons(self.h))
+                self.rows.append((time.perf_counter(), sm, self.mx, [nm for nm, b in bits if r & b]))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return None
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+    def _read(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for t, ln in self.rows:
-            if t < t0 or t > t1 + 0.2:
-                continue
+        for ln in self.proc.stdout:
             f = [x.strip() for x in ln.split(",")]
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                self.rows.append((time.perf_counter(), float(f[0]), float(f[1]),
+                                  [nm for nm, v in zip(names, f[2:]) if v.lower().startswith("active")]))
             except Exception:
                 continue
-            for nm, v in zip(names, f[2:]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
-            for t, ln in self.rows[-3:]:
-                f = [x.strip() for x in ln.split(",")]
-                try:
-                    sm.append(float(f[0])); mx.append(float(f[1]))
-                except Exception:
-                    pass
-        if not sm:
+
+    def window(self, t0, t1):
+        """Median SM clock and the throttle reasons seen between t0 and t1 (perf_counter); the nearest samples if the
+        window is shorter than the sampling period."""
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        source = "during the timed region"
+        if not rows:
+            rows = sorted(self.rows, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))[:3]
+            source = "nearest samples to the timed region"
+        if not rows:
             return None
-        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        reasons = sorted({x for r in rows for x in r[3]})
+        return dict(sm_mhz=statistics.median(r[1] for r in rows), sm_max_mhz=max(r[2] for r in rows), reasons=reasons,
+                    samples=len(rows), sampled=source + (" (NVML)" if self.nvml else " (nvidia-smi)"))
+
+    def stop(self, t0=None, t1=None):
+        out = self.window(t0, t1) if t0 is not None else None
+        self.alive = False
+        if self.proc is not None:
+            self.proc.terminate()
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -409,6 +440,7 @@ def run_b200(args, cfg):
             os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    sampler = ClockSampler(local) if rank == 0 else None       # (started long before the timed region)
     c0 = make_case(cfg)                              # the table and rank 0's atmosphere
     c = perturb_case(c0, rank)
     tab = c["tab"]
@@ -418,6 +450,14 @@ def run_b200(args, cfg):
     NW, NX = cfg["nwave"], cfg["nx"]
     gathered = torch.empty((world, NW, NX + 1), dtype=torch.float64, device="cuda") if world > 1 else None
     block = torch.empty((NW, NX + 1), dtype=torch.float64, device="cuda")
+    if world > 1:
+        # communicator warm-up (not steps): NCCL sets its channels / peer mappings up lazily over the first collectives
+        # of a given size, which can take several ms each for more calls than the W warm-up steps make
+        block.zero_()
+        for _ in range(16):
+            dist.all_gather_into_tensor(gathered, block)
+        torch.cuda.synchronize()
+        dist.barrier()
 
     def step_resident(staged, timers=None):
         spec, dx, _ = hp.run(staged, timers)
@@ -480,7 +520,6 @@ def run_b200(args, cfg):
     kt = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     st = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     launches0 = hp.launches
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     t_wall0 = time.perf_counter()
     st[0].record()
