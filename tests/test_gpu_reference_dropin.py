@@ -164,22 +164,22 @@ def test_coreretOE_with_device_forward_model_and_solver(jupiter):
         assert colerr(getattr(got, name), getattr(ref, name)) < 1e-6, name
 
 
-@pytest.mark.parametrize("driver,kind", [("nemesisSOfmg", "lbl"), ("nemesisLfmg", "k")])
+@pytest.mark.parametrize("driver,kind", [("nemesisSOfmg", "lbl"), ("nemesisLfmg", "k"), ("nemesisSOfmg", "lbl_fil")])
 def test_limb_and_occultation_drivers_on_the_cuda_engine(driver, kind):
     """nemesisSOfmg / nemesisLfmg through install() with the CUDA engine: all tangent paths in one evaluation (layer-space
     gradients when there are >= 4 paths), ansb200_path_mix and the line shape for every geometry at once."""
     from oracle.ref_import import import_reference
     from oracle import make_golden as mg
     from archnemesis_dist_b200 import engine, forward_model as fmod
-    from tests.test_reference_dropin import _tangent_geometries
+    from tests.test_reference_dropin import _tangent_objects
     ans = import_reference()
     root = os.path.join(tempfile.mkdtemp(prefix="ansb200_gso_"), "deck")
-    deck = mg.build_jupiter_lbl_deck(root, fwhm=1.5) if kind == "lbl" else mg.build_jupiter_deck(root)
+    deck = mg.build_jupiter_lbl_deck(root, fwhm=1.5) if kind.startswith("lbl") else mg.build_jupiter_deck(root)
     ref_cls = sys.modules["archnemesis.ForwardModel_0"].ForwardModel_0
     cwd = os.getcwd()
     os.chdir(deck)
     try:
-        ref = mg.make_forward_model(ans, ref_cls, _tangent_geometries(mg.load_jupiter(ans, deck)), deck)
+        ref = mg.make_forward_model(ans, ref_cls, _tangent_objects(ans, mg, deck, kind), deck)
         S_ref, dS_ref = getattr(ref, driver)()
         cls = fmod.install(ans)
         try:
@@ -192,7 +192,7 @@ def test_limb_and_occultation_drivers_on_the_cuda_engine(driver, kind):
                 return orig(self, ev, M, mix, conv_op, Mlay)
             engine.HotPath.forward_jacobian_mix_conv = counting
             try:
-                fm = mg.make_forward_model(ans, ans.ForwardModel_0, _tangent_geometries(mg.load_jupiter(ans, deck)), deck)
+                fm = mg.make_forward_model(ans, ans.ForwardModel_0, _tangent_objects(ans, mg, deck, kind), deck)
                 S, dS = getattr(fm, driver)()
             finally:
                 engine.HotPath.forward_jacobian_mix_conv = orig

@@ -266,8 +266,17 @@ def _tangent_geometries(objs, ngeom=4, lo=20.0, hi=160.0):
     return objs
 
 
+def _tangent_objects(ans, mg, deck, kind):
+    objs = _tangent_geometries(mg.load_jupiter(ans, deck))
+    if kind == "lbl_fil":
+        # filter functions instead of an analytic shape (FWHM < 0: lblconvg_fil_ngeom, Measurement_0.py:2240-2248); the
+        # deck's VFIL / AFIL are the tabulated Gaussian build_ils made
+        objs["Measurement"].FWHM = -1.0
+    return objs
+
+
 @pytest.mark.parametrize("driver,kind", [("nemesisSOfmg", "lbl"), ("nemesisLfmg", "lbl"), ("nemesisSOfmg", "k"),
-                                         ("nemesisLfmg", "k")])
+                                         ("nemesisLfmg", "k"), ("nemesisSOfmg", "lbl_fil")])
 def test_limb_and_occultation_drivers_keep_their_tail_on_the_engine(driver, kind):
     """nemesisSOfmg / nemesisLfmg (ForwardModel_0.py:983-1243, :1372-1518) through install(): all tangent paths in one
     evaluation, then the tangent-height interpolation and the line shape for every geometry at once (IGEOM='All':
@@ -279,12 +288,12 @@ def test_limb_and_occultation_drivers_keep_their_tail_on_the_engine(driver, kind
     from tests import cpu_engine
     ans = import_reference()
     root = os.path.join(tempfile.mkdtemp(prefix="ansb200_so_"), "deck")
-    deck = mg.build_jupiter_lbl_deck(root, fwhm=1.5) if kind == "lbl" else mg.build_jupiter_deck(root)
+    deck = mg.build_jupiter_lbl_deck(root, fwhm=1.5) if kind.startswith("lbl") else mg.build_jupiter_deck(root)
     ref_cls = sys.modules["archnemesis.ForwardModel_0"].ForwardModel_0
     cwd = os.getcwd()
     os.chdir(deck)
     try:
-        objs = _tangent_geometries(mg.load_jupiter(ans, deck))
+        objs = _tangent_objects(ans, mg, deck, kind)
         if kind == "k":
             assert float(objs["Measurement"].FWHM) == 0.0
         ref = mg.make_forward_model(ans, ref_cls, objs, deck)
@@ -300,7 +309,7 @@ def test_limb_and_occultation_drivers_keep_their_tail_on_the_engine(driver, kind
                 return orig(self, ev, M, mix, conv_op, Mlay)
             cpu_engine.HotPath.forward_jacobian_mix_conv = counting
             try:
-                fm = mg.make_forward_model(ans, ans.ForwardModel_0, _tangent_geometries(mg.load_jupiter(ans, deck)), deck)
+                fm = mg.make_forward_model(ans, ans.ForwardModel_0, _tangent_objects(ans, mg, deck, kind), deck)
                 S, dS = getattr(fm, driver)()
             finally:
                 cpu_engine.HotPath.forward_jacobian_mix_conv = orig
