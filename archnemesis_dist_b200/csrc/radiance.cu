@@ -434,7 +434,9 @@ ans_transmission_paths_kernel(RadParams P)
     double *sCs = sC + (layer_space ? (size_t)RADT_GROUP * NG : 0);       // [RADT_GROUP] sum_g c_g
     double *sdcon = sCs + (layer_space ? (size_t)RADT_GROUP : 0);         // [NPAR*NLAY] dtaucon of the wavenumber (grad)
     double *sdk = sdcon + ((grad && P.dtaucon) ? (size_t)NPAR * NLAY : 0);   // [NG*NLAY*NP1] dk of the wavenumber (grad)
-    int *scol = reinterpret_cast<int *>(sdk + ((grad && P.dk) ? (size_t)NG * NLAY * NP1 : 0));   // [NPAR]
+    // (layer space: the dk operands of the tensor-core products come straight from global memory -- every row is
+    // fetched once per CTA by the warp that owns its layer tile -- so the 112 KB slab is not staged and two CTAs fit)
+    int *scol = reinterpret_cast<int *>(sdk + ((grad && P.dk && !layer_space) ? (size_t)NG * NLAY * NP1 : 0));   // [NPAR]
     const int nthr = blockDim.x;
     // NG >= 8: the lanes of a warp are the g-ordinates of its path (phase 1 below); the opacity is then kept
     // layer-major, stau[l][g] = tau + continuum, so that a warp reads one layer's row
@@ -458,7 +460,8 @@ ans_transmission_paths_kernel(RadParams P)
     for (int g = threadIdx.x; g < NG; g += nthr) sdelg[g] = P.delg[g];
     if (grad) {
         if (P.dtaucon) for (int t = threadIdx.x; t < NPAR * NLAY; t += nthr) sdcon[t] = P.dtaucon[(size_t)iw * NPAR * NLAY + t];
-        if (P.dk) for (int t = threadIdx.x; t < NG * NLAY * NP1; t += nthr) sdk[t] = P.dk[(size_t)iw * NG * NLAY * NP1 + t];
+        if (P.dk && !layer_space)
+            for (int t = threadIdx.x; t < NG * NLAY * NP1; t += nthr) sdk[t] = P.dk[(size_t)iw * NG * NLAY * NP1 + t];
         for (int k = threadIdx.x; k < NPAR; k += nthr) {
             int col = -1;
             if (P.dk) {
@@ -590,66 +593,65 @@ ans_transmission_paths_kernel(RadParams P)
         __syncthreads();
         const int npt = (gp1 - gp0 + 7) >> 3, nlt = (NLAY + 7) >> 3;
         const int kk = lane & 3, mm = lane >> 2;
-        // a warp keeps one tile of 8 paths (its C fragments stay in registers) and shares the tile's (parameter, layer
-        // tile) units with the other warps on that tile
+        // a warp takes (layer tile, parameter) pairs: the pair's B fragments (dk[g][l][col], up to KS k-steps) are
+        // loaded once from global memory and stay in registers while the warp walks the path tiles of the group
         const int nwarps = nthr >> 5;
-        const bool many = nwarps >= npt;
         constexpr int KS = 5;                                      // k-steps held in registers (NG <= 20); beyond that the operands are re-read
-        for (int pt = many ? warp % npt : warp; pt < npt; pt += many ? npt : nwarps) {
-            const int wsub = many ? warp / npt : 0, wpt = many ? (nwarps - pt + npt - 1) / npt : 1;
-            const int r = pt * 8 + mm, path = gp0 + r;
-            double af[KS];
+        const double *dkw = P.dk ? P.dk + (size_t)iw * NG * NLAY * NP1 : nullptr;
+        for (int u = warp; u < nlt * NPAR; u += nwarps) {
+            const int lt = u / NPAR, k = u - lt * NPAR;             // (parameters fastest: neighbouring warps share rows)
+            const int col = scol[k];
+            const int lb = lt * 8 + mm;                             // the layer of this lane's B element
+            double bf[KS];
 #pragma unroll
             for (int i = 0; i < KS; ++i) {
                 const int g = 4 * i + kk;
-                af[i] = g < NG ? sC[(size_t)r * NG + g] : 0.0;
+                bf[i] = (col >= 0 && g < NG && lb < NLAY) ? dkw[((size_t)g * NLAY + lb) * NP1 + col] : 0.0;
             }
-            const double cs = sCs[r];
-            const double *srow = sS + (size_t)r * NLAY;
-            int k = wsub / nlt, lt = wsub - k * nlt;
-            while (k < NPAR) {
-                const int col = scol[k];
+            const double unit_k = (col >= 0 && col < P.NGAS) ? 1.0e-4 : 1.0;
+            const int l0 = lt * 8 + 2 * kk;                         // this lane's two output layers
+            const double dc0 = (P.dtaucon && l0 < NLAY) ? sdcon[(size_t)k * NLAY + l0] : 0.0;
+            const double dc1 = (P.dtaucon && l0 + 1 < NLAY) ? sdcon[(size_t)k * NLAY + l0 + 1] : 0.0;
+            for (int pt = 0; pt < npt; ++pt) {
+                const int r = pt * 8 + mm, path = gp0 + r;
                 double d0 = 0.0, d1 = 0.0;
                 if (col >= 0) {
-                    const int lb = lt * 8 + mm;                 // the layer of this lane's B element
-                    const double *bp = sdk + ((size_t)kk * NLAY + (lb < NLAY ? lb : 0)) * NP1 + col;
-                    const size_t bstep = (size_t)4 * NLAY * NP1;
+                    const double *ar = sC + (size_t)r * NG + kk;
 #pragma unroll
                     for (int i = 0; i < KS; ++i) {
                         if (4 * i < NG) {
-                            const double bv = (4 * i + kk < NG && lb < NLAY) ? bp[i * bstep] : 0.0;
+                            const double av = 4 * i + kk < NG ? ar[4 * i] : 0.0;
                             asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                                         : "+d"(d0), "+d"(d1) : "d"(af[i]), "d"(bv));
+                                         : "+d"(d0), "+d"(d1) : "d"(av), "d"(bf[i]));
                         }
                     }
                     for (int g0 = 4 * KS; g0 < NG; g0 += 4) {
                         const int g = g0 + kk;
                         const double av = g < NG ? sC[(size_t)r * NG + g] : 0.0;
-                        const double bv = (g < NG && lb < NLAY) ? sdk[((size_t)g * NLAY + lb) * NP1 + col] : 0.0;
+                        const double bv = (g < NG && lb < NLAY) ? dkw[((size_t)g * NLAY + lb) * NP1 + col] : 0.0;
                         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                                      : "+d"(d0), "+d"(d1) : "d"(av), "d"(bv));
                     }
-                    const double unit_k = col < P.NGAS ? 1.0e-4 : 1.0;
                     d0 *= unit_k;
                     d1 *= unit_k;
                 }
                 if (path < gp1) {
+                    const double cs = sCs[r];
+                    const double *srow = sS + (size_t)r * NLAY;
                     double *out = P.dspec + (((size_t)iw * NPATH + path) * NPAR + k) * NLAY;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int l = lt * 8 + 2 * kk + h;
-                        if (l < NLAY) {
-                            const double scl = srow[l];
-                            double a = h ? d1 : d0;
-                            if (P.dtaucon) a = fma(sdcon[(size_t)k * NLAY + l], cs, a);
-                            double v = scl != 0.0 ? -(a * scl) : 0.0;
-                            if (P.flags & ANSB200_RAD_NAN_TO_NUM) v = tl_nan_to_num_fwd(v);
-                            out[l] = v;
-                        }
+                    if (l0 < NLAY) {
+                        const double scl = srow[l0];
+                        double v = scl != 0.0 ? -(fma(dc0, cs, d0) * scl) : 0.0;
+                        if (P.flags & ANSB200_RAD_NAN_TO_NUM) v = tl_nan_to_num_fwd(v);
+                        out[l0] = v;
+                    }
+                    if (l0 + 1 < NLAY) {
+                        const double scl = srow[l0 + 1];
+                        double v = scl != 0.0 ? -(fma(dc1, cs, d1) * scl) : 0.0;
+                        if (P.flags & ANSB200_RAD_NAN_TO_NUM) v = tl_nan_to_num_fwd(v);
+                        out[l0 + 1] = v;
                     }
                 }
-                lt += wpt;
-                while (lt >= nlt) { lt -= nlt; ++k; }
             }
         }
         __syncthreads();
@@ -1265,7 +1267,7 @@ extern "C" int ansb200_radiance_layer_space(int mode, unsigned flags, int NG, in
         return has_dk && NLAYMAX <= 32 * TL_RQ && thermal_layers_smem(NG, NLAY, NGAS, NPAR) <= 227 * 1024 ? 1 : 0;
     if (mode != 1) return 0;
     const size_t nd_t = (size_t)NG * NLAY + NLAY + NG + (size_t)32 * NG + (has_dtaucon ? (size_t)NPAR * NLAY : 0) +
-                        (size_t)64 * (NLAY + NG + 1) + (has_dk ? (size_t)NG * NLAY * (NGAS + 1) : 0);
+                        (size_t)64 * (NLAY + NG + 1);
     return nd_t * 8 + (size_t)NPAR * 4 + 16 <= 227 * 1024 ? 1 : 0;
 }
 
@@ -1330,12 +1332,15 @@ extern "C" int ansb200_radiance(int mode, unsigned flags, const double *tau, con
         // transmission with several paths: warp-per-path kernel if the wavenumber's slabs fit in shared memory
         const size_t nd_t = (size_t)NG * NLAY + NLAY + NG + (size_t)RADT_WARPS * NG + ((grad && dtaucon) ? (size_t)NPAR * NLAY : 0) +
                             ((grad && layer_space) ? (size_t)RADT_GROUP * (NLAY + NG + 1) : 0) +
-                            ((grad && dk) ? (size_t)NG * NLAY * (NGAS + 1) : 0);
+                            ((grad && dk && !layer_space) ? (size_t)NG * NLAY * (NGAS + 1) : 0);
         const size_t smem_t = nd_t * 8 + (size_t)NPAR * 4 + 16;
         if (smem_t <= 227 * 1024) {
             ANS_CUDA_CHECK(cudaFuncSetAttribute(ans_transmission_paths_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)(smem_t > 48 * 1024 ? smem_t : 48 * 1024)));
-            int warps = NPATH < RADT_WARPS ? NPATH : RADT_WARPS;
+            // layer space: 16 warps per CTA, so that two CTAs (64 registers, ~90 KB each) share an SM and one's
+            // staging / barriers overlap the other's arithmetic; path space keeps the dk slab in shared memory (one CTA)
+            const int wmax = (grad && layer_space) ? RADT_WARPS / 2 : RADT_WARPS;
+            int warps = NPATH < wmax ? NPATH : wmax;
             ans_transmission_paths_kernel<<<(unsigned)NWAVE, warps * 32, smem_t, stream>>>(P);
             ANS_LAUNCH_CHECK();
             return ANSB200_OK;
