@@ -1264,7 +1264,8 @@ extern "C" int ansb200_radiance_layer_space(int mode, unsigned flags, int NG, in
 {
     if (NPATH < 4 || !(flags & ANSB200_RAD_GRAD)) return 0;
     if (mode == 0)      // thermal emission: ans_thermal_layers_kernel
-        return has_dk && NLAYMAX <= 32 * TL_RQ && thermal_layers_smem(NG, NLAY, NGAS, NPAR) <= 227 * 1024 ? 1 : 0;
+        return has_dk && NLAYMAX <= 32 * TL_RQ && NLAY <= 32 * TL_PATHS &&      // (a warp's layers fit a 32-bit mask)
+                       thermal_layers_smem(NG, NLAY, NGAS, NPAR) <= 227 * 1024 ? 1 : 0;
     if (mode != 1) return 0;
     const size_t nd_t = (size_t)NG * NLAY + NLAY + NG + (size_t)32 * NG + (has_dtaucon ? (size_t)NPAR * NLAY : 0) +
                         (size_t)64 * (NLAY + NG + 1);
