@@ -21,7 +21,7 @@ constexpr int PJ_BM = 128, PJ_BN = 64, PJ_BK = 16, PJ_THREADS = 256;
 
 __global__ void __launch_bounds__(PJ_THREADS, 2)
 ans_project_kernel(const double *__restrict__ dspec, const double *__restrict__ M, int NWAVE, int E, int NPATH, int NX,
-                   double *__restrict__ out, size_t mstride)
+                   double *__restrict__ out, size_t mstride, const int32_t *__restrict__ chunks, int nchunks, int listed)
 {
     __shared__ __align__(16) double sA[2][PJ_BK][PJ_BM];      // [k][row]
     __shared__ __align__(16) double sB[2][PJ_BK][PJ_BN];      // [k][col]
@@ -60,13 +60,28 @@ ans_project_kernel(const double *__restrict__ dspec, const double *__restrict__ 
 #pragma unroll
         for (int q = 0; q < 4; ++q) sB[buf][bk][bc + q] = rb[q];
     };
-    fetch(0);
+    // chunks (optional): the 16-row chunks of M that hold a non-zero for ANY path / column, found once on the host --
+    // whole parameters without a state-vector element (a third of the rows at config 4) are then never read
+    const int nch = listed ? nchunks : (E + PJ_BK - 1) / PJ_BK;
+    if (nch == 0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int w = w0 + lane * 4 + r;
+            if (w >= NWAVE) continue;
+            double *o = out + ((size_t)w * NPATH + ipath) * NX + x0 + warp * 8;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (x0 + warp * 8 + c < NX) o[c] = 0.0;
+        }
+        return;
+    }
+    fetch(listed ? chunks[0] * PJ_BK : 0);
     stash(0);
     __syncthreads();
     int buf = 0;
-    for (int e0 = 0; e0 < E; e0 += PJ_BK) {
-        const bool more = e0 + PJ_BK < E;
-        if (more) fetch(e0 + PJ_BK);            // global loads of the next chunk fly during the FMAs
+    for (int ci = 0; ci < nch; ++ci) {
+        const bool more = ci + 1 < nch;
+        if (more) fetch(listed ? chunks[ci + 1] * PJ_BK : (ci + 1) * PJ_BK);   // global loads of the next chunk fly during the FMAs
         // is this warp's 16 x 8 block of M empty?  (lane -> k = lane/2, 4 of the 8 columns)
         const double *bq = &sB[buf][lane >> 1][warp * 8 + (lane & 1) * 4];
         const bool nz = bq[0] != 0.0 || bq[1] != 0.0 || bq[2] != 0.0 || bq[3] != 0.0;
@@ -113,7 +128,27 @@ extern "C" int ansb200_jacobian_project(const double *dspec, const double *M, in
     ANS_REQUIRE(NPATH <= 65535, "jacobian_project: NPATH too large");
     dim3 grid(ans_div_up(NWAVE, PJ_BM), ans_div_up(NX, PJ_BN), NPATH);
     ans_project_kernel<<<grid, PJ_THREADS, 0, stream>>>(dspec, M, NWAVE, NPAR * NLAYMAX, NPATH, NX, out,
-                                                        (size_t)NPAR * NLAYMAX * NX);
+                                                        (size_t)NPAR * NLAYMAX * NX, nullptr, 0, 0);
+    ANS_LAUNCH_CHECK();
+    return ANSB200_OK;
+}
+
+// Both products with the list of non-empty 16-row chunks of M (ascending chunk numbers e0 / 16, on the device): rows of
+// M outside the listed chunks must be zero for every path and column.  shared != 0: one matrix for all paths.
+extern "C" int ansb200_jacobian_project_chunks(const double *dspec, const double *M, int NWAVE, int NPAR, int NLAYMAX,
+                                               int NPATH, int NX, int shared, const int32_t *chunks, int nchunks,
+                                               double *out, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ANS_REQUIRE(dspec && M && out, "jacobian_project: null pointer");
+    ANS_REQUIRE(NWAVE > 0 && NPAR > 0 && NLAYMAX > 0 && NPATH > 0 && NX > 0, "jacobian_project: bad shape");
+    ANS_REQUIRE(NPATH <= 65535, "jacobian_project: NPATH too large");
+    ANS_REQUIRE(nchunks >= 0 && (nchunks == 0 || chunks), "jacobian_project: chunk list missing");
+    ANS_REQUIRE(nchunks <= ans_div_up((long long)NPAR * NLAYMAX, PJ_BK), "jacobian_project: more chunks than M has");
+    dim3 grid(ans_div_up(NWAVE, PJ_BM), ans_div_up(NX, PJ_BN), NPATH);
+    ans_project_kernel<<<grid, PJ_THREADS, 0, stream>>>(dspec, M, NWAVE, NPAR * NLAYMAX, NPATH, NX, out,
+                                                        shared ? (size_t)0 : (size_t)NPAR * NLAYMAX * NX,
+                                                        chunks, nchunks, 1);
     ANS_LAUNCH_CHECK();
     return ANSB200_OK;
 }
@@ -128,7 +163,7 @@ extern "C" int ansb200_jacobian_project_shared(const double *dspec, const double
     ANS_REQUIRE(NWAVE > 0 && NPAR > 0 && NLAY > 0 && NPATH > 0 && NX > 0, "jacobian_project: bad shape");
     ANS_REQUIRE(NPATH <= 65535, "jacobian_project: NPATH too large");
     dim3 grid(ans_div_up(NWAVE, PJ_BM), ans_div_up(NX, PJ_BN), NPATH);
-    ans_project_kernel<<<grid, PJ_THREADS, 0, stream>>>(dspec, M, NWAVE, NPAR * NLAY, NPATH, NX, out, (size_t)0);
+    ans_project_kernel<<<grid, PJ_THREADS, 0, stream>>>(dspec, M, NWAVE, NPAR * NLAY, NPATH, NX, out, (size_t)0, nullptr, 0, 0);
     ANS_LAUNCH_CHECK();
     return ANSB200_OK;
 }

@@ -313,10 +313,17 @@ class HotPath:
             Mlay is not None and s.grad and hasattr(self.ops, "radiance_layer_space_ok") and
             self.ops.radiance_layer_space_ok(ev.mode, self.NG, len(ev.press_atm), self.NGAS, ev.NPAR,
                                              ev.LAYINC.shape[1], ev.LAYINC.shape[0], True, s.dtaucon is not None))
-        if s.layer_space:
-            s.M = st("Mlay", Mlay)
-        else:
-            s.M = st("M", M) if M is not None else None
+        Mh = Mlay if s.layer_space else M
+        s.M = st("Mlay" if s.layer_space else "M", Mh) if Mh is not None else None
+        # the 16-row chunks of M that hold a non-zero (parameters without a state-vector element drop out of the
+        # projection's reads); found on the host while the matrix is small enough for that to cost nothing
+        s.M_chunks = None
+        if Mh is not None and hasattr(self.ops, "PROJECT_CHUNK") and np.size(Mh) <= (1 << 19):
+            Mh = np.asarray(Mh)
+            c, E = self.ops.PROJECT_CHUNK, Mh.shape[1]
+            rows = np.zeros(((E + c - 1) // c) * c, dtype=bool)
+            rows[:E] = np.any(Mh != 0.0, axis=(0, 2))
+            s.M_chunks = st("Mchunks", np.nonzero(rows.reshape(-1, c).any(axis=1))[0].astype(np.int32), i32)
         ev.h2d_bytes = st.bytes
         return s
 
@@ -406,7 +413,10 @@ class HotPath:
         spec, dspec, dtsurf = out
         if s.M is None:
             return spec, dspec, dtsurf
-        dx = self.ops.jacobian_project(dspec, s.M, **({"shared": True} if getattr(s, "layer_space", False) else {}))
+        kw = {"shared": True} if getattr(s, "layer_space", False) else {}
+        if getattr(s, "M_chunks", None) is not None:
+            kw["chunks"] = s.M_chunks
+        dx = self.ops.jacobian_project(dspec, s.M, **kw)
         self.launches += 1
         return spec, dx, dtsurf
 

@@ -262,9 +262,25 @@ def radiance_layer_space_ok(mode, NG, NLAY, NGAS, NPAR, NPATH, NLAYMAX, has_dk=T
                                                          int(NPATH), int(NLAYMAX), int(has_dk), int(has_dtaucon)))
 
 
-def jacobian_project(dspec, M, shared=False):
+PROJECT_CHUNK = 16
+
+
+def project_chunks(M):
+    """The 16-row chunks of a host projection matrix M[P, E, NX] that hold a non-zero for any path or column, as the
+    int32 device list jacobian_project(..., chunks=) takes (whole parameters without a state-vector element drop out)."""
+    M = np.asarray(M)
+    E = M.shape[1]
+    n = (E + PROJECT_CHUNK - 1) // PROJECT_CHUNK
+    rows = np.any(M != 0.0, axis=(0, 2))
+    pad = np.zeros(n * PROJECT_CHUNK, dtype=bool)
+    pad[:E] = rows
+    return to_dev(np.nonzero(pad.reshape(n, PROJECT_CHUNK).any(axis=1))[0].astype(np.int32), torch.int32)
+
+
+def jacobian_project(dspec, M, shared=False, chunks=None):
     """dspec[NWAVE,NPATH,NPAR,NLAYMAX] x M[NPATH,NPAR*NLAYMAX,NX] -> [NWAVE,NPATH,NX] (map2pro+map2xvec).
-    shared: M[1,NPAR*NLAY,NX] is one layer-space matrix for every path (dspec from radiance(layer_space=True))."""
+    shared: M[1,NPAR*NLAY,NX] is one layer-space matrix for every path (dspec from radiance(layer_space=True)).
+    chunks: project_chunks(M) of the host copy of M (optional; rows outside the listed chunks are not read)."""
     _require_cuda()
     if dspec.dim() != 4 or M.dim() != 3:
         raise ValueError("jacobian_project: dspec must be [NWAVE,NPATH,NPAR,NLAYMAX] and M [NPATH,NPAR*NLAYMAX,NX]")
@@ -278,6 +294,11 @@ def jacobian_project(dspec, M, shared=False):
             raise ValueError("jacobian_project: %s must be a contiguous float64 CUDA tensor" % name)
     NX = M.shape[2]
     out = torch.empty((NWAVE, NPATH, NX), dtype=torch.float64, device="cuda")
+    if chunks is not None:
+        _lib.check(_lib.load().ansb200_jacobian_project_chunks(_ptr(dspec), _ptr(M), NWAVE, NPAR, NLM, NPATH, NX, int(bool(shared)),
+                                                               _ptr(chunks) if chunks.numel() else None, int(chunks.numel()),
+                                                               _ptr(out), _stream()))
+        return out
     fn = _lib.load().ansb200_jacobian_project_shared if shared else _lib.load().ansb200_jacobian_project
     _lib.check(fn(_ptr(dspec), _ptr(M), NWAVE, NPAR, NLM, NPATH, NX, _ptr(out), _stream()))
     return out

@@ -189,6 +189,11 @@ int ansb200_jacobian_project(const double *dspec, const double *M, int NWAVE, in
  * (M[k*NLAY + l, x] = sum_pro D_k[l,pro] xmap[x,k,pro]: D does not depend on the path). */
 int ansb200_jacobian_project_shared(const double *dspec, const double *M, int NWAVE, int NPAR, int NLAY, int NPATH,
                                     int NX, double *out, void *stream);
+/* Either product with the list of the non-empty 16-row chunks of M (ascending chunk numbers row/16, int32 on the device;
+ * every row of M outside the listed chunks must be zero for all paths and columns): whole parameters without a
+ * state-vector element are then never read from dspec.  shared != 0: M[1, NPAR*NLAYMAX, NX] for every path. */
+int ansb200_jacobian_project_chunks(const double *dspec, const double *M, int NWAVE, int NPAR, int NLAYMAX, int NPATH,
+                                    int NX, int shared, const int32_t *chunks, int nchunks, double *out, void *stream);
 
 /* ---- tangent-height interpolation of the path spectra ------------------------------------------
  * Replaces the SPECMOD / dSPECMOD loop of nemesisSOfmg / nemesisLfmg (ForwardModel_0.py:1206-1228, :1464-1486):

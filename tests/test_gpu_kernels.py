@@ -631,3 +631,33 @@ def test_kdist_kernel_against_golden_and_oracle():
         assert relerr(got[ib], want[ib]) < 1e-10, sizes[ib]
     with pytest.raises(ValueError):
         ktable.k_distribution(kabs, wave, [wave[3] + 0.01], [wave[3] + 0.02], g)          # a bin without grid points
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_projection_with_chunk_list_equals_full_product(shared):
+    """ansb200_jacobian_project_chunks: the projection that skips the 16-row chunks of M without a non-zero (whole
+    parameters that no state-vector element touches) is the same sum, bit for bit; an all-zero M gives zeros."""
+    import torch
+    from archnemesis_dist_b200 import ops
+    rng = np.random.default_rng(8)
+    nw, npath, npar, nlm, nx = 150, 3, 7, 37, 45            # E = 259: not a multiple of 16
+    dspec = rng.standard_normal((nw, npath, npar, nlm))
+    P = 1 if shared else npath
+    M = np.zeros((P, npar * nlm, nx))
+    for k in (1, 4, 6):                                     # parameters 0, 2, 3, 5 have no state-vector element
+        M[:, k * nlm:(k + 1) * nlm, rng.integers(0, nx, 9)] = rng.standard_normal((P, nlm, 9))
+    d, Md = ops.to_dev(dspec), ops.to_dev(M)
+    full = ops.jacobian_project(d, Md, shared=shared)
+    chunks = ops.project_chunks(M)
+    assert 0 < chunks.numel() < (npar * nlm + 15) // 16
+    # rows of dspec the list leaves out may hold anything (here NaN): they are never read
+    poisoned = dspec.copy()
+    keep = np.zeros(((npar * nlm + 15) // 16) * 16, dtype=bool)
+    keep.reshape(-1, 16)[chunks.cpu().numpy()] = True
+    poisoned.reshape(nw, npath, -1)[:, :, ~keep[:npar * nlm]] = np.nan
+    got = ops.jacobian_project(ops.to_dev(poisoned), Md, shared=shared, chunks=chunks)
+    assert torch.equal(got, full)
+    want = np.einsum("wpe,pex->wpx", dspec.reshape(nw, npath, -1), np.broadcast_to(M, (npath,) + M.shape[1:]))
+    assert colerr(got.cpu().numpy(), want) < 1e-13
+    zero = ops.jacobian_project(d, ops.to_dev(np.zeros_like(M)), shared=shared, chunks=ops.project_chunks(np.zeros_like(M)))
+    assert float(zero.abs().max()) == 0.0
