@@ -28,6 +28,7 @@ EXPORTS = {
     "ansb200_radiance_layer_space": (_i, [_i, _u, _i, _i, _i, _i, _i, _i, _i, _i]),
     "ansb200_jacobian_project_shared": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "ansb200_jacobian_project_chunks": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "ansb200_jacobian_project_sparse": (_i, [_vp] * 5 + [_i, _vp, _vp] + [_i] * 6 + [_vp, _vp]),
     "ansb200_path_mix": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "ansb200_kdist_capacity": (_i, [_i]),
     "ansb200_kdist": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp]),

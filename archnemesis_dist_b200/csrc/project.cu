@@ -168,6 +168,143 @@ extern "C" int ansb200_jacobian_project_shared(const double *dspec, const double
     return ANSB200_OK;
 }
 
+// ---- the same product with M as a sparse operator ------------------------------------------------------------------
+// M is what map2pro + map2xvec fold into: a state-vector element acts on the layers of ONE parameter, and a temperature
+// level on the two or three layers next to it, so M holds a few per cent non-zeros (1.7 % at config 4, 1000 of 60 000)
+// and every column is one short run of consecutive rows.  The dense kernel above then spends its time streaming tiles it
+// mostly skips.  Here the host hands M over by columns (plan.sparse_projection: for column x of path p the run starts at
+// row r0 and holds len values at voff in vals -- zeros inside the run are kept, so there is no index array) and a WARP
+// takes one (wavenumber, path) row of dspec: it stages the row in shared memory with coalesced 16-byte loads -- the only
+// traffic that matters, each byte of dspec once -- and then every lane sums one column (ascending rows, fused
+// multiply-adds, exactly like the dense kernel: bit-identical to it); columns longer than PS_LONG (a gas scaling factor
+// touches every layer) are taken together, a few lanes each.  When one operator serves every row (one path, or layer
+// space) the CTA keeps it in shared memory as well.
+constexpr int PS_WARPS = 8, PS_LONG = 16;
+constexpr int PS_PLAN_BYTES = 24 * 1024;          // operator kept in shared memory up to this size
+
+__global__ void __launch_bounds__(PS_WARPS * 32)
+ans_project_sparse_kernel(const double *__restrict__ dspec, const int32_t *__restrict__ col_r0,
+                          const int32_t *__restrict__ col_len, const int32_t *__restrict__ col_voff,
+                          const double *__restrict__ vals, const int32_t *__restrict__ long_cols,
+                          const int32_t *__restrict__ long_ptr, long long NROW, int E, int NPATH, int NX, int shared,
+                          int nvals, int plan_in_smem, double *__restrict__ out)
+{
+    extern __shared__ __align__(16) double ps_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ES = (E + 1) & ~1;
+    double *a = ps_smem + (size_t)warp * ES;
+    // the operator (one for all rows) in shared memory: vals, then r0 / len / voff
+    const double *pv = vals;
+    const int32_t *pr0 = col_r0, *plen = col_len, *pvo = col_voff;
+    if (plan_in_smem) {
+        double *sv = ps_smem + (size_t)PS_WARPS * ES;
+        int32_t *si = reinterpret_cast<int32_t *>(sv + nvals);
+        for (int t = threadIdx.x; t < nvals; t += blockDim.x) sv[t] = vals[t];
+        for (int t = threadIdx.x; t < NX; t += blockDim.x) {
+            si[t] = col_r0[t];
+            si[NX + t] = col_len[t];
+            si[2 * NX + t] = col_voff[t];
+        }
+        __syncthreads();
+        pv = sv; pr0 = si; plen = si + NX; pvo = si + 2 * NX;
+    }
+    const bool wide = (E & 1) == 0;
+    for (long long row = (long long)blockIdx.x * PS_WARPS + warp; row < NROW; row += (long long)gridDim.x * PS_WARPS) {
+        const int ipath = shared ? 0 : (int)(row % NPATH);
+        const double *src = dspec + (size_t)row * E;
+        if (wide) {
+            const double2 *src2 = reinterpret_cast<const double2 *>(src);
+            double2 *a2 = reinterpret_cast<double2 *>(a);
+            const int n2 = E >> 1;
+            for (int e0 = 0; e0 < n2; e0 += 8 * 32) {
+                double2 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = e0 + u * 32 + lane;
+                    if (e < n2) v[u] = __ldcs(src2 + e);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = e0 + u * 32 + lane;
+                    if (e < n2) a2[e] = v[u];
+                }
+            }
+        } else {
+            for (int e = lane; e < E; e += 32) a[e] = __ldg(src + e);
+        }
+        __syncwarp();
+        const int cb = ipath * NX;
+        double *o = out + (size_t)row * NX;
+        for (int x0 = 0; x0 < NX; x0 += 32) {
+            const int x = x0 + lane;
+            int len = 0, r0 = 0, vo = 0;
+            if (x < NX) { len = plen[cb + x]; r0 = pr0[cb + x]; vo = pvo[cb + x]; }
+            if (len <= PS_LONG) {
+                double acc = 0.0;
+                for (int i = 0; i < len; ++i) acc = fma(a[r0 + i], pv[vo + i], acc);
+                if (x < NX) o[x] = acc;
+            }
+        }
+        // long columns, all at once: S = 32 / (their number, rounded up to a power of two) lanes share a column, each sums
+        // a contiguous slice of it in four running sums, and log2(S) shuffle steps add the slices
+        const int lq0 = long_ptr[ipath], nlong = long_ptr[ipath + 1] - lq0;
+        for (int q0 = 0; q0 < nlong; q0 += 32) {
+            const int nq = min(32, nlong - q0);
+            int S = 32;
+            while (S > 1 && S * nq > 32) S >>= 1;                  // lanes per column
+            const int qi = lane / S, sl = lane - qi * S;
+            double acc = 0.0;
+            int x = -1;
+            if (qi < nq) {
+                x = long_cols[lq0 + q0 + qi];
+                const int len = plen[cb + x], per = (len + S - 1) / S;
+                const int ia = min(len, sl * per), ib = min(len, ia + per);
+                const double *ap = a + pr0[cb + x], *vp = pv + pvo[cb + x];
+                double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+                int i = ia;
+                for (; i + 4 <= ib; i += 4) {
+                    c0 = fma(ap[i], vp[i], c0);
+                    c1 = fma(ap[i + 1], vp[i + 1], c1);
+                    c2 = fma(ap[i + 2], vp[i + 2], c2);
+                    c3 = fma(ap[i + 3], vp[i + 3], c3);
+                }
+                for (; i < ib; ++i) c0 = fma(ap[i], vp[i], c0);
+                acc = (c0 + c1) + (c2 + c3);
+            }
+            for (int d = S >> 1; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+            if (x >= 0 && sl == 0) o[x] = acc;
+        }
+        __syncwarp();
+    }
+}
+
+extern "C" int ansb200_jacobian_project_sparse(const double *dspec, const int32_t *col_r0, const int32_t *col_len,
+                                               const int32_t *col_voff, const double *vals, int nvals,
+                                               const int32_t *long_cols, const int32_t *long_ptr, int NWAVE, int NPAR,
+                                               int NLAYMAX, int NPATH, int NX, int shared, double *out, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ANS_REQUIRE(dspec && col_r0 && col_len && col_voff && long_ptr && out, "jacobian_project_sparse: null pointer");
+    ANS_REQUIRE(NWAVE > 0 && NPAR > 0 && NLAYMAX > 0 && NPATH > 0 && NX > 0 && nvals >= 0, "jacobian_project_sparse: bad shape");
+    const int E = NPAR * NLAYMAX, ES = (E + 1) & ~1;
+    size_t smem = (size_t)PS_WARPS * ES * 8;
+    ANS_REQUIRE(smem <= 200 * 1024, "jacobian_project_sparse: NPAR*NLAYMAX = %d too long for the shared-memory row", E);
+    const size_t plan_bytes = (size_t)nvals * 8 + (size_t)3 * NX * 4;
+    const int plan_in_smem = (shared || NPATH == 1) && plan_bytes <= PS_PLAN_BYTES && smem + plan_bytes <= 220 * 1024;
+    if (plan_in_smem) smem += plan_bytes;
+    ANS_CUDA_CHECK(cudaFuncSetAttribute(ans_project_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
+    const long long NROW = (long long)NWAVE * NPATH;
+    long long nblk = (NROW + PS_WARPS - 1) / PS_WARPS;
+    const long long cap = 148LL * 8;            // persistent over the rows beyond a few CTAs per SM
+    if (nblk > cap) nblk = cap;
+    ans_project_sparse_kernel<<<(unsigned)nblk, PS_WARPS * 32, smem, stream>>>(dspec, col_r0, col_len, col_voff, vals,
+                                                                              long_cols, long_ptr, NROW, E, NPATH, NX,
+                                                                              shared, nvals, plan_in_smem, out);
+    ANS_LAUNCH_CHECK();
+    return ANSB200_OK;
+}
+
 // ---- tangent-height interpolation of the path spectra (nemesisSOfmg / nemesisLfmg) ---------------------------------
 // Reference: ForwardModel_0.py:1206-1228 / :1464-1486.  The limb / occultation drivers compute one spectrum per path
 // (tangent layer) and interpolate the pair of paths that brackets each measured tangent height:

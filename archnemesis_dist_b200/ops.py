@@ -348,6 +348,40 @@ def kdist(kabs, lo, hi, g_ord, w=None, woff=None):
     return out
 
 
+class SparseProjection:
+    """Device copy of a plan.sparse_projection (`put` lets the engine stage the arrays through its pinned buffers)."""
+
+    def __init__(self, sp, put=None):
+        put = put or (lambda name, a, dt: to_dev(a, dt))
+        self.P, self.E, self.NX = sp["shape"]
+        self.col_r0 = put("sp_col_r0", sp["col_r0"], torch.int32)
+        self.col_len = put("sp_col_len", sp["col_len"], torch.int32)
+        self.col_voff = put("sp_col_voff", sp["col_voff"], torch.int32)
+        self.vals = put("sp_vals", sp["vals"], torch.float64)
+        self.long_cols = put("sp_long_cols", sp["long_cols"], torch.int32)
+        self.long_ptr = put("sp_long_ptr", sp["long_ptr"], torch.int32)
+
+
+def jacobian_project_sparse(dspec, sp, shared=False):
+    """dspec[NWAVE,NPATH,NPAR,NLAYMAX] x sparse M (SparseProjection) -> [NWAVE,NPATH,NX]."""
+    _require_cuda()
+    NWAVE, NPATH, NPAR, NLM = dspec.shape
+    if sp.E != NPAR * NLM or sp.P != (1 if shared else NPATH):
+        raise ValueError("jacobian_project_sparse: operator is for (%d, %d, NX), dspec is %s" % (sp.P, sp.E, tuple(dspec.shape)))
+    if dspec.dtype != torch.float64 or not dspec.is_cuda or not dspec.is_contiguous():
+        raise ValueError("jacobian_project_sparse: dspec must be a contiguous float64 CUDA tensor")
+    out = torch.empty((NWAVE, NPATH, sp.NX), dtype=torch.float64, device="cuda")
+    p = lambda t: _ptr(t) if t.numel() else None      # noqa: E731
+    _lib.check(_lib.load().ansb200_jacobian_project_sparse(_ptr(dspec), _ptr(sp.col_r0), _ptr(sp.col_len), _ptr(sp.col_voff),
+                                                           p(sp.vals), int(sp.vals.numel()), p(sp.long_cols), _ptr(sp.long_ptr),
+                                                           NWAVE, NPAR, NLM, NPATH, sp.NX, int(bool(shared)), _ptr(out),
+                                                           _stream()))
+    return out
+
+
+SPARSE_MAX_E = 3200
+
+
 class ConvOperator:
     """Device copy of a plan.conv_operator (Measurement_0.conv / convg for k-tables)."""
 

@@ -254,6 +254,41 @@ def fold_projection_layers(xmap, NLAY, DTE, DAM, DCO, NVMR, NDUST):
     return fold_projection(xmap, ident, np.array([NLAY], dtype=np.int32), DTE, DAM, DCO, NVMR, NDUST)
 
 
+SPARSE_LONG = 16          # columns with more entries are summed by a whole warp (csrc/project.cu PS_LONG)
+
+
+def sparse_projection(M, max_density=0.15, max_fill=4):
+    """A folded projection matrix M[P, E, NX] (fold_projection / fold_projection_layers) by columns, for
+    ansb200_jacobian_project_sparse.  A state-vector element acts on the layers of one parameter, so a column of M is
+    one run of consecutive rows: col_r0 / col_len / col_voff[P*NX] give the run of column x of path p (rows r0 ..
+    r0+len-1, values vals[voff : voff+len], zeros inside the run included), long_cols / long_ptr[P+1] the columns
+    longer than SPARSE_LONG.  Returns None when M is not like that (a column spread over distant rows, or M too dense
+    for the gather to beat the tiled product)."""
+    M = np.asarray(M, dtype=np.float64)
+    P, E, NX = M.shape
+    nz = M != 0.0
+    if nz.mean() > max_density:
+        return None
+    any_nz = nz.any(axis=1)                                   # [P, NX]
+    first = np.where(any_nz, nz.argmax(axis=1), 0)
+    last = np.where(any_nz, E - 1 - nz[:, ::-1, :].argmax(axis=1), -1)
+    length = (last - first + 1).astype(np.int64)
+    count = nz.sum(axis=1)
+    if np.any(length > np.maximum(SPARSE_LONG, max_fill * count)) or length.sum() >= 2 ** 31:
+        return None
+    voff = np.concatenate([[0], np.cumsum(length.reshape(-1))[:-1]])
+    vals = np.empty(int(length.sum()))
+    for p in range(P):
+        for x in np.nonzero(any_nz[p])[0]:
+            o = voff[p * NX + x]
+            vals[o:o + length[p, x]] = M[p, first[p, x]:last[p, x] + 1, x]
+    longs = [np.nonzero(length[p] > SPARSE_LONG)[0].astype(np.int32) for p in range(P)]
+    long_ptr = np.concatenate([[0], np.cumsum([len(q) for q in longs])]).astype(np.int32)
+    return dict(col_r0=first.astype(np.int32).reshape(-1), col_len=length.astype(np.int32).reshape(-1),
+                col_voff=voff.astype(np.int32), vals=vals, long_cols=np.concatenate(longs), long_ptr=long_ptr,
+                shape=(P, E, NX))
+
+
 def tangent_mix(BASEH_TANHE, TANHE):
     """The pair of paths and the weights with which nemesisSOfmg / nemesisLfmg interpolate the path spectra to each
     measured tangent height (ForwardModel_0.py:1206-1228, :1464-1486), as arrays lo, hi (-1: path lo alone), wlo, whi:

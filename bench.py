@@ -558,7 +558,12 @@ def run_b200(args, cfg):
         spec, dspec, dts = ops.radiance(s.mode, tau, dk, s.gas_slot, s.taucia, s.taudust, s.tauray, s.dtaucon, s.layinc,
                                         s.scale, s.nlayin, s.emtemp, s.laypress, hp.wave_d, hp.delg_d, s.emissivity,
                                         s.xfac, None, None, None, None, s.ISPACE, s.TSURF, s.NVMR, s.NPAR, True)
-        evs[2].record(); ops.jacobian_project(dspec, s.M); evs[3].record()
+        evs[2].record()
+        if getattr(s, "M_sparse", None) is not None:
+            ops.jacobian_project_sparse(dspec, s.M_sparse)
+        else:
+            ops.jacobian_project(dspec, s.M)
+        evs[3].record()
         torch.cuda.synchronize()
         sys.stderr.write("stage ms: gas_opacity %.3f radiance %.3f project %.3f\n" % (
             evs[0].elapsed_time(evs[1]), evs[1].elapsed_time(evs[2]), evs[2].elapsed_time(evs[3])))

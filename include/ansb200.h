@@ -194,6 +194,15 @@ int ansb200_jacobian_project_shared(const double *dspec, const double *M, int NW
  * state-vector element are then never read from dspec.  shared != 0: M[1, NPAR*NLAYMAX, NX] for every path. */
 int ansb200_jacobian_project_chunks(const double *dspec, const double *M, int NWAVE, int NPAR, int NLAYMAX, int NPATH,
                                     int NX, int shared, const int32_t *chunks, int nchunks, double *out, void *stream);
+/* The product with M handed over as a sparse operator (host: plan.sparse_projection): column x of path p (p = 0 for
+ * every path when shared != 0) is ONE run of consecutive rows, M[p, r0 : r0+len, x] = vals[voff : voff+len] with
+ * r0 / len / voff = col_r0 / col_len / col_voff[p*NX + x] (len = 0: empty column; zeros inside a run are stored);
+ * long_cols[long_ptr[p] : long_ptr[p+1]] lists the columns longer than 16.  One warp per (wavenumber, path) row of
+ * dspec, NPAR*NLAYMAX*8 bytes of shared memory per warp (NPAR*NLAYMAX <= 3200). */
+int ansb200_jacobian_project_sparse(const double *dspec, const int32_t *col_r0, const int32_t *col_len,
+                                    const int32_t *col_voff, const double *vals, int nvals, const int32_t *long_cols,
+                                    const int32_t *long_ptr, int NWAVE, int NPAR, int NLAYMAX, int NPATH, int NX,
+                                    int shared, double *out, void *stream);
 
 /* ---- tangent-height interpolation of the path spectra ------------------------------------------
  * Replaces the SPECMOD / dSPECMOD loop of nemesisSOfmg / nemesisLfmg (ForwardModel_0.py:1206-1228, :1464-1486):

@@ -661,3 +661,39 @@ def test_projection_with_chunk_list_equals_full_product(shared):
     assert colerr(got.cpu().numpy(), want) < 1e-13
     zero = ops.jacobian_project(d, ops.to_dev(np.zeros_like(M)), shared=shared, chunks=ops.project_chunks(np.zeros_like(M)))
     assert float(zero.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_sparse_projection_equals_dense_product(shared):
+    """ansb200_jacobian_project_sparse (M by columns, a warp per dspec row) against the tiled dense product: columns of
+    at most 16 entries are summed in the same order with fused multiply-adds -- bit-identical; longer ones (a scaling
+    factor that touches every layer) by the whole warp -- equal to rounding; empty columns give zero."""
+    import torch
+    from archnemesis_dist_b200 import ops, plan
+    rng = np.random.default_rng(9)
+    nw, npath, npar, nlm, nx = 70, 3, 7, 37, 45
+    dspec = rng.standard_normal((nw, npath, npar, nlm))
+    P = 1 if shared else npath
+    M = np.zeros((P, npar * nlm, nx))
+    for p in range(P):
+        M[p, 1 * nlm:2 * nlm, 3] = rng.standard_normal(nlm)                 # long column (37 entries)
+        M[p, 4 * nlm:5 * nlm, 40] = rng.standard_normal(nlm)
+        for x in range(8, 30):                                              # short columns: 2-3 neighbouring layers
+            l0 = int(rng.integers(0, nlm - 3))
+            M[p, 6 * nlm + l0:6 * nlm + l0 + 3, x] = rng.standard_normal(3)
+        M[p, 5, 44] = 2.5                                                   # one entry; columns 0-2, 4-7, ... stay empty
+    M[:, 6 * nlm + 10, 12] = 0.0                                            # (a zero inside a run is kept)
+    sp_host = plan.sparse_projection(M)
+    assert sp_host is not None and len(sp_host["long_cols"]) == 2 * P
+    assert plan.sparse_projection(rng.standard_normal((1, 64, 8))) is None   # dense: left to the tiled kernel
+    far = np.zeros((1, 400, 4))
+    far[0, [3, 390], 1] = 1.0
+    assert plan.sparse_projection(far) is None                              # a column spread over distant rows: likewise
+    d = ops.to_dev(dspec)
+    dense = ops.jacobian_project(d, ops.to_dev(M), shared=shared)
+    got = ops.jacobian_project_sparse(d, ops.SparseProjection(sp_host), shared=shared)
+    short = np.ones(nx, dtype=bool)
+    short[[3, 40]] = False
+    assert torch.equal(got[:, :, torch.as_tensor(short)], dense[:, :, torch.as_tensor(short)])
+    assert colerr(got.cpu().numpy(), dense.cpu().numpy()) < 1e-14
+    assert float(got[:, :, 0].abs().max()) == 0.0

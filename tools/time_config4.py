@@ -43,7 +43,11 @@ def main():
             kw = dict(layer_space=True) if lay else {}
             t_rad = timeit(lambda: ops.radiance(*args, **kw))
             _, dspec, _ = ops.radiance(*args, **kw)
-            t_prj = timeit(lambda: ops.jacobian_project(dspec, s.M, shared=lay))
+            if getattr(s, "M_sparse", None) is not None:
+                t_prj = timeit(lambda: ops.jacobian_project_sparse(dspec, s.M_sparse, shared=lay))
+                name += " (sparse M)"
+            else:
+                t_prj = timeit(lambda: ops.jacobian_project(dspec, s.M, shared=lay))
             print("%-12s %-11s radiance %.3f ms  projection %.3f ms  dspec %.2f GB" %
                   (name, "layer space" if lay else "path space", t_rad, t_prj, dspec.numel() * 8 / 1e9))
             del dspec, tau, dk
