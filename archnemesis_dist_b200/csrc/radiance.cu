@@ -1252,6 +1252,179 @@ ans_thermal_layers_kernel(RadParams P)
     }
 }
 
+// ---- thermal emission with gradients, one to three paths: a warp per (wavenumber, path), nothing staged -----------
+// The nadir case of an optimal-estimation iteration (config 2: one path of NLAY visits).  ans_radiance_kernel spends a
+// CTA of NG/2 warps, two shared-memory passes and three CTA barriers on every wavenumber (36 000 warp instructions, issue
+// slots 34 % busy, half its shared-memory wavefronts bank conflicts); here ONE warp does a wavenumber: lanes own
+// contiguous chunks of visits whose layer / scale / Planck value / continuum sit in registers, the g loop scans the path
+// (chunk products, warp scan, reverse scan of the emission terms -- the scan of ans_thermal_layers_kernel) and every
+// lane adds W_j(g) dk[g, l_j, :] to its visits' NGAS+1 running sums, reading tau and dk straight from global memory: a
+// g-ordinate's rows of one wavenumber are contiguous (NLAY*(NGAS+1) doubles) and every byte is used, so the loads need
+// no staging to be efficient.  No shared memory, no barrier.  RQ = visits per lane (2, 4 or 7).
+template <int RQ>
+__device__ __forceinline__ void tn_path(const RadParams &P, int iw, int ipath, int lane)
+{
+    const int NG = P.NG, NLAY = P.NLAY, NLM = P.NLAYMAX, NPATH = P.NPATH, NPAR = P.NPAR, NP1 = P.NGAS + 1;
+    const int n = P.nlayin[ipath];
+    const int CH = (n + 31) / 32;
+    const int j0 = lane * CH, cnt = max(0, min(n, j0 + CH) - j0);
+    const double wv = P.wave[iw];
+    const double xf = P.xfac ? P.xfac[iw] : 1.0;
+    double pl_a, pl_c2y;
+    tl_planck_consts(P.ispace, wv, pl_a, pl_c2y);
+    int lay[RQ];
+    double sc[RQ], Bq[RQ], con[RQ], esq[RQ], wsum[RQ], acc[RQ][TP_NC];
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) {
+        lay[q] = 0; sc[q] = 0.0; Bq[q] = 0.0; con[q] = 0.0; esq[q] = 0.0; wsum[q] = 0.0;
+#pragma unroll
+        for (int c = 0; c < TP_NC; ++c) acc[q][c] = 0.0;
+        if (q < cnt) {
+            const size_t at = (size_t)(j0 + q) * NPATH + ipath;
+            const int l = P.layinc[at];
+            lay[q] = l;
+            sc[q] = P.scale[at];
+            Bq[q] = tl_planck(pl_a, pl_c2y, P.emtemp[at]);
+            double c = 0.0;                                    // TAUCIA + TAUDUST + TAURAY in the reference's order (:3989)
+            if (P.taucia) c += P.taucia[(size_t)iw * NLAY + l];
+            if (P.taudust) c += P.taudust[(size_t)iw * NLAY + l];
+            if (P.tauray) c += P.tauray[(size_t)iw * NLAY + l];
+            con[q] = c;
+        }
+    }
+    // limb / nadir test and ground term (:6353-6365, :6479-6494)
+    double radground = 0.0, dradground = 0.0;
+    bool ground = false;
+    if (n > 0) {
+        const int jh = n / 2 - 1;
+        const double p1 = P.laypress[P.layinc[(size_t)(jh >= 0 ? jh : n - 1) * NPATH + ipath]];
+        const double p2 = P.laypress[P.layinc[(size_t)(n - 1) * NPATH + ipath]];
+        ground = p2 > p1;
+        if (ground) {
+            if (P.tsurf <= 0.0) {
+                ans_planckg(P.ispace, wv, P.emtemp[(size_t)(n - 1) * NPATH + ipath], radground, dradground);
+            } else {
+                ans_planckg(P.ispace, wv, P.tsurf, radground, dradground);
+                const double em = P.emissivity[iw];
+                radground *= em;
+                dradground *= em;
+            }
+        }
+    }
+    double spec = 0.0, dts = 0.0;
+    const double *tw = P.tau + (size_t)iw * NG * NLAY;
+    const double *dw = P.dk + (size_t)iw * NG * NLAY * NP1;
+#pragma unroll 1
+    for (int g = 0; g < NG; ++g) {
+        const double *tg = tw + (size_t)g * NLAY;
+        const double *dg_ = dw + (size_t)g * NLAY * NP1;
+        double Tq[RQ];
+        double loc = 1.0;
+#pragma unroll
+        for (int q = 0; q < RQ; ++q) Tq[q] = tl_expneg((__ldg(tg + lay[q]) + con[q]) * sc[q]);
+#pragma unroll
+        for (int q = 0; q < RQ; ++q) {
+            loc *= Tq[q];
+            Tq[q] = loc;
+        }
+        double incl = loc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double up = rshfl_up(incl, d);
+            asm("{ .reg .pred p; setp.ge.s32 p, %2, %3; @p mul.f64 %0, %0, %1; }" : "+d"(incl) : "d"(up), "r"(lane), "r"(d));
+        }
+        double base = rshfl_up(incl, 1);
+        if (lane == 0) base = 1.0;
+        const double Tn = rshfl_idx(incl, 31);
+        double esum = 0.0;
+#pragma unroll
+        for (int q = 0; q < RQ; ++q) {
+            Tq[q] *= base;
+            const double Tm = q == 0 ? base : Tq[q > 0 ? q - 1 : 0];
+            esum = fma(Tm - Tq[q], Bq[q], esum);
+        }
+        double rincl = esum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double dn = rshfl_down(rincl, d);
+            asm("{ .reg .pred p; setp.lt.s32 p, %2, %3; @p add.f64 %0, %0, %1; }" : "+d"(rincl) : "d"(dn), "r"(lane), "r"(32 - d));
+        }
+        double specg = rshfl_idx(rincl, 0);
+        if (ground) specg += Tn * radground;
+        const double dgv = P.delg[g];
+        const double dgx = dgv * xf;
+        spec += specg * xf * dgv;
+        if (ground) dts += Tn * dradground * xf * dgv;
+        double after = rshfl_down(rincl, 1);
+        if (lane == 31) after = 0.0;
+        double suffix = after + (ground ? Tn * radground : 0.0);
+#pragma unroll
+        for (int qq = 0; qq < RQ; ++qq) {
+            const int q = RQ - 1 - qq;
+            const double Tj = Tq[q], Tm = q == 0 ? base : Tq[q > 0 ? q - 1 : 0];
+            const double W = (Tj * Bq[q] - suffix) * sc[q] * dgx;        // (unused slots: sc = 0)
+            esq[q] = fma(Tm - Tj, dgx, esq[q]);
+            suffix = fma(Tm - Tj, Bq[q], suffix);
+            wsum[q] += W;
+            const double *row = dg_ + (size_t)lay[q] * NP1;
+#pragma unroll
+            for (int c = 0; c < TP_NC; ++c)
+                if (c < NP1) acc[q][c] = fma(W, __ldg(row + c), acc[q][c]);
+        }
+    }
+    if (lane == 0) {
+        P.spec[(size_t)iw * NPATH + ipath] = spec;
+        if (P.dtsurf) P.dtsurf[(size_t)iw * NPATH + ipath] = dts;
+    }
+    // (T_{j-1} - T_j) dB_j/dT summed over g belongs to the temperature parameter (dk column NGAS);
+    // dB/dT = B (1 + B / a) c2 y / T^2 from the Planck value already held
+    const double inv_a = 1.0 / pl_a;
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) {
+        if (q < cnt) {
+            const double temp = P.emtemp[(size_t)(j0 + q) * NPATH + ipath];
+            const double db = Bq[q] * fma(Bq[q], inv_a, 1.0) * (pl_c2y / (temp * temp));
+#pragma unroll
+            for (int c = 0; c < TP_NC; ++c) acc[q][c] += (c == P.NGAS) ? esq[q] * db : 0.0;
+        }
+    }
+    // d spec / d q[k, j] = unit_k acc[j][col_k] + dtaucon[k, l_j] wsum[j]
+    double *out = P.dspec + ((size_t)iw * NPATH + ipath) * NPAR * NLM;
+    const bool ntn = (P.flags & ANSB200_RAD_NAN_TO_NUM) != 0;
+#pragma unroll 1
+    for (int k = 0; k < NPAR; ++k) {
+        int col = -1;
+        if (k == P.NVMR) col = P.NGAS;
+        else for (int i = 0; i < P.NGAS; ++i) if (P.gas_slot[i] == k) col = i;
+        const double unit = (col >= 0 && col < P.NGAS) ? 1.0e-4 : 1.0;
+#pragma unroll
+        for (int q = 0; q < RQ; ++q) {
+            if (q < cnt) {
+                double v = 0.0;
+#pragma unroll
+                for (int c = 0; c < TP_NC; ++c) v = (c == col) ? acc[q][c] * unit : v;
+                if (P.dtaucon) v = fma(P.dtaucon[((size_t)iw * NPAR + k) * NLAY + lay[q]], wsum[q], v);
+                if (ntn) v = tl_nan_to_num(v);
+                out[(size_t)k * NLM + j0 + q] = v;
+            }
+        }
+        for (int j = n + lane; j < NLM; j += 32) out[(size_t)k * NLM + j] = 0.0;    // rows past NLAYIN
+    }
+}
+
+constexpr int TN_WARPS = 4;
+
+template <int RQ>
+__global__ void __launch_bounds__(TN_WARPS * 32, RQ <= 2 ? 4 : (RQ <= 4 ? 3 : 2))
+ans_thermal_nadir_kernel(RadParams P)          // RQ >= NLAYMAX / 32: chosen by the launcher (registers follow RQ)
+{
+    const int lane = threadIdx.x & 31;
+    const long long unit = (long long)blockIdx.x * TN_WARPS + (threadIdx.x >> 5);
+    if (unit >= (long long)P.NWAVE * P.NPATH) return;
+    const int iw = (int)(unit / P.NPATH), ipath = (int)(unit - (long long)iw * P.NPATH);
+    tn_path<RQ>(P, iw, ipath, lane);
+}
+
 static size_t thermal_layers_smem(int NG, int NLAY, int NGAS, int NPAR)
 {
     const int NT = (NGAS + 2 + 7) / 8, GS = NT * 64 + 2;
@@ -1346,6 +1519,17 @@ extern "C" int ansb200_radiance(int mode, unsigned flags, const double *tau, con
             ANS_LAUNCH_CHECK();
             return ANSB200_OK;
         }
+    }
+    if (thermal && grad && dk && NPATH < 4 && NLAYMAX <= 32 * TL_RQ && NGAS + 1 <= TP_NC && NG >= 4) {
+        // thermal emission with gradients, one to three paths (the nadir case of a retrieval): a warp per (wavenumber,
+        // path), operands straight from global memory
+        const long long units = (long long)NWAVE * NPATH;
+        const unsigned nblk = (unsigned)((units + TN_WARPS - 1) / TN_WARPS);
+        if (NLAYMAX <= 64) ans_thermal_nadir_kernel<2><<<nblk, TN_WARPS * 32, 0, stream>>>(P);
+        else if (NLAYMAX <= 128) ans_thermal_nadir_kernel<4><<<nblk, TN_WARPS * 32, 0, stream>>>(P);
+        else ans_thermal_nadir_kernel<7><<<nblk, TN_WARPS * 32, 0, stream>>>(P);
+        ANS_LAUNCH_CHECK();
+        return ANSB200_OK;
     }
     if (thermal && grad && dk && NPATH >= 4 && NLAYMAX <= 32 * TP_RQ && NGAS + 1 <= TP_NC) {
         // thermal emission with gradients over several paths: warp-per-path kernel if the slabs fit
