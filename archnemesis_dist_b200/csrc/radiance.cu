@@ -1252,21 +1252,23 @@ ans_thermal_layers_kernel(RadParams P)
     }
 }
 
-// ---- thermal emission with gradients, one to three paths: a warp per (wavenumber, path), nothing staged -----------
+// ---- thermal emission with gradients, one to three paths: a warp per (wavenumber, path) --------------------------
 // The nadir case of an optimal-estimation iteration (config 2: one path of NLAY visits).  ans_radiance_kernel spends a
 // CTA of NG/2 warps, two shared-memory passes and three CTA barriers on every wavenumber (36 000 warp instructions, issue
 // slots 34 % busy, half its shared-memory wavefronts bank conflicts); here ONE warp does a wavenumber: lanes own
 // contiguous chunks of visits whose layer / scale / Planck value / continuum sit in registers, the g loop scans the path
 // (chunk products, warp scan, reverse scan of the emission terms -- the scan of ans_thermal_layers_kernel) and every
-// lane adds W_j(g) dk[g, l_j, :] to its visits' NGAS+1 running sums, reading tau and dk straight from global memory: a
-// g-ordinate's rows of one wavenumber are contiguous (NLAY*(NGAS+1) doubles) and every byte is used, so the loads need
-// no staging to be efficient.  No shared memory, no barrier.  RQ = visits per lane (2, 4 or 7).
+// lane adds W_j(g) dk[g, l_j, :] to its visits' NGAS+1 running sums.  A g-ordinate's operands of one wavenumber are two
+// contiguous blocks (dk: NLAY*(NGAS+1) doubles, tau: NLAY) that the path uses exactly once: they stream through two
+// buffers of the warp's own shared memory with cp.async, the next g-ordinate's while this one is scanned, so DRAM sees
+// whole lines, the scan sees no load latency and the address arithmetic is 32-bit.  No CTA barrier.  The chunk
+// length is odd (lanes read distinct banks of the staged rows); RQ = 1, 3, 5 or 7 visits per lane.
 template <int RQ>
-__device__ __forceinline__ void tn_path(const RadParams &P, int iw, int ipath, int lane)
+__device__ __forceinline__ void tn_path(const RadParams &P, int iw, int ipath, int lane, double *wbuf)
 {
     const int NG = P.NG, NLAY = P.NLAY, NLM = P.NLAYMAX, NPATH = P.NPATH, NPAR = P.NPAR, NP1 = P.NGAS + 1;
     const int n = P.nlayin[ipath];
-    const int CH = (n + 31) / 32;
+    const int CH = ((n + 31) / 32) | 1;        // odd: lanes then read distinct banks of the staged rows
     const int j0 = lane * CH, cnt = max(0, min(n, j0 + CH) - j0);
     const double wv = P.wave[iw];
     const double xf = P.xfac ? P.xfac[iw] : 1.0;
@@ -1312,16 +1314,49 @@ __device__ __forceinline__ void tn_path(const RadParams &P, int iw, int ipath, i
         }
     }
     double spec = 0.0, dts = 0.0;
+    // A g-ordinate's operands of this wavenumber -- dk[g, :, :] (NLAY*(NGAS+1) doubles) and tau[g, :] -- are two
+    // contiguous blocks that the path uses exactly once: they stream through two shared-memory buffers of the warp
+    // (cp.async, the next g-ordinate while this one is scanned), so DRAM sees full lines and the scan sees no latency.
+    const int BD = NLAY * NP1, BS = (BD + NLAY + 1) & ~1;       // doubles per buffer (16-byte multiple)
     const double *tw = P.tau + (size_t)iw * NG * NLAY;
     const double *dw = P.dk + (size_t)iw * NG * NLAY * NP1;
+    const bool wide = ((BD | NLAY) & 1) == 0;                   // both blocks start 16-byte aligned for every g
+    auto issue = [&](int g, double *dst) {
+        const double *sd = dw + (size_t)g * BD, *st = tw + (size_t)g * NLAY;
+        const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst);
+        if (wide) {
+            for (int e = lane; e < (BD >> 1); e += 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + (unsigned)e * 16u), "l"(sd + 2 * e));
+            for (int e = lane; e < (NLAY >> 1); e += 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + (unsigned)(BD + 2 * e) * 8u), "l"(st + 2 * e));
+        } else {
+            for (int e = lane; e < BD; e += 32)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + (unsigned)e * 8u), "l"(sd + e));
+            for (int e = lane; e < NLAY; e += 32)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + (unsigned)(BD + e) * 8u), "l"(st + e));
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    int rowoff[RQ];                                             // the visit's dk row in a buffer
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) rowoff[q] = lay[q] * NP1;
+    issue(0, wbuf);
 #pragma unroll 1
     for (int g = 0; g < NG; ++g) {
-        const double *tg = tw + (size_t)g * NLAY;
-        const double *dg_ = dw + (size_t)g * NLAY * NP1;
+        const double *buf = wbuf + (g & 1) * BS;
+        if (g + 1 < NG) {
+            issue(g + 1, wbuf + ((g + 1) & 1) * BS);
+            asm volatile("cp.async.wait_group 1;");
+        } else {
+            asm volatile("cp.async.wait_group 0;");
+        }
+        __syncwarp();
+        const double *tg = buf + BD;
+        const double *dg_ = buf;
         double Tq[RQ];
         double loc = 1.0;
 #pragma unroll
-        for (int q = 0; q < RQ; ++q) Tq[q] = tl_expneg((__ldg(tg + lay[q]) + con[q]) * sc[q]);
+        for (int q = 0; q < RQ; ++q) Tq[q] = tl_expneg((tg[lay[q]] + con[q]) * sc[q]);
 #pragma unroll
         for (int q = 0; q < RQ; ++q) {
             loc *= Tq[q];
@@ -1366,11 +1401,12 @@ __device__ __forceinline__ void tn_path(const RadParams &P, int iw, int ipath, i
             esq[q] = fma(Tm - Tj, dgx, esq[q]);
             suffix = fma(Tm - Tj, Bq[q], suffix);
             wsum[q] += W;
-            const double *row = dg_ + (size_t)lay[q] * NP1;
+            const double *row = dg_ + rowoff[q];
 #pragma unroll
             for (int c = 0; c < TP_NC; ++c)
-                if (c < NP1) acc[q][c] = fma(W, __ldg(row + c), acc[q][c]);
+                if (c < NP1) acc[q][c] = fma(W, row[c], acc[q][c]);
         }
+        __syncwarp();          // (this buffer is refilled during the next iteration but one)
     }
     if (lane == 0) {
         P.spec[(size_t)iw * NPATH + ipath] = spec;
@@ -1415,14 +1451,21 @@ __device__ __forceinline__ void tn_path(const RadParams &P, int iw, int ipath, i
 constexpr int TN_WARPS = 4;
 
 template <int RQ>
-__global__ void __launch_bounds__(TN_WARPS * 32, RQ <= 2 ? 4 : (RQ <= 4 ? 3 : 2))
-ans_thermal_nadir_kernel(RadParams P)          // RQ >= NLAYMAX / 32: chosen by the launcher (registers follow RQ)
+__global__ void __launch_bounds__(TN_WARPS * 32, RQ <= 3 ? 4 : (RQ <= 5 ? 3 : 2))
+ans_thermal_nadir_kernel(RadParams P)          // RQ = (NLAYMAX / 32 rounded up) | 1: chosen by the launcher
 {
-    const int lane = threadIdx.x & 31;
-    const long long unit = (long long)blockIdx.x * TN_WARPS + (threadIdx.x >> 5);
+    extern __shared__ __align__(16) unsigned char rad_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long unit = (long long)blockIdx.x * TN_WARPS + warp;
     if (unit >= (long long)P.NWAVE * P.NPATH) return;
     const int iw = (int)(unit / P.NPATH), ipath = (int)(unit - (long long)iw * P.NPATH);
-    tn_path<RQ>(P, iw, ipath, lane);
+    const int BS = (P.NLAY * (P.NGAS + 1) + P.NLAY + 1) & ~1;
+    tn_path<RQ>(P, iw, ipath, lane, reinterpret_cast<double *>(rad_smem) + (size_t)warp * 2 * BS);
+}
+
+static size_t thermal_nadir_smem(int NLAY, int NGAS)
+{
+    return (size_t)TN_WARPS * 2 * ((NLAY * (NGAS + 1) + NLAY + 1) & ~1) * 8;
 }
 
 static size_t thermal_layers_smem(int NG, int NLAY, int NGAS, int NPAR)
@@ -1520,14 +1563,25 @@ extern "C" int ansb200_radiance(int mode, unsigned flags, const double *tau, con
             return ANSB200_OK;
         }
     }
-    if (thermal && grad && dk && NPATH < 4 && NLAYMAX <= 32 * TL_RQ && NGAS + 1 <= TP_NC && NG >= 4) {
+    if (thermal && grad && dk && NPATH < 4 && NLAYMAX <= 32 * TL_RQ && NGAS + 1 <= TP_NC && NG >= 4 &&
+        thermal_nadir_smem(NLAY, NGAS) <= 100 * 1024) {
         // thermal emission with gradients, one to three paths (the nadir case of a retrieval): a warp per (wavenumber,
-        // path), operands straight from global memory
+        // path), a g-ordinate's operands streamed through the warp's own shared-memory buffers
         const long long units = (long long)NWAVE * NPATH;
         const unsigned nblk = (unsigned)((units + TN_WARPS - 1) / TN_WARPS);
-        if (NLAYMAX <= 64) ans_thermal_nadir_kernel<2><<<nblk, TN_WARPS * 32, 0, stream>>>(P);
-        else if (NLAYMAX <= 128) ans_thermal_nadir_kernel<4><<<nblk, TN_WARPS * 32, 0, stream>>>(P);
-        else ans_thermal_nadir_kernel<7><<<nblk, TN_WARPS * 32, 0, stream>>>(P);
+        const size_t smem_n = thermal_nadir_smem(NLAY, NGAS);
+        const int rq = ((NLAYMAX + 31) / 32) | 1;
+#define TN_LAUNCH(RQ)                                                                                                  \
+        do {                                                                                                           \
+            ANS_CUDA_CHECK(cudaFuncSetAttribute(ans_thermal_nadir_kernel<RQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                (int)(smem_n > 48 * 1024 ? smem_n : 48 * 1024)));                     \
+            ans_thermal_nadir_kernel<RQ><<<nblk, TN_WARPS * 32, smem_n, stream>>>(P);                                 \
+        } while (0)
+        if (rq <= 1) TN_LAUNCH(1);
+        else if (rq <= 3) TN_LAUNCH(3);
+        else if (rq <= 5) TN_LAUNCH(5);
+        else TN_LAUNCH(7);
+#undef TN_LAUNCH
         ANS_LAUNCH_CHECK();
         return ANSB200_OK;
     }
