@@ -542,6 +542,61 @@ def test_thermal_many_limb_paths_staged_kernel(mods, want_grad):
         assert relerr(cpu(out), orc.g_integrate(S, None, None, dg)) < 1e-12
 
 
+@pytest.mark.parametrize("nlay,npath,ngas,tsurf,kind", [(13, 1, 4, 150.0, "nadir"), (37, 2, 5, -1.0, "mixed"),
+                                                        (75, 3, 7, 200.0, "mixed"), (100, 1, 6, -1.0, "nadir"),
+                                                        (112, 2, 3, -1.0, "limb")])
+def test_thermal_one_to_three_paths_warp_per_path_kernel(mods, nlay, npath, ngas, tsurf, kind):
+    """NPATH < 4 in thermal mode with gradients takes ans_thermal_nadir_kernel (a warp per (wavenumber, path), the
+    g-ordinate's operands streamed through per-warp shared memory): every chunk length (1, 3, 5, 7 visits per lane),
+    nadir paths with and without a surface, limb paths that cross layers twice next to a nadir path, an odd number of
+    layers (8-byte copies), NGAS + 1 even and at its maximum of 8 -- against the oracle."""
+    ops, orc = mods["ops"], mods["orc"]
+    nw = 5
+    c = _case(mods, nwave=nw, ng=20, ngas=ngas, nlay=nlay, npro=nlay, nx=5, nvmr=ngas + 1, seed=200 + nlay, tsurf=tsurf)
+    rng = np.random.default_rng(nlay)
+    nlm = 2 * nlay if kind != "nadir" else nlay
+    layinc = np.zeros((nlm, npath), np.int32)
+    scale = np.zeros((nlm, npath))
+    nlayin = np.zeros(npath, np.int32)
+    for p in range(npath):
+        if kind == "nadir" or (kind == "mixed" and p == 0):
+            seq = list(range(nlay - 1, -1, -1))                       # top to bottom: ends on the ground
+        else:
+            t = int(rng.integers(0, nlay - 1))
+            seq = list(range(nlay - 1, t - 1, -1)) + list(range(t, nlay))
+        n = len(seq)
+        nlayin[p] = n
+        layinc[:n, p] = seq
+        scale[:n, p] = rng.uniform(1.0, 4.0, n)
+    emtemp = np.zeros((nlm, npath))
+    for p in range(npath):
+        emtemp[:nlayin[p], p] = c["temp"][layinc[:nlayin[p], p]]
+    c.update(LAYINC=layinc, SCALE=scale, NLAYIN=nlayin, EMTEMP=emtemp)
+    c["xfac"] = np.linspace(0.5, 2.0, nw)
+    tab = c["tab"]
+    kr, dr = orc.calc_k(tab["K"], tab["PRESS"], tab["TEMP"], c["press"], c["temp"], want_grad=True)
+    tau, dk = orc.k_overlap(tab["DELG"], kr, c["amount"], dkdT=dr)
+    tau *= 2e-3
+    dk *= 2e-3
+    a = _radiance_inputs(mods, c, tau, dk)
+    spec, dspec, dts = ops.radiance(ops.THERMAL, a["tau"], a["dk"], a["gas_slot"], a["taucia"], None, None, a["dtaucon"],
+                                    a["layinc"], a["scale"], a["nlayin"], a["emtemp"], a["laypress"], a["wave"], a["delg"],
+                                    a["emissivity"], a["xfac"], None, None, None, None, c["ISPACE"], tsurf, c["NVMR"],
+                                    c["NPAR"], True)
+    tl, tp, dtl = orc.assemble_opacity(tau, dk, c["gas_slot"], c["NVMR"], c["NPAR"], c["taucon"], c["dtaucon"], layinc, scale)
+    z = np.zeros(nw)
+    S, dS, dT = orc.thermal_paths(c["ISPACE"], tab["WAVE"], tl, dtl, c["NVMR"], nlayin, emtemp, c["LAYPRESS"], layinc,
+                                  tsurf, c["EMISSIVITY"], c["xfac"], z, z, np.full(npath, 100.0), np.full(npath, 10.0))
+    s_ref, d_ref, t_ref = orc.g_integrate(S, dS, dT, tab["DELG"])
+    assert relerr(cpu(spec), s_ref) < 1e-12
+    got = np.transpose(cpu(dspec), (0, 2, 3, 1))
+    for kpar in range(d_ref.shape[1]):
+        assert colerr(got[:, kpar], d_ref[:, kpar]) < 1e-11, kpar
+    assert relerr(cpu(dts), t_ref) < 1e-12 or float(np.abs(t_ref).max()) == 0.0
+    for p in range(npath):                                            # rows past NLAYIN are written as zeros
+        assert float(np.abs(got[:, :, nlayin[p]:, p]).max(initial=0.0)) == 0.0
+
+
 def test_float32_table_storage_variants():
     """ansb200_table_create_ex: K as float32 is lossless for .kta data (bit-identical k-interp and fused gas opacity);
     K and ln K as float32 -- the FP32 k-interp variant -- stays within 2e-5 of the float64 table; a table that is not
