@@ -62,7 +62,8 @@ def main(nwave=100000, ngas=4, nlay=60, nx=60, nconv=400):
                               s.nlayin, s.emtemp, s.laypress, hp.wave_d, hp.delg_d, s.emissivity, s.xfac, s.solflux,
                               s.reflectance, s.sol_ang, s.emiss_ang, s.ISPACE, s.TSURF, s.NVMR, s.NPAR, True)
         ev_[2].record()
-        dx = hp.ops.jacobian_project(out[1], s.M)
+        dx = hp.ops.jacobian_project_sparse(out[1], s.M_sparse) if getattr(s, "M_sparse", None) is not None else \
+            hp.ops.jacobian_project(out[1], s.M)
         ev_[3].record()
         block = torch.cat([out[0][:, :1], dx[:, 0, :]], dim=1)
         hp.ops.convolve(cop, block)
@@ -81,9 +82,24 @@ def main(nwave=100000, ngas=4, nlay=60, nx=60, nconv=400):
     t0 = time.perf_counter()
     for _ in range(reps):
         o = hp.to_host(hp.forward_jacobian_conv(ev, M, cop, 2, 1.0))
-    print("  %-45s %8.3f ms  (h2d %.1f MB, d2h %.2f MB)" % ("end to end, host arrays in / [NCONV,1+NX] out",
+    print("  %-45s %8.3f ms  (h2d %.1f MB, d2h %.2f MB)" % ("end to end, dense continuum arrays in / [NCONV,1+NX] out",
                                                              (time.perf_counter() - t0) * 1e3 / reps,
                                                              ev.h2d_bytes / 1e6, o.nbytes / 1e6))
+    # the same evaluation with the continuum terms as a PLAN (what the drop-in hands over since round 2: the per-layer
+    # coefficients and the resident cross-section planes; the dense [NWAVE, NPAR, NLAY] arrays are made on the device)
+    cont = syn.make_continuum(nwave, nlay, c["NVMR"], c["NDUST"], seed=5, temp=c["temp"])
+    ev2 = engine.Evaluation(mode=engine.THERMAL, press_atm=c["press"], temp=c["temp"], amount=c["amount"],
+                            gas_slot=c["gas_slot"], NVMR=c["NVMR"], NPAR=c["NPAR"], LAYINC=c["LAYINC"], SCALE=c["SCALE"],
+                            NLAYIN=c["NLAYIN"], EMTEMP=c["EMTEMP"], LAYPRESS=c["LAYPRESS"], continuum=cont,
+                            TSURF=c["TSURF"], EMISSIVITY=c["EMISSIVITY"], xfac=c["xfac"])
+    for _ in range(3):
+        hp.to_host(hp.forward_jacobian_conv(ev2, M, cop, 2, 1.0))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        o = hp.to_host(hp.forward_jacobian_conv(ev2, M, cop, 2, 1.0))
+    print("  %-45s %8.3f ms  (h2d %.2f MB, d2h %.2f MB)" % ("end to end, continuum plan in / [NCONV,1+NX] out",
+                                                             (time.perf_counter() - t0) * 1e3 / reps,
+                                                             ev2.h2d_bytes / 1e6, o.nbytes / 1e6))
     hp.close()
 
 
