@@ -288,7 +288,10 @@ def _layer_space_against_path_space(mods, c4, mode, tol=1e-13):
     tab = c4["tab"]
     nlay, npath, nwave = len(c4["press"]), int(c4["LAYINC"].shape[1]), tab["NWAVE"]
     nx = c4["xmap"].shape[0]
-    hp = engine.HotPath(tab["K"], tab["PRESS"], tab["TEMP"], tab["DELG"], tab["WAVE"])
+    if tab["K"].shape[1] == 1:      # one g-ordinate: a line-by-line table (ILBL = 2), K[NWAVE,NP,NT,NGAS]
+        hp = engine.HotPath(np.ascontiguousarray(tab["K"][:, 0]), tab["PRESS"], tab["TEMP"], np.array([1.0]), tab["WAVE"])
+    else:
+        hp = engine.HotPath(tab["K"], tab["PRESS"], tab["TEMP"], tab["DELG"], tab["WAVE"])
     M = plan.fold_projection(c4["xmap"], c4["LAYINC"], c4["NLAYIN"], c4["DTE"], c4["DAM"], c4["DCO"], c4["NVMR"], c4["NDUST"])
     Mlay = plan.fold_projection_layers(c4["xmap"], nlay, c4["DTE"], c4["DAM"], c4["DCO"], c4["NVMR"], c4["NDUST"])
     assert Mlay.shape == (1, c4["NPAR"] * nlay, nx) and M.shape[1] == c4["NPAR"] * int(c4["LAYINC"].shape[0])
@@ -335,12 +338,16 @@ def test_layer_space_gradients_of_limb_paths(mods, mode_name):
     _layer_space_against_path_space(mods, c4, engine.TRANSMISSION if mode_name == "transmission" else engine.THERMAL)
 
 
-@pytest.mark.parametrize("ng,ngas,nlay,npath", [(18, 7, 37, 13), (16, 3, 64, 5), (20, 6, 100, 9)])
-def test_layer_space_thermal_irregular_paths(mods, ng, ngas, nlay, npath):
-    """ans_thermal_layers_kernel away from the timed shape: NG not a multiple of 4, NGAS + 2 > 8 columns (two column
-    tiles), a number of paths that leaves the last tile ragged, and paths of every kind side by side -- limb paths,
-    nadir paths that end on the ground (surface term), a path that crosses some layers three times, one of a single
-    layer -- against the path-space kernel."""
+@pytest.mark.parametrize("mode_name", ["thermal", "transmission"])
+@pytest.mark.parametrize("ng,ngas,nlay,npath", [(18, 7, 37, 13), (16, 3, 64, 5), (20, 6, 100, 9), (4, 2, 21, 70),
+                                                (10, 5, 50, 33), (1, 4, 30, 6)])
+def test_layer_space_irregular_paths(mods, ng, ngas, nlay, npath, mode_name):
+    """ans_thermal_layers_kernel and the layer-space ans_transmission_paths_kernel away from the timed shape: NG not a
+    multiple of 4 and below 8 (the transmission kernel then keeps a warp's lanes on the visits, not on the g-ordinates),
+    NGAS + 2 > 8 columns (two column tiles), numbers of paths that leave the last tile ragged or need a second group of
+    64, NLAY not a multiple of 8, and paths of every kind side by side -- limb paths, nadir paths that end on the ground
+    (surface term), a path that crosses some layers three times, one of a single layer -- against the path-space
+    kernels."""
     engine = mods["engine"]
     rng = np.random.default_rng(ng * 100 + npath)
     c = mods["syn"].make_fm_case(nwave=12, ng=ng, ngas=ngas, nlay=nlay, npro=nlay, nx=30, nvmr=ngas + 2, seed=11)
@@ -368,4 +375,4 @@ def test_layer_space_thermal_irregular_paths(mods, ng, ngas, nlay, npath):
         scale[:n, p] = 1.0 + rng.uniform(0.0, 3.0, n)
         emtemp[:n, p] = c["temp"][seq]
     c4 = dict(c, LAYINC=layinc, SCALE=scale, NLAYIN=nlayin, EMTEMP=emtemp)
-    _layer_space_against_path_space(mods, c4, engine.THERMAL)
+    _layer_space_against_path_space(mods, c4, engine.THERMAL if mode_name == "thermal" else engine.TRANSMISSION)
