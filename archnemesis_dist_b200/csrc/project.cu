@@ -5,8 +5,8 @@
 // reference's parameter-inclusion rule :699-702) and xmap into one matrix per path,
 //     M[path, k*NLAYMAX + j, x] = sum_pro D_k[LAYINC[j,path], pro] * xmap[x, k, pro],
 // and this kernel is the skinny FP64 product out[w,path,:] = dspec[w,path,:] . M[path].
-// FP64 FMA pipe; nothing here is shaped for tensor cores (0.5 GFLOP at 4000 x 1000 x 60, 61 GFLOP for 64 limb
-// paths of 200 layers).
+// FP64 FMA pipe (0.5 GFLOP at 4000 x 1000 x 60, 61 GFLOP for 64 limb paths of 200 layers, before the zero blocks of M are
+// skipped); when M has its usual structure the sparse kernel further down is used instead.
 #include "common.cuh"
 
 // Tiling: a CTA owns 128 wavenumbers x 64 state-vector columns of one path and walks E = NPAR*NLAYMAX in
