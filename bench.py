@@ -13,12 +13,15 @@ compared with the CPU oracle on the same rows (all NWAVE rows at N = 1, where th
 `cpu_baseline`; 64 strided rows at N > 1) -> `parity`, and the process exits non-zero above 1e-9.
 
 Extra keys (not part of the headline): at N = 1 `extra` carries BASELINE configs 3, 4 and 5 (line-by-line
-generation, 64 limb / occultation paths, NX = 1000); at N > 1 `strong` carries the strong-scaling figures of one
-config-2 evaluation and of the 64-path config 4 under wavenumber sharding (dist.WavenumberShard).
+generation, 64 limb / occultation paths, NX = 1000), the float32 table variants and the k-table quantile kernel, and
+`cpu_baseline_reference` times the UNMODIFIED reference's numba k_overlapg (staged as oracle/_ref by oracle/make_ref.py)
+on 64 rows of the timed case; at N > 1 `strong` carries the strong-scaling figures of one config-2 evaluation and of
+the 64-path config 4 under wavenumber sharding (dist.WavenumberShard).
 
-Prints ONE JSON line (see DESIGN.md "Measurement").  `--impl reference` times the CPU oracle port
-of the reference path on the host cores instead (the reference itself is pure Python + numba and
-is not present on the GPU box): every step is one pass over all NWAVE wavenumbers of the same case.
+Prints ONE JSON line (see DESIGN.md "Measurement").  `--impl reference` times the CPU oracle port of the reference
+path on all host cores instead (bit-identical to the reference's numba functions on the rows compared; the reference
+itself is serial Python + numba and needs ~160 s per evaluation): every step is one pass over all NWAVE wavenumbers
+of the same case.
 """
 import argparse
 import json
