@@ -872,16 +872,18 @@ def run_extras(hp, c, cfg, nthreads):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at config 2, from the
-# `ncu --set full` capture in profiles/r02_ncu_full_config2.txt (304.1 MB read: the touched table planes, some
-# twice; 568.8 MB written: tau + dk are 512 MB; algorithmic B_kio is 715.5 MB).  The same capture says what the kernel
-# IS bound by (it is not HBM): the shared-memory data pipe (82 % of its peak: 240 shuffles of the register sort and
-# ~470 loads/stores per fold), issue slots 64 % busy at 28 resident warps per SM, FP64 pipe 9 %.
+# `ncu --set full` capture of the final build in profiles/r02_ncu_full_config2_final.txt (207.7 MB read: the touched table
+# planes; 498.2 MB written: tau + dk are 512 MB of which the tail was still in L2 when the kernel ended; algorithmic
+# B_kio is 715.5 MB -- nothing is read twice).  The same capture says what the kernel IS bound by (it is not HBM): the
+# shared-memory data pipe (83 % of its peak: 240 shuffles of the register sort and ~470 loads/stores per fold), issue
+# slots 62 % busy at 28 resident warps per SM (largest stalls: instruction fetch, fixed-latency waits, shared-memory
+# scoreboard), FP64 pipe 9 %.
 KERNEL_NAME = ("ans_koverlap_fast_kernel (ansb200_gas_opacity: fused k-interp + random overlap with gradients; the "
                "general ans_koverlap_kernel takes the cells on its work list)")
-TRAFFIC = 872.9e6
-NCU_UTIL = dict(issue_slots_pct=64.1, smem_data_pipe_pct=81.5, fp64_pipe_pct=9.1, warps_active_pct=42.6,
-                warp_instructions=4.50e9,
-                source="profiles/r02_ncu_full_config2.txt (ncu --set full, not taken during the timed run)")
+TRAFFIC = 705.95e6
+NCU_UTIL = dict(issue_slots_pct=62.5, smem_data_pipe_pct=83.5, fp64_pipe_pct=8.7, warps_active_pct=43.5,
+                warp_instructions=4.61e9,
+                source="profiles/r02_ncu_full_config2_final.txt (ncu --set full, not taken during the timed run)")
 
 
 def main():
