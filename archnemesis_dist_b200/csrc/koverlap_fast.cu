@@ -186,7 +186,7 @@ __device__ __forceinline__ void kf_mma(const double *__restrict__ M, const doubl
 {
     static_assert(NG % 4 == 0 && NG <= 24, "three 8-bin tiles, whole k-steps");
     const int kk = lane & 3, mm = lane >> 2;
-#pragma unroll
+#pragma unroll 1
     for (int k0 = 0; k0 < NG; k0 += 4) {
         double b[XS / 8];
 #pragma unroll
@@ -219,7 +219,7 @@ __device__ __forceinline__ bool kf_walk(const unsigned char *__restrict__ bin, c
         const unsigned mbase = (unsigned)__cvta_generic_to_shared(M + lane);
         unsigned ma = mbase + (unsigned)bp[0] * (NG * 8);   // shared-memory address of the current run's slot
         double acc = 0.0;
-#pragma unroll 5
+#pragma unroll 2
         for (int t = 0; t < NG; ++t) {
             const unsigned na = mbase + (unsigned)bp[t * SB] * (NG * 8);
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, %2;\n\t@p st.shared.f64 [%2], %0;\n\t"
