@@ -469,7 +469,7 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                     local = __dadd_rn(local, (double)wf[r]);
                 }
                 double incl = local;
-#pragma unroll
+#pragma unroll 1
                 for (int d = 1; d < 32; d <<= 1) {
                     const double up = shfl_up_d(incl, d);
                     if (lane >= d) incl = __dadd_rn(incl, up);
@@ -478,7 +478,7 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                 int m;
                 {   // number of edges g_ord[1..NG] <= base
                     int lo = 0, hi = NG;
-#pragma unroll
+#pragma unroll 1
                     for (int it = 0; it < 5; ++it) {
                         const int mid = (lo + hi + 1) >> 1;
                         if (S.gord[mid] <= base) lo = mid; else hi = mid - 1;
