@@ -38,6 +38,12 @@
 namespace {
 
 constexpr int KF_NONE = 0xffff;
+#ifndef KF_PARTIAL
+#define KF_PARTIAL 1        // 0: every sorted fold sorts the whole key matrix
+#endif
+#ifndef KF_SKIP
+#define KF_SKIP 1           // 0: all merge levels even for a small head
+#endif
 
 template <int NG>
 struct KfShared {
@@ -46,6 +52,9 @@ struct KfShared {
     float wtabf[NG * NG + 16];      // the same as float32; entry NG*NG = 0 is the padding of the sort
     double stat[2][2][NG * NG];     // [order][rows | columns][m*NG + i]  marginals of the static orders
     unsigned short sstr[2][NG + 1][4];   // [order][edge] -> element before / the straddler / element after
+    double scw[NG + 2];             // row-major order: the (1-frac) part of the weight of edge m's straddler
+    double sbin[(NG * NG + 16) / 8];   // row-major order: the bin every element starts in (bytes; entry NG*NG: padding)
+    unsigned char nedge[NG + 4];    // number of edges whose row-major straddler lies in rows < i
     int ok_f32, ok_static;
 };
 
@@ -70,7 +79,7 @@ struct KfWarpLayout {
 // (koverlap_impl.cuh).  Every lane arrives with a BITONIC sequence (the key loop lays the tail of one row of the key
 // matrix ascending and the head of the next one descending), so the in-lane phases reduce to one 4-stage merge.
 // Cross-lane comparators: "take the partner's word if (partner < mine) != keep_high" is one ISETP.LT.XOR + SEL.
-__device__ __forceinline__ void kf_sort(unsigned (&v)[16], int lane)   // @phase sort
+__device__ __forceinline__ void kf_sort(unsigned (&v)[16], int lane, int klmax)   // @phase sort
 {
 #define KF_CE(x, y) do { const unsigned lo__ = min(x, y), hi__ = max(x, y); x = lo__; y = hi__; } while (0)
 #pragma unroll
@@ -80,7 +89,7 @@ __device__ __forceinline__ void kf_sort(unsigned (&v)[16], int lane)   // @phase
             if ((r & j) == 0) KF_CE(v[r], v[r | j]);
     }
 #pragma unroll 1
-    for (int kl = 2; kl <= 32; kl <<= 1) {
+    for (int kl = 2; kl <= klmax; kl <<= 1) {
         {
             const bool keep_high = (lane & (kl >> 1)) != 0;
 #pragma unroll
@@ -122,13 +131,19 @@ __device__ void kf_static_setup(KfShared<NG> &S)   // @phase cta_setup
         double run = 0.0;
         int ig = 0, prev = KF_NONE, pending = -1;
         bool ok = true;
+        unsigned char *sbin = reinterpret_cast<unsigned char *>(S.sbin);
         for (int m = 0; m <= NG; ++m) { S.sstr[o][m][0] = S.sstr[o][m][1] = S.sstr[o][m][2] = KF_NONE; }
+        if (o == 0) {
+            for (int m = 0; m <= NG + 1; ++m) S.scw[m] = 0.0;
+            for (int e = NG * NG; e < NG * NG + 16; ++e) sbin[e] = 0;
+        }
         for (int q = 0; q < NG; ++q) {
             for (int r = 0; r < NG; ++r) {
                 const int i = o == 0 ? q : r, j = o == 0 ? r : q, e = i * NG + j;
                 if (pending >= 0) { S.sstr[o][pending][2] = (unsigned short)e; pending = -1; }
                 const double w = S.wtabd[e];
                 const double gdn = __dadd_rn(run, w);
+                if (o == 0) sbin[e] = (unsigned char)(ig < NG ? ig : NG - 1);
                 if (ig < NG) {
                     if (gdn < S.gord[ig + 1]) {
                         RA[ig * NG + i] = __dadd_rn(RA[ig * NG + i], w);
@@ -142,6 +157,8 @@ __device__ void kf_static_setup(KfShared<NG> &S)   // @phase cta_setup
                         S.sstr[o][ig][0] = (unsigned short)prev;
                         S.sstr[o][ig][1] = (unsigned short)e;
                         pending = ig;
+                        if (o == 0)      // (the formula of the sorted folds, step 3 of the kernel)
+                            S.scw[ig] = __dmul_rn(__dsub_rn(1.0, __ddiv_rn(__dsub_rn(S.gord[ig], run), w)), w);
                         if (ig < NG) {
                             const double f2 = __dmul_rn(__dsub_rn(1.0, frac), w);
                             RA[ig * NG + i] = __dadd_rn(RA[ig * NG + i], f2);
@@ -155,6 +172,12 @@ __device__ void kf_static_setup(KfShared<NG> &S)   // @phase cta_setup
             }
         }
         if (ig < NG - 1) ok = false;     // some bin never closed
+        if (o == 0)
+            for (int i = 0; i <= NG; ++i) {
+                int c = 0;
+                for (int m = 1; m <= NG; ++m) c += S.sstr[0][m][1] != KF_NONE && S.sstr[0][m][1] < i * NG;
+                S.nedge[i] = (unsigned char)c;
+            }
         if (!ok) atomicAnd(&S.ok_static, 0);
     } else if (o == 32) {
         // in any order: no element may lie over two edges (the host plan checks the same and asks for the
@@ -392,6 +415,15 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
             const bool rowok = __all_sync(FULL, !inner || __dadd_rn(a_l, b_last) <= __dadd_rn(a_n, b_first));
             const bool colok = !rowok && __all_sync(FULL, !inner || __dadd_rn(a_last, b_l) < __dadd_rn(a_first, b_n));
             int ord = rowok ? 0 : (colok ? 1 : -1);
+            // Partly static orders: if no row from some row on interleaves with its neighbours, those rows follow the
+            // rest in row-major order -- only the `hl` rows before them (the head) need sorting, and the bins, straddlers
+            // and straddler fractions of the tail are those of the row-major order (data-independent).
+            int hl = NG;
+            if (KF_PARTIAL && ord < 0) {
+                // (strictly separated here: no key of the head may equal one of the tail)
+                const unsigned rss = __ballot_sync(FULL, !inner || __dadd_rn(a_l, b_last) < __dadd_rn(a_n, b_first));
+                hl = 33 - __clz(~rss);      // last interleaving boundary + 2
+            }
             if (ord >= 0) {
                 // the static straddlers must be strictly separated from their neighbours in the order
                 bool sep = true;
@@ -432,6 +464,8 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
             double cw = 0.0;        // (1-frac) * its weight: goes to the next bin
             bool wbad = false;
             if (ord < 0) {
+                const int nhead = hl * NG;
+                const int mh = S.nedge[hl];        // edges 1 .. mh fall into the head
                 // ---- 1. packed keys, sorted in registers --------------------------------------------   // @phase keys
                 unsigned v[EPL];
                 {
@@ -440,7 +474,7 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                     const int i0 = ebase / NG, j0 = ebase - i0 * NG;
                     const double a0 = av[i0 < NG ? i0 : NG - 1], a1 = av[i0 + 1 < NG ? i0 + 1 : NG - 1];
                     // slots 0 .. n0-1: the tail of row i0, ascending in j; slots n0 .. 15: the head of row i0+1,
-                    // DESCENDING in j -- a bitonic sequence (b is ascending)
+                    // DESCENDING in j -- a bitonic sequence (b is ascending); rows of the tail are padding
                     const int n0 = NG - j0 < EPL ? NG - j0 : EPL;
 #pragma unroll
                     for (int r = 0; r < EPL; ++r) {
@@ -449,10 +483,15 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                         const int e = second ? ebase + n0 + (EPL - 1 - r) : ebase + r;
                         const double key = __dadd_rn(second ? a1 : a0, bv[j]);
                         const int t = max(__double2hiint(key) - basehi, 0);
-                        v[r] = ebase < NN ? (((unsigned)t << 6) & 0xfffffe00u) | (unsigned)e : (0xfffffe00u | (unsigned)NN);
+                        v[r] = e < nhead ? (((unsigned)t << 6) & 0xfffffe00u) | (unsigned)e : (0xfffffe00u | (unsigned)NN);
                     }
                 }
-                kf_sort(v, lane);   // @phase sort_call
+                // the head fills lanes 0 .. ceil(nhead / 16) - 1; the padding above it needs no merging
+                kf_sort(v, lane, KF_SKIP ? 2 << (31 - __clz(((nhead + EPL - 1) >> 4) - 1)) : 32);   // @phase sort_call
+                if (KF_PARTIAL && nhead < NN) {
+                    double *bd = reinterpret_cast<double *>(bin);
+                    for (int t = lane; t < (NN + 16) / 8; t += 32) bd[t] = S.sbin[t];
+                }
                 // sorted words for the straddler checks (16-byte units, lane-interleaved: conflict-free)
                 {
                     uint4 *vb4 = reinterpret_cast<uint4 *>(vbuf);
@@ -505,10 +544,30 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                 __syncwarp();
                 // ---- 3. the straddler of edge `lane` ---------------------------------------------------   // @phase resolve
                 bool bad = false;
-                if (lane >= 1 && lane <= NG) {
+                if (KF_PARTIAL && lane > mh && lane <= NG) {
+                    // an edge of the tail: the straddler of the row-major order, if it is strictly separated from its
+                    // neighbours there (as for the fully static orders)
+                    const int pe = S.sstr[0][lane][0], s2 = S.sstr[0][lane][1], ne = S.sstr[0][lane][2];
+                    if (spos[lane] != KF_NONE) {
+                        bad = true;            // found in the head as well: the two counts disagree
+                        why = 2;
+                    } else if (s2 != KF_NONE) {
+                        const double ks = __dadd_rn(av[s2 / NG], bv[s2 % NG]);
+                        bool sep = true;
+                        if (pe != KF_NONE) sep &= __dadd_rn(av[pe / NG], bv[pe % NG]) < ks;
+                        if (ne != KF_NONE) sep &= ks < __dadd_rn(av[ne / NG], bv[ne % NG]);
+                        bad = !sep;
+                        if (bad) why = 4;
+                        se = s2;
+                        cw = S.scw[lane];
+                    } else {
+                        bad = lane < NG;       // only the last edge may stay open (:6025-6027)
+                        if (bad) why = 2;
+                    }
+                } else if (lane >= 1 && lane <= NG) {
                     const int p = spos[lane];
                     if (p == KF_NONE) {
-                        bad = lane < NG;       // only the last edge may stay open (:6025-6027)
+                        bad = lane < NG || nhead < NN;       // only the last edge may stay open (:6025-6027)
                         if (bad) why = 2;
                     } else {
                         const unsigned vp = vbuf[kf_vaddr(p)];
