@@ -157,3 +157,37 @@ def test_float64_quadrature_goes_to_the_general_kernel(mods):
     assert relerr(cpu(tau), rt) < 1e-13
     for col in range(rd.shape[-1]):
         assert colerr(cpu(dk)[..., col], rd[..., col]) < 1e-13, col
+
+
+def test_partly_static_orders(mods):
+    """Key matrices whose rows stop interleaving from some row on: the fast kernel sorts the head only and takes the
+    bins / straddlers of the tail from the row-major tables.  Every head length 2 .. 20 occurs, with smooth and with
+    grid-valued operands (exact ties inside the head, between the head and the tail, and on bin edges -- the latter go
+    to the general kernel); both must give the oracle's numbers."""
+    rng = np.random.default_rng(11)
+    ng, nlay, reps = 20, 19 * 2, 12
+    _, delg = mods["syn"].gauss_legendre_01(ng)
+    k = np.zeros((reps, ng, nlay, 2))
+    for w in range(reps):
+        for l in range(nlay):
+            hl = 2 + l % 19                      # rows hl-1 | hl is the last boundary that may interleave
+            grid = l >= 19
+            if grid:
+                b = 1.0 + np.arange(ng) * rng.integers(1, 4) / 32.0
+                spread = b[-1] - b[0]
+                inc = np.where(np.arange(ng - 1) < hl - 1, rng.integers(1, 16, ng - 1) / 32.0,
+                               spread + rng.integers(0, 3, ng - 1) / 32.0)      # (0: the boundary ties exactly)
+                a = 0.5 + np.concatenate([[0.0], np.cumsum(inc)])
+            else:
+                b = 10.0 ** rng.uniform(-3, 3) * 1.3 ** np.arange(ng)
+                spread = b[-1] - b[0]
+                inc = np.where(np.arange(ng - 1) < hl - 1, spread * rng.uniform(0.05, 0.9, ng - 1),
+                               spread * (1.0 + rng.uniform(0.01, 2.0, ng - 1)))
+                a = b[0] * rng.uniform(0.1, 10.0) + np.concatenate([[0.0], np.cumsum(inc)])
+            k[w, :, l, 0] = a
+            k[w, :, l, 1] = b
+    dkdT = k * rng.uniform(-0.01, 0.01, size=k.shape)
+    c = dict(tab=dict(DELG=delg), amount=np.ones((2, nlay)))
+    st, st0 = _check(mods, c, k, dkdT)
+    assert st["sorted_folds"] > reps * nlay // 4
+    assert st["handed_over"] < reps * nlay
