@@ -12,8 +12,9 @@
 // with the marginals  R[i][m] = sum_j omega_m(i,j),  C[j][m] = sum_i omega_m(i,j).  The bins, as sets, and
 // the element that straddles each edge depend on the ORDER of the keys only where an edge falls, so the
 // sort needs to be exact only there:
-//   1. keys are packed as (23 key bits | 9-bit element number) -- 6 exponent bits below the largest key and the
-//      17 leading mantissa bits, cut straight out of the float64 pattern (truncation is monotone) -- and
+//   1. keys are packed as (23 key bits | 9-bit element number) -- the exponent bits the fold's keys need (at most 6:
+//      62 binades below the largest key) and the 17 to 20 leading mantissa bits that fit beside them, cut straight
+//      out of the float64 pattern (truncation is monotone) -- and
 //      sorted by the 32-bit min/max bitonic network of koverlap_impl.cuh, in registers;
 //   2. cumulative weights: lane-local sums + one warp scan (exact: float32-born weights); every element
 //      stores the bin it starts in (one byte), the straddler of every edge its position and the cumulative
@@ -469,7 +470,11 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                 // ---- 1. packed keys, sorted in registers --------------------------------------------   // @phase keys
                 unsigned v[EPL];
                 {
-                    const int basehi = (ek - 62) << 20;
+                    // key bits = the leading 23 bits of (high word of the key - high word of the base), the base being
+                    // the binade of the smallest key (at most 62 binades below the largest): the fewer binades the
+                    // keys span, the more mantissa bits take part (one binade of head room keeps them below the padding)
+                    const int basehi = max(max(__double2hiint(__dadd_rn(a_first, b_first)), 0) & 0x7ff00000, (ek - 62) << 20);
+                    const int sh = min(__clz(__double2hiint(kmax) - basehi + (1 << 20)), 11);
                     const int ebase = lane * EPL;
                     const int i0 = ebase / NG, j0 = ebase - i0 * NG;
                     const double a0 = av[i0 < NG ? i0 : NG - 1], a1 = av[i0 + 1 < NG ? i0 + 1 : NG - 1];
@@ -483,7 +488,7 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                         const int e = second ? ebase + n0 + (EPL - 1 - r) : ebase + r;
                         const double key = __dadd_rn(second ? a1 : a0, bv[j]);
                         const int t = max(__double2hiint(key) - basehi, 0);
-                        v[r] = e < nhead ? (((unsigned)t << 6) & 0xfffffe00u) | (unsigned)e : (0xfffffe00u | (unsigned)NN);
+                        v[r] = e < nhead ? (((unsigned)t << sh) & 0xfffffe00u) | (unsigned)e : (0xfffffe00u | (unsigned)NN);
                     }
                 }
                 // the head fills lanes 0 .. ceil(nhead / 16) - 1; the padding above it needs no merging
