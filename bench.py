@@ -8,6 +8,10 @@ projection (ansb200_jacobian_project) [-> NCCL all-gather of the KK rows when N 
 Weak scaling: every rank evaluates its own geometry (atmosphere state seeded by rank) against a
 full replica of the table and the ranks' [spectrum | Jacobian] blocks are all-gathered.
 
+`e2e` is the same step through HotPath.forward_jacobian with HOST arrays: pinned H2D of the inputs, kernels, and rank 0's
+read-back of the result block(s) on a copy stream while the next evaluation is staged (all inside the timed region);
+`e2e.latency_ms_per_call` is one synchronous call.
+
 After the timed loops rank 0 checks the numbers it timed: the [spectrum | Jacobian] rows of the timed case are
 compared with the CPU oracle on the same rows (all NWAVE rows at N = 1, where that pass is also the
 `cpu_baseline`; 64 strided rows at N > 1) -> `parity`, and the process exits non-zero above 1e-9.
@@ -488,49 +492,50 @@ def run_b200(args, cfg):
                 res_pending[i].wait()
                 res_pending[i] = None
 
-    host_out = torch.empty((NW, NX + 1), dtype=torch.float64, pin_memory=True)
     # the assembled YN / KK rows are wanted on ONE host (the optimal-estimation update runs once): rank 0 reads the
     # gathered block back, the other ranks keep their device copy
     host_all = [torch.empty((world, NW, NX + 1), dtype=torch.float64, pin_memory=True) for _ in range(2)] \
-        if world > 1 and rank == 0 else None
-    # N > 1: rank 0's read-back of the eight blocks (15.6 MB at N = 8: 0.3 ms of PCIe time) runs on a copy stream into
-    # one of two pinned buffers while the next evaluation computes; every step's block reaches the host inside the timed
-    # region (drain_e2e).  The all-gather keeps the ranks in step, so the other ranks need no host synchronisation.
-    e2e_gathered = [gathered, torch.empty_like(gathered)] if world > 1 else None
-    e2e_copy_stream = torch.cuda.Stream() if world > 1 and rank == 0 else None
+        if rank == 0 else None
+    # Rank 0's read-back of the blocks (15.6 MB at N = 8: 0.3 ms of PCIe time) runs on a copy stream into one of two
+    # pinned buffers while the next evaluation is staged and computes; every step's block reaches the host inside the
+    # timed region (drain_e2e).  At N > 1 the all-gather keeps the ranks in step, so the other ranks need no host
+    # synchronisation.  The evaluations of a step sequence are independent (geometries, Jacobian columns, the members of
+    # a nested-sampling batch); the latency of ONE synchronous call is reported next to the throughput.
+    e2e_gathered = [gathered if world > 1 else torch.empty((1, NW, NX + 1), dtype=torch.float64, device="cuda"),
+                    torch.empty((world, NW, NX + 1), dtype=torch.float64, device="cuda")]
+    e2e_copy_stream = torch.cuda.Stream() if rank == 0 else None
     e2e_done = [None, None]
     e2e_count = [0]
 
     def step_e2e():
         spec, dx, _ = hp.forward_jacobian(ev, M)          # public API: host arrays in
+        slot = e2e_count[0] & 1
+        e2e_count[0] += 1
+        if e2e_done[slot] is not None:
+            e2e_done[slot].synchronize()                  # the copy out of this buffer set, two steps ago
         if world > 1:
-            slot = e2e_count[0] & 1
-            e2e_count[0] += 1
-            if e2e_done[slot] is not None:
-                e2e_done[slot].synchronize()              # the copy out of this buffer set, two steps ago
             block[:, 0] = spec[:, 0]
             block[:, 1:] = dx[:, 0, :]
             dist.all_gather_into_tensor(e2e_gathered[slot], block)
-            if rank == 0:
-                ready = torch.cuda.Event()
-                ready.record()
-                with torch.cuda.stream(e2e_copy_stream):
-                    e2e_copy_stream.wait_event(ready)
-                    host_all[slot].copy_(e2e_gathered[slot], non_blocking=True)
-                    e2e_done[slot] = torch.cuda.Event()
-                    e2e_done[slot].record()
         else:
             # one contiguous [NWAVE, 1+NX] device block, one DMA into pinned memory (strided D2H copies go
             # through a bounce buffer and a second launch each)
-            host_out.copy_(torch.cat([spec[:, :1], dx[:, 0, :]], dim=1), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            e2e_gathered[slot][0, :, 0] = spec[:, 0]
+            e2e_gathered[slot][0, :, 1:] = dx[:, 0, :]
+        if rank == 0:
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(e2e_copy_stream):
+                e2e_copy_stream.wait_event(ready)
+                host_all[slot].copy_(e2e_gathered[slot], non_blocking=True)
+                e2e_done[slot] = torch.cuda.Event()
+                e2e_done[slot].record()
 
     def drain_e2e():
-        if world > 1:
-            for e in e2e_done:
-                if e is not None:
-                    e.synchronize()
-            torch.cuda.current_stream().synchronize()
+        for e in e2e_done:
+            if e is not None:
+                e.synchronize()
+        torch.cuda.current_stream().synchronize()
 
     def barrier():
         if world > 1:
@@ -600,7 +605,16 @@ def run_b200(args, cfg):
     e2e_ms = reduce_max(e0.elapsed_time(e1))
     h2d = int(ev.h2d_bytes)
     d2h = int((world if world > 1 else 1) * NW * (NX + 1) * 8)
-    e2e_block = (host_all[(e2e_count[0] - 1) & 1][0] if world > 1 else host_out).numpy() if rank == 0 else None
+    e2e_block = host_all[(e2e_count[0] - 1) & 1][0].numpy().copy() if rank == 0 else None
+    # latency of one synchronous call (host arrays in, result on the host), nothing overlapped
+    lat = []
+    for _ in range(4):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step_e2e()
+        drain_e2e()
+        lat.append((time.perf_counter() - t0) * 1e3)
+    e2e_latency_ms = reduce_max(min(lat[1:]))
 
     if args.stage_times and rank == 0:
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -693,9 +707,10 @@ def run_b200(args, cfg):
                     data="synthetic", config=config_dict(cfg, world),
                     e2e=dict(value=world * 1e3 / (e2e_ms / K), unit="spectra/s", h2d_bytes_per_step=h2d,
                              d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / K,
-                             readback=("every step's result is synchronised to the host before the next step starts" if world == 1
-                                       else "rank 0 reads all ranks' blocks back on a copy stream while the next evaluation "
-                                            "computes; every block is on the host before the timed region ends")),
+                             latency_ms_per_call=e2e_latency_ms,
+                             readback=("rank 0 reads every step's block(s) back on a copy stream while the next evaluation is "
+                                       "staged and computes; every block is on the host before the timed region ends; "
+                                       "latency_ms_per_call is one synchronous call, nothing overlapped")),
                     gpu_launches=launches, roofline=roof, clocks=clocks, parity=parity)
         if cb is not None:
             line["cpu_baseline"] = cb
@@ -872,17 +887,17 @@ def run_extras(hp, c, cfg, nthreads):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at config 2, from the
-# `ncu --set full` capture of the final build in profiles/r02_ncu_full_config2_final.txt (207.7 MB read: the touched table
-# planes; 498.2 MB written: tau + dk are 512 MB of which the tail was still in L2 when the kernel ended; algorithmic
+# `ncu --set full` capture of the final build in profiles/r02_ncu_full_config2_final.txt (208.3 MB read: the touched table
+# planes; 495.3 MB written: tau + dk are 512 MB of which the tail was still in L2 when the kernel ended; algorithmic
 # B_kio is 715.5 MB -- nothing is read twice).  The same capture says what the kernel IS bound by (it is not HBM): the
-# shared-memory data pipe (83 % of its peak: 240 shuffles of the register sort and ~470 loads/stores per fold), issue
-# slots 62 % busy at 28 resident warps per SM (largest stalls: instruction fetch, fixed-latency waits, shared-memory
-# scoreboard), FP64 pipe 9 %.
+# shared-memory data pipe (82 % of its peak: the shuffles of the register sort and ~450 loads/stores per fold) and the
+# issue slots (70 % busy at 28 resident warps per SM; largest stalls: fixed-latency waits, shared-memory scoreboard,
+# not selected, instruction fetch), FP64 pipe 10 %.
 KERNEL_NAME = ("ans_koverlap_fast_kernel (ansb200_gas_opacity: fused k-interp + random overlap with gradients; the "
                "general ans_koverlap_kernel takes the cells on its work list)")
-TRAFFIC = 705.95e6
-NCU_UTIL = dict(issue_slots_pct=62.5, smem_data_pipe_pct=83.5, fp64_pipe_pct=8.7, warps_active_pct=43.5,
-                warp_instructions=4.61e9,
+TRAFFIC = 703.58e6
+NCU_UTIL = dict(issue_slots_pct=70.5, smem_data_pipe_pct=81.9, fp64_pipe_pct=9.6, warps_active_pct=43.5,
+                warp_instructions=4.86e9,
                 source="profiles/r02_ncu_full_config2_final.txt (ncu --set full, not taken during the timed run)")
 
 
