@@ -55,6 +55,7 @@ struct KfShared {
     unsigned short sstr[2][NG + 1][4];   // [order][edge] -> element before / the straddler / element after
     double scw[NG + 2];             // row-major order: the (1-frac) part of the weight of edge m's straddler
     double sbin[(NG * NG + 16) / 8];   // row-major order: the bin every element starts in (bytes; entry NG*NG: padding)
+    double rwid[NG + 4];            // 1 / weight of bin m (the sum over a bin's marginals in any order)
     unsigned char nedge[NG + 4];    // number of edges whose row-major straddler lies in rows < i
     int ok_f32, ok_static;
 };
@@ -200,13 +201,13 @@ __device__ void kf_static_setup(KfShared<NG> &S)   // @phase cta_setup
 // 3 tiles of 8 bins (the last one half empty), XS/8 tiles of 8 columns, NG/4 steps of 4 rows.
 // Fragments (PTX ISA, mma.m8n8k4 .f64): a = A[lane>>2][lane&3], b = B[lane&3][lane>>2], d = D[lane>>2][2*(lane&3) + {0,1}].
 // With the marginals stored [bin][t] at stride NG = 20 the sixteen 8-byte words of a half-warp's A load fall in
-// sixteen different bank pairs.  `rsum` gathers the lane's share of sum_t M[bin][t] (the normalisation).
+// sixteen different bank pairs.  (The normalisation sum_t M[bin][t] is the weight of the bin: a constant, KfShared::rwid.)
 // The second operand is read through one pointer and one stride per lane and column tile (NULL = the column is zero):
 // for the row terms that is X[t][column]; the column terms {b_t, bT_t, 0 .., k_t in the column of the gas being
 // folded, 0 ..} are read where they lie (kf_yptr), no matrix of them is built.
-template <int NG, int XS, bool SUM>
+template <int NG, int XS>
 __device__ __forceinline__ void kf_mma(const double *__restrict__ M, const double *const (&bp)[XS / 8],   // @phase mma
-                                       const int (&bs)[XS / 8], int lane, double (&d)[3][XS / 8][2], double (&rsum)[3])
+                                       const int (&bs)[XS / 8], int lane, double (&d)[3][XS / 8][2])
 {
     static_assert(NG % 4 == 0 && NG <= 24, "three 8-bin tiles, whole k-steps");
     const int kk = lane & 3, mm = lane >> 2;
@@ -218,7 +219,6 @@ __device__ __forceinline__ void kf_mma(const double *__restrict__ M, const doubl
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
             const double a = M[(8 * t + mm) * NG + k0 + kk];     // (bins >= NG: whatever follows; those rows are dropped)
-            if (SUM) rsum[t] = __dadd_rn(rsum[t], a);
 #pragma unroll
             for (int n = 0; n < XS / 8; ++n)
                 asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -312,6 +312,12 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
     }
     __syncthreads();
     kf_static_setup<NG>(S);
+    __syncthreads();
+    if (threadIdx.x < NG) {
+        double w = 0.0;
+        for (int i = 0; i < NG; ++i) w = __dadd_rn(w, S.stat[0][0][threadIdx.x * NG + i]);
+        S.rwid[threadIdx.x] = __ddiv_rn(1.0, w);
+    }
     __syncthreads();
     const long long ncell = (long long)P.NWAVE * NLAY;
     if (!S.ok_f32 || !S.ok_static) {
@@ -441,10 +447,9 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
             if (fb_why && lane == 0) atomicAdd(fb_why + (ord >= 0 ? 5 : 6), 1);
 
             constexpr int NT8 = XS / 8;   // @phase static_mma
-            double dfr[3][NT8][2], rsum[3];
+            double dfr[3][NT8][2];
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
-                rsum[t] = 0.0;
 #pragma unroll
                 for (int n = 0; n < NT8; ++n) dfr[t][n][0] = dfr[t][n][1] = 0.0;
             }
@@ -652,7 +657,7 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                 kf_correct<NG>(RC, lane, se >= 0 ? se / NG : -1, cw);
             }
             // (one copy of each product for both kinds of fold: the hot code must stay inside the instruction cache)
-            kf_mma<NG, XS, true>(ord >= 0 ? S.stat[ord][0] : RC, xp, xs, lane, dfr, rsum);
+            kf_mma<NG, XS>(ord >= 0 ? S.stat[ord][0] : RC, xp, xs, lane, dfr);
             if (ord < 0) {
                 __syncwarp();
                 {
@@ -664,27 +669,18 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                 __syncwarp();
                 kf_correct<NG>(RC, lane, se >= 0 ? se % NG : -1, cw);
             }
-            kf_mma<NG, XS, false>(ord >= 0 ? S.stat[ord][1] : RC, yp, ys, lane, dfr, rsum);
+            kf_mma<NG, XS>(ord >= 0 ? S.stat[ord][1] : RC, yp, ys, lane, dfr);
             if (__any_sync(FULL, wbad)) { fallback = true; why = 16; break; }
             __syncwarp();
             // ---- bin m: normalise (ForwardModel_0.py:6016-6017, :6026-6027) and store -------------------   // @phase normalise
             {
-                // sum of the marginals of a bin: the four lanes of a fragment row hold a quarter each
-                double *sws = gbs;
-#pragma unroll
-                for (int t = 0; t < 3; ++t) {
-                    rsum[t] = __dadd_rn(rsum[t], shfl_xor_d(rsum[t], 1));
-                    rsum[t] = __dadd_rn(rsum[t], shfl_xor_d(rsum[t], 2));
-                    if ((lane & 3) == 0 && 8 * t + (lane >> 2) < NG) sws[8 * t + (lane >> 2)] = rsum[t];
-                }
-                __syncwarp();
-                if (lane < NG) sws[lane] = __ddiv_rn(1.0, sws[lane]);
-                __syncwarp();
+                // the sum of the marginals of a bin is the weight of the bin, whatever the order of the keys: 1 / weight
+                // is a table of the CTA set-up
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
                     const int mrow = 8 * t + (lane >> 2);
                     if (mrow < NG) {
-                        const double rs = sws[mrow];
+                        const double rs = S.rwid[mrow];
 #pragma unroll
                         for (int n = 0; n < NT8; ++n) {
                             const double x0 = __dmul_rn(dfr[t][n][0], rs), x1 = __dmul_rn(dfr[t][n][1], rs);
