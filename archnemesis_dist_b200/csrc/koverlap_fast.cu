@@ -160,7 +160,7 @@ __device__ void kf_static_setup(KfShared<NG> &S)   // @phase cta_setup
                         S.sstr[o][ig][1] = (unsigned short)e;
                         pending = ig;
                         if (o == 0)      // (the formula of the sorted folds, step 3 of the kernel)
-                            S.scw[ig] = __dmul_rn(__dsub_rn(1.0, __ddiv_rn(__dsub_rn(S.gord[ig], run), w)), w);
+                            S.scw[ig] = __dsub_rn(__dadd_rn(run, w), S.gord[ig]);
                         if (ig < NG) {
                             const double f2 = __dmul_rn(__dsub_rn(1.0, frac), w);
                             RA[ig * NG + i] = __dadd_rn(RA[ig * NG + i], f2);
@@ -640,8 +640,8 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                             }
                         }
                         const double w = S.wtabd[se];
-                        const double frac = __ddiv_rn(__dsub_rn(S.gord[lane], gb), w);
-                        cw = __dmul_rn(__dsub_rn(1.0, frac), w);
+                        // (1 - frac) * w with frac = (g_ord - gb) / w (:6009-6024) is what lies beyond the edge: no division
+                        cw = __dsub_rn(__dadd_rn(gb, w), S.gord[lane]);
                     }
                 }
                 if (__any_sync(FULL, bad)) { fallback = true; break; }
