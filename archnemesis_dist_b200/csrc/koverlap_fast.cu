@@ -486,14 +486,22 @@ ans_koverlap_fast_kernel(OvParams P, int *__restrict__ fb_count, int *__restrict
                     // slots 0 .. n0-1: the tail of row i0, ascending in j; slots n0 .. 15: the head of row i0+1,
                     // DESCENDING in j -- a bitonic sequence (b is ascending); rows of the tail are padding
                     const int n0 = NG - j0 < EPL ? NG - j0 : EPL;
+                    // (j0 and n0 are multiples of 4: a group of four slots lies on one side of n0)
+                    static_assert(NG % 4 == 0 && EPL % 4 == 0, "groups of four slots");
 #pragma unroll
-                    for (int r = 0; r < EPL; ++r) {
-                        const bool second = r >= n0;
-                        const int j = second ? EPL - 1 - r : j0 + r;
-                        const int e = second ? ebase + n0 + (EPL - 1 - r) : ebase + r;
-                        const double key = __dadd_rn(second ? a1 : a0, bv[j]);
-                        const int t = max(__double2hiint(key) - basehi, 0);
-                        v[r] = e < nhead ? (((unsigned)t << sh) & 0xfffffe00u) | (unsigned)e : (0xfffffe00u | (unsigned)NN);
+                    for (int g = 0; g < EPL / 4; ++g) {
+                        const bool second = g > 0 && 4 * g >= n0;
+                        const double ag = second ? a1 : a0;
+                        const int sg = second ? -1 : 1;                               // slot r holds column jg + sg * r,
+                        const double *bg = bv + (second ? EPL - 1 : j0);
+                        const int eg = second ? ebase + n0 + (EPL - 1) : ebase;       // element eg + sg * r
+                        const bool real = (second ? i0 + 1 : i0) < hl;
+#pragma unroll
+                        for (int r = 4 * g; r < 4 * g + 4; ++r) {
+                            const double key = __dadd_rn(ag, bg[sg * r]);
+                            const int t = max(__double2hiint(key) - basehi, 0);
+                            v[r] = real ? (((unsigned)t << sh) & 0xfffffe00u) | (unsigned)(eg + sg * r) : (0xfffffe00u | (unsigned)NN);
+                        }
                     }
                 }
                 // the head fills lanes 0 .. ceil(nhead / 16) - 1; the padding above it needs no merging
