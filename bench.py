@@ -887,17 +887,17 @@ def run_extras(hp, c, cfg, nthreads):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at config 2, from the
-# `ncu --set full` capture of the final build in profiles/r02_ncu_full_config2_final.txt (208.3 MB read: the touched table
-# planes; 495.3 MB written: tau + dk are 512 MB of which the tail was still in L2 when the kernel ended; algorithmic
+# `ncu --set full` capture of the final build in profiles/r02_ncu_full_config2_final.txt (206.4 MB read: the touched table
+# planes; 477.6 MB written: tau + dk are 512 MB of which the tail was still in L2 when the kernel ended; algorithmic
 # B_kio is 715.5 MB -- nothing is read twice).  The same capture says what the kernel IS bound by (it is not HBM): the
-# shared-memory data pipe (82 % of its peak: the shuffles of the register sort and ~450 loads/stores per fold) and the
-# issue slots (70 % busy at 28 resident warps per SM; largest stalls: fixed-latency waits, shared-memory scoreboard,
-# not selected, instruction fetch), FP64 pipe 10 %.
+# shared-memory data pipe (87 % of its peak: the shuffles of the register sort and ~430 loads/stores per fold) and the
+# issue slots (73 % busy at 28 resident warps per SM; largest stalls: fixed-latency waits, shared-memory scoreboard,
+# not selected), FP64 pipe 9 %.
 KERNEL_NAME = ("ans_koverlap_fast_kernel (ansb200_gas_opacity: fused k-interp + random overlap with gradients; the "
                "general ans_koverlap_kernel takes the cells on its work list)")
-TRAFFIC = 703.58e6
-NCU_UTIL = dict(issue_slots_pct=70.5, smem_data_pipe_pct=81.9, fp64_pipe_pct=9.6, warps_active_pct=43.5,
-                warp_instructions=4.86e9,
+TRAFFIC = 683.99e6
+NCU_UTIL = dict(issue_slots_pct=73.4, smem_data_pipe_pct=87.4, fp64_pipe_pct=8.9, warps_active_pct=43.5,
+                warp_instructions=4.49e9,
                 source="profiles/r02_ncu_full_config2_final.txt (ncu --set full, not taken during the timed run)")
 
 
