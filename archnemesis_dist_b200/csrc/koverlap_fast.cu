@@ -9,7 +9,8 @@
 // term (key = a_i + b_j; d/d amount of an already folded gas = dk_i; of the gas being folded = k_j;
 // d/dT = dT_i + bT_j), so
 //     bin m = [ sum_i R[i][m] X[i][:] + sum_j C[j][m] Y[j][:] ] / sum_i R[i][m]
-// with the marginals  R[i][m] = sum_j omega_m(i,j),  C[j][m] = sum_i omega_m(i,j).  The bins, as sets, and
+// with the marginals  R[i][m] = sum_j omega_m(i,j),  C[j][m] = sum_i omega_m(i,j); the denominator is the weight
+// that falls into bin m, the same in every order of the keys (KfShared::rwid).  The bins, as sets, and
 // the element that straddles each edge depend on the ORDER of the keys only where an edge falls, so the
 // sort needs to be exact only there:
 //   1. keys are packed as (23 key bits | 9-bit element number) -- the exponent bits the fold's keys need (at most 6:
